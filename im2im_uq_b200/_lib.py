@@ -1,0 +1,99 @@
+"""ctypes binding of libim2im_uq.so (the C ABI in include/im2im_uq.h) + the in-tree nvcc build recipe.
+
+This is the stub a maintainer of the reference would add.  No torch types cross the boundary:
+tensors are passed as raw device pointers, sizes and element strides; the CUDA stream is torch's current stream.
+"""
+import ctypes
+import glob
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+CSRC = os.path.join(_PKG, "csrc")
+LIB_DIR = os.path.join(_PKG, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libim2im_uq.so")
+HEADER = os.path.join(_ROOT, "include", "im2im_uq.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+IM2IM_RCPS_ZERO_OUTPUTS = 1
+IM2IM_RCPS_FORCE_GENERIC = 2
+IM2IM_HEAD_QUANTILES = 0
+IM2IM_RCPS_MAX_LAMBDAS = 8192
+
+_lib = None
+
+
+class Im2ImError(RuntimeError):
+    """A C-ABI call returned a negative code."""
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into lib/libim2im_uq.so (nvcc cross-compiles without a GPU)."""
+    srcs = sources()
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + [HEADER]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def _declare(lib):
+    c = ctypes
+    vp, i64, i32, u32, f32 = c.c_void_p, c.c_int64, c.c_int32, c.c_uint32, c.c_float
+    lib.im2im_abi_version.restype = c.c_int
+    lib.im2im_abi_version.argtypes = []
+    lib.im2im_last_error.restype = c.c_char_p
+    lib.im2im_last_error.argtypes = []
+    lib.im2im_launch_count.restype = c.c_ulonglong
+    lib.im2im_launch_count.argtypes = []
+    lib.im2im_rcps_miss_counts.restype = c.c_int
+    lib.im2im_rcps_miss_counts.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, i32, i32, vp, vp, u32, vp]
+    lib.im2im_rcps_loss_table.restype = c.c_int
+    lib.im2im_rcps_loss_table.argtypes = [vp, i64, i32, i64, i32, vp, vp]
+    lib.im2im_quantile_nested_sets.restype = c.c_int
+    lib.im2im_quantile_nested_sets.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, f32, i32, vp, vp, vp]
+    lib.im2im_rcps_miss_map.restype = c.c_int
+    lib.im2im_rcps_miss_map.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32, i32, vp, u32, vp]
+
+
+EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im_rcps_miss_counts",
+           "im2im_rcps_loss_table", "im2im_quantile_nested_sets", "im2im_rcps_miss_map"]
+
+
+def load():
+    """Load the CUDA library; fails loudly if it was not built (there is no CPU path behind this package)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Im2ImError(f"{LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(im2im_uq_b200 has no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        _declare(lib)
+        if lib.im2im_abi_version() != 1:
+            raise Im2ImError("libim2im_uq.so ABI version mismatch - rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().im2im_last_error().decode("utf-8", "replace")
+        raise Im2ImError(f"{what} failed with code {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().im2im_launch_count())

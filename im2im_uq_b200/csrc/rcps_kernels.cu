@@ -1,0 +1,479 @@
+// RCPS conformal-calibration kernels for sm_100a (Path A of DESIGN.md).
+//
+// One pass over the scores replaces the reference's one-pass-per-lambda sweep
+// (core/calibration/calibrate_model.py:134-136 in the reference tree).  Per pixel the fp32 miss predicate of
+//   quantile_layer.py:39-42 -> add_uncertainty.py:35-36 -> calibrate_model.py:77-78
+// is monotone non-increasing in lambda (every op is a correctly rounded monotone function of lambda for a
+// non-negative width), so a pixel is summarised by k = #{j : missed at lambda_j} and
+//   counts[i, j] = #{pixels of image i with k > j}.
+// k is found from an arithmetic guess and then VERIFIED with the exact predicate (same op order, no FMA), so the
+// counts are bit-identical to evaluating every lambda separately.
+//
+// HBM-bound design: persistent CTAs (one per SM); a producer warp streams 4-plane tiles into a shared-memory ring
+// with cp.async.bulk (UBLKCP) + mbarrier transaction counts; 16 consumer warps read the tile with LDS.128, rank the
+// pixels and bump a per-image shared-memory histogram; a block-wide suffix scan turns the histogram into the
+// image's row of counts.
+#include "common.cuh"
+
+namespace im2im {
+namespace {
+
+constexpr int kConsumerWarps = 16;
+constexpr int kConsumerThreads = kConsumerWarps * 32;  // 512
+constexpr int kThreads = kConsumerThreads + 32;        // + one producer warp
+constexpr int kPxPerThread = 4;
+constexpr int kTilePx = kConsumerThreads * kPxPerThread;  // 2048 pixels of each of the 4 planes per stage (32 KB)
+constexpr int kStages = 4;                                // 128 KB in flight per SM
+constexpr int kFlushBarrier = 1;                          // named barrier id for the consumer warps
+constexpr size_t kMaxSmemOptin = 232448;                  // 227 KB per CTA on sm_100
+
+struct RcpsParams {
+    const float* plane[4];  // lower, pred, upper, label
+    long long stride[4];    // elements between consecutive images of each plane
+    long long n_images;
+    long long px;           // C*H*W values per image
+    long long tiles_per_image;
+    long long total_tiles;
+    const float* lambdas;   // device, sorted ascending
+    int n_lambdas;
+    int* counts;                  // [n_images, n_lambdas]
+    unsigned long long* totals;   // [n_lambdas] or null
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-pixel rank.  Exactness notes (all fp32, round-to-nearest, no contraction):
+//   pm = p - 1e-6f, pp = p + 1e-6f
+//   reference upper miss: max(lam*(max(u,pp)-p)+p, pp) < y   <=>  (pp < y) && (lam*du + p < y)   [NaN -> false]
+//   reference lower miss: min(p-lam*(p-min(l,pm)), pm) > y   <=>  (pm > y) && (p - lam*dl > y)
+//   pm <= p <= pp, so at most one side can ever miss; the lower side is folded onto the upper-side form by
+//   negation, which is exact:  p - x > y  <=>  x + (-p) < -y.
+//   torch.minimum/maximum propagate NaN: a NaN u (resp. l) makes that side's predicate false for every lambda,
+//   a NaN p or y makes both comparisons false.  fmaxf/fminf are only evaluated on non-NaN operands that matter.
+struct PixelQuery {
+    float d, P, Y;
+    bool active;
+};
+
+__device__ __forceinline__ PixelQuery make_query(float l, float p, float u, float y) {
+    const float pm = __fsub_rn(p, 1e-6f);
+    const float pp = __fadd_rn(p, 1e-6f);
+    const bool up = pp < y;
+    const bool lo = pm > y;
+    PixelQuery q;
+    const float a = up ? fmaxf(u, pp) : p;
+    const float b = up ? p : fminf(l, pm);
+    q.d = __fsub_rn(a, b);           // du = max(u,pp)-p   or   dl = p-min(l,pm);   >= 0
+    q.P = up ? p : -p;
+    q.Y = up ? y : -y;
+    q.active = up ? (u == u) : (lo && (l == l));
+    return q;
+}
+
+__device__ __forceinline__ bool missed(const PixelQuery& q, float lam) {
+    return __fadd_rn(__fmul_rn(lam, q.d), q.P) < q.Y;
+}
+
+// Number of grid points at which the pixel is missed = index of the first lambda that covers it.
+__device__ __forceinline__ int pixel_rank(const PixelQuery& q, const float* __restrict__ s_lam, int L, float lam0,
+                                          float inv_dlam) {
+    if (!q.active) return 0;
+    // real-valued crossing lam* = (Y-P)/d ; on a uniform grid #{lam_j < lam*} = ceil((lam*-lam0)/dlam)
+    const float t = __fdividef(__fsub_rn(q.Y, q.P), q.d);
+    int g = __float2int_ru((t - lam0) * inv_dlam);  // saturating; NaN -> 0
+    g = max(0, min(g, L));
+    int moved = 0;
+    while (g < L && missed(q, s_lam[g])) {
+        ++g;
+        if (++moved > 2) goto bisect;
+    }
+    if (moved == 0) {
+        while (g > 0 && !missed(q, s_lam[g - 1])) {
+            --g;
+            if (++moved > 2) goto bisect;
+        }
+    }
+    return g;
+bisect: {
+    // bad guess (non-uniform grid, inf/NaN widths ...): exact binary search for the first covered lambda
+    int lo = 0, hi = L;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (missed(q, s_lam[mid])) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// hist[1..L] -> counts row (suffix sums), accumulate per-CTA totals, zero the histogram.  Consumer threads only.
+__device__ __forceinline__ void flush_image(unsigned* hist, unsigned long long* tot, unsigned* warp_sums, int L,
+                                            int* counts_row, bool exclusive, int ctid) {
+    named_bar_sync(kFlushBarrier, kConsumerThreads);  // all histogram atomics of this image have landed
+    const int per_thread = (L + kConsumerThreads - 1) / kConsumerThreads;
+    const int r0 = ctid * per_thread;  // r = L-1-j : position counted from the top of the grid
+    const int lane = ctid & 31, warp = ctid >> 5;
+    unsigned local = 0;
+    for (int e = 0; e < per_thread; ++e) {
+        const int r = r0 + e;
+        if (r < L) local += hist[L - r];
+    }
+    unsigned incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    named_bar_sync(kFlushBarrier, kConsumerThreads);
+    unsigned run = incl - local;
+    for (int w = 0; w < warp; ++w) run += warp_sums[w];
+    for (int e = 0; e < per_thread; ++e) {
+        const int r = r0 + e;
+        if (r < L) {
+            run += hist[L - r];
+            hist[L - r] = 0;
+            const int j = L - 1 - r;
+            if (run != 0) {
+                if (exclusive) counts_row[j] = static_cast<int>(run);
+                else atomicAdd(&counts_row[j], static_cast<int>(run));
+                tot[j] += run;
+            }
+        }
+    }
+    named_bar_sync(kFlushBarrier, kConsumerThreads);  // histogram is clean, warp_sums reusable
+}
+
+template <bool STAGED>
+__global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(const RcpsParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int L = prm.n_lambdas;
+    // layout: [stage ring | STAGED only] [tot u64 x L] [mbarriers] [lambda f32 x L] [hist u32 x (L+1)] [warp sums]
+    unsigned char* cursor = smem_raw;
+    float* ring = reinterpret_cast<float*>(cursor);
+    if (STAGED) cursor += sizeof(float) * kStages * 4 * kTilePx;
+    unsigned long long* tot = reinterpret_cast<unsigned long long*>(cursor);
+    cursor += sizeof(unsigned long long) * L;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(cursor);
+    uint64_t* empty_bar = full_bar + kStages;
+    cursor += sizeof(uint64_t) * 2 * kStages;
+    float* s_lam = reinterpret_cast<float*>(cursor);
+    cursor += sizeof(float) * L;
+    unsigned* hist = reinterpret_cast<unsigned*>(cursor);
+    cursor += sizeof(unsigned) * (L + 1);
+    unsigned* warp_sums = reinterpret_cast<unsigned*>(cursor);
+
+    const int tid = threadIdx.x;
+    for (int j = tid; j < L; j += kThreads) {
+        s_lam[j] = prm.lambdas[j];
+        tot[j] = 0ull;
+    }
+    for (int j = tid; j <= L; j += kThreads) hist[j] = 0u;
+    if (STAGED && tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // contiguous run of tiles for this CTA -> it touches a contiguous run of images
+    const long long t_begin = prm.total_tiles * blockIdx.x / gridDim.x;
+    const long long t_end = prm.total_tiles * (blockIdx.x + 1) / gridDim.x;
+    const long long tpi = prm.tiles_per_image;
+
+    if (tid >= kConsumerThreads) {
+        // ------------------------------------------------------------------ producer warp
+        if (STAGED && tid == kConsumerThreads) {
+            long long img = t_begin / tpi;
+            long long r = t_begin - img * tpi;
+            long long it = 0;
+            for (long long t = t_begin; t < t_end; ++t, ++it) {
+                const int s = static_cast<int>(it % kStages);
+                if (it >= kStages) mbar_wait(&empty_bar[s], static_cast<unsigned>((it / kStages) - 1) & 1u);
+                const long long off = r * kTilePx;
+                const long long rem = prm.px - off;
+                const unsigned bytes = static_cast<unsigned>(rem < kTilePx ? rem : kTilePx) * 4u;
+                mbar_arrive_expect_tx(&full_bar[s], 4u * bytes);
+#pragma unroll
+                for (int pl = 0; pl < 4; ++pl)
+                    bulk_g2s(ring + (s * 4 + pl) * kTilePx, prm.plane[pl] + img * prm.stride[pl] + off, bytes,
+                             &full_bar[s]);
+                if (++r == tpi) { r = 0; ++img; }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    const int ctid = tid;
+    const int lane = ctid & 31;
+    const float lam0 = s_lam[0];
+    const float span = s_lam[L - 1] - lam0;
+    const float inv_dlam = (L > 1 && span > 0.f) ? static_cast<float>(L - 1) / span : 0.f;
+
+    long long img = t_begin / tpi;
+    long long r = t_begin - img * tpi;
+    bool image_started_here = (r == 0);  // did this CTA see tile 0 of the current image?
+    long long it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+        const long long off = r * kTilePx;
+        const long long rem = prm.px - off;
+        const int npx = static_cast<int>(rem < kTilePx ? rem : kTilePx);
+        float l[kPxPerThread], p[kPxPerThread], u[kPxPerThread], y[kPxPerThread];
+        bool valid[kPxPerThread];
+        if (STAGED) {
+            const int s = static_cast<int>(it % kStages);
+            mbar_wait(&full_bar[s], static_cast<unsigned>(it / kStages) & 1u);
+            const int e0 = ctid * kPxPerThread;
+            if (e0 < npx) {  // npx % 4 == 0 on this path
+                const float* base = ring + s * 4 * kTilePx + e0;
+                const float4 vl = *reinterpret_cast<const float4*>(base);
+                const float4 vp = *reinterpret_cast<const float4*>(base + kTilePx);
+                const float4 vu = *reinterpret_cast<const float4*>(base + 2 * kTilePx);
+                const float4 vy = *reinterpret_cast<const float4*>(base + 3 * kTilePx);
+                l[0] = vl.x; l[1] = vl.y; l[2] = vl.z; l[3] = vl.w;
+                p[0] = vp.x; p[1] = vp.y; p[2] = vp.z; p[3] = vp.w;
+                u[0] = vu.x; u[1] = vu.y; u[2] = vu.z; u[3] = vu.w;
+                y[0] = vy.x; y[1] = vy.y; y[2] = vy.z; y[3] = vy.w;
+#pragma unroll
+                for (int m = 0; m < kPxPerThread; ++m) valid[m] = true;
+            } else {
+#pragma unroll
+                for (int m = 0; m < kPxPerThread; ++m) valid[m] = false;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);  // values are in registers: hand the slot back early
+        } else {
+            const float* gl = prm.plane[0] + img * prm.stride[0] + off;
+            const float* gp = prm.plane[1] + img * prm.stride[1] + off;
+            const float* gu = prm.plane[2] + img * prm.stride[2] + off;
+            const float* gy = prm.plane[3] + img * prm.stride[3] + off;
+#pragma unroll
+            for (int m = 0; m < kPxPerThread; ++m) {
+                const int e = m * kConsumerThreads + ctid;  // coalesced 4-byte loads
+                valid[m] = e < npx;
+                if (valid[m]) {
+                    l[m] = ldg_stream_f32(gl + e); p[m] = ldg_stream_f32(gp + e);
+                    u[m] = ldg_stream_f32(gu + e); y[m] = ldg_stream_f32(gy + e);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kPxPerThread; ++m) {
+            if (valid[m]) {
+                const PixelQuery q = make_query(l[m], p[m], u[m], y[m]);
+                const int k = pixel_rank(q, s_lam, L, lam0, inv_dlam);
+                if (k > 0) atomicAdd(&hist[k], 1u);
+            }
+        }
+        const bool image_ends_here = (r == tpi - 1);
+        if (image_ends_here || t == t_end - 1) {
+            flush_image(hist, tot, warp_sums, L, prm.counts + img * L, image_started_here && image_ends_here, ctid);
+        }
+        if (++r == tpi) { r = 0; ++img; image_started_here = true; }
+    }
+    if (prm.totals != nullptr) {
+        const int per_thread = (L + kConsumerThreads - 1) / kConsumerThreads;
+        for (int e = 0; e < per_thread; ++e) {
+            const int rr = ctid * per_thread + e;
+            if (rr < L) {
+                const int j = L - 1 - rr;  // same ownership as flush_image: no cross-thread hazard on tot[]
+                if (tot[j] != 0ull) atomicAdd(&prm.totals[j], tot[j]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rcps_loss_table_kernel(const int* __restrict__ counts, long long n_elems,
+                                                              int L, float px, int first_visited,
+                                                              float* __restrict__ table) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n_elems; e += stride) {
+        const int j = static_cast<int>(e % L);
+        table[e] = (j >= first_visited) ? __fdiv_rn(static_cast<float>(counts[e]), px) : 0.f;
+    }
+}
+
+// torch.minimum / torch.maximum semantics (NaN propagates)
+__device__ __forceinline__ float t_min(float a, float b) { return (a != a) ? a : ((b != b) ? b : fminf(a, b)); }
+__device__ __forceinline__ float t_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
+
+__device__ __forceinline__ void nested_set(float l, float p, float u, float lam, float& lo2, float& up2, float& l1,
+                                           float& u1) {
+    const float pm = __fsub_rn(p, 1e-6f), pp = __fadd_rn(p, 1e-6f);
+    l1 = t_min(l, pm);
+    u1 = t_max(u, pp);
+    const float upper = __fadd_rn(__fmul_rn(lam, __fsub_rn(u1, p)), p);
+    const float lower = __fsub_rn(p, __fmul_rn(lam, __fsub_rn(p, l1)));
+    up2 = t_max(upper, pp);
+    lo2 = t_min(lower, pm);
+}
+
+__global__ void __launch_bounds__(256) nested_sets_kernel(float* lower, const float* __restrict__ pred, float* upper,
+                                                          long long n_images, long long px, long long sl,
+                                                          long long sp, long long su, float lam, int write_back,
+                                                          float* __restrict__ lower_out,
+                                                          float* __restrict__ upper_out) {
+    const long long total = n_images * px;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const long long i = e / px, k = e - i * px;
+        float lo2, up2, l1, u1;
+        nested_set(lower[i * sl + k], ldg_stream_f32(pred + i * sp + k), upper[i * su + k], lam, lo2, up2, l1, u1);
+        lower_out[e] = lo2;
+        upper_out[e] = up2;
+        if (write_back) {  // the reference's in-place clamp of `output` (quantile_layer.py:39-40)
+            lower[i * sl + k] = l1;
+            upper[i * su + k] = u1;
+        }
+    }
+}
+
+// map[k] += #{images in this block's slab whose pixel k is missed}; threads run along pixels (coalesced).
+__global__ void __launch_bounds__(256) miss_map_kernel(const float* __restrict__ lower, const float* __restrict__ pred,
+                                                       const float* __restrict__ upper,
+                                                       const float* __restrict__ label, long long n_images,
+                                                       long long px, long long sl, long long sp, long long su,
+                                                       long long sy, float lam, int images_per_slab,
+                                                       int* __restrict__ map) {
+    const long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= px) return;
+    const long long i0 = static_cast<long long>(blockIdx.y) * images_per_slab;
+    const long long i1 = min(i0 + images_per_slab, n_images);
+    int acc = 0;
+    for (long long i = i0; i < i1; ++i) {
+        float lo2, up2, l1, u1;
+        nested_set(ldg_stream_f32(lower + i * sl + k), ldg_stream_f32(pred + i * sp + k),
+                   ldg_stream_f32(upper + i * su + k), lam, lo2, up2, l1, u1);
+        const float y = ldg_stream_f32(label + i * sy + k);
+        acc += ((lo2 > y) || (up2 < y)) ? 1 : 0;
+    }
+    if (acc) atomicAdd(&map[k], acc);
+}
+
+size_t hist_smem_bytes(bool staged, int L) {
+    size_t b = staged ? sizeof(float) * kStages * 4 * kTilePx : 0;
+    b += sizeof(unsigned long long) * L + sizeof(uint64_t) * 2 * kStages + sizeof(float) * L +
+         sizeof(unsigned) * (L + 1) + sizeof(unsigned) * kConsumerWarps;
+    return b;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+}  // namespace im2im
+
+using namespace im2im;
+
+extern "C" int im2im_rcps_miss_counts(const float* d_lower, const float* d_pred, const float* d_upper,
+                                      const float* d_label, int64_t n_images, int64_t px, int64_t stride_lower,
+                                      int64_t stride_pred, int64_t stride_upper, int64_t stride_label,
+                                      const float* d_lambdas, int32_t n_lambdas, int32_t head_kind,
+                                      int32_t* d_counts, unsigned long long* d_totals, uint32_t flags,
+                                      void* stream) {
+    if (head_kind != IM2IM_HEAD_QUANTILES) return fail(IM2IM_ENOTSUP, "head_kind %d not implemented", head_kind);
+    if (n_images < 0 || px < 0) return fail(IM2IM_EINVAL, "negative size (n_images=%lld px=%lld)",
+                                            (long long)n_images, (long long)px);
+    if (n_lambdas < 1 || n_lambdas > IM2IM_RCPS_MAX_LAMBDAS)
+        return fail(IM2IM_ERANGE, "n_lambdas=%d outside [1, %d]", n_lambdas, IM2IM_RCPS_MAX_LAMBDAS);
+    if (px >= (1ll << 24)) return fail(IM2IM_ERANGE, "px=%lld >= 2^24: fp32 per-image mean is not exact", (long long)px);
+    if (d_lambdas == nullptr || d_counts == nullptr) return fail(IM2IM_EINVAL, "null lambda grid or counts");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (flags & IM2IM_RCPS_ZERO_OUTPUTS) {
+        if (n_images > 0)
+            IM2IM_CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * n_images * n_lambdas, st));
+        if (d_totals) IM2IM_CUDA_TRY(cudaMemsetAsync(d_totals, 0, sizeof(unsigned long long) * n_lambdas, st));
+    }
+    if (n_images == 0 || px == 0) return IM2IM_OK;  // empty calibration set: all counts stay zero
+    if (!d_lower || !d_pred || !d_upper || !d_label) return fail(IM2IM_EINVAL, "null score plane");
+
+    bool fast = !(flags & IM2IM_RCPS_FORCE_GENERIC) && (px % 4 == 0) && aligned16(d_lower) &&
+                      aligned16(d_pred) && aligned16(d_upper) && aligned16(d_label) && (stride_lower % 4 == 0) &&
+                      (stride_pred % 4 == 0) && (stride_upper % 4 == 0) && (stride_label % 4 == 0);
+    RcpsParams prm;
+    prm.plane[0] = d_lower; prm.plane[1] = d_pred; prm.plane[2] = d_upper; prm.plane[3] = d_label;
+    prm.stride[0] = stride_lower; prm.stride[1] = stride_pred; prm.stride[2] = stride_upper; prm.stride[3] = stride_label;
+    prm.n_images = n_images;
+    prm.px = px;
+    prm.tiles_per_image = (px + kTilePx - 1) / kTilePx;
+    prm.total_tiles = prm.tiles_per_image * n_images;
+    prm.lambdas = d_lambdas;
+    prm.n_lambdas = n_lambdas;
+    prm.counts = d_counts;
+    prm.totals = d_totals;
+
+    if (fast && hist_smem_bytes(true, n_lambdas) > kMaxSmemOptin) fast = false;  // very long grids: no room for the ring
+    const size_t smem = hist_smem_bytes(fast, n_lambdas);
+    const int sms = sm_count();
+    if (fast) {
+        IM2IM_CUDA_TRY(cudaFuncSetAttribute(rcps_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem)));
+        const long long grid = prm.total_tiles < sms ? prm.total_tiles : sms;
+        rcps_hist_kernel<true><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(prm);
+        return check_launch("rcps_hist_kernel<staged>");
+    }
+    IM2IM_CUDA_TRY(cudaFuncSetAttribute(rcps_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    const long long cap = 2ll * sms;
+    const long long grid = prm.total_tiles < cap ? prm.total_tiles : cap;
+    rcps_hist_kernel<false><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(prm);
+    return check_launch("rcps_hist_kernel<generic>");
+}
+
+extern "C" int im2im_rcps_loss_table(const int32_t* d_counts, int64_t n_images, int32_t n_lambdas, int64_t px,
+                                     int32_t first_visited_col, float* d_table, void* stream) {
+    if (n_images < 0 || n_lambdas < 1 || px < 1) return fail(IM2IM_EINVAL, "bad table shape");
+    if (n_images == 0) return IM2IM_OK;
+    if (!d_counts || !d_table) return fail(IM2IM_EINVAL, "null counts/table");
+    const long long n = static_cast<long long>(n_images) * n_lambdas;
+    const long long blocks = (n + 255) / 256;
+    const long long cap = 8ll * sm_count();
+    rcps_loss_table_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0,
+                             static_cast<cudaStream_t>(stream)>>>(d_counts, n, n_lambdas, static_cast<float>(px),
+                                                                  first_visited_col, d_table);
+    return check_launch("rcps_loss_table_kernel");
+}
+
+extern "C" int im2im_quantile_nested_sets(float* d_lower, const float* d_pred, float* d_upper, int64_t n_images,
+                                          int64_t px, int64_t stride_lower, int64_t stride_pred,
+                                          int64_t stride_upper, float lam, int32_t write_back_clamp,
+                                          float* d_lower_out, float* d_upper_out, void* stream) {
+    if (n_images < 0 || px < 0) return fail(IM2IM_EINVAL, "negative size");
+    if (n_images == 0 || px == 0) return IM2IM_OK;
+    if (!d_lower || !d_pred || !d_upper || !d_lower_out || !d_upper_out) return fail(IM2IM_EINVAL, "null plane");
+    const long long n = static_cast<long long>(n_images) * px;
+    const long long blocks = (n + 255) / 256;
+    const long long cap = 16ll * sm_count();
+    nested_sets_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0,
+                         static_cast<cudaStream_t>(stream)>>>(d_lower, d_pred, d_upper, n_images, px, stride_lower,
+                                                              stride_pred, stride_upper, lam, write_back_clamp,
+                                                              d_lower_out, d_upper_out);
+    return check_launch("nested_sets_kernel");
+}
+
+extern "C" int im2im_rcps_miss_map(const float* d_lower, const float* d_pred, const float* d_upper,
+                                   const float* d_label, int64_t n_images, int64_t px, int64_t stride_lower,
+                                   int64_t stride_pred, int64_t stride_upper, int64_t stride_label, float lam,
+                                   int32_t head_kind, int32_t* d_map, uint32_t flags, void* stream) {
+    if (head_kind != IM2IM_HEAD_QUANTILES) return fail(IM2IM_ENOTSUP, "head_kind %d not implemented", head_kind);
+    if (n_images < 0 || px < 0) return fail(IM2IM_EINVAL, "negative size");
+    if (px == 0) return IM2IM_OK;
+    if (!d_map) return fail(IM2IM_EINVAL, "null map");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (flags & IM2IM_RCPS_ZERO_OUTPUTS) IM2IM_CUDA_TRY(cudaMemsetAsync(d_map, 0, sizeof(int32_t) * px, st));
+    if (n_images == 0) return IM2IM_OK;
+    if (!d_lower || !d_pred || !d_upper || !d_label) return fail(IM2IM_EINVAL, "null score plane");
+    const unsigned bx = static_cast<unsigned>((px + 255) / 256);
+    // enough image slabs to fill the GPU when the image is small
+    long long slabs = (4ll * sm_count() + bx - 1) / bx;
+    if (slabs < 1) slabs = 1;
+    if (slabs > n_images) slabs = n_images;
+    if (slabs > 65535) slabs = 65535;
+    const int per_slab = static_cast<int>((n_images + slabs - 1) / slabs);
+    const unsigned by = static_cast<unsigned>((n_images + per_slab - 1) / per_slab);
+    miss_map_kernel<<<dim3(bx, by), 256, 0, st>>>(d_lower, d_pred, d_upper, d_label, n_images, px, stride_lower,
+                                                  stride_pred, stride_upper, stride_label, lam, per_slab, d_map);
+    return check_launch("miss_map_kernel");
+}

@@ -1,0 +1,132 @@
+"""Tensor-level wrappers over the RCPS entry points of the C ABI (include/im2im_uq.h).
+
+All tensors are CUDA fp32; outputs follow the reference's head layout (N, 3, C, H, W) = (lower, pred, upper)
+(core/models/finallayers/quantile_layer.py:19-21) and labels (N, C, H, W).
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.Im2ImError(f"{name} must be a CUDA tensor: im2im_uq_b200 has no CPU path (got device {t.device})")
+    if t.dtype != torch.float32:
+        raise _lib.Im2ImError(f"{name} must be float32 (got {t.dtype})")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _score_planes(outputs: torch.Tensor, labels: Optional[torch.Tensor]):
+    """Raw pointers/strides of the (lower, pred, upper[, label]) planes without copying when the layout allows."""
+    _require_cuda(outputs, "outputs")
+    if outputs.dim() < 3 or outputs.shape[1] != 3:
+        raise _lib.Im2ImError(f"outputs must be (N, 3, ...) = (lower, pred, upper); got {tuple(outputs.shape)}")
+    n = outputs.shape[0]
+    px = 1
+    for s in outputs.shape[2:]:
+        px *= s
+    inner_contig = outputs[0, 0].is_contiguous() if n > 0 and px > 0 else True
+    if not inner_contig:
+        outputs = outputs.contiguous()
+    s_img, s_plane = (outputs.stride(0), outputs.stride(1)) if n > 0 and px > 0 else (3 * px, px)
+    base = outputs.data_ptr()
+    ptrs = [base, base + 4 * s_plane, base + 8 * s_plane]
+    strides = [s_img, s_img, s_img]
+    keep = [outputs]
+    if labels is not None:
+        _require_cuda(labels, "labels")
+        if labels.shape[0] != n or labels.numel() != n * px:
+            raise _lib.Im2ImError(f"labels {tuple(labels.shape)} do not match outputs {tuple(outputs.shape)}")
+        if n > 0 and px > 0 and not labels[0].is_contiguous():
+            labels = labels.contiguous()
+        ptrs.append(labels.data_ptr())
+        strides.append(labels.stride(0) if n > 0 and px > 0 else px)
+        keep.append(labels)
+    return n, px, ptrs, strides, keep
+
+
+def miss_counts(outputs: torch.Tensor, labels: torch.Tensor, lambdas_sorted: torch.Tensor,
+                counts: Optional[torch.Tensor] = None, totals: Optional[torch.Tensor] = None,
+                zero: bool = True, force_generic: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """counts[i, j] = #pixels of image i missed at lambdas_sorted[j]; totals[j] += column sums (int64).
+
+    One pass over HBM for the whole grid (im2im_rcps_miss_counts).  ``lambdas_sorted`` is a CUDA fp32 vector,
+    finite and ascending.  ``counts``/``totals`` may be preallocated (e.g. to accumulate chunks with zero=False).
+    """
+    lib = _lib.load()
+    n, px, ptrs, strides, keep = _score_planes(outputs, labels)
+    _require_cuda(lambdas_sorted, "lambdas_sorted")
+    lambdas_sorted = lambdas_sorted.contiguous()
+    n_lam = lambdas_sorted.numel()
+    dev = outputs.device
+    if counts is None:
+        counts = torch.empty((n, n_lam), dtype=torch.int32, device=dev)
+        zero = True
+    if totals is None:
+        totals = torch.empty((n_lam,), dtype=torch.int64, device=dev)
+        zero = True
+    assert counts.is_contiguous() and counts.dtype == torch.int32 and tuple(counts.shape) == (n, n_lam)
+    assert totals.is_contiguous() and totals.dtype == torch.int64 and totals.numel() == n_lam
+    flags = (_lib.IM2IM_RCPS_ZERO_OUTPUTS if zero else 0) | (_lib.IM2IM_RCPS_FORCE_GENERIC if force_generic else 0)
+    with torch.cuda.device(dev):
+        rc = lib.im2im_rcps_miss_counts(ptrs[0], ptrs[1], ptrs[2], ptrs[3], n, px, strides[0], strides[1], strides[2],
+                                        strides[3], lambdas_sorted.data_ptr(), n_lam, _lib.IM2IM_HEAD_QUANTILES,
+                                        counts.data_ptr(), totals.data_ptr(), flags, _stream_ptr(dev))
+    _lib.check(rc, "im2im_rcps_miss_counts")
+    del keep
+    return counts, totals
+
+
+def loss_table(counts: torch.Tensor, px: int, first_visited_col: int = 0,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 table[i,j] = float(counts[i,j])/float(px); columns below first_visited_col are zero."""
+    lib = _lib.load()
+    assert counts.is_cuda and counts.dtype == torch.int32 and counts.is_contiguous() and counts.dim() == 2
+    n, n_lam = counts.shape
+    if out is None:
+        out = torch.empty((n, n_lam), dtype=torch.float32, device=counts.device)
+    with torch.cuda.device(counts.device):
+        rc = lib.im2im_rcps_loss_table(counts.data_ptr(), n, n_lam, px, first_visited_col, out.data_ptr(),
+                                       _stream_ptr(counts.device))
+    _lib.check(rc, "im2im_rcps_loss_table")
+    return out
+
+
+def quantile_nested_sets(outputs: torch.Tensor, lam: float, write_back_clamp: bool = True):
+    """(lower_edge, prediction, upper_edge) at one lambda; prediction is a view of outputs[:, 1].
+
+    write_back_clamp reproduces the reference's in-place clamp of ``outputs`` (quantile_layer.py:39-40).
+    """
+    lib = _lib.load()
+    n, px, ptrs, strides, keep = _score_planes(outputs, None)
+    src = keep[0]
+    if write_back_clamp and src.data_ptr() != outputs.data_ptr():
+        write_back_clamp = False  # a contiguous copy was made; nothing the caller could observe
+    shape = tuple(outputs.shape[:1]) + tuple(outputs.shape[2:])
+    lower = torch.empty(shape, dtype=torch.float32, device=outputs.device)
+    upper = torch.empty(shape, dtype=torch.float32, device=outputs.device)
+    with torch.cuda.device(outputs.device):
+        rc = lib.im2im_quantile_nested_sets(ptrs[0], ptrs[1], ptrs[2], n, px, strides[0], strides[1], strides[2],
+                                            float(lam), 1 if write_back_clamp else 0, lower.data_ptr(),
+                                            upper.data_ptr(), _stream_ptr(outputs.device))
+    _lib.check(rc, "im2im_quantile_nested_sets")
+    return lower, src[:, 1], upper
+
+
+def miss_map(outputs: torch.Tensor, labels: torch.Tensor, lam: float) -> torch.Tensor:
+    """int32 map over (C,H,W): number of images whose pixel is missed at ``lam``."""
+    lib = _lib.load()
+    n, px, ptrs, strides, keep = _score_planes(outputs, labels)
+    out = torch.empty(tuple(outputs.shape[2:]), dtype=torch.int32, device=outputs.device)
+    with torch.cuda.device(outputs.device):
+        rc = lib.im2im_rcps_miss_map(ptrs[0], ptrs[1], ptrs[2], ptrs[3], n, px, strides[0], strides[1], strides[2],
+                                     strides[3], float(lam), _lib.IM2IM_HEAD_QUANTILES, out.data_ptr(),
+                                     _lib.IM2IM_RCPS_ZERO_OUTPUTS, _stream_ptr(outputs.device))
+    _lib.check(rc, "im2im_rcps_miss_map")
+    del keep
+    return out

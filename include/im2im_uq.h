@@ -1,0 +1,114 @@
+/*
+ * im2im_uq.h - C ABI of libim2im_uq.so: the B200 (sm_100a) hot path of aangelopoulos/im2im-uq.
+ *
+ * The reference is pure Python/PyTorch, so its "FFI" for this path is the set of torch calls made by the functions
+ * cited at each entry point (paths relative to the reference root).  A maintainer binds these symbols with ctypes
+ * (INTEGRATION.md shows the stub); im2im_uq_b200/_lib.py is exactly that binding.
+ *
+ * Conventions
+ *   - plain C symbols, POD arguments, no torch types; every pointer named d_* is a DEVICE pointer
+ *   - the caller allocates every buffer; the library never frees or keeps caller memory
+ *   - all work is enqueued on the cudaStream_t passed as `stream` (void* so this header needs no CUDA include);
+ *     no hidden cudaDeviceSynchronize, no default-stream use
+ *   - return 0 on success, a negative IM2IM_E* code on failure; im2im_last_error() gives a thread-local message
+ *   - re-entrant per (device, stream)
+ */
+#ifndef IM2IM_UQ_H_
+#define IM2IM_UQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IM2IM_ABI_VERSION 1
+
+#define IM2IM_OK 0
+#define IM2IM_EINVAL (-22)     /* bad argument (null pointer, negative size, unsorted lambda grid ...) */
+#define IM2IM_ERANGE (-34)     /* size outside what the kernel supports (n_lambdas, pixels per image) */
+#define IM2IM_ECUDA (-5)       /* a CUDA runtime call or launch failed; see im2im_last_error() */
+#define IM2IM_ENOTSUP (-95)    /* head kind / option not implemented */
+
+/* head kinds (core/models/add_uncertainty.py:56-85 `uncertainty_type`) */
+#define IM2IM_HEAD_QUANTILES 0 /* planes = (lower, prediction, upper); core/models/finallayers/quantile_layer.py */
+
+/* flags for im2im_rcps_miss_counts */
+#define IM2IM_RCPS_ZERO_OUTPUTS 1u  /* memset d_counts and d_totals on `stream` before the pass */
+#define IM2IM_RCPS_FORCE_GENERIC 2u /* use the scalar-load kernel even when the bulk-copy fast path applies (tests) */
+
+#define IM2IM_RCPS_MAX_LAMBDAS 8192
+
+int im2im_abi_version(void);
+const char* im2im_last_error(void);
+
+/*
+ * RCPS per-pixel miss counts for EVERY lambda of a sorted grid in ONE pass over the scores.
+ *
+ * Replaces, for all lambda steps at once, the body of the reference's sweep
+ *     core/calibration/calibrate_model.py:134-136  (loop over lambdas -> get_rcps_losses_from_outputs :21-29)
+ *       -> core/models/add_uncertainty.py:33-38             nested_sets_from_output (+/-1e-6 clamp)
+ *       -> core/models/finallayers/quantile_layer.py:34-44  quantile_regression_nested_sets_from_output
+ *       -> core/calibration/calibrate_model.py:76-80        fraction_missed_loss
+ * and the dense table loop of core/scripts/eval.py:115-125 (get_loss_table).
+ *
+ * counts[i, j] = number of pixels of image i with  lower(lam_j) > y  or  upper(lam_j) < y, evaluated with the
+ * reference's exact fp32 operation order (no FMA contraction).  The reference's per-image loss is exactly
+ * float(counts[i,j]) / float(px) (im2im_rcps_loss_table).
+ *
+ *   d_lower/d_pred/d_upper/d_label : fp32 planes; image i of a plane starts at base + i*stride_* (in elements)
+ *                                    and holds `px` = C*H*W contiguous values.  For the reference's
+ *                                    (N,3,C,H,W) output tensor: d_pred = d_lower + px, d_upper = d_lower + 2*px,
+ *                                    strides 3*px; labels stride px.
+ *   d_lambdas  : DEVICE fp32[n_lambdas], finite, sorted ascending (host-computed, e.g. lambdas - dlambda)
+ *   d_counts   : DEVICE int32[n_images, n_lambdas], row-major.  Must be zero on entry unless
+ *                IM2IM_RCPS_ZERO_OUTPUTS is set (images that straddle two thread blocks are accumulated atomically)
+ *   d_totals   : DEVICE uint64[n_lambdas]; column sums of counts are ADDED to it (so a caller can feed the
+ *                calibration set in chunks); may be NULL
+ * Limits: 1 <= n_lambdas <= IM2IM_RCPS_MAX_LAMBDAS, px < 2^24 (beyond that the reference's fp32 mean is no longer
+ * an exact integer ratio).  The bulk-copy (TMA) fast path needs 16-byte aligned planes and px % 4 == 0; anything
+ * else runs the scalar-load kernel with identical results.
+ */
+int im2im_rcps_miss_counts(const float* d_lower, const float* d_pred, const float* d_upper, const float* d_label,
+                           int64_t n_images, int64_t px, int64_t stride_lower, int64_t stride_pred,
+                           int64_t stride_upper, int64_t stride_label, const float* d_lambdas, int32_t n_lambdas,
+                           int32_t head_kind, int32_t* d_counts, unsigned long long* d_totals, uint32_t flags,
+                           void* stream);
+
+/*
+ * counts -> the reference's fp32 loss table: table[i,j] = float(counts[i,j]) / float(px) for j >= first_visited_col,
+ * 0 for j < first_visited_col (columns the early-stopped sweep never wrote, calibrate_model.py:133,136,144).
+ */
+int im2im_rcps_loss_table(const int32_t* d_counts, int64_t n_images, int32_t n_lambdas, int64_t px,
+                          int32_t first_visited_col, float* d_table, void* stream);
+
+/*
+ * Interval endpoints at one lambda: ModelWithUncertainty.nested_sets_from_output
+ * (core/models/add_uncertainty.py:33-38 over core/models/finallayers/quantile_layer.py:34-44).
+ * Writes lower/upper as dense (n_images, px) fp32; the prediction plane is returned by the caller as a view.
+ * The reference clamps its `output` argument in place (quantile_layer.py:39-40: lower plane = min(lower, pred-1e-6),
+ * upper plane = max(upper, pred+1e-6)); with write_back_clamp != 0 the same side effect is applied to
+ * d_lower / d_upper, otherwise the inputs are left untouched.
+ */
+int im2im_quantile_nested_sets(float* d_lower, const float* d_pred, float* d_upper, int64_t n_images, int64_t px,
+                               int64_t stride_lower, int64_t stride_pred, int64_t stride_upper, float lam,
+                               int32_t write_back_clamp, float* d_lower_out, float* d_upper_out, void* stream);
+
+/*
+ * Per-pixel miss map at one lambda, summed over images: map[k] = #{i : pixel k of image i is missed}
+ * (get_rcps_metrics_from_outputs, core/calibration/calibrate_model.py:47,55 "spatial_miscoverage" numerator).
+ * d_map: DEVICE int32[px], accumulated into (zero it first, or set IM2IM_RCPS_ZERO_OUTPUTS).
+ */
+int im2im_rcps_miss_map(const float* d_lower, const float* d_pred, const float* d_upper, const float* d_label,
+                        int64_t n_images, int64_t px, int64_t stride_lower, int64_t stride_pred,
+                        int64_t stride_upper, int64_t stride_label, float lam, int32_t head_kind, int32_t* d_map,
+                        uint32_t flags, void* stream);
+
+/* Number of kernel launches this library has enqueued in this process (bench.py's `gpu_launches`). */
+unsigned long long im2im_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IM2IM_UQ_H_ */

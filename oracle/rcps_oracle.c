@@ -1,0 +1,131 @@
+/*
+ * ORACLE - TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+ *
+ * CPU restatement, op for op in IEEE fp32 without contraction, of the reference's RCPS per-pixel chain for the
+ * quantile head.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library, and only as the checker / the timed CPU baseline - never behind the product API.
+ *
+ * Parity status: PINNED.  Checked against tests/golden/rcps_*.npz, which were produced by running the unmodified
+ * reference (calibrate_model + nested_sets_from_output + fraction_missed_loss) in the authoring container
+ * (tests/golden/make_golden.py).  The reference itself ships no golden vectors.
+ *
+ * Reference lines restated (paths relative to the reference root):
+ *   core/models/finallayers/quantile_layer.py:39-40   in-place clamp  l = min(l, p-1e-6), u = max(u, p+1e-6)
+ *   core/models/finallayers/quantile_layer.py:41-42   upper = lam*(u-p)+p ; lower = p-lam*(p-l)   (each op rounded)
+ *   core/models/add_uncertainty.py:35-36              upper = max(upper, p+1e-6) ; lower = min(lower, p-1e-6)
+ *   core/calibration/calibrate_model.py:77-80         misses = (lower>y)+(upper<y); clip to 1; mean over pixels
+ *   core/calibration/calibrate_model.py:134-136       one full pass over the data PER lambda step
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off, no -ffast-math, optional -fopenmp).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stddef.h>
+
+/* torch.minimum / torch.maximum propagate NaN (unlike fminf/fmaxf). */
+static inline float t_min(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+static inline float t_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+
+/* volatile stores force every intermediate to be rounded to fp32 even if a compiler would keep excess precision */
+static inline float f_add(float a, float b) { volatile float r = a + b; return r; }
+static inline float f_sub(float a, float b) { volatile float r = a - b; return r; }
+static inline float f_mul(float a, float b) { volatile float r = a * b; return r; }
+
+static const float EPS = 1e-6f; /* python scalar 1e-6 enters fp32 tensor ops as float32(1e-6) */
+
+/* Endpoints for one pixel at one lambda; returns them through lo2/up2. */
+static inline void pixel_sets(float l, float p, float u, float lam, float* lo2, float* up2) {
+    float l1 = t_min(l, f_sub(p, EPS));                 /* quantile_layer.py:39 */
+    float u1 = t_max(u, f_add(p, EPS));                 /* quantile_layer.py:40 */
+    float upper = f_add(f_mul(lam, f_sub(u1, p)), p);   /* quantile_layer.py:41 */
+    float lower = f_sub(p, f_mul(lam, f_sub(p, l1)));   /* quantile_layer.py:42 */
+    *up2 = t_max(upper, f_add(p, EPS));                 /* add_uncertainty.py:35 */
+    *lo2 = t_min(lower, f_sub(p, EPS));                 /* add_uncertainty.py:36 */
+}
+
+static inline int pixel_miss(float l, float p, float u, float y, float lam) {
+    float lo2, up2;
+    pixel_sets(l, p, u, lam, &lo2, &up2);
+    float m = (float)(lo2 > y) + (float)(up2 < y);      /* calibrate_model.py:77 */
+    if (m > 1.0f) m = 1.0f;                             /* calibrate_model.py:78 */
+    return (int)m;
+}
+
+/* One lambda step = one full pass (what calibrate_model.py:135 costs): integer miss count per image. */
+void oracle_quantile_miss_counts(const float* lower, const float* pred, const float* upper, const float* label,
+                                 int64_t n_images, int64_t px, int64_t stride_lower, int64_t stride_pred,
+                                 int64_t stride_upper, int64_t stride_label, float lam, int32_t* counts) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t i = 0; i < n_images; ++i) {
+        const float* l = lower + i * stride_lower;
+        const float* p = pred + i * stride_pred;
+        const float* u = upper + i * stride_upper;
+        const float* y = label + i * stride_label;
+        int32_t c = 0;
+        for (int64_t k = 0; k < px; ++k) c += pixel_miss(l[k], p[k], u[k], y[k], lam);
+        counts[i] = c;
+    }
+}
+
+/* Dense table: counts[i*n_lambdas + j] for every lambda in lams (one pass per lambda, like the reference). */
+void oracle_quantile_miss_table(const float* lower, const float* pred, const float* upper, const float* label,
+                                int64_t n_images, int64_t px, int64_t stride_lower, int64_t stride_pred,
+                                int64_t stride_upper, int64_t stride_label, const float* lams, int64_t n_lambdas,
+                                int32_t* counts) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) collapse(2)
+#endif
+    for (int64_t j = 0; j < n_lambdas; ++j) {
+        for (int64_t i = 0; i < n_images; ++i) {
+            const float* l = lower + i * stride_lower;
+            const float* p = pred + i * stride_pred;
+            const float* u = upper + i * stride_upper;
+            const float* y = label + i * stride_label;
+            const float lam = lams[j];
+            int32_t c = 0;
+            for (int64_t k = 0; k < px; ++k) c += pixel_miss(l[k], p[k], u[k], y[k], lam);
+            counts[i * n_lambdas + j] = c;
+        }
+    }
+}
+
+/* Interval endpoints (ModelWithUncertainty.nested_sets_from_output). */
+void oracle_quantile_nested_sets(const float* lower, const float* pred, const float* upper, int64_t n_images,
+                                 int64_t px, int64_t stride_lower, int64_t stride_pred, int64_t stride_upper,
+                                 float lam, float* lower_out, float* upper_out) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t i = 0; i < n_images; ++i) {
+        const float* l = lower + i * stride_lower;
+        const float* p = pred + i * stride_pred;
+        const float* u = upper + i * stride_upper;
+        for (int64_t k = 0; k < px; ++k)
+            pixel_sets(l[k], p[k], u[k], lam, &lower_out[i * px + k], &upper_out[i * px + k]);
+    }
+}
+
+/* Per-pixel miss map summed over images at one lambda (get_rcps_metrics_from_outputs, calibrate_model.py:47,55). */
+void oracle_quantile_miss_map(const float* lower, const float* pred, const float* upper, const float* label,
+                              int64_t n_images, int64_t px, int64_t stride_lower, int64_t stride_pred,
+                              int64_t stride_upper, int64_t stride_label, float lam, int32_t* map_counts) {
+    for (int64_t k = 0; k < px; ++k) map_counts[k] = 0;
+    for (int64_t i = 0; i < n_images; ++i) {
+        const float* l = lower + i * stride_lower;
+        const float* p = pred + i * stride_pred;
+        const float* u = upper + i * stride_upper;
+        const float* y = label + i * stride_label;
+        for (int64_t k = 0; k < px; ++k) map_counts[k] += pixel_miss(l[k], p[k], u[k], y[k], lam);
+    }
+}
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+    extern int omp_get_max_threads(void);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
