@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: RCPS calibration images/sec on a 10k-image 320x320 calibration set (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  the reference's algorithm on the host CPU cores
+
+A "step" is one complete calibration of the whole set with the scores already resident in HBM: zero the outputs, the
+one-pass miss-count kernel over every lambda, (N>1: one NCCL all-reduce of the per-lambda totals), the host replay of
+the reference's stopping rule (device->host copy of the totals + any replayed columns), and the fp32 loss-table
+kernel.  The set is split evenly over the ranks (strong scaling, as BASELINE.json's north_star asks: "10k-image set,
+1->8 GPUs").  `e2e` times the public entry point `calibrate_from_outputs` on HOST (pinned) score tensors, so the
+host->device copy of the scores and the device->host copy of the loss table are inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "calibration images/sec (320x320, 10k set)"
+UNIT = "images/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=10000, help="calibration images in the whole job")
+    ap.add_argument("--side", type=int, default=320)
+    ap.add_argument("--lambdas", type=int, default=1000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=192, help="images in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(args, device):
+    return dict(alpha=0.1, delta=0.1, device=device, uncertainty_type="quantiles", minimum_lambda=0.0,
+                maximum_lambda=6.0, num_lambdas=args.lambdas, rcps_loss="fraction_missed", dataset="synthetic",
+                batch_size=78, q_lo=0.05, q_hi=0.95, q_lo_weight=1.0, q_hi_weight=1.0, mse_weight=1.0)
+
+
+def workload_name(args):
+    return f"fastmri_test RCPS calibration: {args.images} x 1x{args.side}x{args.side} fp32 quantile-head outputs, " \
+           f"lambda grid [0,6]x{args.lambdas}, alpha=delta=0.1"
+
+
+def synth(n, side, device, seed):
+    """SURVEY.md §8c probe recipe (lambda-hat lands mid-grid); generated on `device`."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    shape = (n, 1, side, side)
+    out = torch.empty((n, 3, 1, side, side), dtype=torch.float32, device=device)
+    lab = torch.empty(shape, dtype=torch.float32, device=device)
+    step = max(1, min(n, 512))
+    for lo in range(0, n, step):  # chunked so temporaries stay small next to a 16 GB score tensor
+        hi = min(n, lo + step)
+        s = (hi - lo, 1, side, side)
+        pred = torch.rand(s, generator=g, device=device)
+        sig = 0.02 + 0.1 * torch.rand(s, generator=g, device=device)
+        out[lo:hi, 0] = pred - sig * (0.5 + torch.rand(s, generator=g, device=device))
+        out[lo:hi, 1] = pred
+        out[lo:hi, 2] = pred + sig * (0.5 + torch.rand(s, generator=g, device=device))
+        lab[lo:hi] = pred + sig * torch.randn(s, generator=g, device=device)
+    return out, lab
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.gpu_index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = sorted(float(r[1]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [nm for k, nm in enumerate(names) if any("Active" in r[4 + k] and "Not" not in r[4 + k] for r in rows)]
+            out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][2]) if rows else None,
+                   "reasons": reasons, "samples": len(rows),
+                   "power_w_max": max(float(r[3]) for r in rows) if rows else None}
+        except Exception as e:  # never let monitoring break the benchmark
+            out["error"] = repr(e)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy, of measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+# --------------------------------------------------------------------------------------------- reference / CPU leg
+def cpu_reference_sweep(sample_out, sample_lab, cfg, stop_full, n_full):
+    """The reference's algorithm (calibrate_model.py:130-145): one full pass over the sample PER visited lambda, fp32
+    mean, HB bound - restated in C (oracle port, all host threads).  The number of visited steps is pinned to what
+    the full workload visits (columns L-1 .. stop_full) so the sample costs what its share of the real job costs."""
+    import torch
+    from oracle import rcps_oracle as orc
+    lambdas = torch.linspace(cfg["minimum_lambda"], cfg["maximum_lambda"], cfg["num_lambdas"])
+    dlambda = lambdas[1] - lambdas[0]
+    px = float(sample_out[0, 0].size)
+    t0 = time.perf_counter()
+    steps = 0
+    for j in reversed(range(max(stop_full, 0), cfg["num_lambdas"])):
+        counts = orc.c_miss_counts(sample_out, sample_lab, float(lambdas[j] - dlambda))
+        losses = torch.from_numpy(counts.astype("float32")) / px
+        rhat = losses.mean()
+        orc.hb_mu_plus(rhat.item(), n_full, cfg["delta"])
+        steps += 1
+    return time.perf_counter() - t0, steps
+
+
+def run_reference_arm(args):
+    """bench.py --impl reference: rank 0 only; K steps, each a bounded sample of the workload on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from oracle import rcps_oracle as orc
+    orc.build()
+    cfg = config_dict(args, "cpu")
+    s = max(8, args.cpu_sample // 4)
+    out, lab = synth(s, args.side, "cpu", 1234)
+    out, lab = out.numpy(), lab.numpy()
+    stop_full = int(0.39 * args.lambdas)  # where the full 10k workload stops on this recipe (index ~390 of 1000)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_sweep(out[:2], lab[:2], cfg, args.lambdas - 3, args.images)
+    times = []
+    for _ in range(args.steps):
+        dt, visited = cpu_reference_sweep(out, lab, cfg, stop_full, args.images)
+        times.append(dt)
+    total = sum(times)
+    value = s * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "inputs": "host memory"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                             "sample": f"{s} images x {visited} visited lambda steps (one full pass per step + fp32 "
+                                       f"mean + HB bound per step), C/OpenMP restatement of the reference loop; "
+                                       f"cost is linear in images"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from im2im_uq_b200 import _lib, rcps
+    from im2im_uq_b200.calibration import calibrate_model as cm
+    from im2im_uq_b200.calibration import sweep
+    from im2im_uq_b200.models.add_uncertainty import ModelWithUncertainty
+    from im2im_uq_b200.models.quantile_layer import (quantile_regression_loss_fn,
+                                                     quantile_regression_nested_sets_from_output)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    _lib.load()
+
+    cfg = config_dict(args, str(dev))
+    cuts = [args.images * r // world for r in range(world + 1)]
+    n_local = cuts[rank + 1] - cuts[rank]
+    px = args.side * args.side
+    out, lab = synth(n_local, args.side, dev, 1000 + rank)
+    lambdas, dlambda, lam_prime, default_lhat = sweep.lambda_grid(cfg)
+    lam_dev = lam_prime.to(dev)
+    L = args.lambdas
+    counts = torch.empty((n_local, L), dtype=torch.int32, device=dev)
+    totals = torch.empty((L,), dtype=torch.int64, device=dev)
+    table = torch.empty((n_local, L), dtype=torch.float32, device=dev)
+    k_start = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k_end = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def column_to_losses(col):
+        return rcps.loss_table(col.reshape(-1, 1).contiguous(), px)[:, 0]
+
+    result = {}
+
+    def step(i=None):
+        counts.zero_(); totals.zero_()  # torch memset kernels on the current stream (plumbing)
+        if i is not None:
+            k_start[i].record()
+        rcps.miss_counts(out, lab, lam_dev, counts=counts, totals=totals, zero=False)
+        if i is not None:
+            k_end[i].record()
+        stats = {}
+        lhat, stop, visited = sweep.sweep_from_counts(counts, totals, px, cfg, column_to_losses, ascending=True,
+                                                      group=group, stats=stats)
+        rcps.loss_table(counts, px, first_visited_col=max(stop, 0), out=table)
+        result.update(lhat=float(lhat), stop=stop, replayed=stats.get("replayed_columns"))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_start.record()
+    for i in range(args.steps):
+        step(i)
+    t_end.record()
+    sync_all()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+    kernel_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(k_start, k_end)) / args.steps],
+                             dtype=torch.float64, device=dev)
+    launches_t = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kernel_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches_t, op=dist.ReduceOp.SUM)
+    ms_per_step = float(ms_total) / args.steps
+    value = args.images / (ms_per_step * 1e-3)
+
+    # ------------------------------------------------------------------ e2e: public API on HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        class _Id(torch.nn.Module):
+            def forward(self, x):
+                return x
+        model = ModelWithUncertainty(_Id(), _Id(), quantile_regression_loss_fn,
+                                     quantile_regression_nested_sets_from_output, cfg)
+        host_out = torch.empty(out.shape, dtype=torch.float32, pin_memory=True)
+        host_lab = torch.empty(lab.shape, dtype=torch.float32, pin_memory=True)
+        host_out.copy_(out); host_lab.copy_(lab)
+        torch.cuda.synchronize()
+        del out, lab
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            m, tbl = cm.calibrate_from_outputs(model, host_out, host_lab, cfg, group=group)
+            return float(m.lhat), tbl  # tbl is a CPU tensor: the device->host read of the step's result
+
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            lh, tbl = e2e_step()
+        sync_all()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert abs(lh - result["lhat"]) == 0.0, (lh, result)
+        e2e = {"value": args.images * args.e2e_steps / float(dt), "unit": UNIT,
+               "h2d_bytes_per_step": args.images * px * 16 + L * 4 * world,
+               "d2h_bytes_per_step": args.images * L * 4 + L * 8 * world, "steps": args.e2e_steps,
+               "api": "im2im_uq_b200.calibration.calibrate_model.calibrate_from_outputs(model, outputs_cpu, labels_cpu, config)"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_bytes = n_local * px * 16 + n_local * L * 4
+        achieved = alg_bytes / (float(kernel_ms) * 1e-3) / 1e9
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "rcps_hist_ncu_summary.json")))
+            if prof.get("images") == n_local and prof.get("side") == args.side:
+                traffic = prof.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args), "images_per_gpu": n_local,
+                           "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % (n_local * px * 16 / 1e9),
+                           "lhat": result["lhat"], "lhat_index": result["stop"],
+                           "replayed_columns": result["replayed"], "parallelism": f"image shards x{world}, "
+                           "one NCCL all-reduce of int64[L] totals" if world > 1 else "single GPU"},
+                "roofline": {"bound": "hbm", "kernel": "rcps_hist_kernel<staged>", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": float(kernel_ms),
+                             "peak_source": peak_src},
+                "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches_t)}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import rcps_oracle as orc
+            orc.build()
+            s_out, s_lab = synth(args.cpu_sample, args.side, "cpu", 1234)
+            dt, visited = cpu_reference_sweep(s_out.numpy(), s_lab.numpy(), config_dict(args, "cpu"),
+                                              result["stop"], args.images)
+            line["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": orc.num_threads(),
+                                    "kind": "port",
+                                    "sample": f"{args.cpu_sample} images x {visited} visited lambda steps (the steps the "
+                                              f"full set visits; one full pass + fp32 mean + HB bound per step), "
+                                              f"{dt:.1f} s; cost is linear in images"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -70,8 +70,16 @@ def _declare(lib):
     lib.im2im_rcps_miss_map.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32, i32, vp, u32, vp]
 
 
+def _declare_more(lib):
+    c = ctypes
+    vp, i64 = c.c_void_p, c.c_int64
+    lib.im2im_fraction_missed_counts.restype = c.c_int
+    lib.im2im_fraction_missed_counts.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, vp, vp]
+
+
 EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im_rcps_miss_counts",
-           "im2im_rcps_loss_table", "im2im_quantile_nested_sets", "im2im_rcps_miss_map"]
+           "im2im_rcps_loss_table", "im2im_quantile_nested_sets", "im2im_rcps_miss_map",
+           "im2im_fraction_missed_counts"]
 
 
 def load():
@@ -83,6 +91,7 @@ def load():
                              "(im2im_uq_b200 has no CPU fallback)")
         lib = ctypes.CDLL(LIB_PATH)
         _declare(lib)
+        _declare_more(lib)
         if lib.im2im_abi_version() != 1:
             raise Im2ImError("libim2im_uq.so ABI version mismatch - rebuild")
         _lib = lib

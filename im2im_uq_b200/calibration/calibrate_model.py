@@ -1,0 +1,325 @@
+"""RCPS calibration with the reference's entry points, running on hand-written sm_100a kernels.
+
+Mirror of ``core/calibration/calibrate_model.py`` of aangelopoulos/im2im-uq - same function names, argument meaning,
+return types and error behaviour:
+
+    get_rcps_losses_from_outputs(model, out_dataset, rcps_loss_fn, lam, device)      reference :21-29
+    get_rcps_metrics_from_outputs(model, out_dataset, rcps_loss_fn, device)          reference :31-60
+    evaluate_from_loss_table(loss_table, n, alpha, delta)                            reference :62-74
+    fraction_missed_loss(pset, label)                                                reference :76-80
+    get_rcps_loss_fn(config)                                                         reference :82-87
+    calibrate_model(model, dataset, config) -> (model, calib_loss_table)             reference :89-145
+
+What is different underneath: the scores stay resident in HBM, every lambda column is produced by ONE pass of
+``im2im_rcps_miss_counts`` (include/im2im_uq.h), and the stopping rule is replayed on the host from exact integer
+counts (sweep.py).  There is no CPU path: ``config['device']`` must name a CUDA device.
+
+Deliberate deviation: the reference's ``fraction_missed_loss`` squeezes away a batch of one (N % 64 == 1 makes
+``calibrate_model`` raise on a shape mismatch); here every image always yields one loss.
+"""
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from scipy.stats import spearmanr
+from torch.utils.data import DataLoader, TensorDataset
+
+from .. import _lib, rcps
+from . import sweep
+from .bounds import HB_mu_plus, hb_stop_bracket
+
+_CHUNK_BYTES = 2 << 30  # host->device staging granularity for CPU-resident score tensors
+
+
+def _cuda_device(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.Im2ImError(f"im2im_uq_b200 runs its hot path on CUDA only (config['device']={device!r}); "
+                              "there is no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+# ------------------------------------------------------------------------------------------------ loss functions
+def fraction_missed_loss(pset, label):
+    """Per-image fraction of pixels outside [lower, upper]: ``(lower>y)+(upper<y)``, clipped to 1, mean over pixels.
+
+    pset = (lower_edge, prediction, upper_edge) CUDA tensors of shape (B, ...); returns a (B,) fp32 CUDA tensor equal
+    to float(count)/float(pixels) - exactly what the reference's fp32 mean of 0/1 values produces.
+    """
+    counts = rcps.fraction_missed_counts(pset[0], pset[2], label)
+    px = label[0].numel() if label.shape[0] > 0 else 1
+    return rcps.loss_table(counts.reshape(-1, 1), max(px, 1))[:, 0]
+
+
+def get_rcps_loss_fn(config):
+    string = config['rcps_loss']
+    if string == 'fraction_missed':
+        return fraction_missed_loss
+    else:
+        raise NotImplementedError
+
+
+# ------------------------------------------------------------------------------------------------ score access
+def _dataset_tensors(out_dataset) -> Tuple[torch.Tensor, torch.Tensor]:
+    if isinstance(out_dataset, TensorDataset) and len(out_dataset.tensors) == 2:
+        return out_dataset.tensors
+    if isinstance(out_dataset, (tuple, list)) and len(out_dataset) == 2 and torch.is_tensor(out_dataset[0]):
+        return out_dataset[0], out_dataset[1]
+    # generic map-style dataset of (output, label) pairs
+    loader = DataLoader(out_dataset, batch_size=64, shuffle=False, num_workers=0)
+    xs, ys = zip(*[(b[0], b[1]) for b in loader])
+    return torch.cat(xs, dim=0), torch.cat(ys, dim=0)
+
+
+def _is_fused_quantile(model, rcps_loss_fn) -> bool:
+    from ..models.quantile_layer import quantile_regression_nested_sets_from_output
+    return (rcps_loss_fn is fraction_missed_loss and
+            getattr(model, "in_nested_sets_from_output_fn", None) is quantile_regression_nested_sets_from_output)
+
+
+def _resolve_lambda(model, lam):
+    if lam is None:
+        if model.lhat is None:
+            raise Exception("You have to specify lambda unless your model is already calibrated.")
+        lam = model.lhat
+    return lam
+
+
+def _chunks(n: int, bytes_per_image: int):
+    step = max(1, _CHUNK_BYTES // max(bytes_per_image, 1))
+    for lo in range(0, n, step):
+        yield lo, min(n, lo + step)
+
+
+def _miss_counts_any_device(outputs, labels, lam_sorted_dev, device, counts=None, totals=None):
+    """One-pass miss counts for scores that live on `device` already, or on the host (staged in pinned chunks)."""
+    n = outputs.shape[0]
+    n_lam = lam_sorted_dev.numel()
+    if counts is None:
+        counts = torch.zeros((n, n_lam), dtype=torch.int32, device=device)
+    if totals is None:
+        totals = torch.zeros((n_lam,), dtype=torch.int64, device=device)
+    if outputs.is_cuda and labels.is_cuda:
+        rcps.miss_counts(outputs, labels, lam_sorted_dev, counts=counts, totals=totals, zero=False)
+        return counts, totals
+    per_image = (outputs[0].numel() + labels[0].numel()) * 4 if n else 1
+    copy_stream = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream(device)
+    prev = None
+    for lo, hi in _chunks(n, per_image):
+        with torch.cuda.stream(copy_stream):
+            x = outputs[lo:hi].to(device, non_blocking=True)
+            y = labels[lo:hi].to(device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        main.wait_event(ready)
+        rcps.miss_counts(x, y, lam_sorted_dev, counts=counts[lo:hi], totals=totals, zero=False)
+        x.record_stream(main)
+        y.record_stream(main)
+        prev = (x, y)
+    del prev
+    return counts, totals
+
+
+# ------------------------------------------------------------------------------------------------ reference API
+def get_rcps_losses_from_outputs(model, out_dataset, rcps_loss_fn, lam, device):
+    """Per-image RCPS losses at ONE lambda; returns an (N,) fp32 CPU tensor like the reference."""
+    device = _cuda_device(device)
+    model = model.to(device)
+    outputs, labels = _dataset_tensors(out_dataset)
+    lam = _resolve_lambda(model, lam)
+    with torch.no_grad():
+        if _is_fused_quantile(model, rcps_loss_fn):
+            lam_dev = torch.as_tensor(lam, dtype=torch.float32).reshape(1).to(device)
+            counts, _ = _miss_counts_any_device(outputs, labels, lam_dev, device)
+            px = outputs[0, 0].numel() if outputs.shape[0] else 1
+            return rcps.loss_table(counts, px)[:, 0].cpu()
+        losses = []
+        for lo in range(0, outputs.shape[0], 64):
+            x = outputs[lo:lo + 64].to(device).clone()
+            sets = model.nested_sets_from_output(x, lam)
+            losses = losses + [rcps_loss_fn(sets, labels[lo:lo + 64].to(device)).cpu(), ]
+        return torch.cat(losses, dim=0)
+
+
+def get_rcps_metrics_from_outputs(model, out_dataset, rcps_loss_fn, device):
+    """Risk, sampled set sizes, Spearman(size, residual), size-stratified risk, mse, (H,W) spatial miscoverage at lhat.
+
+    RNG parity: the reference draws ``np.random.choice(pixels, size=batch)`` once per batch of 64, in order, then one
+    ``torch.rand(N)`` for the jitter (:44,:51); the same calls are made here in the same order.
+    """
+    device = _cuda_device(device)
+    model = model.to(device)
+    outputs, labels = _dataset_tensors(out_dataset)
+    lam = _resolve_lambda(model, None)
+    n = outputs.shape[0]
+    px = labels[0].numel()
+    with torch.no_grad():
+        if not _is_fused_quantile(model, rcps_loss_fn):
+            raise NotImplementedError("metrics are implemented for the quantile head + fraction_missed loss")
+        outputs_d = outputs if outputs.is_cuda else outputs.to(device)
+        labels_d = labels if labels.is_cuda else labels.to(device)
+        lam_dev = torch.as_tensor(lam, dtype=torch.float32).reshape(1).to(device)
+        counts, _ = rcps.miss_counts(outputs_d, labels_d, lam_dev)
+        losses = rcps.loss_table(counts, px)[:, 0]
+        # one random pixel per image, drawn batch by batch like the reference
+        idx_parts = []
+        for lo in range(0, n, 64):
+            b = min(64, n - lo)
+            idx_parts.append(np.random.choice(px, size=b))
+        idx = torch.from_numpy(np.concatenate(idx_parts)).to(device)
+        rows = torch.arange(n, device=device)
+        picked = outputs_d.reshape(n, 3, px)[rows, :, idx].reshape(n, 3, 1).contiguous()
+        lo_e, pred_e, up_e = rcps.quantile_nested_sets(picked, float(lam), write_back_clamp=False)
+        sizes = (up_e - lo_e).reshape(n).cpu()
+        residuals = (labels_d.reshape(n, px)[rows, idx] - pred_e.reshape(n)).abs()
+        miss_map = rcps.miss_map(outputs_d, labels_d, float(lam))
+    sizes = sizes + torch.rand(size=sizes.shape).to(sizes.device) * 1e-6
+    residuals = residuals.detach().cpu().numpy()
+    spearman = spearmanr(residuals, sizes)[0]
+    mse = (residuals * residuals).mean().item()
+    # numpy fp32 mean over images (exact integer sum / N), then over the channel axis - as the reference does on host
+    spatial_miscoverage = (miss_map.cpu().numpy().astype(np.float32) / np.float32(n)).reshape(labels.shape[1:]).mean(axis=0)
+    size_bins = torch.tensor([0, torch.quantile(sizes, 0.25), torch.quantile(sizes, 0.5), torch.quantile(sizes, 0.75)])
+    buckets = torch.bucketize(sizes, size_bins) - 1
+    losses_c = losses.cpu()
+    stratified_risks = torch.tensor([losses_c[buckets == bucket].mean() for bucket in range(size_bins.shape[0])])
+    return losses, sizes, spearman, stratified_risks, mse, spatial_miscoverage
+
+
+def evaluate_from_loss_table(loss_table, n, alpha, delta):
+    """Random calibration/validation split of a saved loss table; returns the validation risk at the first lambda
+    whose HB bound is <= delta (the reference compares against ``delta`` here, :70 - kept as is).
+
+    Host-only like the reference.  The per-column bound is screened through the cached level set of HB_mu_plus and
+    evaluated exactly only around the decision, instead of one brentq solve per column.
+    """
+    with torch.no_grad():
+        perm = torch.randperm(loss_table.shape[0])
+        loss_table = loss_table[perm]
+        calib_table, val_table = loss_table[:n], loss_table[n:]
+        Rhats = calib_table.mean(dim=0)
+        idx_lambda = _first_accepted_column(Rhats, n, delta)
+        if idx_lambda is None:
+            print("No rejections made!")
+            idx_lambda = 0
+        return val_table[:, idx_lambda].mean()
+
+
+def _first_accepted_column(Rhats: torch.Tensor, n: int, delta: float) -> Optional[int]:
+    """Smallest j with HB_mu_plus(Rhats[j], n, delta) <= delta, or None."""
+    r = Rhats.double().numpy()
+    r_lo, r_hi = hb_stop_bracket(int(n), float(delta), float(delta))  # level set of HB > delta
+    slack = 1e-9
+    for j in range(r.shape[0]):
+        m = float(Rhats[j])
+        if m > 0 and np.isfinite(r_hi) and m > r_hi + slack:
+            continue  # certainly HB > delta
+        if m > 0 and np.isfinite(r_lo) and m < r_lo - slack:
+            return j  # certainly HB <= delta
+        if HB_mu_plus(Rhats[j], n, delta) <= delta:
+            return j
+    return None
+
+
+# ------------------------------------------------------------------------------------------------ the sweep
+def rcps_sweep(outputs: torch.Tensor, labels: torch.Tensor, config: dict, device=None, group=None,
+               verbose: bool = False, stats: Optional[dict] = None):
+    """lambda-hat and the loss table from head outputs (N,3,C,H,W) + labels (N,C,H,W), CPU- or CUDA-resident.
+
+    Returns (lhat 0-dim fp32 CPU tensor, stop index or -1, counts int32 CUDA (N_local, L), visited bool mask (L,)).
+    With a torch.distributed ``group`` every rank passes its own contiguous shard of images; the per-lambda totals are
+    all-reduced (one int64 vector of length L over NCCL) and every rank reaches the same decision.
+    """
+    device = _cuda_device(device if device is not None else config['device'])
+    lambdas, dlambda, lam_prime, default_lhat = sweep.lambda_grid(config)
+    L = lambdas.shape[0]
+    if not bool(torch.isfinite(lam_prime).all()):
+        raise ValueError("lambda grid must be finite")
+    ascending = bool((lam_prime[1:] >= lam_prime[:-1]).all())
+    if ascending:
+        order = None
+        lam_sorted = lam_prime
+    else:  # e.g. minimum_lambda > maximum_lambda: rank on the sorted grid, un-permute the columns afterwards
+        lam_sorted, order = torch.sort(lam_prime)
+    n_local = outputs.shape[0]
+    px = labels[0].numel() if n_local else 0
+    lam_dev = lam_sorted.to(device)
+    counts, totals = _miss_counts_any_device(outputs, labels, lam_dev, device)
+    if order is not None:
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(L)
+        counts = counts[:, inv.to(device)].contiguous()
+        totals = totals[inv.to(device)].contiguous()
+    def column_to_losses(col: torch.Tensor) -> torch.Tensor:
+        return rcps.loss_table(col.reshape(-1, 1).contiguous(), px)[:, 0]
+
+    lhat, stop, visited = sweep.sweep_from_counts(counts, totals, px, config, column_to_losses, ascending=ascending,
+                                                  group=group, verbose=verbose, stats=stats)
+    return lhat, stop, counts, visited
+
+
+def calibrate_from_outputs(model, outputs: torch.Tensor, labels: torch.Tensor, config: dict, group=None,
+                           table_device: str = "cpu", stats: Optional[dict] = None):
+    """Stage 2 of ``calibrate_model`` on precomputed head outputs: sets ``model.lhat`` and returns the loss table.
+
+    The table is (N, L) fp32 with never-visited columns zero (calibrate_model.py:133-136), on the CPU by default like
+    the reference's; pass table_device='cuda' to keep it in HBM.
+    """
+    device = _cuda_device(config['device'])
+    with torch.no_grad():
+        lhat, stop, counts, visited = rcps_sweep(outputs, labels, config, device=device, group=group, stats=stats)
+        model.set_lhat(lhat)
+        px = labels[0].numel()
+        L = counts.shape[1]
+        first = int(torch.nonzero(visited)[0]) if bool(visited.any()) else L
+        contiguous_suffix = bool(visited[first:].all())
+        table = rcps.loss_table(counts, px, first_visited_col=first if contiguous_suffix else 0)
+        if not contiguous_suffix:  # duplicate lambdas: a non-suffix set of columns was written
+            table = table * visited.to(device=table.device, dtype=table.dtype)[None, :]
+        if table_device == "cpu":
+            host = torch.empty(table.shape, dtype=torch.float32, pin_memory=True)
+            host.copy_(table, non_blocking=False)
+            table = host
+        return model, table
+
+
+def collect_outputs(model, dataset, config, device):
+    """Stage 1 of ``calibrate_model`` (reference :106-123): run the model over the calibration set.
+
+    The reference parks outputs and labels on the CPU and re-uploads them at every lambda step; here they stay in HBM.
+    """
+    if config['dataset'] == 'temca':
+        labels = torch.cat([x[1].unsqueeze(0).to(device) for x in iter(dataset)], dim=0)
+        outputs = torch.cat([model(x[0].unsqueeze(0).to(device)) for x in iter(dataset)])
+        return outputs, labels
+    labels_shape = list(dataset[0][1].unsqueeze(0).shape)
+    labels_shape[0] = len(dataset)
+    labels = torch.zeros(tuple(labels_shape), device=device)
+    outputs_shape = list(model(dataset[0][0].unsqueeze(0).to(device)).shape)
+    outputs_shape[0] = len(dataset)
+    outputs = torch.zeros(tuple(outputs_shape), device=device)
+    loader = DataLoader(dataset, num_workers=0, batch_size=config['batch_size'], pin_memory=True)
+    counter = 0
+    for batch in loader:
+        b = batch[0].shape[0]
+        outputs[counter:counter + b] = model(batch[0].to(device, non_blocking=True))
+        labels[counter:counter + b] = batch[1].to(device, non_blocking=True)
+        counter += b
+    return outputs, labels
+
+
+def calibrate_model(model, dataset, config):
+    """Drop-in for the reference's ``calibrate_model``: returns ``(model, calib_loss_table)`` with ``model.lhat`` set."""
+    with torch.no_grad():
+        print(f"Calibrating...")
+        model.eval()
+        device = _cuda_device(config['device'])
+        get_rcps_loss_fn(config)  # raises NotImplementedError for unknown losses, like the reference
+        model = model.to(device)
+        outputs, labels = collect_outputs(model, dataset, config, device)
+        model, calib_loss_table = calibrate_from_outputs(model, outputs, labels, config)
+        print(f"Model's lhat set to {model.lhat}")
+        return model, calib_loss_table

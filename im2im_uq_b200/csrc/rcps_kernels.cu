@@ -45,27 +45,26 @@ struct RcpsParams {
 //   pm = p - 1e-6f, pp = p + 1e-6f
 //   reference upper miss: max(lam*(max(u,pp)-p)+p, pp) < y   <=>  (pp < y) && (lam*du + p < y)   [NaN -> false]
 //   reference lower miss: min(p-lam*(p-min(l,pm)), pm) > y   <=>  (pm > y) && (p - lam*dl > y)
-//   pm <= p <= pp, so at most one side can ever miss; the lower side is folded onto the upper-side form by
-//   negation, which is exact:  p - x > y  <=>  x + (-p) < -y.
+//   pm <= p <= pp, so only the upper side can miss when y > p and only the lower side when y < p.
+//   The lower side is folded onto the upper-side form by negating (l,p,y) -> (U,P,Y) = (-l,-p,-y): negation is
+//   exact and rounding is symmetric, so  P+1e-6 = -pm,  max(U,PP)-P = p-min(l,pm) = dl  and
+//   p - lam*dl > y  <=>  lam*dl + P < Y  bit for bit.
 //   torch.minimum/maximum propagate NaN: a NaN u (resp. l) makes that side's predicate false for every lambda,
-//   a NaN p or y makes both comparisons false.  fmaxf/fminf are only evaluated on non-NaN operands that matter.
+//   a NaN p or y makes every comparison false - both are covered by `active`.
 struct PixelQuery {
     float d, P, Y;
     bool active;
 };
 
 __device__ __forceinline__ PixelQuery make_query(float l, float p, float u, float y) {
-    const float pm = __fsub_rn(p, 1e-6f);
-    const float pp = __fadd_rn(p, 1e-6f);
-    const bool up = pp < y;
-    const bool lo = pm > y;
+    const bool up = y > p;
+    const float U = up ? u : -l;
     PixelQuery q;
-    const float a = up ? fmaxf(u, pp) : p;
-    const float b = up ? p : fminf(l, pm);
-    q.d = __fsub_rn(a, b);           // du = max(u,pp)-p   or   dl = p-min(l,pm);   >= 0
     q.P = up ? p : -p;
     q.Y = up ? y : -y;
-    q.active = up ? (u == u) : (lo && (l == l));
+    const float PP = __fadd_rn(q.P, 1e-6f);
+    q.active = (PP < q.Y) && (U == U);
+    q.d = __fsub_rn(fmaxf(U, PP), q.P);  // du or dl, >= 0 (NaN only when inactive)
     return q;
 }
 
@@ -73,35 +72,32 @@ __device__ __forceinline__ bool missed(const PixelQuery& q, float lam) {
     return __fadd_rn(__fmul_rn(lam, q.d), q.P) < q.Y;
 }
 
-// Number of grid points at which the pixel is missed = index of the first lambda that covers it.
-__device__ __forceinline__ int pixel_rank(const PixelQuery& q, const float* __restrict__ s_lam, int L, float lam0,
-                                          float inv_dlam) {
-    if (!q.active) return 0;
-    // real-valued crossing lam* = (Y-P)/d ; on a uniform grid #{lam_j < lam*} = ceil((lam*-lam0)/dlam)
-    const float t = __fdividef(__fsub_rn(q.Y, q.P), q.d);
-    int g = __float2int_ru((t - lam0) * inv_dlam);  // saturating; NaN -> 0
-    g = max(0, min(g, L));
-    int moved = 0;
-    while (g < L && missed(q, s_lam[g])) {
-        ++g;
-        if (++moved > 2) goto bisect;
-    }
-    if (moved == 0) {
-        while (g > 0 && !missed(q, s_lam[g - 1])) {
-            --g;
-            if (++moved > 2) goto bisect;
-        }
-    }
-    return g;
-bisect: {
-    // bad guess (non-uniform grid, inf/NaN widths ...): exact binary search for the first covered lambda
+// exact binary search for the first covered lambda (rare: guess off by more than the checked window)
+__device__ __noinline__ int rank_bisect(float d, float P, float Y, const float* s_lam, int L) {
     int lo = 0, hi = L;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (missed(q, s_lam[mid])) lo = mid + 1; else hi = mid;
+        if (__fadd_rn(__fmul_rn(s_lam[mid], d), P) < Y) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
+
+// Number of grid points at which the pixel is missed = index of the first lambda that covers it.
+// guess_scale/guess_bias map the real-valued crossing lam* = (Y-P)/d onto the (uniform) grid:
+// #{lam_j < lam*} = ceil((lam*-lam0)/dlam).  The guess is then verified with the exact predicate at g-1 and g.
+__device__ __forceinline__ int pixel_rank(const PixelQuery& q, const float* __restrict__ s_lam, int L,
+                                          float guess_scale, float guess_bias) {
+    float rcp;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(q.d));
+    const float t = (q.Y - q.P) * rcp;
+    int g = __float2int_ru(fmaf(t, guess_scale, guess_bias));  // saturating; NaN -> 0
+    g = max(0, min(g, L));
+    const float la = s_lam[max(g - 1, 0)];
+    const float lb = s_lam[min(g, L - 1)];
+    const bool below_ok = (g == 0) || missed(q, la);   // missed at every grid point below g
+    const bool above_ok = (g == L) || !missed(q, lb);  // covered from g upwards
+    if (q.active && !(below_ok && above_ok)) g = rank_bisect(q.d, q.P, q.Y, s_lam, L);
+    return q.active ? g : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -187,18 +183,19 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
         if (STAGED && tid == kConsumerThreads) {
             long long img = t_begin / tpi;
             long long r = t_begin - img * tpi;
-            long long it = 0;
-            for (long long t = t_begin; t < t_end; ++t, ++it) {
-                const int s = static_cast<int>(it % kStages);
-                if (it >= kStages) mbar_wait(&empty_bar[s], static_cast<unsigned>((it / kStages) - 1) & 1u);
+            int stage = 0;
+            unsigned phase = 1;  // first pass over the ring: the slots are free, parity 1 of a fresh barrier succeeds
+            for (long long t = t_begin; t < t_end; ++t) {
+                mbar_wait(&empty_bar[stage], phase);
                 const long long off = r * kTilePx;
                 const long long rem = prm.px - off;
                 const unsigned bytes = static_cast<unsigned>(rem < kTilePx ? rem : kTilePx) * 4u;
-                mbar_arrive_expect_tx(&full_bar[s], 4u * bytes);
+                mbar_arrive_expect_tx(&full_bar[stage], 4u * bytes);
 #pragma unroll
                 for (int pl = 0; pl < 4; ++pl)
-                    bulk_g2s(ring + (s * 4 + pl) * kTilePx, prm.plane[pl] + img * prm.stride[pl] + off, bytes,
-                             &full_bar[s]);
+                    bulk_g2s(ring + (stage * 4 + pl) * kTilePx, prm.plane[pl] + img * prm.stride[pl] + off, bytes,
+                             &full_bar[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 if (++r == tpi) { r = 0; ++img; }
             }
         }
@@ -210,68 +207,73 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
     const int lane = ctid & 31;
     const float lam0 = s_lam[0];
     const float span = s_lam[L - 1] - lam0;
-    const float inv_dlam = (L > 1 && span > 0.f) ? static_cast<float>(L - 1) / span : 0.f;
+    const float guess_scale = (L > 1 && span > 0.f) ? static_cast<float>(L - 1) / span : 0.f;
+    const float guess_bias = -lam0 * guess_scale;
+    const int tpi32 = static_cast<int>(tpi);
+    const int last_npx = static_cast<int>(prm.px - (tpi - 1) * kTilePx);  // pixels in the last tile of an image
 
     long long img = t_begin / tpi;
-    long long r = t_begin - img * tpi;
+    int r = static_cast<int>(t_begin - img * tpi);
     bool image_started_here = (r == 0);  // did this CTA see tile 0 of the current image?
-    long long it = 0;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
-        const long long off = r * kTilePx;
-        const long long rem = prm.px - off;
-        const int npx = static_cast<int>(rem < kTilePx ? rem : kTilePx);
-        float l[kPxPerThread], p[kPxPerThread], u[kPxPerThread], y[kPxPerThread];
-        bool valid[kPxPerThread];
+    int stage = 0;
+    unsigned phase = 0;
+    const long long n_my_tiles = t_end - t_begin;
+    for (long long it = 0; it < n_my_tiles; ++it) {
+        const bool image_ends_here = (r == tpi32 - 1);
+        const int npx = image_ends_here ? last_npx : kTilePx;
         if (STAGED) {
-            const int s = static_cast<int>(it % kStages);
-            mbar_wait(&full_bar[s], static_cast<unsigned>(it / kStages) & 1u);
+            mbar_wait(&full_bar[stage], phase);
             const int e0 = ctid * kPxPerThread;
-            if (e0 < npx) {  // npx % 4 == 0 on this path
-                const float* base = ring + s * 4 * kTilePx + e0;
-                const float4 vl = *reinterpret_cast<const float4*>(base);
-                const float4 vp = *reinterpret_cast<const float4*>(base + kTilePx);
-                const float4 vu = *reinterpret_cast<const float4*>(base + 2 * kTilePx);
-                const float4 vy = *reinterpret_cast<const float4*>(base + 3 * kTilePx);
-                l[0] = vl.x; l[1] = vl.y; l[2] = vl.z; l[3] = vl.w;
-                p[0] = vp.x; p[1] = vp.y; p[2] = vp.z; p[3] = vp.w;
-                u[0] = vu.x; u[1] = vu.y; u[2] = vu.z; u[3] = vu.w;
-                y[0] = vy.x; y[1] = vy.y; y[2] = vy.z; y[3] = vy.w;
-#pragma unroll
-                for (int m = 0; m < kPxPerThread; ++m) valid[m] = true;
-            } else {
-#pragma unroll
-                for (int m = 0; m < kPxPerThread; ++m) valid[m] = false;
+            const bool have = e0 < npx;  // npx % 4 == 0 on this path: all four pixels or none
+            float4 vl, vp, vu, vy;
+            if (have) {
+                const float* base = ring + stage * 4 * kTilePx + e0;
+                vl = *reinterpret_cast<const float4*>(base);
+                vp = *reinterpret_cast<const float4*>(base + kTilePx);
+                vu = *reinterpret_cast<const float4*>(base + 2 * kTilePx);
+                vy = *reinterpret_cast<const float4*>(base + 3 * kTilePx);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);  // values are in registers: hand the slot back early
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);  // values are in registers: hand the slot back early
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            if (have) {
+                const float l[4] = {vl.x, vl.y, vl.z, vl.w}, p[4] = {vp.x, vp.y, vp.z, vp.w};
+                const float u[4] = {vu.x, vu.y, vu.z, vu.w}, y[4] = {vy.x, vy.y, vy.z, vy.w};
+                int k[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    k[m] = pixel_rank(make_query(l[m], p[m], u[m], y[m]), s_lam, L, guess_scale, guess_bias);
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (k[m] > 0) atomicAdd(&hist[k[m]], 1u);
+            }
         } else {
+            const long long off = static_cast<long long>(r) * kTilePx;
             const float* gl = prm.plane[0] + img * prm.stride[0] + off;
             const float* gp = prm.plane[1] + img * prm.stride[1] + off;
             const float* gu = prm.plane[2] + img * prm.stride[2] + off;
             const float* gy = prm.plane[3] + img * prm.stride[3] + off;
+            float l[kPxPerThread], p[kPxPerThread], u[kPxPerThread], y[kPxPerThread];
 #pragma unroll
             for (int m = 0; m < kPxPerThread; ++m) {
                 const int e = m * kConsumerThreads + ctid;  // coalesced 4-byte loads
-                valid[m] = e < npx;
-                if (valid[m]) {
+                if (e < npx) {
                     l[m] = ldg_stream_f32(gl + e); p[m] = ldg_stream_f32(gp + e);
                     u[m] = ldg_stream_f32(gu + e); y[m] = ldg_stream_f32(gy + e);
+                } else {
+                    l[m] = p[m] = u[m] = y[m] = 0.f;  // y == p: inactive, rank 0
                 }
             }
-        }
 #pragma unroll
-        for (int m = 0; m < kPxPerThread; ++m) {
-            if (valid[m]) {
-                const PixelQuery q = make_query(l[m], p[m], u[m], y[m]);
-                const int k = pixel_rank(q, s_lam, L, lam0, inv_dlam);
+            for (int m = 0; m < kPxPerThread; ++m) {
+                const int k = pixel_rank(make_query(l[m], p[m], u[m], y[m]), s_lam, L, guess_scale, guess_bias);
                 if (k > 0) atomicAdd(&hist[k], 1u);
             }
         }
-        const bool image_ends_here = (r == tpi - 1);
-        if (image_ends_here || t == t_end - 1) {
+        if (image_ends_here || it == n_my_tiles - 1) {
             flush_image(hist, tot, warp_sums, L, prm.counts + img * L, image_started_here && image_ends_here, ctid);
         }
-        if (++r == tpi) { r = 0; ++img; image_started_here = true; }
+        if (++r == tpi32) { r = 0; ++img; image_started_here = true; }
     }
     if (prm.totals != nullptr) {
         const int per_thread = (L + kConsumerThreads - 1) / kConsumerThreads;
@@ -353,6 +355,29 @@ __global__ void __launch_bounds__(256) miss_map_kernel(const float* __restrict__
     if (acc) atomicAdd(&map[k], acc);
 }
 
+// counts[i] = #{k : lower[i,k] > y[i,k] or upper[i,k] < y[i,k]} for already-computed endpoints
+// (fraction_missed_loss, core/calibration/calibrate_model.py:76-80).  One CTA per (image, slab) pair.
+__global__ void __launch_bounds__(256) fraction_missed_kernel(const float* __restrict__ lower,
+                                                              const float* __restrict__ upper,
+                                                              const float* __restrict__ label, long long px,
+                                                              long long sl, long long su, long long sy,
+                                                              int* __restrict__ counts) {
+    const long long i = blockIdx.y;
+    const float* l = lower + i * sl;
+    const float* u = upper + i * su;
+    const float* y = label + i * sy;
+    int acc = 0;
+    for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < px;
+         k += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float yy = ldg_stream_f32(y + k);
+        // (lower>y)+(upper<y) clipped to 1  ==  logical or
+        acc += ((ldg_stream_f32(l + k) > yy) || (ldg_stream_f32(u + k) < yy)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&counts[i], acc);
+}
+
 size_t hist_smem_bytes(bool staged, int L) {
     size_t b = staged ? sizeof(float) * kStages * 4 * kTilePx : 0;
     b += sizeof(unsigned long long) * L + sizeof(uint64_t) * 2 * kStages + sizeof(float) * L +
@@ -379,14 +404,20 @@ extern "C" int im2im_rcps_miss_counts(const float* d_lower, const float* d_pred,
     if (n_lambdas < 1 || n_lambdas > IM2IM_RCPS_MAX_LAMBDAS)
         return fail(IM2IM_ERANGE, "n_lambdas=%d outside [1, %d]", n_lambdas, IM2IM_RCPS_MAX_LAMBDAS);
     if (px >= (1ll << 24)) return fail(IM2IM_ERANGE, "px=%lld >= 2^24: fp32 per-image mean is not exact", (long long)px);
-    if (d_lambdas == nullptr || d_counts == nullptr) return fail(IM2IM_EINVAL, "null lambda grid or counts");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_images == 0 || px == 0) {  // empty calibration set / empty images: nothing is missed
+        if ((flags & IM2IM_RCPS_ZERO_OUTPUTS) && d_totals)
+            IM2IM_CUDA_TRY(cudaMemsetAsync(d_totals, 0, sizeof(unsigned long long) * n_lambdas, st));
+        if ((flags & IM2IM_RCPS_ZERO_OUTPUTS) && d_counts && n_images > 0)
+            IM2IM_CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * n_images * n_lambdas, st));
+        return IM2IM_OK;
+    }
+    if (d_lambdas == nullptr || d_counts == nullptr) return fail(IM2IM_EINVAL, "null lambda grid or counts");
     if (flags & IM2IM_RCPS_ZERO_OUTPUTS) {
         if (n_images > 0)
             IM2IM_CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * n_images * n_lambdas, st));
         if (d_totals) IM2IM_CUDA_TRY(cudaMemsetAsync(d_totals, 0, sizeof(unsigned long long) * n_lambdas, st));
     }
-    if (n_images == 0 || px == 0) return IM2IM_OK;  // empty calibration set: all counts stay zero
     if (!d_lower || !d_pred || !d_upper || !d_label) return fail(IM2IM_EINVAL, "null score plane");
 
     bool fast = !(flags & IM2IM_RCPS_FORCE_GENERIC) && (px % 4 == 0) && aligned16(d_lower) &&
@@ -476,4 +507,25 @@ extern "C" int im2im_rcps_miss_map(const float* d_lower, const float* d_pred, co
     miss_map_kernel<<<dim3(bx, by), 256, 0, st>>>(d_lower, d_pred, d_upper, d_label, n_images, px, stride_lower,
                                                   stride_pred, stride_upper, stride_label, lam, per_slab, d_map);
     return check_launch("miss_map_kernel");
+}
+
+extern "C" int im2im_fraction_missed_counts(const float* d_lower_edge, const float* d_upper_edge,
+                                            const float* d_label, int64_t n_images, int64_t px,
+                                            int64_t stride_lower, int64_t stride_upper, int64_t stride_label,
+                                            int32_t* d_counts, void* stream) {
+    if (n_images < 0 || px < 0) return fail(IM2IM_EINVAL, "negative size");
+    if (n_images > 65535) return fail(IM2IM_ERANGE, "n_images=%lld > 65535 per call", (long long)n_images);
+    if (n_images == 0) return IM2IM_OK;
+    if (!d_counts) return fail(IM2IM_EINVAL, "null counts");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    IM2IM_CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * n_images, st));
+    if (px == 0) return IM2IM_OK;
+    if (!d_lower_edge || !d_upper_edge || !d_label) return fail(IM2IM_EINVAL, "null plane");
+    long long bx = (px + 255) / 256;
+    const long long want = (8ll * sm_count() + n_images - 1) / n_images;  // fill the GPU when there are few images
+    if (bx > want) bx = want;
+    if (bx < 1) bx = 1;
+    fraction_missed_kernel<<<dim3(static_cast<unsigned>(bx), static_cast<unsigned>(n_images)), 256, 0, st>>>(
+        d_lower_edge, d_upper_edge, d_label, px, stride_lower, stride_upper, stride_label, d_counts);
+    return check_launch("fraction_missed_kernel");
 }

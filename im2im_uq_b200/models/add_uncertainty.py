@@ -1,0 +1,61 @@
+"""The reference's plugin surface - mirror of ``core/models/add_uncertainty.py``.
+
+  ModelWithUncertainty   :15-49   forward / loss_fn / nested_sets_from_output / nested_sets / set_lhat, buffer lhat
+  add_uncertainty        :51-87   trunk + head selected by params["uncertainty_type"]
+
+Only the quantile head (the one BASELINE.json's north_star names) is implemented natively; the reference's other six
+``uncertainty_type`` values raise NotImplementedError here (listed as "next" in SURVEY.md §8f).
+"""
+import torch
+import torch.nn as nn
+
+from .quantile_layer import (QuantileRegressionLayer, quantile_regression_loss_fn,
+                             quantile_regression_nested_sets_from_output)
+
+
+class ModelWithUncertainty(nn.Module):
+    def __init__(self, baseModel, last_layer, in_train_loss_fn, in_nested_sets_from_output_fn, params):
+        super(ModelWithUncertainty, self).__init__()
+        self.baseModel = baseModel
+        self.last_layer = last_layer
+        self.register_buffer('lhat', None)
+        self.in_train_loss_fn = in_train_loss_fn
+        self.in_nested_sets_from_output_fn = in_nested_sets_from_output_fn
+        self.params = params
+
+    def forward(self, x):
+        x = self.baseModel(x)
+        return self.last_layer(x)
+
+    def loss_fn(self, pred, target):
+        return self.in_train_loss_fn(pred, target, self.params)
+
+    # Always outputs [0,1] valued nested sets
+    def nested_sets_from_output(self, output, lam=None):
+        lower_edge, prediction, upper_edge = self.in_nested_sets_from_output_fn(self, output, lam)
+        if self.in_nested_sets_from_output_fn is not quantile_regression_nested_sets_from_output:
+            # heads without a fused kernel: apply the reference's lower bound on the set size (:35-36)
+            upper_edge = torch.maximum(upper_edge, prediction + 1e-6)
+            lower_edge = torch.minimum(lower_edge, prediction - 1e-6)
+        return lower_edge, prediction, upper_edge
+
+    def nested_sets(self, x, lam=None):
+        if lam is None:
+            if self.lhat is None:
+                raise Exception("You have to specify lambda unless your model is already calibrated.")
+            lam = self.lhat
+        output = self(*x)
+        return self.nested_sets_from_output(output, lam=lam)
+
+    def set_lhat(self, lhat):
+        self.lhat = lhat
+
+
+def add_uncertainty(model, params):
+    if params["uncertainty_type"] == "quantiles":
+        last_layer = QuantileRegressionLayer(model.n_channels_middle, model.n_channels_out, params)
+        train_loss_fn = quantile_regression_loss_fn
+        nested_sets_from_output_fn = quantile_regression_nested_sets_from_output
+    else:
+        raise NotImplementedError
+    return ModelWithUncertainty(model, last_layer, train_loss_fn, nested_sets_from_output_fn, params)

@@ -130,3 +130,33 @@ def miss_map(outputs: torch.Tensor, labels: torch.Tensor, lam: float) -> torch.T
     _lib.check(rc, "im2im_rcps_miss_map")
     del keep
     return out
+
+
+def fraction_missed_counts(lower_edge: torch.Tensor, upper_edge: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """int32 miss count per image for already computed endpoints (any (B, ...) shapes with equal numel per image)."""
+    lib = _lib.load()
+    for name, t in (("lower_edge", lower_edge), ("upper_edge", upper_edge), ("label", label)):
+        _require_cuda(t, name)
+    n = label.shape[0]
+    lower_edge = lower_edge.reshape(n, -1)
+    upper_edge = upper_edge.reshape(n, -1)
+    label = label.reshape(n, -1)
+    px = label.shape[1]
+    if lower_edge.shape != label.shape or upper_edge.shape != label.shape:
+        raise _lib.Im2ImError("fraction_missed_counts: endpoint and label shapes differ")
+    if px > 0 and n > 0:
+        lower_edge = lower_edge if lower_edge.stride(1) == 1 else lower_edge.contiguous()
+        upper_edge = upper_edge if upper_edge.stride(1) == 1 else upper_edge.contiguous()
+        label = label if label.stride(1) == 1 else label.contiguous()
+    counts = torch.empty((n,), dtype=torch.int32, device=label.device)
+    with torch.cuda.device(label.device):
+        for lo in range(0, max(n, 1), 65535):
+            hi = min(n, lo + 65535)
+            if hi <= lo:
+                break
+            rc = lib.im2im_fraction_missed_counts(lower_edge[lo:hi].data_ptr(), upper_edge[lo:hi].data_ptr(),
+                                                  label[lo:hi].data_ptr(), hi - lo, px, lower_edge.stride(0),
+                                                  upper_edge.stride(0), label.stride(0), counts[lo:hi].data_ptr(),
+                                                  _stream_ptr(label.device))
+            _lib.check(rc, "im2im_fraction_missed_counts")
+    return counts

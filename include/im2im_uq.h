@@ -105,6 +105,15 @@ int im2im_rcps_miss_map(const float* d_lower, const float* d_pred, const float* 
                         int64_t stride_upper, int64_t stride_label, float lam, int32_t head_kind, int32_t* d_map,
                         uint32_t flags, void* stream);
 
+/*
+ * fraction_missed_loss on ALREADY COMPUTED interval endpoints (core/calibration/calibrate_model.py:76-80):
+ * counts[i] = #{k : lower_edge[i,k] > label[i,k] or upper_edge[i,k] < label[i,k]}; the loss is counts[i]/px.
+ * d_counts: DEVICE int32[n_images], overwritten.  n_images <= 65535 per call.
+ */
+int im2im_fraction_missed_counts(const float* d_lower_edge, const float* d_upper_edge, const float* d_label,
+                                 int64_t n_images, int64_t px, int64_t stride_lower, int64_t stride_upper,
+                                 int64_t stride_label, int32_t* d_counts, void* stream);
+
 /* Number of kernel launches this library has enqueued in this process (bench.py's `gpu_launches`). */
 unsigned long long im2im_launch_count(void);
 

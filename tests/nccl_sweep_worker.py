@@ -1,0 +1,37 @@
+"""Worker for tests/test_rcps_gpu.py::test_two_rank_nccl_sweep (launched by torch.distributed.run, one rank per GPU)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from conftest import load_golden  # noqa: E402
+from im2im_uq_b200.calibration import calibrate_model as cm  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for case in ("fastmri_small", "temca_small", "top_risk_zero", "never_stops", "nasty_ragged"):
+        g = load_golden(case)
+        n = g["outputs"].shape[0]
+        cuts = [n * r // world for r in range(world + 1)]
+        lo, hi = cuts[rank], cuts[rank + 1]
+        cfg = dict(g["config"], device=str(dev))
+        out = torch.from_numpy(g["outputs"][lo:hi]).to(dev); lab = torch.from_numpy(g["labels"][lo:hi]).to(dev)
+        lhat, stop, counts, visited = cm.rcps_sweep(out, lab, cfg, group=dist.group.WORLD)
+        assert stop == int(g["stop_idx"]), (case, rank, stop)
+        assert np.float32(lhat.numpy()) == g["lhat"]
+        assert np.array_equal(counts.cpu().numpy(), g["counts_prime"][lo:hi])
+    dist.barrier()
+    if rank == 0:
+        print("NCCL_SWEEP_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
