@@ -133,7 +133,8 @@ def measured_peak():
 def cpu_reference_sweep(sample_out, sample_lab, cfg, stop_full, n_full):
     """The reference's algorithm (calibrate_model.py:130-145): one full pass over the sample PER visited lambda, fp32
     mean, HB bound - restated in C (oracle port, all host threads).  The number of visited steps is pinned to what
-    the full workload visits (columns L-1 .. stop_full) so the sample costs what its share of the real job costs."""
+    the full workload visits (columns L-1 .. stop_full, or its own early stop with the bound at the full set size) so
+    the sample costs what its share of the real job costs."""
     import torch
     from oracle import rcps_oracle as orc
     lambdas = torch.linspace(cfg["minimum_lambda"], cfg["maximum_lambda"], cfg["num_lambdas"])
@@ -141,12 +142,17 @@ def cpu_reference_sweep(sample_out, sample_lab, cfg, stop_full, n_full):
     px = float(sample_out[0, 0].size)
     t0 = time.perf_counter()
     steps = 0
-    for j in reversed(range(max(stop_full, 0), cfg["num_lambdas"])):
+    first = 0 if stop_full is None else max(stop_full, 0)
+    for j in reversed(range(first, cfg["num_lambdas"])):
         counts = orc.c_miss_counts(sample_out, sample_lab, float(lambdas[j] - dlambda))
         losses = torch.from_numpy(counts.astype("float32")) / px
         rhat = losses.mean()
-        orc.hb_mu_plus(rhat.item(), n_full, cfg["delta"])
+        rhat_plus = orc.hb_mu_plus(rhat.item(), n_full, cfg["delta"])
         steps += 1
+        # stop_full=None: the reference's own early stop, with the bound evaluated at the FULL set size so the sample
+        # visits the lambda steps the whole job would (risk per lambda is a population quantity)
+        if stop_full is None and (rhat >= cfg["alpha"] or rhat_plus > cfg["alpha"]):
+            break
     return time.perf_counter() - t0, steps
 
 
@@ -163,7 +169,7 @@ def run_reference_arm(args):
     s = max(8, args.cpu_sample // 4)
     out, lab = synth(s, args.side, "cpu", 1234)
     out, lab = out.numpy(), lab.numpy()
-    stop_full = int(0.39 * args.lambdas)  # where the full 10k workload stops on this recipe (index ~390 of 1000)
+    stop_full = None  # early stop decided on the sample with the HB bound at the full set size
     for _ in range(max(args.warmup, 1)):
         cpu_reference_sweep(out[:2], lab[:2], cfg, args.lambdas - 3, args.images)
     times = []

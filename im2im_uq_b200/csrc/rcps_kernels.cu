@@ -84,19 +84,31 @@ __device__ __noinline__ int rank_bisect(float d, float P, float Y, const float* 
 
 // Number of grid points at which the pixel is missed = index of the first lambda that covers it.
 // guess_scale/guess_bias map the real-valued crossing lam* = (Y-P)/d onto the (uniform) grid:
-// #{lam_j < lam*} = ceil((lam*-lam0)/dlam).  The guess is then verified with the exact predicate at g-1 and g.
-__device__ __forceinline__ int pixel_rank(const PixelQuery& q, const float* __restrict__ s_lam, int L,
-                                          float guess_scale, float guess_bias) {
+// #{lam_j < lam*} = ceil((lam*-lam0)/dlam).  The guess g is then verified with the exact predicate at g-1 and g;
+// s_pair[g] = (lam[g-1], lam[g]) (with -inf / +inf sentinels at the ends) so both neighbours come from one 64-bit
+// shared load.
+// Returns the guess and sets `ok` when the verification passed (or the pixel can never miss); branch-free so that
+// the pixels of a thread interleave.  A failed verification is resolved by rank_bisect (rare).
+__device__ __forceinline__ int rank_guess(const PixelQuery& q, const float2* __restrict__ s_pair, int L,
+                                          float guess_scale, float guess_bias, bool& ok) {
     float rcp;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(q.d));
     const float t = (q.Y - q.P) * rcp;
-    int g = __float2int_ru(fmaf(t, guess_scale, guess_bias));  // saturating; NaN -> 0
+    // The conversion is done in opaque PTX on purpose: cvt.rpi.s32.f32 saturates and maps NaN to 0 by specification,
+    // whereas a C++ float->int conversion of NaN (inf*0 for p = +/-inf) is undefined and NVVM was seen to fold the
+    // later `g == L` test into a float compare that is true for NaN.
+    int g;
+    asm("cvt.rpi.s32.f32 %0, %1;" : "=r"(g) : "f"(fmaf(t, guess_scale, guess_bias)));
     g = max(0, min(g, L));
-    const float la = s_lam[max(g - 1, 0)];
-    const float lb = s_lam[min(g, L - 1)];
-    const bool below_ok = (g == 0) || missed(q, la);   // missed at every grid point below g
-    const bool above_ok = (g == L) || !missed(q, lb);  // covered from g upwards
-    if (q.active && !(below_ok && above_ok)) g = rank_bisect(q.d, q.P, q.Y, s_lam, L);
+    // s_pair carries sentinels (-inf below the grid, +inf above it), so g == 0 and g == L need no special case:
+    // lam = -inf is "missed" and lam = +inf is "covered" for every active pixel with a positive width.  (A zero
+    // width gives NaN at the -inf sentinel, fails the check and is resolved by the bisection - still exact.)
+    // Testing `g == L` on the clamped value directly is avoided on purpose: ptxas 12.9 lowers clamp+compare to a
+    // VIMNMX.RELU predicate output that was observed to be true for g == 0 as well.
+    const float2 nb = s_pair[g];
+    const bool below_ok = missed(q, nb.x);   // missed at every grid point below g
+    const bool above_ok = !missed(q, nb.y);  // covered from g upwards
+    ok = !q.active || (below_ok && above_ok);
     return q.active ? g : 0;
 }
 
@@ -143,7 +155,8 @@ template <bool STAGED>
 __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(const RcpsParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int L = prm.n_lambdas;
-    // layout: [stage ring | STAGED only] [tot u64 x L] [mbarriers] [lambda f32 x L] [hist u32 x (L+1)] [warp sums]
+    // layout: [stage ring | STAGED only] [tot u64 x L] [mbarriers] [lambda pairs f32x2 x (L+1)] [lambda f32 x L]
+    //         [hist u32 x (L+1)] [warp sums]
     unsigned char* cursor = smem_raw;
     float* ring = reinterpret_cast<float*>(cursor);
     if (STAGED) cursor += sizeof(float) * kStages * 4 * kTilePx;
@@ -152,6 +165,8 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(cursor);
     uint64_t* empty_bar = full_bar + kStages;
     cursor += sizeof(uint64_t) * 2 * kStages;
+    float2* s_pair = reinterpret_cast<float2*>(cursor);  // (lam[g-1], lam[g]) for g = 0..L
+    cursor += sizeof(float2) * (L + 1);
     float* s_lam = reinterpret_cast<float*>(cursor);
     cursor += sizeof(float) * L;
     unsigned* hist = reinterpret_cast<unsigned*>(cursor);
@@ -163,7 +178,10 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
         s_lam[j] = prm.lambdas[j];
         tot[j] = 0ull;
     }
-    for (int j = tid; j <= L; j += kThreads) hist[j] = 0u;
+    for (int j = tid; j <= L; j += kThreads) {
+        hist[j] = 0u;
+        s_pair[j] = make_float2(j > 0 ? prm.lambdas[j - 1] : -INFINITY, j < L ? prm.lambdas[j] : INFINITY);
+    }
     if (STAGED && tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -239,10 +257,19 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
             if (have) {
                 const float l[4] = {vl.x, vl.y, vl.z, vl.w}, p[4] = {vp.x, vp.y, vp.z, vp.w};
                 const float u[4] = {vu.x, vu.y, vu.z, vu.w}, y[4] = {vy.x, vy.y, vy.z, vy.w};
+                PixelQuery q[4];
                 int k[4];
+                bool ok[4];
 #pragma unroll
-                for (int m = 0; m < 4; ++m)
-                    k[m] = pixel_rank(make_query(l[m], p[m], u[m], y[m]), s_lam, L, guess_scale, guess_bias);
+                for (int m = 0; m < 4; ++m) {
+                    q[m] = make_query(l[m], p[m], u[m], y[m]);
+                    k[m] = rank_guess(q[m], s_pair, L, guess_scale, guess_bias, ok[m]);
+                }
+                if (!(ok[0] && ok[1] && ok[2] && ok[3])) {  // rare: guess off by more than the checked window
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        if (!ok[m]) k[m] = rank_bisect(q[m].d, q[m].P, q[m].Y, s_lam, L);
+                }
 #pragma unroll
                 for (int m = 0; m < 4; ++m)
                     if (k[m] > 0) atomicAdd(&hist[k[m]], 1u);
@@ -264,10 +291,18 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
                     l[m] = p[m] = u[m] = y[m] = 0.f;  // y == p: inactive, rank 0
                 }
             }
+            PixelQuery q[kPxPerThread];
+            int k[kPxPerThread];
+            bool ok[kPxPerThread];
 #pragma unroll
             for (int m = 0; m < kPxPerThread; ++m) {
-                const int k = pixel_rank(make_query(l[m], p[m], u[m], y[m]), s_lam, L, guess_scale, guess_bias);
-                if (k > 0) atomicAdd(&hist[k], 1u);
+                q[m] = make_query(l[m], p[m], u[m], y[m]);
+                k[m] = rank_guess(q[m], s_pair, L, guess_scale, guess_bias, ok[m]);
+            }
+#pragma unroll
+            for (int m = 0; m < kPxPerThread; ++m) {
+                if (!ok[m]) k[m] = rank_bisect(q[m].d, q[m].P, q[m].Y, s_lam, L);
+                if (k[m] > 0) atomicAdd(&hist[k[m]], 1u);
             }
         }
         if (image_ends_here || it == n_my_tiles - 1) {
@@ -380,8 +415,8 @@ __global__ void __launch_bounds__(256) fraction_missed_kernel(const float* __res
 
 size_t hist_smem_bytes(bool staged, int L) {
     size_t b = staged ? sizeof(float) * kStages * 4 * kTilePx : 0;
-    b += sizeof(unsigned long long) * L + sizeof(uint64_t) * 2 * kStages + sizeof(float) * L +
-         sizeof(unsigned) * (L + 1) + sizeof(unsigned) * kConsumerWarps;
+    b += sizeof(unsigned long long) * L + sizeof(uint64_t) * 2 * kStages + sizeof(float2) * (L + 1) +
+         sizeof(float) * L + sizeof(unsigned) * (L + 1) + sizeof(unsigned) * kConsumerWarps;
     return b;
 }
 
