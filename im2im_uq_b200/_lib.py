@@ -75,11 +75,14 @@ def _declare_more(lib):
     vp, i64 = c.c_void_p, c.c_int64
     lib.im2im_fraction_missed_counts.restype = c.c_int
     lib.im2im_fraction_missed_counts.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, vp, vp]
+    i32 = c.c_int32
+    lib.im2im_conv_igemm_bf16.restype = c.c_int
+    lib.im2im_conv_igemm_bf16.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
 
 
 EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im_rcps_miss_counts",
            "im2im_rcps_loss_table", "im2im_quantile_nested_sets", "im2im_rcps_miss_map",
-           "im2im_fraction_missed_counts"]
+           "im2im_fraction_missed_counts", "im2im_conv_igemm_bf16"]
 
 
 def load():

@@ -1,0 +1,46 @@
+"""Tensor-level wrappers over the tcgen05 convolution entry points of the C ABI (include/im2im_uq.h).
+
+Activations are NHWC bf16 CUDA tensors; weights are packed once to [c_out, taps, c_in] bf16 (K-major rows).
+"""
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def pack_conv_weight(weight: torch.Tensor) -> torch.Tensor:
+    """torch Conv2d weight [c_out, c_in, kh, kw] -> bf16 [c_out, kh*kw, c_in] (tap-major K), contiguous."""
+    c_out, c_in, kh, kw = weight.shape
+    return weight.detach().permute(0, 2, 3, 1).reshape(c_out, kh * kw, c_in).contiguous().to(torch.bfloat16)
+
+
+def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    """NCHW float -> NHWC bf16 contiguous."""
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def conv_igemm(x1: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+               x2: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """3x3 (pad 1) or 1x1 convolution on tcgen05: x1 (and optionally x2, concatenated after x1 on channels) NHWC bf16."""
+    lib = _lib.load()
+    assert x1.is_cuda and x1.dtype == torch.bfloat16 and x1.is_contiguous() and x1.dim() == 4
+    B, H, W, c1 = x1.shape
+    c2 = 0
+    if x2 is not None:
+        assert x2.is_cuda and x2.dtype == torch.bfloat16 and x2.is_contiguous() and tuple(x2.shape[:3]) == (B, H, W)
+        c2 = x2.shape[3]
+    c_out, taps, c_in = weight_packed.shape
+    assert weight_packed.dtype == torch.bfloat16 and weight_packed.is_contiguous() and c_in == c1 + c2
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == c_out and bias.is_cuda
+    out = torch.empty((B, H, W, c_out), dtype=out_dtype, device=x1.device)
+    with torch.cuda.device(x1.device):
+        rc = lib.im2im_conv_igemm_bf16(x1.data_ptr(), c1, x2.data_ptr() if x2 is not None else None, c2,
+                                       weight_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                       B, H, W, c_out, taps, 1 if relu else 0,
+                                       out.data_ptr() if out_dtype == torch.bfloat16 else None,
+                                       out.data_ptr() if out_dtype == torch.float32 else None,
+                                       torch.cuda.current_stream(x1.device).cuda_stream)
+    _lib.check(rc, "im2im_conv_igemm_bf16")
+    return out

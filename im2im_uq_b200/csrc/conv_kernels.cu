@@ -1,0 +1,365 @@
+// UNet convolution path for sm_100a (Path B of DESIGN.md): 3x3 / 1x1 convolution as an implicit GEMM on tcgen05.
+//
+// Replaces the library convolutions behind the reference's trunk
+//   core/models/trunks/unet_parts.py:16-21 (DoubleConv: conv3x3 -> BN -> ReLU, twice), :90 (OutConv 1x1)
+// for inference (BatchNorm folded into weight/bias on the host, ReLU fused in the epilogue).
+//
+// GEMM view:  D[pixel, cout] = sum_{tap, cin} X[pixel shifted by tap, cin] * W[cout, tap, cin]
+//   M tile = 128 output pixels = one TMA box (BW x BH x BB) of an NHWC bf16 activation tensor; the shifted box of a
+//            tap is the same box at coordinates (w0+dx, h0+dy): out-of-range rows/columns are ZERO-FILLED by TMA,
+//            which is exactly the convolution's zero padding - no im2col buffer, no halo handling.
+//   N tile = BN output channels (<= 256), K step = 64 input channels of one tap (128 B rows, SWIZZLE_128B).
+//   Channel concatenation (unet_parts.py:68 torch.cat([x2, x1])) = two tensor maps walked by one K loop.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, tcgen05.mma kind::f16, fp32 accumulator
+// in TMEM), warps 2-5 = epilogue (tcgen05.ld -> +bias -> ReLU -> bf16 -> global NHWC).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace im2im {
+namespace {
+
+constexpr int kConvThreads = 192;     // 6 warps
+constexpr int kTileM = 128;           // output pixels per CTA
+constexpr int kKStep = 64;            // bf16 channels per K step = 128 bytes = one swizzle row
+constexpr int kUmmaK = 16;            // K of one tcgen05.mma for 16-bit inputs
+constexpr int kATileBytes = kTileM * kKStep * 2;  // 16 KB
+
+struct ConvParams {
+    int taps;          // 9 (3x3, pad 1) or 1 (1x1)
+    int c_in1, c_in2;  // channels of the first / second (concatenated) input; c_in2 may be 0
+    int c_out;
+    int B, H, W;
+    int bw, bh, bb;    // TMA box extents along W, H, batch (bw*bh*bb == 128)
+    int tiles_w, tiles_h, tiles_b;
+    int bn;            // N tile
+    int stages;
+    int relu;
+    const float* bias;       // [c_out] or null
+    __nv_bfloat16* out_bf16; // NHWC [B,H,W,c_out] or null
+    float* out_f32;          // NHWC fp32 or null
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05 ops of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor for a K-major, SWIZZLE_128B tile whose rows are 128 bytes (64 bf16):
+// start address (>>4), LBO = 1 (ignored for swizzled K-major), SBO = 1024 B between 8-row groups, version 1 (sm_100),
+// layout type 2 (SWIZZLE_128B).  The tile base must be 1024-byte aligned (base_offset = 0).
+__device__ __forceinline__ uint64_t make_sw128_desc(const void* smem_ptr) {
+    const uint32_t addr = smem_u32(smem_ptr);
+    uint64_t desc = 0;
+    desc |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+    desc |= static_cast<uint64_t>(1) << 16;            // leading byte offset (16 B units)
+    desc |= static_cast<uint64_t>(1024 >> 4) << 32;    // stride byte offset
+    desc |= static_cast<uint64_t>(1) << 46;            // descriptor version (Blackwell)
+    desc |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
+    return desc;
+}
+// Instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = bn
+__device__ __forceinline__ uint32_t make_idesc_bf16(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
+           (static_cast<uint32_t>(kTileM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
+                  const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // layout: [stages x (A tile 16 KB | B tile bn*128 B)] [full barriers] [empty barriers] [accum barrier] [tmem ptr]
+    const int b_tile_bytes = p.bn * kKStep * 2;
+    const int stage_bytes = kATileBytes + b_tile_bytes;
+    // SWIZZLE_128B tiles need 1024-byte alignment; the runtime only guarantees 16 for dynamic shared memory
+    unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(p.stages) * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* accum_bar = empty_bar + p.stages;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t tmem_cols = p.bn < 32 ? 32u : static_cast<uint32_t>(p.bn);  // power of two >= 32 (bn in {32,64,128,256})
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_x1);
+        if (p.c_in2 > 0) prefetch_tmap(&map_x2);
+        prefetch_tmap(&map_w);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_smem, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    const int tb = t;
+    const int w0 = tw * p.bw, h0 = th * p.bh, b0 = tb * p.bb;
+    const int n0 = blockIdx.y * p.bn;
+    const int c_in = p.c_in1 + p.c_in2;
+    const int kblocks_per_tap = c_in / kKStep;
+    const int n_k = p.taps * kblocks_per_tap;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            unsigned phase = 1;  // fresh barriers: waiting on parity 1 passes immediately
+            for (int it = 0; it < n_k; ++it) {
+                const int tap = it / kblocks_per_tap;
+                const int cblk = it - tap * kblocks_per_tap;
+                const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+                const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+                mbar_wait(&empty_bar[stage], phase);
+                unsigned char* a_dst = tiles + static_cast<size_t>(stage) * stage_bytes;
+                unsigned char* b_dst = a_dst + kATileBytes;
+                mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(stage_bytes));
+                const int c0 = cblk * kKStep;
+                if (c0 < p.c_in1) tma_load_4d(a_dst, &map_x1, &full_bar[stage], c0, w0 + dx, h0 + dy, b0);
+                else tma_load_4d(a_dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0 + dx, h0 + dy, b0);
+                tma_load_2d(b_dst, &map_w, &full_bar[stage], tap * c_in + c0, n0);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(p.bn);
+            int stage = 0;
+            unsigned phase = 0;
+            for (int it = 0; it < n_k; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const unsigned char* a_src = tiles + static_cast<size_t>(stage) * stage_bytes;
+                const uint64_t desc_a = make_sw128_desc(a_src);
+                const uint64_t desc_b = make_sw128_desc(a_src + kATileBytes);
+#pragma unroll
+                for (int k = 0; k < kKStep / kUmmaK; ++k) {
+                    // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                    umma_bf16(tmem_base, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
+                              idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(accum_bar);  // accumulator complete
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue warps (2..5)
+        const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;        // row of the 128-pixel tile
+        int r = row;
+        const int iw = r % p.bw; r /= p.bw;
+        const int ih = r % p.bh; r /= p.bh;
+        const int ib = r;
+        const int w = w0 + iw, h = h0 + ih, b = b0 + ib;
+        const bool in_range = (w < p.W) && (h < p.H) && (b < p.B);
+        const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        for (int c = 0; c < p.bn; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c), v);
+            tmem_ld_wait();
+            if (in_range) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    if (p.bias) x += __ldg(p.bias + n0 + c + j);
+                    if (p.relu) x = fmaxf(x, 0.f);
+                    f[j] = x;
+                }
+                if (p.out_bf16) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.c_out + n0 + c);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 pk;
+                        __nv_bfloat162 h0_ = __floats2bfloat162_rn(f[8 * q + 0], f[8 * q + 1]);
+                        __nv_bfloat162 h1_ = __floats2bfloat162_rn(f[8 * q + 2], f[8 * q + 3]);
+                        __nv_bfloat162 h2_ = __floats2bfloat162_rn(f[8 * q + 4], f[8 * q + 5]);
+                        __nv_bfloat162 h3_ = __floats2bfloat162_rn(f[8 * q + 6], f[8 * q + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0_); pk.y = *reinterpret_cast<uint32_t*>(&h1_);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2_); pk.w = *reinterpret_cast<uint32_t*>(&h3_);
+                        dst[q] = pk;
+                    }
+                }
+                if (p.out_f32) {
+                    float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.c_out + n0 + c);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// NHWC bf16 activation [B,H,W,C] with a (64 ch, bw, bh, bb) box
+int make_act_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int bw, int bh, int bb) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(IM2IM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kKStep, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(IM2IM_ECUDA, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
+    return IM2IM_OK;
+}
+
+// weights [c_out, K] bf16 (K = taps*c_in contiguous) with a (64, bn) box
+int make_weight_map(CUtensorMap* map, const void* base, int c_out, int K, int bn) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(IM2IM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)c_out};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kKStep, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(IM2IM_ECUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    return IM2IM_OK;
+}
+
+// pick a 128-pixel box (bw, bh, bb) that tiles (W, H, B) with the least padding
+void pick_box(int B, int H, int W, int& bw, int& bh, int& bb) {
+    long long best = -1;
+    for (int cw = 1; cw <= 128; cw <<= 1) {
+        for (int ch = 1; cw * ch <= 128; ch <<= 1) {
+            const int cb = 128 / (cw * ch);
+            if (cw > 256 || ch > 256 || cb > 256) continue;
+            const long long tiles = (long long)((W + cw - 1) / cw) * ((H + ch - 1) / ch) * ((B + cb - 1) / cb);
+            // prefer fewer tiles (less padding); tie-break towards wide boxes (longer contiguous rows)
+            const long long score = tiles * 1024 - cw;
+            if (best < 0 || score < best) { best = score; bw = cw; bh = ch; bb = cb; }
+        }
+    }
+}
+
+}  // namespace
+}  // namespace im2im
+
+using namespace im2im;
+
+extern "C" int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2,
+                                     const void* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W,
+                                     int32_t c_out, int32_t taps, int32_t relu, void* d_out_bf16, float* d_out_f32,
+                                     void* stream) {
+    if (taps != 9 && taps != 1) return fail(IM2IM_EINVAL, "taps must be 9 (3x3) or 1 (1x1), got %d", taps);
+    if (B <= 0 || H <= 0 || W <= 0) return fail(IM2IM_EINVAL, "bad activation shape %dx%dx%d", B, H, W);
+    if (c_in1 <= 0 || c_in1 % kKStep || c_in2 < 0 || c_in2 % kKStep)
+        return fail(IM2IM_ERANGE, "input channels must be multiples of %d (got %d + %d)", kKStep, c_in1, c_in2);
+    if (c_out < 32 || c_out % 32) return fail(IM2IM_ERANGE, "c_out must be a multiple of 32 (got %d)", c_out);
+    if (!d_x1 || !d_weight || (!d_out_bf16 && !d_out_f32) || (c_in2 > 0 && !d_x2))
+        return fail(IM2IM_EINVAL, "null tensor");
+    ConvParams p;
+    p.taps = taps; p.c_in1 = c_in1; p.c_in2 = c_in2; p.c_out = c_out; p.B = B; p.H = H; p.W = W;
+    pick_box(B, H, W, p.bw, p.bh, p.bb);
+    p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh; p.tiles_b = (B + p.bb - 1) / p.bb;
+    p.bn = (c_out % 256 == 0) ? 256 : (c_out % 128 == 0) ? 128 : (c_out % 64 == 0) ? 64 : 32;
+    const int stage_bytes = kATileBytes + p.bn * kKStep * 2;
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    p.relu = relu; p.bias = d_bias;
+    p.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16); p.out_f32 = d_out_f32;
+    CUtensorMap m1, m2, mw;
+    int rc = make_act_map(&m1, d_x1, B, H, W, c_in1, p.bw, p.bh, p.bb);
+    if (rc) return rc;
+    if (c_in2 > 0) { rc = make_act_map(&m2, d_x2, B, H, W, c_in2, p.bw, p.bh, p.bb); if (rc) return rc; }
+    else m2 = m1;
+    rc = make_weight_map(&mw, d_weight, c_out, taps * (c_in1 + c_in2), p.bn);
+    if (rc) return rc;
+    const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(static_cast<unsigned>(p.tiles_w * p.tiles_h * p.tiles_b), static_cast<unsigned>(c_out / p.bn));
+    conv_igemm_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(m1, m2, mw, p);
+    return check_launch("conv_igemm_kernel");
+}

@@ -114,6 +114,21 @@ int im2im_fraction_missed_counts(const float* d_lower_edge, const float* d_upper
                                  int64_t n_images, int64_t px, int64_t stride_lower, int64_t stride_upper,
                                  int64_t stride_label, int32_t* d_counts, void* stream);
 
+/*
+ * 3x3 (pad 1) or 1x1 convolution, NHWC bf16, as an implicit GEMM on tcgen05 tensor cores (fp32 accumulation in TMEM).
+ * Replaces the library convolution + (folded) BatchNorm + ReLU of the reference's trunk for inference:
+ *   core/models/trunks/unet_parts.py:16-21 (DoubleConv), :90 (OutConv 1x1); the channel concatenation of
+ *   unet_parts.py:68 `torch.cat([x2, x1], dim=1)` is expressed by passing the two tensors (x1 = skip, x2 = upsampled).
+ *   d_x1 / d_x2 : DEVICE bf16 [B,H,W,c_in1] / [B,H,W,c_in2] (c_in2 = 0 and d_x2 = NULL for a single input); channel
+ *                 counts must be multiples of 64
+ *   d_weight    : DEVICE bf16 [c_out, taps, c_in1+c_in2] (taps = 9: ky*3+kx row-major; 1 for 1x1)
+ *   d_bias      : DEVICE fp32 [c_out] or NULL;  relu != 0 applies max(x, 0)
+ *   outputs     : DEVICE NHWC [B,H,W,c_out] as bf16 and/or fp32 (either may be NULL, not both); c_out % 32 == 0
+ */
+int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2, const void* d_weight,
+                          const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps,
+                          int32_t relu, void* d_out_bf16, float* d_out_f32, void* stream);
+
 /* Number of kernel launches this library has enqueued in this process (bench.py's `gpu_launches`). */
 unsigned long long im2im_launch_count(void);
 

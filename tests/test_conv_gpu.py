@@ -1,0 +1,67 @@
+"""GPU (-m gpu): the tcgen05 implicit-GEMM convolution (C ABI im2im_conv_igemm_bf16) against a plain PyTorch fp32
+reference of the same op on the same bf16-rounded operands.
+
+Tolerance: inputs/weights are bf16 (exactly representable in the fp32 reference), accumulation is fp32 in TMEM, so the
+only differences are summation order (<= 1e-4 relative to the output scale, checked on the fp32 output) and the final
+bf16 rounding of the output (2^-9 relative, checked as 1e-2 of the output scale)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from im2im_uq_b200 import _lib, conv
+    DEV = torch.device("cuda:0")
+
+
+def _ref_and_got(B, H, W, c1, c2, cout, taps, relu, bias, out_dtype, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    k = 3 if taps == 9 else 1
+    x1 = torch.randn(B, c1, H, W, device=DEV, generator=g).to(torch.bfloat16)
+    x2 = torch.randn(B, c2, H, W, device=DEV, generator=g).to(torch.bfloat16) if c2 else None
+    w = (torch.randn(cout, c1 + c2, k, k, device=DEV, generator=g) / ((c1 + c2) * taps) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(cout, device=DEV, generator=g) if bias else None
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        xin = x1.float() if not c2 else torch.cat([x1.float(), x2.float()], dim=1)  # unet_parts.py:68 order
+        ref = F.conv2d(xin, w.float(), b, padding=k // 2)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    if relu:
+        ref = ref.relu()
+    got = conv.conv_igemm(conv.to_nhwc_bf16(x1), conv.pack_conv_weight(w), b, relu,
+                          conv.to_nhwc_bf16(x2) if c2 else None, out_dtype)
+    return ref, got.float().permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("shape", [
+    (1, 16, 16, 64, 0, 64, 9),       # one tile
+    (2, 40, 40, 128, 0, 128, 9),     # box 8x8x2 tiling of a 40x40 map
+    (3, 20, 20, 256, 0, 512, 9),     # batch-padded boxes, two N tiles of 256
+    (2, 32, 32, 64, 64, 64, 9),      # concatenated skip + upsampled inputs
+    (1, 37, 29, 64, 0, 256, 9),      # ragged map: TMA zero fill on every border
+    (2, 16, 8, 64, 0, 32, 1),        # 1x1 OutConv (64 -> 32)
+    (1, 320, 320, 64, 0, 64, 9),     # the reference's full-resolution layer
+    (5, 20, 20, 512, 512, 512, 9),   # up1 first conv (1024 -> 512), batch not a multiple of the box
+])
+def test_conv_matches_fp32_reference(shape):
+    B, H, W, c1, c2, cout, taps = shape
+    ref, got = _ref_and_got(B, H, W, c1, c2, cout, taps, relu=False, bias=True, out_dtype=torch.float32)
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= 1e-4 * scale
+    ref, got = _ref_and_got(B, H, W, c1, c2, cout, taps, relu=True, bias=True, out_dtype=torch.bfloat16, seed=1)
+    assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert float(got.min()) >= 0.0
+
+
+def test_conv_argument_validation():
+    x = torch.zeros(1, 8, 8, 48, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(64, 9, 48, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(_lib.Im2ImError, match="multiples of 64"):
+        conv.conv_igemm(x, w)
+    x = torch.zeros(1, 8, 8, 64, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(24, 9, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(_lib.Im2ImError, match="c_out"):
+        conv.conv_igemm(x, w)
