@@ -1,0 +1,251 @@
+// CUDA-core kernels around the tcgen05 convolutions of the UNet forward (Path B of DESIGN.md).  All are bandwidth-bound
+// elementwise / small-stencil passes over NHWC bf16 activations, vectorised to 16 bytes (8 channels) per thread.
+//   first conv   core/models/trunks/unet.py:20  DoubleConv(n_channels_in, 64) first 3x3 (K = 9*C_in is too small for UMMA)
+//   max pool     core/models/trunks/unet_parts.py:34  nn.MaxPool2d(2)
+//   upsample     core/models/trunks/unet_parts.py:50,63  bilinear x2 align_corners=True, then F.pad to the skip's size
+//   head         core/models/finallayers/quantile_layer.py:15-20  three 3x3 convs 32 -> C_out stacked on dim 1
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace im2im {
+namespace {
+
+union Bf16x8 {
+    uint4 u;
+    __nv_bfloat162 h[4];
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// x: fp32 NCHW [B, c_in, H, W] (c_in <= 8) -> y: bf16 NHWC [B, H, W, c_out], 3x3 pad 1, + bias, ReLU.
+// One thread = one pixel x 8 output channels.  Weights fp32 [c_out, c_in, 3, 3] staged in shared memory.
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, int B, int c_in, int H,
+                                                         int W, int c_out, int relu, __nv_bfloat16* __restrict__ y) {
+    extern __shared__ float s_w[];  // [c_out][c_in*9] then bias [c_out]
+    const int kk = c_in * 9;
+    for (int i = threadIdx.x; i < c_out * kk; i += blockDim.x) s_w[i] = w[i];
+    float* s_b = s_w + c_out * kk;
+    for (int i = threadIdx.x; i < c_out; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int groups = c_out / 8;
+    const long long total = static_cast<long long>(B) * H * W * groups;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(e % groups);
+        long long pix = e / groups;
+        const int xw = static_cast<int>(pix % W);
+        const int yh = static_cast<int>((pix / W) % H);
+        const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = s_b[g * 8 + j];
+        for (int ci = 0; ci < c_in; ++ci) {
+            const float* xp = x + (static_cast<long long>(b) * c_in + ci) * H * W;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
+                const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + static_cast<long long>(yy) * W + xx) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, s_w[(g * 8 + j) * kk + ci * 9 + t], acc[j]);
+            }
+        }
+        Bf16x8 o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a0 = acc[2 * j], a1 = acc[2 * j + 1];
+            if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+            o.h[j] = __floats2bfloat162_rn(a0, a1);
+        }
+        *reinterpret_cast<uint4*>(y + pix * c_out + g * 8) = o.u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2x2 max pool, stride 2 (floor), NHWC bf16.
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W,
+                                                         int C, __nv_bfloat16* __restrict__ y) {
+    const int Ho = H / 2, Wo = W / 2, groups = C / 8;
+    const long long total = static_cast<long long>(B) * Ho * Wo * groups;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(e % groups);
+        long long pix = e / groups;
+        const int ox = static_cast<int>(pix % Wo);
+        const int oy = static_cast<int>((pix / Wo) % Ho);
+        const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+        const __nv_bfloat16* p = x + ((static_cast<long long>(b) * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+        Bf16x8 a, c, d, f, o;
+        a.u = *reinterpret_cast<const uint4*>(p);
+        c.u = *reinterpret_cast<const uint4*>(p + C);
+        d.u = *reinterpret_cast<const uint4*>(p + static_cast<long long>(W) * C);
+        f.u = *reinterpret_cast<const uint4*>(p + static_cast<long long>(W) * C + C);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o.h[j] = __hmax2(__hmax2(a.h[j], c.h[j]), __hmax2(d.h[j], f.h[j]));
+        *reinterpret_cast<uint4*>(y + pix * C + g * 8) = o.u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bilinear x2 upsample with align_corners=True of x [B,h,w,C], written into y [B,Ho,Wo,C] at offset (pad_top, pad_left)
+// with zeros elsewhere (F.pad to the skip connection's size).  Source index and weights follow ATen's
+// upsample_bilinear2d: src = dst * (in-1)/(out-1) in fp32, i0 = (int)src, frac = src - i0.
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int B, int h, int w,
+                                                         int C, int Ho, int Wo, int pad_top, int pad_left,
+                                                         __nv_bfloat16* __restrict__ y) {
+    const int uh = 2 * h, uw = 2 * w, groups = C / 8;
+    const float sy = uh > 1 ? static_cast<float>(h - 1) / static_cast<float>(uh - 1) : 0.f;
+    const float sx = uw > 1 ? static_cast<float>(w - 1) / static_cast<float>(uw - 1) : 0.f;
+    const long long total = static_cast<long long>(B) * Ho * Wo * groups;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(e % groups);
+        long long pix = e / groups;
+        const int ox = static_cast<int>(pix % Wo);
+        const int oy = static_cast<int>((pix / Wo) % Ho);
+        const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+        const int uy = oy - pad_top, ux = ox - pad_left;
+        Bf16x8 o;
+        if (uy < 0 || uy >= uh || ux < 0 || ux >= uw) {
+            o.u = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            const float fy = sy * uy, fx = sx * ux;
+            const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+            const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+            const float ly = fy - y0, lx = fx - x0;
+            const float hy = 1.f - ly, hx = 1.f - lx;
+            const __nv_bfloat16* base = x + static_cast<long long>(b) * h * w * C + g * 8;
+            Bf16x8 v00, v01, v10, v11;
+            v00.u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * w + x0) * C);
+            v01.u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * w + x1) * C);
+            v10.u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * w + x0) * C);
+            v11.u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * w + x1) * C);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 a = __bfloat1622float2(v00.h[j]), c = __bfloat1622float2(v01.h[j]);
+                const float2 d = __bfloat1622float2(v10.h[j]), f = __bfloat1622float2(v11.h[j]);
+                const float r0 = hy * (hx * a.x + lx * c.x) + ly * (hx * d.x + lx * f.x);
+                const float r1 = hy * (hx * a.y + lx * c.y) + ly * (hx * d.y + lx * f.y);
+                o.h[j] = __floats2bfloat162_rn(r0, r1);
+            }
+        }
+        *reinterpret_cast<uint4*>(y + pix * C + g * 8) = o.u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Head: x bf16 NHWC [B,H,W,c_mid] -> y fp32 [B, n_out, H, W] (n_out = 3*C_out planes: lower.., prediction.., upper..),
+// 3x3 pad 1, fp32 weights [n_out, c_mid, 3, 3] + bias.  One thread = one pixel, all outputs (n_out <= 12).
+template <int N_OUT>
+__global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, int B, int H, int W, int c_mid,
+                                                        float* __restrict__ y) {
+    extern __shared__ float s_w[];  // [tap][c_mid][N_OUT]
+    for (int i = threadIdx.x; i < 9 * c_mid * N_OUT; i += blockDim.x) {
+        const int o = i % N_OUT, c = (i / N_OUT) % c_mid, t = i / (N_OUT * c_mid);
+        s_w[i] = w[(static_cast<long long>(o) * c_mid + c) * 9 + t];
+    }
+    __syncthreads();
+    const long long total = static_cast<long long>(B) * H * W;
+    for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < total;
+         pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int xw = static_cast<int>(pix % W);
+        const int yh = static_cast<int>((pix / W) % H);
+        const long long b = pix / (static_cast<long long>(W) * H);
+        float acc[N_OUT];
+#pragma unroll
+        for (int o = 0; o < N_OUT; ++o) acc[o] = bias ? __ldg(bias + o) : 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const __nv_bfloat16* p = x + ((b * H + yy) * W + xx) * c_mid;
+            const float* wt = s_w + t * c_mid * N_OUT;
+            for (int c = 0; c < c_mid; c += 8) {
+                Bf16x8 v;
+                v.u = *reinterpret_cast<const uint4*>(p + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(v.h[j]);
+#pragma unroll
+                    for (int o = 0; o < N_OUT; ++o) {
+                        acc[o] = fmaf(f.x, wt[(c + 2 * j) * N_OUT + o], acc[o]);
+                        acc[o] = fmaf(f.y, wt[(c + 2 * j + 1) * N_OUT + o], acc[o]);
+                    }
+                }
+            }
+        }
+        const long long hw = static_cast<long long>(H) * W;
+#pragma unroll
+        for (int o = 0; o < N_OUT; ++o) y[(b * N_OUT + o) * hw + static_cast<long long>(yh) * W + xw] = acc[o];
+    }
+}
+
+unsigned grid_for(long long work_items, int threads) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = 16ll * sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<unsigned>(blocks);
+}
+
+}  // namespace
+}  // namespace im2im
+
+using namespace im2im;
+
+extern "C" int im2im_conv_first_bf16(const float* d_x, const float* d_weight, const float* d_bias, int32_t B,
+                                     int32_t c_in, int32_t H, int32_t W, int32_t c_out, int32_t relu, void* d_out,
+                                     void* stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || c_in <= 0 || c_in > 8) return fail(IM2IM_ERANGE, "conv_first: bad shape (c_in=%d)", c_in);
+    if (c_out <= 0 || c_out % 8) return fail(IM2IM_ERANGE, "conv_first: c_out must be a multiple of 8");
+    if (!d_x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "null tensor");
+    const size_t smem = sizeof(float) * (static_cast<size_t>(c_out) * c_in * 9 + c_out);
+    if (smem > 48 * 1024) return fail(IM2IM_ERANGE, "conv_first: weights do not fit shared memory");
+    const long long items = static_cast<long long>(B) * H * W * (c_out / 8);
+    conv_first_kernel<<<grid_for(items, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        d_x, d_weight, d_bias, B, c_in, H, W, c_out, relu, static_cast<__nv_bfloat16*>(d_out));
+    return check_launch("conv_first_kernel");
+}
+
+extern "C" int im2im_maxpool2x2_bf16(const void* d_x, int32_t B, int32_t H, int32_t W, int32_t C, void* d_out,
+                                     void* stream) {
+    if (B <= 0 || H < 2 || W < 2 || C <= 0 || C % 8) return fail(IM2IM_ERANGE, "maxpool: bad shape");
+    if (!d_x || !d_out) return fail(IM2IM_EINVAL, "null tensor");
+    const long long items = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+    maxpool2x2_kernel<<<grid_for(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(d_x), B, H, W, C, static_cast<__nv_bfloat16*>(d_out));
+    return check_launch("maxpool2x2_kernel");
+}
+
+extern "C" int im2im_upsample2x_bilinear_bf16(const void* d_x, int32_t B, int32_t h, int32_t w, int32_t C,
+                                              int32_t H_out, int32_t W_out, void* d_out, void* stream) {
+    if (B <= 0 || h <= 0 || w <= 0 || C <= 0 || C % 8) return fail(IM2IM_ERANGE, "upsample: bad shape");
+    if (H_out < 2 * h || W_out < 2 * w) return fail(IM2IM_ERANGE, "upsample: output smaller than 2x input");
+    if (!d_x || !d_out) return fail(IM2IM_EINVAL, "null tensor");
+    const int pad_top = (H_out - 2 * h) / 2, pad_left = (W_out - 2 * w) / 2;  // F.pad split of unet_parts.py:63-64
+    const long long items = static_cast<long long>(B) * H_out * W_out * (C / 8);
+    upsample2x_kernel<<<grid_for(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(d_x), B, h, w, C, H_out, W_out, pad_top, pad_left,
+        static_cast<__nv_bfloat16*>(d_out));
+    return check_launch("upsample2x_kernel");
+}
+
+extern "C" int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias, int32_t B,
+                                      int32_t H, int32_t W, int32_t c_mid, int32_t n_out, float* d_out, void* stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || c_mid <= 0 || c_mid % 8) return fail(IM2IM_ERANGE, "head: bad shape");
+    if (!d_x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "null tensor");
+    const size_t smem = sizeof(float) * 9 * c_mid * n_out;
+    if (smem > 48 * 1024) return fail(IM2IM_ERANGE, "head: weights do not fit shared memory");
+    const long long items = static_cast<long long>(B) * H * W;
+    const unsigned grid = grid_for(items, 128);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(d_x);
+    switch (n_out) {
+        case 3: head_conv_kernel<3><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, d_out); break;
+        case 6: head_conv_kernel<6><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, d_out); break;
+        case 9: head_conv_kernel<9><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, d_out); break;
+        default: return fail(IM2IM_ENOTSUP, "head: n_out=%d (3*C_out with C_out in 1..3 supported)", n_out);
+    }
+    return check_launch("head_conv_kernel");
+}

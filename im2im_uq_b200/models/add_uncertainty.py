@@ -24,6 +24,15 @@ class ModelWithUncertainty(nn.Module):
         self.params = params
 
     def forward(self, x):
+        # eval-mode CUDA forwards under no_grad run on the native sm_100a engine (tcgen05 convolutions);
+        # training forwards go through the module graph so autograd sees them.
+        from .unet_engine import UNetInferenceEngine, native_forward_applicable
+        if native_forward_applicable(self, x):
+            eng = self.__dict__.get("_native_engine")
+            if eng is None:
+                eng = UNetInferenceEngine(self)
+                self.__dict__["_native_engine"] = eng
+            return eng.forward(x)
         x = self.baseModel(x)
         return self.last_layer(x)
 

@@ -1,0 +1,146 @@
+"""Native sm_100a inference forward of UNet + quantile head (Path B, inference half).
+
+Replaces, for ``model.eval()`` forwards on CUDA under ``torch.no_grad()``, the library calls behind
+``ModelWithUncertainty.forward`` (core/models/add_uncertainty.py:25-27) -> ``UNet.forward``
+(core/models/trunks/unet.py:33-46) -> ``QuantileRegressionLayer.forward`` (core/models/finallayers/quantile_layer.py:19-21):
+BatchNorm (running statistics) is folded into each convolution's weight/bias, activations are NHWC bf16, the 3x3 / 1x1
+convolutions run as implicit GEMMs on tcgen05 (fp32 accumulation), ReLU is fused, the skip concatenation is never
+materialised, and the head writes the reference's (B, 3, C_out, H, W) fp32 tensor directly.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..conv import conv_igemm, pack_conv_weight
+
+
+def _fold_bn(conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """conv -> BN(eval) == conv with w*s and (b-mean)*s+beta, s = gamma/sqrt(var+eps) (fp32)."""
+    w = conv.weight.detach().float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    if bn is not None:
+        s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * s[:, None, None, None]
+        b = (b - bn.running_mean.detach().float()) * s + bn.bias.detach().float()
+    return w.contiguous(), b.contiguous()
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class UNetInferenceEngine:
+    """Folded/packed weights + the launch sequence of the native forward for one ModelWithUncertainty."""
+
+    def __init__(self, model):
+        self.model = model
+        self._stamp = None
+        self.refresh()
+
+    # ---- weights
+    def _param_stamp(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters()) + \
+            tuple((b.data_ptr(), b._version) for n, b in self.model.named_buffers() if b is not None and n != "lhat")
+
+    def refresh(self):
+        trunk, head = self.model.baseModel, self.model.last_layer
+
+        def double(dc):
+            seq = dc.double_conv
+            return _fold_bn(seq[0], seq[1]), _fold_bn(seq[3], seq[4])
+
+        def packed(wb):
+            w, b = wb
+            return pack_conv_weight(w), b
+
+        (w0, b0), second = double(trunk.inc)
+        self.first = (w0.contiguous(), b0)  # fp32 [64, c_in, 3, 3]
+        self.inc2 = packed(second)
+        self.down = []
+        for blk in (trunk.down1, trunk.down2, trunk.down3, trunk.down4):
+            a, b = double(blk.maxpool_conv[1])
+            self.down.append((packed(a), packed(b)))
+        self.up = []
+        for blk in (trunk.up1, trunk.up2, trunk.up3, trunk.up4):
+            a, b = double(blk.conv)
+            self.up.append((packed(a), packed(b)))
+        self.out = packed(_fold_bn(trunk.out.conv, None))
+        hw = torch.cat([head.lower.weight, head.prediction.weight, head.upper.weight], dim=0).detach().float().contiguous()
+        hb = torch.cat([head.lower.bias, head.prediction.bias, head.upper.bias], dim=0).detach().float().contiguous()
+        self.head = (hw, hb)
+        self.c_out = head.lower.weight.shape[0]
+        self._stamp = self._param_stamp()
+
+    # ---- single launches
+    @staticmethod
+    def _conv_first(x, w, b):
+        lib = _lib.load()
+        B, c_in, H, W = x.shape
+        c_out = w.shape[0]
+        y = torch.empty((B, H, W, c_out), dtype=torch.bfloat16, device=x.device)
+        _lib.check(lib.im2im_conv_first_bf16(x.data_ptr(), w.data_ptr(), b.data_ptr(), B, c_in, H, W, c_out, 1,
+                                             y.data_ptr(), _stream(x.device)), "im2im_conv_first_bf16")
+        return y
+
+    @staticmethod
+    def _pool(x):
+        lib = _lib.load()
+        B, H, W, C = x.shape
+        y = torch.empty((B, H // 2, W // 2, C), dtype=torch.bfloat16, device=x.device)
+        _lib.check(lib.im2im_maxpool2x2_bf16(x.data_ptr(), B, H, W, C, y.data_ptr(), _stream(x.device)),
+                   "im2im_maxpool2x2_bf16")
+        return y
+
+    @staticmethod
+    def _upsample_to(x, H_out, W_out):
+        lib = _lib.load()
+        B, h, w, C = x.shape
+        y = torch.empty((B, H_out, W_out, C), dtype=torch.bfloat16, device=x.device)
+        _lib.check(lib.im2im_upsample2x_bilinear_bf16(x.data_ptr(), B, h, w, C, H_out, W_out, y.data_ptr(),
+                                                      _stream(x.device)), "im2im_upsample2x_bilinear_bf16")
+        return y
+
+    def _head(self, x):
+        lib = _lib.load()
+        B, H, W, C = x.shape
+        hw, hb = self.head
+        n_out = hw.shape[0]
+        y = torch.empty((B, n_out, H, W), dtype=torch.float32, device=x.device)
+        _lib.check(lib.im2im_head_conv3x3_f32(x.data_ptr(), hw.data_ptr(), hb.data_ptr(), B, H, W, C, n_out,
+                                              y.data_ptr(), _stream(x.device)), "im2im_head_conv3x3_f32")
+        return y.view(B, 3, self.c_out, H, W)
+
+    # ---- the forward
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._stamp != self._param_stamp():
+            self.refresh()
+        if not x.is_cuda:
+            raise _lib.Im2ImError("native UNet forward needs a CUDA tensor")
+        x = x.contiguous().float()
+        with torch.cuda.device(x.device):
+            a = self._conv_first(x, *self.first)
+            skips: List[torch.Tensor] = [conv_igemm(a, self.inc2[0], self.inc2[1], relu=True)]
+            for (c1, c2) in self.down:
+                p = self._pool(skips[-1])
+                p = conv_igemm(p, c1[0], c1[1], relu=True)
+                skips.append(conv_igemm(p, c2[0], c2[1], relu=True))
+            y = skips.pop()
+            for (c1, c2) in self.up:
+                skip = skips.pop()
+                u = self._upsample_to(y, skip.shape[1], skip.shape[2])
+                y = conv_igemm(skip, c1[0], c1[1], relu=True, x2=u)   # torch.cat([skip, up]) without the copy
+                y = conv_igemm(y, c2[0], c2[1], relu=True)
+            m = conv_igemm(y, self.out[0], self.out[1], relu=False)  # 1x1, 64 -> 32
+            return self._head(m)
+
+
+def native_forward_applicable(model, x) -> bool:
+    from .quantile_layer import QuantileRegressionLayer
+    from .unet import UNet
+    return (not model.training and torch.is_tensor(x) and x.is_cuda and not torch.is_grad_enabled()
+            and type(model.baseModel) is UNet and model.baseModel.bilinear
+            and type(model.last_layer) is QuantileRegressionLayer and getattr(model, "use_native_inference", True)
+            and x.dim() == 4 and x.shape[1] <= 8 and min(x.shape[2], x.shape[3]) >= 16
+            and model.last_layer.lower.weight.shape[0] <= 3)

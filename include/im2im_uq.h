@@ -129,6 +129,25 @@ int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void* d_x2, int
                           const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps,
                           int32_t relu, void* d_out_bf16, float* d_out_f32, void* stream);
 
+/*
+ * The CUDA-core passes around the tcgen05 convolutions of the UNet forward (all NHWC bf16 unless noted):
+ *   im2im_conv_first_bf16          first 3x3 conv of DoubleConv(n_channels_in, 64) (core/models/trunks/unet.py:20):
+ *                                  x fp32 NCHW [B,c_in<=8,H,W], weight fp32 [c_out,c_in,3,3] (+bias, ReLU) -> bf16 NHWC
+ *   im2im_maxpool2x2_bf16          nn.MaxPool2d(2) (core/models/trunks/unet_parts.py:34)
+ *   im2im_upsample2x_bilinear_bf16 nn.Upsample(x2, bilinear, align_corners=True) + F.pad to (H_out, W_out)
+ *                                  (unet_parts.py:50,63-64; pad split floor/ceil like the reference)
+ *   im2im_head_conv3x3_f32         QuantileRegressionLayer (core/models/finallayers/quantile_layer.py:15-20): the three
+ *                                  3x3 convs stacked as n_out = 3*C_out output planes; x bf16 NHWC [B,H,W,c_mid],
+ *                                  weight fp32 [n_out,c_mid,3,3] -> fp32 [B,n_out,H,W] == the (B,3,C_out,H,W) tensor
+ */
+int im2im_conv_first_bf16(const float* d_x, const float* d_weight, const float* d_bias, int32_t B, int32_t c_in,
+                          int32_t H, int32_t W, int32_t c_out, int32_t relu, void* d_out, void* stream);
+int im2im_maxpool2x2_bf16(const void* d_x, int32_t B, int32_t H, int32_t W, int32_t C, void* d_out, void* stream);
+int im2im_upsample2x_bilinear_bf16(const void* d_x, int32_t B, int32_t h, int32_t w, int32_t C, int32_t H_out,
+                                   int32_t W_out, void* d_out, void* stream);
+int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W,
+                           int32_t c_mid, int32_t n_out, float* d_out, void* stream);
+
 /* Number of kernel launches this library has enqueued in this process (bench.py's `gpu_launches`). */
 unsigned long long im2im_launch_count(void);
 

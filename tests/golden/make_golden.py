@@ -170,7 +170,31 @@ def quantile_loss_kats():
     print("[golden] quantile loss: 3 cases")
 
 
+def unet_forward_kat():
+    """Reference UNet(1,1)+quantile head: seeded init, BN running stats moved by 3 train-mode batches, eval forward.
+    core/models/trunks/unet.py:10-46, core/models/finallayers/quantile_layer.py:8-21, add_uncertainty.py:25-27."""
+    params = dict(uncertainty_type="quantiles", q_lo=0.05, q_hi=0.95, q_lo_weight=1.0, q_hi_weight=1.0, mse_weight=1.0)
+    torch.manual_seed(0)
+    model = ref.add_uncertainty.add_uncertainty(ref.unet.UNet(1, 1), params)
+    g = torch.Generator().manual_seed(1)
+    model.train()
+    with torch.no_grad():
+        for _ in range(3):
+            model(torch.randn(4, 1, 32, 32, generator=g))
+    model.eval()
+    x = torch.randn(2, 1, 48, 32, generator=g)
+    with torch.no_grad():
+        y = model(x)
+    sd = model.state_dict()
+    checksum = float(sum(v.double().abs().sum() for k, v in sd.items() if v is not None and v.dtype.is_floating_point))
+    np.savez_compressed(os.path.join(HERE, "unet_forward_kat.npz"), x=x.numpy(), y=y.numpy(),
+                        state_checksum=np.float64(checksum), n_params=np.int64(sum(p.numel() for p in model.parameters())),
+                        keys=json.dumps(list(sd.keys())))
+    print(f"[golden] unet forward: y {tuple(y.shape)} checksum {checksum:.6f}")
+
+
 if __name__ == "__main__":
+    unet_forward_kat()
     hb_kats()
     quantile_loss_kats()
     #        name            seed  n   c  h   w   kind      lam_min lam_max L     alpha delta
