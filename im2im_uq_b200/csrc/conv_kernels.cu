@@ -15,6 +15,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace im2im {
@@ -262,6 +264,179 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_const
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------ persistent kernel
+// Same tile math as conv_igemm_kernel, but one CTA per SM walks many tiles and the three roles run decoupled:
+// the TMA ring and the MMA issuer run ahead into the next tile while the epilogue warps drain the previous
+// accumulator (two TMEM accumulator buffers of bn columns each).  This removes the per-tile launch / barrier-init /
+// TMEM-alloc / pipeline-fill cost that dominates the short-K (64-channel, 320x320) layers.
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
+                             const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int b_tile_bytes = p.bn * kKStep * 2;
+    const int stage_bytes = kATileBytes + b_tile_bytes;
+    unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(p.stages) * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tmem_full = empty_bar + p.stages;   // [2] accumulator ready for the epilogue
+    uint64_t* tmem_empty = tmem_full + 2;         // [2] accumulator drained, MMA may overwrite
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t acc_cols = p.bn < 32 ? 32u : static_cast<uint32_t>(p.bn);
+    const uint32_t tmem_cols = 2 * acc_cols;  // power of two: 64..512
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_x1);
+        if (p.c_in2 > 0) prefetch_tmap(&map_x2);
+        prefetch_tmap(&map_w);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 4);  // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_smem, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int n_tiles_n = p.c_out / p.bn;
+    const int n_tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
+    const int n_tiles = n_tiles_m * n_tiles_n;
+    const int c_in = p.c_in1 + p.c_in2;
+    const int kblocks_per_tap = c_in / kKStep;
+    const int n_k = p.taps * kblocks_per_tap;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            unsigned phase = 1;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int tn = tile % n_tiles_n;
+                int t = tile / n_tiles_n;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                const int w0 = tw * p.bw, h0 = th * p.bh, b0 = t * p.bb, n0 = tn * p.bn;
+                for (int it = 0; it < n_k; ++it) {
+                    const int tap = it / kblocks_per_tap;
+                    const int cblk = it - tap * kblocks_per_tap;
+                    const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+                    const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+                    mbar_wait(&empty_bar[stage], phase);
+                    unsigned char* a_dst = tiles + static_cast<size_t>(stage) * stage_bytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(stage_bytes));
+                    const int c0 = cblk * kKStep;
+                    if (c0 < p.c_in1) tma_load_4d(a_dst, &map_x1, &full_bar[stage], c0, w0 + dx, h0 + dy, b0);
+                    else tma_load_4d(a_dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0 + dx, h0 + dy, b0);
+                    tma_load_2d(a_dst + kATileBytes, &map_w, &full_bar[stage], tap * c_in + c0, n0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(p.bn);
+            int stage = 0;
+            unsigned phase = 0;
+            unsigned acc_phase = 3u;  // bit b = parity to wait for on tmem_empty[b]; fresh barriers: parity 1 passes
+            int buf = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[buf], (acc_phase >> buf) & 1u);
+                acc_phase ^= 1u << buf;
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf) * acc_cols;
+                for (int it = 0; it < n_k; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const unsigned char* a_src = tiles + static_cast<size_t>(stage) * stage_bytes;
+                    const uint64_t desc_a = make_sw128_desc(a_src);
+                    const uint64_t desc_b = make_sw128_desc(a_src + kATileBytes);
+#pragma unroll
+                    for (int k = 0; k < kKStep / kUmmaK; ++k)
+                        umma_bf16(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
+                                  idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tmem_full[buf]);
+                buf ^= 1;
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        int r = row;
+        const int iw = r % p.bw; r /= p.bw;
+        const int ih = r % p.bh; r /= p.bh;
+        const int ib = r;
+        unsigned full_phase = 0u;  // bit b = parity to wait for on tmem_full[b]
+        int buf = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int tn = tile % n_tiles_n;
+            int t = tile / n_tiles_n;
+            const int tw = t % p.tiles_w; t /= p.tiles_w;
+            const int th = t % p.tiles_h; t /= p.tiles_h;
+            const int w = tw * p.bw + iw, h = th * p.bh + ih, b = t * p.bb + ib, n0 = tn * p.bn;
+            const bool in_range = (w < p.W) && (h < p.H) && (b < p.B);
+            const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
+            mbar_wait(&tmem_full[buf], (full_phase >> buf) & 1u);
+            full_phase ^= 1u << buf;
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(buf) * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
+            for (int c = 0; c < p.bn; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_acc + static_cast<uint32_t>(c), v);
+                tmem_ld_wait();
+                if (c + 32 >= p.bn) {  // last read of this accumulator: hand it back to the MMA warp early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                }
+                if (in_range) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(v[j]);
+                        if (p.bias) x += __ldg(p.bias + n0 + c + j);
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        f[j] = x;
+                    }
+                    if (p.out_bf16) {
+                        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.c_out + n0 + c);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 pk;
+                            __nv_bfloat162 h0_ = __floats2bfloat162_rn(f[8 * q + 0], f[8 * q + 1]);
+                            __nv_bfloat162 h1_ = __floats2bfloat162_rn(f[8 * q + 2], f[8 * q + 3]);
+                            __nv_bfloat162 h2_ = __floats2bfloat162_rn(f[8 * q + 4], f[8 * q + 5]);
+                            __nv_bfloat162 h3_ = __floats2bfloat162_rn(f[8 * q + 6], f[8 * q + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0_); pk.y = *reinterpret_cast<uint32_t*>(&h1_);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2_); pk.w = *reinterpret_cast<uint32_t*>(&h3_);
+                            dst[q] = pk;
+                        }
+                    }
+                    if (p.out_f32) {
+                        float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.c_out + n0 + c);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                    }
+                }
+            }
+            buf ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -357,9 +532,19 @@ extern "C" int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void
     else m2 = m1;
     rc = make_weight_map(&mw, d_weight, c_out, taps * (c_in1 + c_in2), p.bn);
     if (rc) return rc;
-    const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
-    IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(static_cast<unsigned>(p.tiles_w * p.tiles_h * p.tiles_b), static_cast<unsigned>(c_out / p.bn));
-    conv_igemm_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(m1, m2, mw, p);
-    return check_launch("conv_igemm_kernel");
+    const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + (2 * p.stages + 4) * sizeof(uint64_t) + 16 + 1024;
+    static const bool use_v1 = (getenv("IM2IM_CONV_V1") != nullptr);  // bring-up switch: one tile per CTA
+    if (use_v1) {
+        IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(static_cast<unsigned>(p.tiles_w * p.tiles_h * p.tiles_b), static_cast<unsigned>(c_out / p.bn));
+        conv_igemm_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(m1, m2, mw, p);
+        return check_launch("conv_igemm_kernel");
+    }
+    IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    const long long n_tiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_b * (c_out / p.bn);
+    const int sms = sm_count();
+    const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
+    conv_igemm_persistent_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(m1, m2, mw, p);
+    return check_launch("conv_igemm_persistent_kernel");
 }

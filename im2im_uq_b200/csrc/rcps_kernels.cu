@@ -325,11 +325,51 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rcps_loss_table_kernel(const int* __restrict__ counts, long long n_elems,
                                                               int L, float px, int first_visited,
+                                                              const int* __restrict__ d_first_visited,
                                                               float* __restrict__ table) {
+    if (d_first_visited != nullptr) first_visited = *d_first_visited;  // decided on the device (rcps_decide_kernel)
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n_elems; e += stride) {
         const int j = static_cast<int>(e % L);
         table[e] = (j >= first_visited) ? __fdiv_rn(static_cast<float>(counts[e]), px) : 0.f;
+    }
+}
+
+// Device-side screening of the reference's stopping rule (host twin: calibration/sweep.py::_classify + the scan of
+// find_stop_index).  Per column j: exact risk R = totals[j]/(N*px); the reference's fp32 Rhat lies in
+// [R(1-gamma), R(1+gamma)]; the rule `Rhat >= alpha or HB(Rhat) > alpha` is certainly true / certainly false / unsure.
+// Scanning from the top of the grid, the first column that is not "certainly false" decides:
+//   result[0] = stop index (-1: ran off the grid)     result[1] = 1 decided, 0 the host must replay from result[2]
+//   result[2] = first unsure column                   result[3] = first visited column for the loss table
+__global__ void __launch_bounds__(256) rcps_decide_kernel(const unsigned long long* __restrict__ totals, int L,
+                                                          double n_px, double gamma, double alpha32, double r_lo,
+                                                          double r_hi, double slack, int* __restrict__ result) {
+    __shared__ int s_first;  // highest column index whose verdict is not "certainly false"
+    __shared__ int s_verdict;
+    if (threadIdx.x == 0) { s_first = -1; s_verdict = 0; }
+    __syncthreads();
+    int best = -1, best_v = 0;
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        const unsigned long long t = totals[j];
+        const double R = static_cast<double>(t) / n_px;
+        const double lo = R * (1.0 - gamma), hi = R * (1.0 + gamma);
+        bool sure_true = lo >= alpha32 * (1.0 + 1e-6);
+        if (isfinite(r_hi)) sure_true = sure_true || (lo > r_hi + slack);
+        bool sure_false = hi < alpha32 * (1.0 - 1e-6);
+        if (isfinite(r_lo)) sure_false = sure_false && (hi < r_lo - slack);
+        int v = sure_true ? 1 : (sure_false ? -1 : 0);
+        if (t == 0ull) v = 0;  // HB_mu_plus(0) takes the reference's exception path: never guessed
+        if (v >= 0 && j > best) { best = j; best_v = v; }
+    }
+    if (best >= 0) atomicMax(&s_first, best);
+    __syncthreads();
+    if (best >= 0 && best == s_first) s_verdict = best_v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int first = s_first;
+        if (first < 0) { result[0] = -1; result[1] = 1; result[2] = -1; result[3] = 0; }
+        else if (s_verdict > 0) { result[0] = first; result[1] = 1; result[2] = -1; result[3] = first; }
+        else { result[0] = -1; result[1] = 0; result[2] = first; result[3] = 0; }
     }
 }
 
@@ -498,8 +538,33 @@ extern "C" int im2im_rcps_loss_table(const int32_t* d_counts, int64_t n_images, 
     const long long cap = 8ll * sm_count();
     rcps_loss_table_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0,
                              static_cast<cudaStream_t>(stream)>>>(d_counts, n, n_lambdas, static_cast<float>(px),
-                                                                  first_visited_col, d_table);
+                                                                  first_visited_col, nullptr, d_table);
     return check_launch("rcps_loss_table_kernel");
+}
+
+extern "C" int im2im_rcps_loss_table_dev(const int32_t* d_counts, int64_t n_images, int32_t n_lambdas, int64_t px,
+                                         const int32_t* d_first_visited_col, float* d_table, void* stream) {
+    if (n_images < 0 || n_lambdas < 1 || px < 1) return fail(IM2IM_EINVAL, "bad table shape");
+    if (n_images == 0) return IM2IM_OK;
+    if (!d_counts || !d_table || !d_first_visited_col) return fail(IM2IM_EINVAL, "null counts/table/first column");
+    const long long n = static_cast<long long>(n_images) * n_lambdas;
+    const long long blocks = (n + 255) / 256;
+    const long long cap = 8ll * sm_count();
+    rcps_loss_table_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0,
+                             static_cast<cudaStream_t>(stream)>>>(d_counts, n, n_lambdas, static_cast<float>(px), 0,
+                                                                  d_first_visited_col, d_table);
+    return check_launch("rcps_loss_table_kernel");
+}
+
+extern "C" int im2im_rcps_decide(const unsigned long long* d_totals, int32_t n_lambdas, double n_images_times_px,
+                                 double gamma, double alpha32, double r_lo, double r_hi, double slack,
+                                 int32_t* d_result, void* stream) {
+    if (n_lambdas < 1 || n_lambdas > IM2IM_RCPS_MAX_LAMBDAS) return fail(IM2IM_ERANGE, "n_lambdas=%d", n_lambdas);
+    if (!d_totals || !d_result) return fail(IM2IM_EINVAL, "null totals/result");
+    if (!(n_images_times_px > 0)) return fail(IM2IM_EINVAL, "empty calibration set");
+    rcps_decide_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_totals, n_lambdas, n_images_times_px,
+                                                                          gamma, alpha32, r_lo, r_hi, slack, d_result);
+    return check_launch("rcps_decide_kernel");
 }
 
 extern "C" int im2im_quantile_nested_sets(float* d_lower, const float* d_pred, float* d_upper, int64_t n_images,

@@ -83,6 +83,23 @@ int im2im_rcps_miss_counts(const float* d_lower, const float* d_pred, const floa
 int im2im_rcps_loss_table(const int32_t* d_counts, int64_t n_images, int32_t n_lambdas, int64_t px,
                           int32_t first_visited_col, float* d_table, void* stream);
 
+/* Same as im2im_rcps_loss_table but the first visited column is read from DEVICE memory (result[3] of im2im_rcps_decide),
+ * so the table can be produced without a host round trip. */
+int im2im_rcps_loss_table_dev(const int32_t* d_counts, int64_t n_images, int32_t n_lambdas, int64_t px,
+                              const int32_t* d_first_visited_col, float* d_table, void* stream);
+
+/*
+ * Device-side screening of the reference's stopping rule (core/calibration/calibrate_model.py:137-140) from the exact
+ * per-lambda totals: R_j = totals[j] / n_images_times_px; the reference's fp32 Rhat lies within +/- gamma*R_j; the rule
+ * `Rhat >= alpha or HB_mu_plus(Rhat) > alpha` is certainly true above max(alpha32, r_hi+slack) and certainly false below
+ * min(alpha32, r_lo-slack), where (r_lo, r_hi) brackets the level set of HB_mu_plus (host: bounds.hb_stop_bracket;
+ * pass +inf when no muhat exceeds alpha).  The grid is scanned from the top like the reference.
+ * d_result: DEVICE int32[4] = {stop index or -1, decided (1) / host must replay (0), first unsure column,
+ *                              first visited column for im2im_rcps_loss_table_dev}.
+ */
+int im2im_rcps_decide(const unsigned long long* d_totals, int32_t n_lambdas, double n_images_times_px, double gamma,
+                      double alpha32, double r_lo, double r_hi, double slack, int32_t* d_result, void* stream);
+
 /*
  * Interval endpoints at one lambda: ModelWithUncertainty.nested_sets_from_output
  * (core/models/add_uncertainty.py:33-38 over core/models/finallayers/quantile_layer.py:34-44).
