@@ -237,6 +237,7 @@ def main():
         return rcps.loss_table(col.reshape(-1, 1).contiguous(), px)[:, 0]
 
     result = {}
+    decide = cm.device_decide_fn(px, cfg)
 
     def step(i=None):
         counts.zero_(); totals.zero_()  # torch memset kernels on the current stream (plumbing)
@@ -245,11 +246,21 @@ def main():
         rcps.miss_counts(out, lab, lam_dev, counts=counts, totals=totals, zero=False)
         if i is not None:
             k_end[i].record()
-        stats = {}
-        lhat, stop, visited = sweep.sweep_from_counts(counts, totals, px, cfg, column_to_losses, ascending=True,
-                                                      group=group, stats=stats)
-        rcps.loss_table(counts, px, first_visited_col=max(stop, 0), out=table)
-        result.update(lhat=float(lhat), stop=stop, replayed=stats.get("replayed_columns"))
+        if group is not None:
+            dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)  # the one collective: int64[L] over NCCL
+        res = decide(totals, args.images, read=False)                    # stop rule screened on the device
+        rcps.loss_table(counts, px, out=table, first_visited_dev=res[3:])
+        host = res.cpu()                                                 # 16-byte device->host read = the step's result
+        stop, replayed = int(host[0]), 0
+        if not bool(host[1]):  # a column fell inside the guard band: replay the reference's expression on the host
+            stats = {}
+            lhat_t, stop, visited = sweep.sweep_from_counts(counts, totals, px, cfg, column_to_losses, ascending=True,
+                                                            group=group, stats=stats, n_total=args.images,
+                                                            totals_already_reduced=True)
+            rcps.loss_table(counts, px, first_visited_col=max(stop, 0), out=table)
+            replayed = stats.get("replayed_columns")
+        lhat = float(lambdas[stop]) if stop >= 0 else float(default_lhat)
+        result.update(lhat=lhat, stop=stop, replayed=replayed)
 
     def sync_all():
         torch.cuda.synchronize()

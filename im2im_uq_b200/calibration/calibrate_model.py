@@ -225,8 +225,31 @@ def _first_accepted_column(Rhats: torch.Tensor, n: int, delta: float) -> Optiona
 
 
 # ------------------------------------------------------------------------------------------------ the sweep
+def device_decide_fn(px: int, config: dict, result: Optional[torch.Tensor] = None):
+    """f(totals, n_total) -> (stop, decided): the stopping-rule screen on the device (im2im_rcps_decide) followed by a
+    16-byte device->host read.  ``result`` (int32[4], CUDA) is left holding the kernel's output, so a caller can feed
+    result[3:] to ``rcps.loss_table(first_visited_dev=...)`` before the read."""
+    lib = _lib.load()
+
+    def decide(totals: torch.Tensor, n_total: int, read: bool = True):
+        nonlocal result
+        if result is None:
+            result = torch.empty(4, dtype=torch.int32, device=totals.device)
+        n_px, gamma, alpha32, r_lo, r_hi, slack = sweep.screening_constants(n_total, px, config['alpha'], config['delta'])
+        with torch.cuda.device(totals.device):
+            rc = lib.im2im_rcps_decide(totals.data_ptr(), totals.numel(), n_px, gamma, alpha32, r_lo, r_hi, slack,
+                                       result.data_ptr(), torch.cuda.current_stream(totals.device).cuda_stream)
+        _lib.check(rc, "im2im_rcps_decide")
+        if not read:
+            return result
+        host = result.cpu()
+        return int(host[0]), bool(host[1])
+
+    return decide
+
+
 def rcps_sweep(outputs: torch.Tensor, labels: torch.Tensor, config: dict, device=None, group=None,
-               verbose: bool = False, stats: Optional[dict] = None):
+               verbose: bool = False, stats: Optional[dict] = None, n_total: Optional[int] = None):
     """lambda-hat and the loss table from head outputs (N,3,C,H,W) + labels (N,C,H,W), CPU- or CUDA-resident.
 
     Returns (lhat 0-dim fp32 CPU tensor, stop index or -1, counts int32 CUDA (N_local, L), visited bool mask (L,)).
@@ -257,7 +280,8 @@ def rcps_sweep(outputs: torch.Tensor, labels: torch.Tensor, config: dict, device
         return rcps.loss_table(col.reshape(-1, 1).contiguous(), px)[:, 0]
 
     lhat, stop, visited = sweep.sweep_from_counts(counts, totals, px, config, column_to_losses, ascending=ascending,
-                                                  group=group, verbose=verbose, stats=stats)
+                                                  group=group, verbose=verbose, stats=stats, n_total=n_total,
+                                                  device_decide=None if verbose else device_decide_fn(px, config))
     return lhat, stop, counts, visited
 
 

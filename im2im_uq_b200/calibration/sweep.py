@@ -46,13 +46,20 @@ def exact_stop_condition(losses: torch.Tensor, n: int, alpha: float, delta: floa
     return bool(Rhat >= alpha or RhatPlus > alpha)
 
 
-def _classify(totals: np.ndarray, n: int, px: int, alpha: float, delta: float):
-    """Per column: +1 certainly stops, -1 certainly continues, 0 must be replayed exactly."""
-    R = totals.astype(np.float64) / (float(n) * float(px))
+def screening_constants(n: int, px: int, alpha: float, delta: float):
+    """(N*px, gamma, alpha32, r_lo, r_hi, slack): the numbers both the host screen (_classify) and the device screen
+    (im2im_rcps_decide) are built from."""
     gamma = (n + 8) * _U * 1.01
-    lo_R, hi_R = R * (1.0 - gamma), R * (1.0 + gamma)  # the reference's fp32 Rhat lies in [lo_R, hi_R]
     alpha32 = float(np.float32(alpha))  # `Rhat >= alpha` compares in fp32 (0-dim fp32 tensor vs python float)
     r_lo, r_hi = hb_stop_bracket(int(n), float(alpha), float(delta))
+    return float(n) * float(px), gamma, alpha32, r_lo, r_hi, _HB_SLACK
+
+
+def _classify(totals: np.ndarray, n: int, px: int, alpha: float, delta: float):
+    """Per column: +1 certainly stops, -1 certainly continues, 0 must be replayed exactly."""
+    n_px, gamma, alpha32, r_lo, r_hi, _ = screening_constants(n, px, alpha, delta)
+    R = totals.astype(np.float64) / n_px
+    lo_R, hi_R = R * (1.0 - gamma), R * (1.0 + gamma)  # the reference's fp32 Rhat lies in [lo_R, hi_R]
     verdict = np.zeros(R.shape, dtype=np.int8)
     # certainly true: either clause certainly true
     sure_true = lo_R >= alpha32 * (1.0 + 1e-6)
@@ -130,7 +137,8 @@ def visited_mask(lambdas: torch.Tensor, stop: int) -> torch.Tensor:
 
 
 def sweep_from_counts(counts: torch.Tensor, totals: torch.Tensor, px: int, config: dict, column_to_losses,
-                      ascending: bool = True, group=None, verbose: bool = False, stats: Optional[dict] = None):
+                      ascending: bool = True, group=None, verbose: bool = False, stats: Optional[dict] = None,
+                      n_total: Optional[int] = None, device_decide=None, totals_already_reduced: bool = False):
     """Stopping rule + lambda-hat from this rank's integer miss counts; the multi-GPU exchange lives here.
 
     counts            (N_local, L) int32, rows = this rank's images in order, columns = the ORIGINAL grid order
@@ -138,24 +146,48 @@ def sweep_from_counts(counts: torch.Tensor, totals: torch.Tensor, px: int, confi
     column_to_losses  f(counts[:, j]) -> (N_local,) fp32 per-image losses (count/px as the device or host computes it)
     group             None for one process, else a torch.distributed process group: ranks hold contiguous shards of
                       the calibration set in rank order.  Collectives: ONE all_reduce of the int64 totals (8*L bytes),
-                      one all_gather of the shard sizes, and an all_gather of N fp32 values per replayed column.
+                      one all_gather of the shard sizes (skipped when ``n_total`` is given and no column has to be
+                      replayed), and an all_gather of N fp32 values per replayed column.
+    n_total           total number of images over all ranks, if the caller knows it
+    device_decide     optional f(totals, n_total) -> (stop, decided) running the screen on the device
+                      (im2im_rcps_decide); when it decides, the host never sees the totals.
     Returns (lhat 0-dim fp32 CPU tensor, stop index or -1, visited bool mask (L,)).
     """
     lambdas, dlambda, lam_prime, default_lhat = lambda_grid(config)
     n_local = counts.shape[0]
     sizes = None
-    n_total = n_local
-    if group is not None:
+
+    def exchange_sizes():
+        nonlocal sizes, px
         import torch.distributed as dist
-        dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
         meta = torch.tensor([n_local, px], dtype=torch.int64, device=totals.device)
         gathered = [torch.zeros_like(meta) for _ in range(dist.get_world_size(group))]
         dist.all_gather(gathered, meta, group=group)
         sizes = [int(t[0]) for t in gathered]
         px = max(int(t[1]) for t in gathered)
-        n_total = sum(sizes)
+        return sum(sizes)
+
+    if group is not None:
+        import torch.distributed as dist
+        if not totals_already_reduced:
+            dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
+        if n_total is None:
+            n_total = exchange_sizes()
+    elif n_total is None:
+        n_total = n_local
     if n_total == 0:
         raise ValueError("empty calibration set")
+    if device_decide is not None and ascending:
+        stop, decided = device_decide(totals, n_total)
+        if decided:
+            if stats is not None:
+                stats["replayed_columns"] = 0
+                stats["screened"] = True
+                stats["decided_on_device"] = True
+            lhat = lambdas[stop] if stop >= 0 else default_lhat
+            return lhat, stop, visited_mask(lambdas, stop)
+    if group is not None and sizes is None:
+        exchange_sizes()
     totals_host = totals.cpu().numpy()
 
     def column_losses(j: int) -> torch.Tensor:

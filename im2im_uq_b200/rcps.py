@@ -82,17 +82,25 @@ def miss_counts(outputs: torch.Tensor, labels: torch.Tensor, lambdas_sorted: tor
     return counts, totals
 
 
-def loss_table(counts: torch.Tensor, px: int, first_visited_col: int = 0,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """fp32 table[i,j] = float(counts[i,j])/float(px); columns below first_visited_col are zero."""
+def loss_table(counts: torch.Tensor, px: int, first_visited_col: int = 0, out: Optional[torch.Tensor] = None,
+               first_visited_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 table[i,j] = float(counts[i,j])/float(px); columns below first_visited_col are zero.
+
+    ``first_visited_dev`` (int32 CUDA tensor, first element used) takes the column from device memory instead, e.g.
+    ``result[3:]`` of im2im_rcps_decide, so no host round trip is needed between the decision and the table."""
     lib = _lib.load()
     assert counts.is_cuda and counts.dtype == torch.int32 and counts.is_contiguous() and counts.dim() == 2
     n, n_lam = counts.shape
     if out is None:
         out = torch.empty((n, n_lam), dtype=torch.float32, device=counts.device)
     with torch.cuda.device(counts.device):
-        rc = lib.im2im_rcps_loss_table(counts.data_ptr(), n, n_lam, px, first_visited_col, out.data_ptr(),
-                                       _stream_ptr(counts.device))
+        if first_visited_dev is not None:
+            assert first_visited_dev.is_cuda and first_visited_dev.dtype == torch.int32
+            rc = lib.im2im_rcps_loss_table_dev(counts.data_ptr(), n, n_lam, px, first_visited_dev.data_ptr(),
+                                               out.data_ptr(), _stream_ptr(counts.device))
+        else:
+            rc = lib.im2im_rcps_loss_table(counts.data_ptr(), n, n_lam, px, first_visited_col, out.data_ptr(),
+                                           _stream_ptr(counts.device))
     _lib.check(rc, "im2im_rcps_loss_table")
     return out
 

@@ -219,6 +219,23 @@ def test_lambda_count_limits_and_irregular_grids():
         rcps.miss_counts(out, lab, torch.linspace(0, 6, 8193, device=DEV))
 
 
+def test_device_decide_agrees_with_host_screen(golden):
+    """im2im_rcps_decide == sweep._classify + scan on the same totals (decided stop or the same first unsure column)."""
+    cfg = golden["config"]
+    px = int(np.prod(golden["outputs"].shape[2:]))
+    n = golden["outputs"].shape[0]
+    totals = torch.from_numpy(golden["counts_prime"].sum(0, dtype=np.int64)).to(DEV)
+    stop, decided = cm.device_decide_fn(px, cfg)(totals, n)
+    verdict = sweep._classify(totals.cpu().numpy(), n, px, cfg["alpha"], cfg["delta"])
+    nonfalse = np.nonzero(verdict >= 0)[0]
+    if nonfalse.size == 0:
+        assert decided and stop == -1
+    elif verdict[nonfalse[-1]] > 0:
+        assert decided and stop == int(nonfalse[-1]) == int(golden["stop_idx"])
+    else:
+        assert not decided
+
+
 def test_descending_grid_and_batch_of_65():
     g = load_golden("batch65")  # N % 64 == 2; also run N % 64 == 1 (the reference itself raises there)
     for n in (66, 65):
@@ -292,6 +309,7 @@ def test_full_size_calibration_decision_matches_linear_scan():
             ref_stop = j
             break
     assert stop == ref_stop and 300 < stop < 500 and stats["replayed_columns"] <= 3
+    assert stats.get("decided_on_device") or stats["replayed_columns"] >= 1  # device screen, host replay only in the band
     lambdas = torch.linspace(0.0, 6.0, 1000)
     assert torch.equal(lhat, lambdas[stop]) and int(visited.sum()) == 1000 - stop
 
