@@ -83,6 +83,8 @@ def _declare_more(lib):
     lib.im2im_rcps_decide.argtypes = [vp, i32, f64, f64, f64, f64, f64, f64, vp, vp]
     lib.im2im_conv_igemm_bf16.restype = c.c_int
     lib.im2im_conv_igemm_bf16.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.im2im_conv_wgrad_bf16.restype = c.c_int
+    lib.im2im_conv_wgrad_bf16.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.im2im_conv_first_bf16.restype = c.c_int
     lib.im2im_conv_first_bf16.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.im2im_maxpool2x2_bf16.restype = c.c_int
@@ -96,7 +98,7 @@ def _declare_more(lib):
 EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im_rcps_miss_counts",
            "im2im_rcps_loss_table", "im2im_quantile_nested_sets", "im2im_rcps_miss_map",
            "im2im_fraction_missed_counts", "im2im_rcps_loss_table_dev", "im2im_rcps_decide",
-           "im2im_conv_igemm_bf16", "im2im_conv_first_bf16",
+           "im2im_conv_igemm_bf16", "im2im_conv_wgrad_bf16", "im2im_conv_first_bf16",
            "im2im_maxpool2x2_bf16", "im2im_upsample2x_bilinear_bf16", "im2im_head_conv3x3_f32"]
 
 

@@ -44,3 +44,28 @@ def conv_igemm(x1: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[tor
                                        torch.cuda.current_stream(x1.device).cuda_stream)
     _lib.check(rc, "im2im_conv_igemm_bf16")
     return out
+
+
+def conv_wgrad(x: torch.Tensor, dz: torch.Tensor, taps: int = 9, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 dW [c_out, taps, c_in] (+= when ``out`` is given) from NHWC bf16 input ``x`` and output gradient ``dz``."""
+    lib = _lib.load()
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and dz.dtype == torch.bfloat16 and dz.is_contiguous()
+    B, H, W, c_in = x.shape
+    assert tuple(dz.shape[:3]) == (B, H, W)
+    c_out = dz.shape[3]
+    if out is None:
+        out = torch.zeros((c_out, taps, c_in), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.im2im_conv_wgrad_bf16(x.data_ptr(), dz.data_ptr(), B, H, W, c_in, c_out, taps, out.data_ptr(),
+                                       torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "im2im_conv_wgrad_bf16")
+    return out
+
+
+def pack_dgrad_weight(weight: torch.Tensor) -> torch.Tensor:
+    """Weights for the data gradient: dX = conv3x3(dZ, W') with W'[ci, tap', co] = W[co, ci, flipped tap].
+
+    torch weight [c_out, c_in, kh, kw] -> bf16 [c_in, kh*kw, c_out] with the taps reversed (180 degree rotation)."""
+    c_out, c_in, kh, kw = weight.shape
+    w = weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(c_in, kh * kw, c_out)
+    return w.contiguous().to(torch.bfloat16)

@@ -437,6 +437,147 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dW[co, tap, ci] = sum over pixels p of dZ[p, co] * X[p + shift(tap), ci]        (autograd of the conv above)
+// GEMM per CTA:  D[128 co][up to 256 (tap,ci) columns] += A * B^T with K = pixels.  Both operands are consumed
+// exactly as they lie in the NHWC tensors - pixel rows of 64 contiguous channels - i.e. "MN-major" for UMMA: one TMA
+// box (64 ch x 128 px, SWIZZLE_128B) is a [K=128][MN=64] slab; M = 128 uses two slabs of dZ (the second is zero-filled
+// by TMA when c_out == 64), N packs up to four slabs of X, one per (tap, 64-channel block) pair, each loaded at its own
+// tap-shifted origin (zero fill = padding).  Split-K over pixel tiles; partial tiles are reduced with fp32 atomics.
+struct WgradParams {
+    int taps;
+    int c_in, c_out;
+    int B, H, W;
+    int bw, bh, bb;
+    int tiles_w, tiles_h, tiles_b;
+    int n_slabs;        // taps * c_in / 64  (tap, channel-block) column slabs of dW
+    int slab_groups;    // ceil(n_slabs / 4)
+    int splits;         // split-K factor
+    int stages;
+    float* dw;          // fp32 [c_out, taps, c_in], accumulated into
+};
+
+constexpr int kSlabBytes = kTileM * kKStep * 2;  // 16 KB: 128 pixel rows x 64 channels
+
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(const void* smem_ptr, uint32_t lbo_bytes) {
+    const uint32_t addr = smem_u32(smem_ptr);
+    uint64_t desc = 0;
+    desc |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+    desc |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;  // between 64-element MN slabs
+    desc |= static_cast<uint64_t>(1024 >> 4) << 32;       // between 8-row K groups
+    desc |= static_cast<uint64_t>(1) << 46;
+    desc |= static_cast<uint64_t>(2) << 61;               // SWIZZLE_128B
+    return desc;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x,
+                  const WgradParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // stage = [2 dZ slabs | 4 X slabs] = 96 KB
+    constexpr int kStageBytes = 6 * kSlabBytes;
+    unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(p.stages) * kStageBytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* accum_bar = empty_bar + p.stages;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_dz);
+        prefetch_tmap(&map_x);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_smem, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // work decomposition: blockIdx.x -> (split, slab group), blockIdx.y -> 128-row block of c_out
+    const int group = blockIdx.x % p.slab_groups;
+    const int split = blockIdx.x / p.slab_groups;
+    const int m0 = blockIdx.y * kTileM;
+    const int slab0 = group * 4;
+    const int n_slab = min(4, p.n_slabs - slab0);          // slabs (64 columns each) in this group
+    const int cblocks = p.c_in / kKStep;
+    const int n_pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    const int k_begin = static_cast<int>(static_cast<long long>(n_pix_tiles) * split / p.splits);
+    const int k_end = static_cast<int>(static_cast<long long>(n_pix_tiles) * (split + 1) / p.splits);
+    const int bn = n_slab * 64;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            unsigned phase = 1;
+            for (int kt = k_begin; kt < k_end; ++kt) {
+                int t = kt;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                const int w0 = tw * p.bw, h0 = th * p.bh, b0 = t * p.bb;
+                mbar_wait(&empty_bar[stage], phase);
+                unsigned char* dst = tiles + static_cast<size_t>(stage) * kStageBytes;
+                mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>((2 + n_slab) * kSlabBytes));
+                tma_load_4d(dst, &map_dz, &full_bar[stage], m0, w0, h0, b0);
+                tma_load_4d(dst + kSlabBytes, &map_dz, &full_bar[stage], m0 + 64, w0, h0, b0);  // zero fill if >= c_out
+                for (int sl = 0; sl < n_slab; ++sl) {
+                    const int slab = slab0 + sl;
+                    const int tap = slab / cblocks, cb = slab - tap * cblocks;
+                    const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+                    const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+                    tma_load_4d(dst + (2 + sl) * kSlabBytes, &map_x, &full_bar[stage], cb * kKStep, w0 + dx, h0 + dy, b0);
+                }
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && k_end > k_begin) {
+            // D = F32, A = B = BF16, both MN-major (bits 15, 16), M = 128, N = bn
+            const uint32_t idesc = make_idesc_bf16(bn) | (1u << 15) | (1u << 16);
+            int stage = 0;
+            unsigned phase = 0;
+            for (int kt = k_begin; kt < k_end; ++kt) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const unsigned char* src = tiles + static_cast<size_t>(stage) * kStageBytes;
+#pragma unroll
+                for (int k = 0; k < kTileM / kUmmaK; ++k) {  // 8 MMAs, 16 pixel rows (2 KB) each
+                    const uint64_t desc_a = make_sw128_mn_desc(src + k * 2048, kSlabBytes);
+                    const uint64_t desc_b = make_sw128_mn_desc(src + 2 * kSlabBytes + k * 2048, kSlabBytes);
+                    umma_bf16(tmem_base, desc_a, desc_b, idesc, (kt > k_begin || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(accum_bar);
+        }
+    } else if (k_end > k_begin) {
+        const int quad = warp & 3;
+        const int co = m0 + quad * 32 + lane;  // row of dW
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int K_total = p.taps * p.c_in;
+        for (int c = 0; c < bn; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c), v);
+            tmem_ld_wait();
+            if (co < p.c_out) {
+                // column c of this group -> slab (tap, channel block) -> offset tap*c_in + cb*64 + (c % 64) in a dW row
+                const int slab = slab0 + c / 64;
+                float* dst = p.dw + static_cast<size_t>(co) * K_total + static_cast<size_t>(slab) * 64 + (c % 64);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
 // ------------------------------------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -547,4 +688,38 @@ extern "C" int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void
     const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
     conv_igemm_persistent_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(m1, m2, mw, p);
     return check_launch("conv_igemm_persistent_kernel");
+}
+
+extern "C" int im2im_conv_wgrad_bf16(const void* d_x, const void* d_dz, int32_t B, int32_t H, int32_t W, int32_t c_in,
+                                     int32_t c_out, int32_t taps, float* d_dw, void* stream) {
+    if (taps != 9 && taps != 1) return fail(IM2IM_EINVAL, "taps must be 9 or 1");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(IM2IM_EINVAL, "bad activation shape");
+    if (c_in <= 0 || c_in % kKStep) return fail(IM2IM_ERANGE, "c_in must be a multiple of %d (got %d)", kKStep, c_in);
+    if (c_out <= 0 || c_out % kKStep) return fail(IM2IM_ERANGE, "c_out must be a multiple of %d (got %d)", kKStep, c_out);
+    if (!d_x || !d_dz || !d_dw) return fail(IM2IM_EINVAL, "null tensor");
+    WgradParams p;
+    p.taps = taps; p.c_in = c_in; p.c_out = c_out; p.B = B; p.H = H; p.W = W;
+    pick_box(B, H, W, p.bw, p.bh, p.bb);
+    p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh; p.tiles_b = (B + p.bb - 1) / p.bb;
+    p.n_slabs = taps * c_in / kKStep;
+    p.slab_groups = (p.n_slabs + 3) / 4;
+    const int m_blocks = (c_out + kTileM - 1) / kTileM;
+    const int out_tiles = p.slab_groups * m_blocks;
+    const int n_pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    int splits = (2 * sm_count() + out_tiles - 1) / out_tiles;   // ~2 CTAs worth of work items per SM
+    if (splits > n_pix_tiles) splits = n_pix_tiles;
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    p.stages = 2;
+    p.dw = d_dw;
+    CUtensorMap mdz, mx;
+    int rc = make_act_map(&mdz, d_dz, B, H, W, c_out, p.bw, p.bh, p.bb);
+    if (rc) return rc;
+    rc = make_act_map(&mx, d_x, B, H, W, c_in, p.bw, p.bh, p.bb);
+    if (rc) return rc;
+    const size_t smem = static_cast<size_t>(p.stages) * 6 * kSlabBytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(static_cast<unsigned>(p.slab_groups * splits), static_cast<unsigned>(m_blocks));
+    conv_wgrad_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(mdz, mx, p);
+    return check_launch("conv_wgrad_kernel");
 }

@@ -147,6 +147,16 @@ int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void* d_x2, int
                           int32_t relu, void* d_out_bf16, float* d_out_f32, void* stream);
 
 /*
+ * Weight gradient of the convolution above (autograd of nn.Conv2d inside core/models/trunks/unet_parts.py:16-21, as
+ * driven by core/scripts/train.py:160 `loss.backward()`):  dW[co, tap, ci] += sum_p dZ[p, co] * X[p + shift(tap), ci].
+ *   d_x  : DEVICE bf16 NHWC [B,H,W,c_in]  (the conv's input);   d_dz : DEVICE bf16 NHWC [B,H,W,c_out] (grad of its output)
+ *   d_dw : DEVICE fp32 [c_out, taps, c_in], ACCUMULATED into (zero it first); c_in, c_out multiples of 64
+ * tcgen05 GEMM with K = pixels, operands consumed MN-major straight from the NHWC tensors; split-K with fp32 atomics.
+ */
+int im2im_conv_wgrad_bf16(const void* d_x, const void* d_dz, int32_t B, int32_t H, int32_t W, int32_t c_in,
+                          int32_t c_out, int32_t taps, float* d_dw, void* stream);
+
+/*
  * The CUDA-core passes around the tcgen05 convolutions of the UNet forward (all NHWC bf16 unless noted):
  *   im2im_conv_first_bf16          first 3x3 conv of DoubleConv(n_channels_in, 64) (core/models/trunks/unet.py:20):
  *                                  x fp32 NCHW [B,c_in<=8,H,W], weight fp32 [c_out,c_in,3,3] (+bias, ReLU) -> bf16 NHWC
