@@ -95,11 +95,35 @@ def _declare_more(lib):
     lib.im2im_head_conv3x3_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
 
 
+def _declare_train(lib):
+    c = ctypes
+    vp, i64, i32, f32 = c.c_void_p, c.c_int64, c.c_int32, c.c_float
+    sigs = {
+        "im2im_channel_stats_bf16": [vp, i64, i32, vp, vp],
+        "im2im_bn_finalize": [vp, i64, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp],
+        "im2im_bn_apply_relu_bf16": [vp, vp, vp, i64, i32, vp, vp],
+        "im2im_bn_relu_bwd_bf16": [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp],
+        "im2im_maxpool2x2_bwd_bf16": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
+        "im2im_upsample2x_bilinear_bwd_bf16": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
+        "im2im_quantile_loss_f32": [vp, vp, i64, i64, f32, f32, f32, f32, f32, vp, vp, vp],
+        "im2im_adam_step_f32": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
+        "im2im_head_bwd": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+        "im2im_conv_first_wgrad": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = c.c_int
+        fn.argtypes = args
+
+
 EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im_rcps_miss_counts",
            "im2im_rcps_loss_table", "im2im_quantile_nested_sets", "im2im_rcps_miss_map",
            "im2im_fraction_missed_counts", "im2im_rcps_loss_table_dev", "im2im_rcps_decide",
            "im2im_conv_igemm_bf16", "im2im_conv_wgrad_bf16", "im2im_conv_first_bf16",
-           "im2im_maxpool2x2_bf16", "im2im_upsample2x_bilinear_bf16", "im2im_head_conv3x3_f32"]
+           "im2im_maxpool2x2_bf16", "im2im_upsample2x_bilinear_bf16", "im2im_head_conv3x3_f32",
+           "im2im_channel_stats_bf16", "im2im_bn_finalize", "im2im_bn_apply_relu_bf16", "im2im_bn_relu_bwd_bf16",
+           "im2im_maxpool2x2_bwd_bf16", "im2im_upsample2x_bilinear_bwd_bf16", "im2im_quantile_loss_f32",
+           "im2im_adam_step_f32", "im2im_head_bwd", "im2im_conv_first_wgrad"]
 
 
 def load():
@@ -112,6 +136,7 @@ def load():
         lib = ctypes.CDLL(LIB_PATH)
         _declare(lib)
         _declare_more(lib)
+        _declare_train(lib)
         if lib.im2im_abi_version() != 1:
             raise Im2ImError("libim2im_uq.so ABI version mismatch - rebuild")
         _lib = lib

@@ -1,0 +1,624 @@
+// Training-side CUDA-core kernels of the UNet path (Path B of DESIGN.md, rows b4/b5 of SURVEY.md §8):
+// BatchNorm (batch statistics) forward/backward fused with ReLU, max-pool / bilinear-upsample backward, the head's and the
+// first convolution's gradients, the fused pinball+MSE loss with its gradient, and a fused Adam step.
+// All activation tensors are NHWC bf16, statistics / parameters / gradients fp32.  Everything here is bandwidth-bound.
+//   BatchNorm2d + ReLU      core/models/trunks/unet_parts.py:17-18,20-21 (train mode: per-replica batch statistics)
+//   MaxPool2d / Upsample    unet_parts.py:34, :50,:63
+//   loss                    core/models/finallayers/quantile_layer.py:23-32, core/models/losses/pinball.py:12-24
+//   Adam                    core/scripts/train.py:120,162 (torch.optim.Adam defaults: betas .9/.999, eps 1e-8, no decay)
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace im2im {
+namespace {
+
+union Bf16x8 {
+    uint4 u;
+    __nv_bfloat162 h[4];
+};
+
+__device__ __forceinline__ void unpack8(const Bf16x8& v, float* f) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 t = __bfloat1622float2(v.h[j]);
+        f[2 * j] = t.x;
+        f[2 * j + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    Bf16x8 v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v.h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    return v.u;
+}
+
+unsigned grid_for(long long work_items, int threads, int per_sm = 8) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = static_cast<long long>(per_sm) * sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<unsigned>(blocks);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-channel reductions over pixels of NHWC bf16 tensors.  Block = 256 threads = (256/groups) pixel lanes x groups,
+// groups = C/8; each thread keeps 8 channels in registers, partial sums are combined in shared memory and added to the
+// global accumulators with one atomicAdd per channel per block.
+//   MODE 0: sums[c] += z, sums[C+c] += z*z                                  (BN statistics; also plain channel sums)
+//   MODE 1: xhat = (z-mean)*rstd;  g = dy * (xhat*gamma+beta > 0);  sums[c] += g, sums[C+c] += g*xhat  (BN+ReLU backward)
+// (a = z or dy; in MODE 1 `a` is dy and `zt` is the saved pre-normalisation convolution output z)
+template <int MODE>
+__global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16* __restrict__ a,
+                                                             const __nv_bfloat16* __restrict__ zt,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, long long n_pix, int C,
+                                                             float* __restrict__ sums) {
+    __shared__ float s_part[2][256][8 + 1];
+    const int groups = C / 8;
+    const int g = threadIdx.x % groups;
+    const int lane_p = threadIdx.x / groups;
+    const int lanes = 256 / groups;
+    float acc0[8], acc1[8], sc[8], sh[8], mu[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        acc0[j] = acc1[j] = 0.f;
+        if (MODE == 1) {
+            mu[j] = mean[g * 8 + j];
+            rs[j] = rstd[g * 8 + j];
+            sc[j] = gamma[g * 8 + j] * rs[j];              // the forward's scale/shift, recomputed with the same ops
+            sh[j] = beta[g * 8 + j] - mu[j] * sc[j];
+        }
+    }
+    for (long long p = static_cast<long long>(blockIdx.x) * lanes + lane_p; p < n_pix;
+         p += static_cast<long long>(gridDim.x) * lanes) {
+        Bf16x8 va;
+        va.u = *reinterpret_cast<const uint4*>(a + p * C + g * 8);
+        float fa[8];
+        unpack8(va, fa);
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc0[j] += fa[j]; acc1[j] = fmaf(fa[j], fa[j], acc1[j]); }
+        } else {
+            Bf16x8 vz;
+            vz.u = *reinterpret_cast<const uint4*>(zt + p * C + g * 8);
+            float fz[8];
+            unpack8(vz, fz);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gj = fmaf(fz[j], sc[j], sh[j]) > 0.f ? fa[j] : 0.f;   // ReLU mask exactly as the forward saw it
+                acc0[j] += gj;
+                acc1[j] = fmaf(gj, (fz[j] - mu[j]) * rs[j], acc1[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_part[0][threadIdx.x][j] = acc0[j]; s_part[1][threadIdx.x][j] = acc1[j]; }
+    __syncthreads();
+    // thread t < 2*C finalises (which, channel)
+    for (int t = threadIdx.x; t < 2 * C; t += 256) {
+        const int which = t / C, c = t % C;
+        const int gg = c / 8, j = c % 8;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += s_part[which][l * groups + gg][j];
+        atomicAdd(&sums[which * C + c], s);
+    }
+}
+
+// mean/var from the sums -> per-channel affine (scale, shift) for y = relu(z*scale + shift), saved mean / rstd, and the
+// running-statistics update of nn.BatchNorm2d (momentum, unbiased variance).  conv_bias (may be null) only shifts the
+// mean that is recorded in running_mean: z is the bias-free convolution output and the batch mean cancels the bias.
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, double count, const float* __restrict__ conv_bias,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, int C, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = static_cast<double>(sums[c]) / count;
+    double var = static_cast<double>(sums[C + c]) / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - static_cast<float>(mean) * sc;
+    save_mean[c] = static_cast<float>(mean);
+    save_rstd[c] = rstd;
+    if (running_mean) {
+        const float m_full = static_cast<float>(mean) + (conv_bias ? conv_bias[c] : 0.f);
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m_full;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    }
+}
+
+// y = relu(z*scale + shift)
+__global__ void __launch_bounds__(256) bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ z,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, long long n_pix, int C,
+                                                            __nv_bfloat16* __restrict__ y) {
+    const int groups = C / 8;
+    const long long total = n_pix * groups;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(e % groups);
+        Bf16x8 v;
+        v.u = *reinterpret_cast<const uint4*>(z + e * 8);
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], __ldg(scale + g * 8 + j), __ldg(shift + g * 8 + j)), 0.f);
+        *reinterpret_cast<uint4*>(y + e * 8) = pack8(f);
+    }
+}
+
+// dz = gamma*rstd * (g - sum(g)/M - xhat * sum(g*xhat)/M),  xhat = (z-mean)*rstd,  g = dy * (xhat*gamma+beta > 0)
+__global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                const __nv_bfloat16* __restrict__ z,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd,
+                                                                const float* __restrict__ sums, float inv_count,
+                                                                long long n_pix, int C, __nv_bfloat16* __restrict__ dz) {
+    const int groups = C / 8;
+    const long long total = n_pix * groups;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(e % groups);
+        Bf16x8 vd, vz;
+        vd.u = *reinterpret_cast<const uint4*>(dy + e * 8);
+        vz.u = *reinterpret_cast<const uint4*>(z + e * 8);
+        float fd[8], fz[8], o[8];
+        unpack8(vd, fd);
+        unpack8(vz, fz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            const float gm = __ldg(gamma + c), rs = __ldg(rstd + c), mu = __ldg(mean + c);
+            const float sc = gm * rs, sh = __ldg(beta + c) - mu * sc;
+            const float xhat = (fz[j] - mu) * rs;
+            const float gj = fmaf(fz[j], sc, sh) > 0.f ? fd[j] : 0.f;
+            o[j] = sc * (gj - __ldg(sums + c) * inv_count - xhat * __ldg(sums + C + c) * inv_count);
+        }
+        *reinterpret_cast<uint4*>(dz + e * 8) = pack8(o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Max-pool backward: the gradient of each 2x2 window goes to its first maximal element (ATen's argmax order);
+// accumulate != 0 adds into dx (skip tensors receive a second gradient from the up path).
+__global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             const __nv_bfloat16* __restrict__ dy, int B, int H, int W,
+                                                             int C, int accumulate, __nv_bfloat16* __restrict__ dx) {
+    const int Ho = H / 2, Wo = W / 2, groups = C / 8;
+    // one thread per (input 2x2 window, channel group); odd trailing rows/columns get zero (handled by a second loop)
+    const long long total = static_cast<long long>(B) * Ho * Wo * groups;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(e % groups);
+        long long pix = e / groups;
+        const int ox = static_cast<int>(pix % Wo);
+        const int oy = static_cast<int>((pix / Wo) % Ho);
+        const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+        const long long base = ((static_cast<long long>(b) * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+        const long long offs[4] = {0, C, static_cast<long long>(W) * C, static_cast<long long>(W) * C + C};
+        float v[4][8], d[8], out[4][8];
+        Bf16x8 t;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { t.u = *reinterpret_cast<const uint4*>(x + base + offs[q]); unpack8(t, v[q]); }
+        t.u = *reinterpret_cast<const uint4*>(dy + pix * C + g * 8);
+        unpack8(t, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int arg = 0;
+            float m = v[0][j];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) if (v[q][j] > m) { m = v[q][j]; arg = q; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[q][j] = (q == arg) ? d[j] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (accumulate) {
+                float prev[8];
+                t.u = *reinterpret_cast<const uint4*>(dx + base + offs[q]);
+                unpack8(t, prev);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) out[q][j] += prev[j];
+            }
+            *reinterpret_cast<uint4*>(dx + base + offs[q]) = pack8(out[q]);
+        }
+    }
+}
+
+// Bilinear x2 (align_corners=True) + pad backward, gather form: dx[b,iy,ix,:] = sum over the (<=4x4) output pixels whose
+// bilinear footprint contains (iy,ix), with the forward's own fp32 weights.
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ du, int B, int h, int w,
+                                                             int C, int Ho, int Wo, int pad_top, int pad_left,
+                                                             __nv_bfloat16* __restrict__ dx) {
+    const int uh = 2 * h, uw = 2 * w, groups = C / 8;
+    const float sy = uh > 1 ? static_cast<float>(h - 1) / static_cast<float>(uh - 1) : 0.f;
+    const float sx = uw > 1 ? static_cast<float>(w - 1) / static_cast<float>(uw - 1) : 0.f;
+    const long long total = static_cast<long long>(B) * h * w * groups;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(e % groups);
+        long long pix = e / groups;
+        const int ix = static_cast<int>(pix % w);
+        const int iy = static_cast<int>((pix / w) % h);
+        const int b = static_cast<int>(pix / (static_cast<long long>(w) * h));
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int uy = max(0, 2 * iy - 2); uy <= min(uh - 1, 2 * iy + 2); ++uy) {
+            const float fy = sy * uy;
+            const int y0 = static_cast<int>(fy);
+            const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+            const float ly = fy - y0;
+            float wy = 0.f;
+            if (y0 == iy) wy += 1.f - ly;
+            if (y1 == iy) wy += ly;
+            if (wy == 0.f) continue;
+            for (int ux = max(0, 2 * ix - 2); ux <= min(uw - 1, 2 * ix + 2); ++ux) {
+                const float fx = sx * ux;
+                const int x0 = static_cast<int>(fx);
+                const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+                const float lx = fx - x0;
+                float wx = 0.f;
+                if (x0 == ix) wx += 1.f - lx;
+                if (x1 == ix) wx += lx;
+                if (wx == 0.f) continue;
+                Bf16x8 t;
+                t.u = *reinterpret_cast<const uint4*>(
+                    du + ((static_cast<long long>(b) * Ho + uy + pad_top) * Wo + ux + pad_left) * C + g * 8);
+                float f[8];
+                unpack8(t, f);
+                const float wgt = wy * wx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, f[j], acc[j]);
+            }
+        }
+        *reinterpret_cast<uint4*>(dx + pix * C + g * 8) = pack8(acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Loss: w_lo*pinball_qlo(pred[:,0], y) + w_hi*pinball_qhi(pred[:,2], y) + w_mse*mse(pred[:,1], y), each a mean over
+// B*C*H*W.  Writes d loss / d pred and accumulates the three partial sums (double) into loss_parts[3].
+// pinball(e = out - target): q*|e| for e<0, (1-q)*|e| for e>0, 0 at e == 0  ->  d/d out = -q, (1-q), 0.
+__global__ void __launch_bounds__(256) quantile_loss_kernel(const float* __restrict__ pred,
+                                                            const float* __restrict__ target, long long n_images,
+                                                            long long px, float q_lo, float q_hi, float w_lo,
+                                                            float w_hi, float w_mse, float inv_count,
+                                                            float* __restrict__ dpred, double* __restrict__ loss_parts) {
+    double part[3] = {0.0, 0.0, 0.0};
+    const long long total = n_images * px;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long i = e / px, k = e - i * px;
+        const float t = target[e];
+        const long long o = i * 3 * px + k;
+        const float e_lo = pred[o] - t, e_mid = pred[o + px] - t, e_hi = pred[o + 2 * px] - t;
+        part[0] += e_lo < 0.f ? q_lo * fabsf(e_lo) : (e_lo > 0.f ? (1.f - q_lo) * fabsf(e_lo) : 0.f);
+        part[1] += e_hi < 0.f ? q_hi * fabsf(e_hi) : (e_hi > 0.f ? (1.f - q_hi) * fabsf(e_hi) : 0.f);
+        part[2] += e_mid * e_mid;
+        if (dpred) {
+            dpred[o] = w_lo * inv_count * (e_lo < 0.f ? -q_lo : (e_lo > 0.f ? 1.f - q_lo : 0.f));
+            dpred[o + px] = w_mse * inv_count * 2.f * e_mid;
+            dpred[o + 2 * px] = w_hi * inv_count * (e_hi < 0.f ? -q_hi : (e_hi > 0.f ? 1.f - q_hi : 0.f));
+        }
+    }
+    __shared__ double s_part[3][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double v = part[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[q][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int wv = 0; wv < 8; ++wv) v += s_part[threadIdx.x][wv];
+        atomicAdd(&loss_parts[threadIdx.x], v);
+    }
+}
+
+// torch.optim.Adam (single tensor semantics, no amsgrad / weight decay / maximize):
+//   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                                                   float b1, float b2, float eps, float bc1, float bc2_sqrt,
+                                                   float grad_scale) {
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float gr = g[e] * grad_scale;
+        const float mm = b1 * m[e] + (1.f - b1) * gr;
+        const float vv = b2 * v[e] + (1.f - b2) * gr * gr;
+        m[e] = mm;
+        v[e] = vv;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p[e] -= (lr / bc1) * (mm / denom);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Head backward (QuantileRegressionLayer: n_out = 3*C_out planes from c_mid channels, 3x3 pad 1).
+// (a) data gradient: dm[p, c] = sum_o sum_t dOut[o, p - shift(t)] * W[o, c, t]    (bf16 NHWC, row stride c_stride;
+//     channels c_mid..c_stride-1 are written as zero so the tensor can feed the 64-channel tensor-core kernels)
+template <int N_OUT>
+__global__ void __launch_bounds__(128) head_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ w,
+                                                         int B, int H, int W, int c_mid, int c_stride,
+                                                         __nv_bfloat16* __restrict__ dm) {
+    extern __shared__ float s_w[];  // [tap][o][c]
+    for (int i = threadIdx.x; i < 9 * N_OUT * c_mid; i += blockDim.x) {
+        const int c = i % c_mid, o = (i / c_mid) % N_OUT, t = i / (c_mid * N_OUT);
+        s_w[i] = w[(static_cast<long long>(o) * c_mid + c) * 9 + t];
+    }
+    __syncthreads();
+    const long long hw = static_cast<long long>(H) * W;
+    const long long total = static_cast<long long>(B) * hw;
+    for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < total;
+         pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int xw = static_cast<int>(pix % W);
+        const int yh = static_cast<int>((pix / W) % H);
+        const long long b = pix / hw;
+        float g[9][N_OUT];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            // output pixel q = p - shift(t) received x[p] through tap t
+            const int yy = yh - (t / 3 - 1), xx = xw - (t % 3 - 1);
+            const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+            for (int o = 0; o < N_OUT; ++o)
+                g[t][o] = in ? __ldg(dout + (b * N_OUT + o) * hw + static_cast<long long>(yy) * W + xx) : 0.f;
+        }
+        __nv_bfloat16* dst = dm + pix * c_stride;
+        for (int c = 0; c < c_mid; c += 8) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int o = 0; o < N_OUT; ++o)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[t][o], s_w[(t * N_OUT + o) * c_mid + c + j], acc[j]);
+            *reinterpret_cast<uint4*>(dst + c) = pack8(acc);
+        }
+        for (int c = c_mid; c < c_stride; c += 8) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// (b) weight/bias gradient: dW[o, c, t] += sum_p dOut[o, p] * m[p + shift(t), c];  db[o] += sum_p dOut[o, p].
+// lane = channel c (c_mid <= 32), each of the 4 warps walks its own pixels, 9*N_OUT accumulators per lane.
+template <int N_OUT>
+__global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict__ dout,
+                                                         const __nv_bfloat16* __restrict__ m, int B, int H, int W,
+                                                         int c_mid, int c_stride, float* __restrict__ dw,
+                                                         float* __restrict__ db) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long hw = static_cast<long long>(H) * W;
+    const long long total = static_cast<long long>(B) * hw;
+    float acc[9][N_OUT], accb[N_OUT];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int o = 0; o < N_OUT; ++o) acc[t][o] = 0.f;
+#pragma unroll
+    for (int o = 0; o < N_OUT; ++o) accb[o] = 0.f;
+    for (long long pix = static_cast<long long>(blockIdx.x) * 4 + warp; pix < total;
+         pix += static_cast<long long>(gridDim.x) * 4) {
+        const int xw = static_cast<int>(pix % W);
+        const int yh = static_cast<int>((pix / W) % H);
+        const long long b = pix / hw;
+        float d[N_OUT];
+#pragma unroll
+        for (int o = 0; o < N_OUT; ++o) {
+            d[o] = __ldg(dout + (b * N_OUT + o) * hw + static_cast<long long>(yh) * W + xw);
+            accb[o] += d[o];
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const float v = lane < c_mid ? __bfloat162float(m[((b * H + yy) * W + xx) * c_stride + lane]) : 0.f;
+#pragma unroll
+            for (int o = 0; o < N_OUT; ++o) acc[t][o] = fmaf(d[o], v, acc[t][o]);
+        }
+    }
+    __shared__ float s_acc[4][9 * N_OUT][32 + 1];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int o = 0; o < N_OUT; ++o) s_acc[warp][t * N_OUT + o][lane] = acc[t][o];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * N_OUT * 32; i += 128) {
+        const int c = i % 32, to = i / 32;
+        const int t = to / N_OUT, o = to % N_OUT;
+        float s = 0.f;
+        for (int wv = 0; wv < 4; ++wv) s += s_acc[wv][to][c];
+        if (c < c_mid) atomicAdd(&dw[(static_cast<long long>(o) * c_mid + c) * 9 + t], s);
+    }
+    if (lane == 0)
+#pragma unroll
+        for (int o = 0; o < N_OUT; ++o) atomicAdd(&db[o], accb[o]);
+}
+
+// First convolution's weight gradient: dW[co, ci, t] += sum_p dz[p, co] * x[b, ci, p + shift(t)]   (x fp32 NCHW)
+// thread = output channel co (64 per pixel stream), 4 pixel streams per block.
+__global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __restrict__ x,
+                                                               const __nv_bfloat16* __restrict__ dz, int B, int c_in,
+                                                               int H, int W, int c_out, float* __restrict__ dw) {
+    const int co = threadIdx.x % c_out;
+    const int stream = threadIdx.x / c_out;
+    const int n_streams = blockDim.x / c_out;
+    const long long hw = static_cast<long long>(H) * W;
+    const long long total = static_cast<long long>(B) * hw;
+    float acc[8 * 9];
+    for (int i = 0; i < c_in * 9; ++i) acc[i] = 0.f;
+    for (long long pix = static_cast<long long>(blockIdx.x) * n_streams + stream; pix < total;
+         pix += static_cast<long long>(gridDim.x) * n_streams) {
+        const int xw = static_cast<int>(pix % W);
+        const int yh = static_cast<int>((pix / W) % H);
+        const long long b = pix / hw;
+        const float d = __bfloat162float(dz[pix * c_out + co]);
+        for (int ci = 0; ci < c_in; ++ci) {
+            const float* xp = x + (b * c_in + ci) * hw;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
+                const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + static_cast<long long>(yy) * W + xx) : 0.f;
+                acc[ci * 9 + t] = fmaf(d, v, acc[ci * 9 + t]);
+            }
+        }
+    }
+    for (int i = 0; i < c_in * 9; ++i) atomicAdd(&dw[static_cast<long long>(co) * c_in * 9 + i], acc[i]);
+}
+
+}  // namespace
+}  // namespace im2im
+
+using namespace im2im;
+
+#define ST(stream) static_cast<cudaStream_t>(stream)
+#define BF(p) static_cast<const __nv_bfloat16*>(p)
+#define BFW(p) static_cast<__nv_bfloat16*>(p)
+
+static int check_channels(int C, const char* what) {
+    if (C <= 0 || C % 8 || 256 % (C / 8) || C > 2048 / 8 * 8) return fail(IM2IM_ERANGE, "%s: C=%d unsupported", what, C);
+    return IM2IM_OK;
+}
+
+extern "C" int im2im_channel_stats_bf16(const void* d_z, int64_t n_pix, int32_t C, float* d_sums, void* stream) {
+    if (int rc = check_channels(C, "channel_stats")) return rc;
+    if (n_pix <= 0 || !d_z || !d_sums) return fail(IM2IM_EINVAL, "channel_stats: bad arguments");
+    const int lanes = 256 / (C / 8);
+    channel_reduce_kernel<0><<<grid_for(n_pix, lanes, 4), 256, 0, ST(stream)>>>(BF(d_z), nullptr, nullptr, nullptr, nullptr,
+                                                                               nullptr, n_pix, C, d_sums);
+    return check_launch("channel_reduce_kernel<stats>");
+}
+
+extern "C" int im2im_bn_finalize(const float* d_sums, int64_t count, const float* d_conv_bias, const float* d_gamma,
+                                 const float* d_beta, float eps, float momentum, int32_t C, float* d_running_mean,
+                                 float* d_running_var, float* d_scale, float* d_shift, float* d_save_mean,
+                                 float* d_save_rstd, void* stream) {
+    if (C <= 0 || count <= 0 || !d_sums || !d_gamma || !d_beta || !d_scale || !d_shift || !d_save_mean || !d_save_rstd)
+        return fail(IM2IM_EINVAL, "bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(d_sums, static_cast<double>(count), d_conv_bias, d_gamma,
+                                                                d_beta, eps, momentum, C, d_running_mean, d_running_var,
+                                                                d_scale, d_shift, d_save_mean, d_save_rstd);
+    return check_launch("bn_finalize_kernel");
+}
+
+extern "C" int im2im_bn_apply_relu_bf16(const void* d_z, const float* d_scale, const float* d_shift, int64_t n_pix,
+                                        int32_t C, void* d_y, void* stream) {
+    if (C <= 0 || C % 8 || n_pix <= 0 || !d_z || !d_scale || !d_shift || !d_y) return fail(IM2IM_EINVAL, "bn_apply: bad arguments");
+    bn_apply_relu_kernel<<<grid_for(n_pix * (C / 8), 256, 16), 256, 0, ST(stream)>>>(BF(d_z), d_scale, d_shift, n_pix, C,
+                                                                                    BFW(d_y));
+    return check_launch("bn_apply_relu_kernel");
+}
+
+extern "C" int im2im_bn_relu_bwd_bf16(const void* d_dy, const void* d_z, const float* d_gamma, const float* d_beta,
+                                      const float* d_mean, const float* d_rstd, int64_t n_pix, int32_t C,
+                                      float* d_sums, void* d_dz, void* stream) {
+    if (int rc = check_channels(C, "bn_relu_bwd")) return rc;
+    if (n_pix <= 0 || !d_dy || !d_z || !d_gamma || !d_beta || !d_mean || !d_rstd || !d_sums || !d_dz)
+        return fail(IM2IM_EINVAL, "bn_relu_bwd: bad arguments");
+    IM2IM_CUDA_TRY(cudaMemsetAsync(d_sums, 0, sizeof(float) * 2 * C, ST(stream)));
+    const int lanes = 256 / (C / 8);
+    channel_reduce_kernel<1><<<grid_for(n_pix, lanes, 4), 256, 0, ST(stream)>>>(BF(d_dy), BF(d_z), d_gamma, d_beta, d_mean,
+                                                                               d_rstd, n_pix, C, d_sums);
+    if (int rc = check_launch("channel_reduce_kernel<bn_bwd>")) return rc;
+    bn_relu_bwd_apply_kernel<<<grid_for(n_pix * (C / 8), 256, 16), 256, 0, ST(stream)>>>(
+        BF(d_dy), BF(d_z), d_gamma, d_beta, d_mean, d_rstd, d_sums, 1.f / static_cast<float>(n_pix), n_pix, C, BFW(d_dz));
+    return check_launch("bn_relu_bwd_apply_kernel");
+}
+
+extern "C" int im2im_maxpool2x2_bwd_bf16(const void* d_x, const void* d_dy, int32_t B, int32_t H, int32_t W, int32_t C,
+                                         int32_t accumulate, void* d_dx, void* stream) {
+    if (B <= 0 || H < 2 || W < 2 || C <= 0 || C % 8 || !d_x || !d_dy || !d_dx) return fail(IM2IM_EINVAL, "maxpool_bwd: bad arguments");
+    if ((H % 2 || W % 2) && !accumulate)  // trailing odd row/column never reaches the pool: its gradient is zero
+        IM2IM_CUDA_TRY(cudaMemsetAsync(d_dx, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(B) * H * W * C, ST(stream)));
+    const long long items = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+    maxpool2x2_bwd_kernel<<<grid_for(items, 256, 16), 256, 0, ST(stream)>>>(BF(d_x), BF(d_dy), B, H, W, C, accumulate,
+                                                                           BFW(d_dx));
+    return check_launch("maxpool2x2_bwd_kernel");
+}
+
+extern "C" int im2im_upsample2x_bilinear_bwd_bf16(const void* d_du, int32_t B, int32_t h, int32_t w, int32_t C,
+                                                  int32_t H_out, int32_t W_out, void* d_dx, void* stream) {
+    if (B <= 0 || h <= 0 || w <= 0 || C <= 0 || C % 8 || H_out < 2 * h || W_out < 2 * w || !d_du || !d_dx)
+        return fail(IM2IM_EINVAL, "upsample_bwd: bad arguments");
+    const int pad_top = (H_out - 2 * h) / 2, pad_left = (W_out - 2 * w) / 2;
+    const long long items = static_cast<long long>(B) * h * w * (C / 8);
+    upsample2x_bwd_kernel<<<grid_for(items, 256, 16), 256, 0, ST(stream)>>>(BF(d_du), B, h, w, C, H_out, W_out, pad_top,
+                                                                           pad_left, BFW(d_dx));
+    return check_launch("upsample2x_bwd_kernel");
+}
+
+extern "C" int im2im_quantile_loss_f32(const float* d_pred, const float* d_target, int64_t n_images, int64_t px,
+                                       float q_lo, float q_hi, float w_lo, float w_hi, float w_mse, float* d_dpred,
+                                       double* d_loss_parts, void* stream) {
+    if (n_images <= 0 || px <= 0 || !d_pred || !d_target || !d_loss_parts) return fail(IM2IM_EINVAL, "quantile_loss: bad arguments");
+    IM2IM_CUDA_TRY(cudaMemsetAsync(d_loss_parts, 0, sizeof(double) * 3, ST(stream)));
+    const long long n = n_images * px;
+    quantile_loss_kernel<<<grid_for(n, 256, 8), 256, 0, ST(stream)>>>(d_pred, d_target, n_images, px, q_lo, q_hi, w_lo,
+                                                                     w_hi, w_mse, 1.f / static_cast<float>(n), d_dpred,
+                                                                     d_loss_parts);
+    return check_launch("quantile_loss_kernel");
+}
+
+extern "C" int im2im_adam_step_f32(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
+                                   int64_t n, float lr, float beta1, float beta2, float eps, int32_t step,
+                                   float grad_scale, void* stream) {
+    if (n < 0 || step < 1) return fail(IM2IM_EINVAL, "adam: bad arguments");
+    if (n == 0) return IM2IM_OK;
+    if (!d_param || !d_grad || !d_exp_avg || !d_exp_avg_sq) return fail(IM2IM_EINVAL, "adam: null tensor");
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+    adam_kernel<<<grid_for(n, 256, 16), 256, 0, ST(stream)>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, lr, beta1,
+                                                             beta2, eps, static_cast<float>(bc1),
+                                                             static_cast<float>(sqrt(bc2)), grad_scale);
+    return check_launch("adam_kernel");
+}
+
+extern "C" int im2im_head_bwd(const float* d_dout, const void* d_m, const float* d_weight, int32_t B, int32_t H,
+                              int32_t W, int32_t c_mid, int32_t c_stride, int32_t n_out, void* d_dm, float* d_dw,
+                              float* d_db, void* stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || c_mid <= 0 || c_mid > 32 || c_mid % 8 || c_stride < c_mid || c_stride % 8)
+        return fail(IM2IM_ERANGE, "head_bwd: bad shape (c_mid=%d c_stride=%d)", c_mid, c_stride);
+    if (!d_dout || !d_m || !d_weight || !d_dm || !d_dw || !d_db) return fail(IM2IM_EINVAL, "head_bwd: null tensor");
+    const long long pixels = static_cast<long long>(B) * H * W;
+    const size_t smem = sizeof(float) * 9 * n_out * c_mid;
+    const unsigned g1 = grid_for(pixels, 128, 8);
+    const unsigned g2 = static_cast<unsigned>(8 * sm_count());
+    switch (n_out) {
+        case 3:
+            head_dgrad_kernel<3><<<g1, 128, smem, ST(stream)>>>(d_dout, d_weight, B, H, W, c_mid, c_stride, BFW(d_dm));
+            if (int rc = check_launch("head_dgrad_kernel")) return rc;
+            head_wgrad_kernel<3><<<g2, 128, 0, ST(stream)>>>(d_dout, BF(d_m), B, H, W, c_mid, c_stride, d_dw, d_db);
+            break;
+        case 6:
+            head_dgrad_kernel<6><<<g1, 128, smem, ST(stream)>>>(d_dout, d_weight, B, H, W, c_mid, c_stride, BFW(d_dm));
+            if (int rc = check_launch("head_dgrad_kernel")) return rc;
+            head_wgrad_kernel<6><<<g2, 128, 0, ST(stream)>>>(d_dout, BF(d_m), B, H, W, c_mid, c_stride, d_dw, d_db);
+            break;
+        default:
+            return fail(IM2IM_ENOTSUP, "head_bwd: n_out=%d (3 or 6 supported)", n_out);
+    }
+    return check_launch("head_wgrad_kernel");
+}
+
+extern "C" int im2im_conv_first_wgrad(const float* d_x, const void* d_dz, int32_t B, int32_t c_in, int32_t H, int32_t W,
+                                      int32_t c_out, float* d_dw, void* stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || c_in <= 0 || c_in > 8 || c_out <= 0 || 256 % c_out)
+        return fail(IM2IM_ERANGE, "conv_first_wgrad: bad shape (c_in=%d c_out=%d)", c_in, c_out);
+    if (!d_x || !d_dz || !d_dw) return fail(IM2IM_EINVAL, "conv_first_wgrad: null tensor");
+    conv_first_wgrad_kernel<<<static_cast<unsigned>(4 * sm_count()), 256, 0, ST(stream)>>>(d_x, BF(d_dz), B, c_in, H, W,
+                                                                                          c_out, d_dw);
+    return check_launch("conv_first_wgrad_kernel");
+}

@@ -33,6 +33,9 @@ class ModelWithUncertainty(nn.Module):
                 eng = UNetInferenceEngine(self)
                 self.__dict__["_native_engine"] = eng
             return eng.forward(x)
+        from .unet_train import native_train_applicable, native_train_forward
+        if native_train_applicable(self, x):
+            return native_train_forward(self, x)  # training step on the native engine, bridged into autograd
         x = self.baseModel(x)
         return self.last_layer(x)
 

@@ -32,6 +32,10 @@ class QuantileRegressionLayer(nn.Module):
 
 
 def quantile_regression_loss_fn(pred, target, params):
+    if (pred.is_cuda and pred.dtype == torch.float32 and pred.dim() == 5 and pred.shape[1] == 3
+            and target.numel() * 3 == pred.numel()):
+        from .unet_train import native_quantile_loss
+        return native_quantile_loss(pred, target, params)  # fused pinball+MSE forward/backward kernel
     q_lo_loss = PinballLoss(quantile=params["q_lo"])
     q_hi_loss = PinballLoss(quantile=params["q_hi"])
     mse_loss = nn.MSELoss()

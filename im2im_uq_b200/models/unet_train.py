@@ -1,0 +1,396 @@
+"""Native sm_100a training step of UNet + quantile head (Path B, training half).
+
+Replaces the library calls behind the reference's hot training loop (core/scripts/train.py:147-165):
+    labels_pred = net(*x)                    -> UNetTrainEngine.forward   (tcgen05 convs, BatchNorm batch statistics)
+    loss = net.loss_fn(labels_pred, labels)  -> fused pinball+MSE kernel  (quantile_layer.py:23-32)
+    loss.backward()                          -> UNetTrainEngine.backward  (dgrad = igemm with flipped weights, wgrad =
+                                                tcgen05 MN-major GEMM over pixels, BN/ReLU/pool/upsample backward)
+    optimizer.step()                         -> FusedAdam (one kernel over the flat fp32 parameter buffer)
+Data-parallel: one process per GPU, per-replica BatchNorm statistics (nn.DataParallel semantics, train.py:112-115),
+ONE NCCL all-reduce of the flat fp32 gradient buffer (69 MB) per step.
+
+The engine plugs in behind ``ModelWithUncertainty.forward`` through a torch.autograd.Function, so the reference's own
+loop (forward, loss_fn, backward, optimizer.step) runs unchanged.
+
+Precision: activations and GEMM operands bf16, accumulation / statistics / parameters / gradients fp32.
+Known deviation: convolution biases that feed a BatchNorm receive an exactly-zero gradient (their true gradient is
+zero up to rounding noise, because the batch mean cancels them); torch produces ~1e-9 noise there instead.
+"""
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..conv import conv_igemm, conv_wgrad, pack_conv_weight, pack_dgrad_weight
+
+
+def _st(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return t.data_ptr() if t is not None else None
+
+
+class _ConvBN:
+    """conv3x3 (tensor cores) -> BatchNorm(batch stats) -> ReLU, with what backward needs."""
+
+    def __init__(self, conv: nn.Conv2d, bn: nn.BatchNorm2d):
+        self.conv, self.bn = conv, bn
+        self.c_out, self.c_in = conv.weight.shape[0], conv.weight.shape[1]
+
+    def pack(self):
+        self.w_fwd = pack_conv_weight(self.conv.weight)
+        self.w_bwd = pack_dgrad_weight(self.conv.weight)
+
+
+class UNetTrainEngine:
+    def __init__(self, model):
+        from .quantile_layer import QuantileRegressionLayer
+        from .unet import UNet
+        assert type(model.baseModel) is UNet and type(model.last_layer) is QuantileRegressionLayer
+        self.model = model
+        t, self.head = model.baseModel, model.last_layer
+        self.lib = _lib.load()
+
+        def dc(d):
+            s = d.double_conv
+            return _ConvBN(s[0], s[1]), _ConvBN(s[3], s[4])
+
+        self.inc = dc(t.inc)
+        self.down = [dc(b.maxpool_conv[1]) for b in (t.down1, t.down2, t.down3, t.down4)]
+        self.up = [dc(b.conv) for b in (t.up1, t.up2, t.up3, t.up4)]
+        self.out_conv = t.out.conv
+        self.c_mid = self.out_conv.weight.shape[0]      # 32
+        self.n_out = 3 * self.head.lower.weight.shape[0]
+
+    # ------------------------------------------------------------------------------------------- primitive launches
+    def _bn_relu(self, z: torch.Tensor, layer: _ConvBN, saved: dict):
+        lib, dev = self.lib, z.device
+        B, H, W, C = z.shape
+        n_pix = B * H * W
+        bn = layer.bn
+        sums = torch.zeros(2 * C, dtype=torch.float32, device=dev)
+        scale = torch.empty(C, dtype=torch.float32, device=dev)
+        shift = torch.empty_like(scale)
+        rstd = torch.empty_like(scale)
+        mean = torch.empty_like(scale)
+        _lib.check(lib.im2im_channel_stats_bf16(z.data_ptr(), n_pix, C, sums.data_ptr(), _st(dev)), "channel_stats")
+        momentum = bn.momentum if bn.momentum is not None else 0.1
+        track = bn.track_running_stats and bn.running_mean is not None
+        _lib.check(lib.im2im_bn_finalize(sums.data_ptr(), n_pix, _ptr(layer.conv.bias), bn.weight.data_ptr(),
+                                         bn.bias.data_ptr(), bn.eps, momentum, C,
+                                         _ptr(bn.running_mean) if track else None,
+                                         _ptr(bn.running_var) if track else None, scale.data_ptr(), shift.data_ptr(),
+                                         mean.data_ptr(), rstd.data_ptr(), _st(dev)), "bn_finalize")
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        y = torch.empty_like(z)
+        _lib.check(lib.im2im_bn_apply_relu_bf16(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), n_pix, C,
+                                                y.data_ptr(), _st(dev)), "bn_apply_relu")
+        saved["z"], saved["mean"], saved["rstd"] = z, mean, rstd  # backward needs xhat everywhere: keep z, not y
+        return y
+
+    def _bn_relu_bwd(self, dy: torch.Tensor, layer: _ConvBN, saved: dict, grads: Dict):
+        lib, dev = self.lib, dy.device
+        z = saved["z"]
+        B, H, W, C = z.shape
+        sums = torch.empty(2 * C, dtype=torch.float32, device=dev)
+        dz = torch.empty_like(z)
+        _lib.check(lib.im2im_bn_relu_bwd_bf16(dy.data_ptr(), z.data_ptr(), layer.bn.weight.data_ptr(),
+                                              layer.bn.bias.data_ptr(), saved["mean"].data_ptr(),
+                                              saved["rstd"].data_ptr(), B * H * W, C, sums.data_ptr(), dz.data_ptr(),
+                                              _st(dev)), "bn_relu_bwd")
+        grads[layer.bn.bias] = sums[:C]
+        grads[layer.bn.weight] = sums[C:]
+        if layer.conv.bias is not None:
+            grads[layer.conv.bias] = torch.zeros_like(layer.conv.bias)  # cancelled by the batch mean (see module doc)
+        return dz
+
+    @staticmethod
+    def _w_to_torch(dw: torch.Tensor, c_in: int):
+        c_out, taps, _ = dw.shape
+        k = 3 if taps == 9 else 1
+        return dw.view(c_out, k, k, c_in).permute(0, 3, 1, 2)
+
+    def _pool(self, x):
+        B, H, W, C = x.shape
+        y = torch.empty((B, H // 2, W // 2, C), dtype=torch.bfloat16, device=x.device)
+        _lib.check(self.lib.im2im_maxpool2x2_bf16(x.data_ptr(), B, H, W, C, y.data_ptr(), _st(x.device)), "maxpool")
+        return y
+
+    def _upsample_to(self, x, Ho, Wo):
+        B, h, w, C = x.shape
+        y = torch.empty((B, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+        _lib.check(self.lib.im2im_upsample2x_bilinear_bf16(x.data_ptr(), B, h, w, C, Ho, Wo, y.data_ptr(),
+                                                           _st(x.device)), "upsample")
+        return y
+
+    # ------------------------------------------------------------------------------------------- forward
+    def forward(self, x: torch.Tensor):
+        lib, dev = self.lib, x.device
+        x = x.contiguous().float()
+        B, c_in, H, W = x.shape
+        for a, b in [self.inc] + self.down + self.up:
+            b.pack()
+            if a is not self.inc[0]:
+                a.pack()
+        ctx = {"x": x, "layers": []}
+        with torch.cuda.device(dev):
+            # first conv (CUDA cores), no bias (cancelled by BN), no ReLU: z0
+            first = self.inc[0]
+            w0 = first.conv.weight.detach().float().contiguous()
+            z = torch.empty((B, H, W, first.c_out), dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.im2im_conv_first_bf16(x.data_ptr(), w0.data_ptr(), None, B, c_in, H, W, first.c_out, 0,
+                                                 z.data_ptr(), _st(dev)), "conv_first")
+            s0 = {}
+            y0 = self._bn_relu(z, first, s0)
+            s1 = {"x_in": y0}
+            x1 = self._bn_relu(conv_igemm(y0, self.inc[1].w_fwd), self.inc[1], s1)
+            ctx["inc"] = (s0, s1)
+            skips = [x1]
+            ctx["down"] = []
+            for (a, b) in self.down:
+                p = self._pool(skips[-1])
+                sa = {"x_in": p}
+                ya = self._bn_relu(conv_igemm(p, a.w_fwd), a, sa)
+                sb = {"x_in": ya}
+                skips.append(self._bn_relu(conv_igemm(ya, b.w_fwd), b, sb))
+                ctx["down"].append((sa, sb))
+            ctx["skips"] = list(skips)
+            y = skips.pop()
+            ctx["up"] = []
+            for (a, b) in self.up:
+                skip = skips.pop()
+                u = self._upsample_to(y, skip.shape[1], skip.shape[2])
+                sa = {"x_in": skip, "x_in2": u, "low_shape": tuple(y.shape)}
+                ya = self._bn_relu(conv_igemm(skip, a.w_fwd, x2=u), a, sa)
+                sb = {"x_in": ya}
+                y = self._bn_relu(conv_igemm(ya, b.w_fwd), b, sb)
+                ctx["up"].append((sa, sb))
+            # 1x1 out conv, output channels zero-padded 32 -> 64 so the result feeds the 64-channel kernels
+            w_out = self.out_conv.weight.detach()
+            c_feat = w_out.shape[1]
+            w_pad = torch.zeros((64, 1, c_feat), dtype=torch.bfloat16, device=dev)
+            w_pad[:self.c_mid, 0] = w_out.view(self.c_mid, c_feat).to(torch.bfloat16)
+            b_pad = torch.zeros(64, dtype=torch.float32, device=dev)
+            b_pad[:self.c_mid] = self.out_conv.bias.detach().float()
+            m = conv_igemm(y, w_pad, b_pad, relu=False)
+            ctx["y_last"], ctx["m"], ctx["w_out_pad"] = y, m, w_pad
+            # head (CUDA cores): weights zero-padded to the 64-channel row stride of m
+            hw_ = torch.cat([self.head.lower.weight, self.head.prediction.weight, self.head.upper.weight], 0).detach().float()
+            hw_pad = torch.zeros((self.n_out, 64, 3, 3), dtype=torch.float32, device=dev)
+            hw_pad[:, :self.c_mid] = hw_
+            hb = torch.cat([self.head.lower.bias, self.head.prediction.bias, self.head.upper.bias], 0).detach().float().contiguous()
+            out = torch.empty((B, self.n_out, H, W), dtype=torch.float32, device=dev)
+            _lib.check(lib.im2im_head_conv3x3_f32(m.data_ptr(), hw_pad.data_ptr(), hb.data_ptr(), B, H, W, 64,
+                                                  self.n_out, out.data_ptr(), _st(dev)), "head_conv")
+            ctx["head_w"] = hw_.contiguous()
+        return out.view(B, 3, self.n_out // 3, H, W), ctx
+
+    # ------------------------------------------------------------------------------------------- backward
+    def _conv_bwd(self, layer: _ConvBN, saved: dict, dz: torch.Tensor, grads: Dict, need_dx: bool = True):
+        """wgrad (+ dgrad) of a tensor-core conv layer; returns (dx for x_in, dx for x_in2 or None)."""
+        x1, x2 = saved["x_in"], saved.get("x_in2")
+        dw1 = conv_wgrad(x1, dz, 9)
+        if x2 is None:
+            grads[layer.conv.weight] = self._w_to_torch(dw1, layer.c_in)
+        else:
+            dw2 = conv_wgrad(x2, dz, 9)
+            c1, c2 = x1.shape[3], x2.shape[3]
+            grads[layer.conv.weight] = torch.cat([self._w_to_torch(dw1, c1), self._w_to_torch(dw2, c2)], dim=1)
+        if not need_dx:
+            return None, None
+        if x2 is None:
+            return conv_igemm(dz, layer.w_bwd), None
+        c1 = x1.shape[3]
+        return conv_igemm(dz, layer.w_bwd[:c1]), conv_igemm(dz, layer.w_bwd[c1:])
+
+    def backward(self, ctx: dict, dout: torch.Tensor) -> Dict[torch.Tensor, torch.Tensor]:
+        lib, dev = self.lib, dout.device
+        grads: Dict[torch.Tensor, torch.Tensor] = {}
+        x = ctx["x"]
+        B, c_in, H, W = x.shape
+        dout = dout.contiguous().float().view(B, self.n_out, H, W)
+        with torch.cuda.device(dev):
+            m, y_last = ctx["m"], ctx["y_last"]
+            dm = torch.empty_like(m)
+            dwh = torch.zeros((self.n_out, self.c_mid, 3, 3), dtype=torch.float32, device=dev)
+            dbh = torch.zeros(self.n_out, dtype=torch.float32, device=dev)
+            _lib.check(lib.im2im_head_bwd(dout.data_ptr(), m.data_ptr(), ctx["head_w"].data_ptr(), B, H, W, self.c_mid,
+                                          64, self.n_out, dm.data_ptr(), dwh.data_ptr(), dbh.data_ptr(), _st(dev)),
+                       "head_bwd")
+            co = self.n_out // 3
+            for i, conv in enumerate((self.head.lower, self.head.prediction, self.head.upper)):
+                grads[conv.weight] = dwh[i * co:(i + 1) * co]
+                grads[conv.bias] = dbh[i * co:(i + 1) * co]
+            # 1x1 out conv: wgrad, bias grad (channel sums of dm), dgrad
+            dw_out = conv_wgrad(y_last, dm, 1)                       # [64 (32 real), 1, 64]
+            grads[self.out_conv.weight] = dw_out[:self.c_mid].view(self.c_mid, -1, 1, 1)
+            sums = torch.zeros(128, dtype=torch.float32, device=dev)
+            _lib.check(lib.im2im_channel_stats_bf16(dm.data_ptr(), B * H * W, 64, sums.data_ptr(), _st(dev)), "dbias")
+            grads[self.out_conv.bias] = sums[:self.c_mid]
+            w_out_bwd = ctx["w_out_pad"].permute(2, 1, 0).contiguous()  # [64 ci, 1, 64 co]
+            dy = conv_igemm(dm, w_out_bwd)
+            # up path, reversed
+            skip_grads: List[Optional[torch.Tensor]] = [None] * 4      # for x1..x4
+            for k in range(3, -1, -1):
+                (a, b), (sa, sb) = self.up[k], ctx["up"][k]
+                dz = self._bn_relu_bwd(dy, b, sb, grads)
+                d_ya, _ = self._conv_bwd(b, sb, dz, grads)
+                dz = self._bn_relu_bwd(d_ya, a, sa, grads)
+                d_skip, d_u = self._conv_bwd(a, sa, dz, grads)
+                skip_grads[3 - k] = d_skip                              # up1 uses x4, ..., up4 uses x1
+                lb, lh, lw, lc = sa["low_shape"]
+                dy = torch.empty(sa["low_shape"], dtype=torch.bfloat16, device=dev)
+                _lib.check(lib.im2im_upsample2x_bilinear_bwd_bf16(d_u.data_ptr(), lb, lh, lw, lc, d_u.shape[1],
+                                                                  d_u.shape[2], dy.data_ptr(), _st(dev)), "upsample_bwd")
+            # dy is now the gradient of x5; down path, reversed
+            skips = ctx["skips"]                                        # [x1, x2, x3, x4, x5]
+            for k in range(3, -1, -1):
+                (a, b), (sa, sb) = self.down[k], ctx["down"][k]
+                dz = self._bn_relu_bwd(dy, b, sb, grads)
+                d_ya, _ = self._conv_bwd(b, sb, dz, grads)
+                dz = self._bn_relu_bwd(d_ya, a, sa, grads)
+                d_p, _ = self._conv_bwd(a, sa, dz, grads)
+                src = skips[k]                                          # input of this block's max-pool
+                dy = skip_grads[k]                                      # gradient from the up path, accumulated into
+                sb_, sh, sw, sc = src.shape
+                _lib.check(lib.im2im_maxpool2x2_bwd_bf16(src.data_ptr(), d_p.data_ptr(), sb_, sh, sw, sc, 1,
+                                                         dy.data_ptr(), _st(dev)), "maxpool_bwd")
+            # inc block
+            s0, s1 = ctx["inc"]
+            dz = self._bn_relu_bwd(dy, self.inc[1], s1, grads)
+            d_y0, _ = self._conv_bwd(self.inc[1], s1, dz, grads)
+            dz0 = self._bn_relu_bwd(d_y0, self.inc[0], s0, grads)
+            first = self.inc[0]
+            dw0 = torch.zeros((first.c_out, c_in, 3, 3), dtype=torch.float32, device=dev)
+            _lib.check(lib.im2im_conv_first_wgrad(x.data_ptr(), dz0.data_ptr(), B, c_in, H, W, first.c_out,
+                                                  dw0.data_ptr(), _st(dev)), "conv_first_wgrad")
+            grads[first.conv.weight] = dw0
+        return grads
+
+
+class _NativeTrainFn(torch.autograd.Function):
+    """Autograd bridge: forward/backward of the whole UNet + head run on the native engine; parameter gradients are
+    returned to autograd so ``loss.backward()`` / any torch optimizer work as in the reference's loop."""
+
+    @staticmethod
+    def forward(ctx, x, engine, *params):
+        out, saved = engine.forward(x)
+        ctx.engine, ctx.saved, ctx.params = engine, saved, params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = ctx.engine.backward(ctx.saved, dout)
+        ctx.saved = None
+        return (None, None) + tuple(grads.get(p) for p in ctx.params)
+
+
+def native_train_applicable(model, x) -> bool:
+    from .quantile_layer import QuantileRegressionLayer
+    from .unet import UNet
+    return (model.training and torch.is_tensor(x) and x.is_cuda and torch.is_grad_enabled()
+            and type(model.baseModel) is UNet and model.baseModel.bilinear
+            and type(model.last_layer) is QuantileRegressionLayer and getattr(model, "use_native_training", True)
+            and x.dim() == 4 and x.shape[1] <= 8 and min(x.shape[2], x.shape[3]) >= 16
+            and model.last_layer.lower.weight.shape[0] <= 2)
+
+
+def native_train_forward(model, x):
+    eng = model.__dict__.get("_native_train_engine")
+    if eng is None:
+        eng = UNetTrainEngine(model)
+        model.__dict__["_native_train_engine"] = eng
+    params = tuple(model.parameters())
+    return _NativeTrainFn.apply(x, eng, *params)
+
+
+# ------------------------------------------------------------------------------------------------ loss + optimizer
+class _QuantileLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, q_lo, q_hi, w_lo, w_hi, w_mse):
+        lib = _lib.load()
+        pred_c, target_c = pred.contiguous(), target.contiguous().float()
+        n = pred_c.shape[0]
+        px = target_c[0].numel()
+        dpred = torch.empty_like(pred_c)
+        parts = torch.empty(3, dtype=torch.float64, device=pred.device)
+        with torch.cuda.device(pred.device):
+            _lib.check(lib.im2im_quantile_loss_f32(pred_c.data_ptr(), target_c.data_ptr(), n, px, q_lo, q_hi, w_lo, w_hi,
+                                                   w_mse, dpred.data_ptr(), parts.data_ptr(), _st(pred.device)),
+                       "quantile_loss")
+        ctx.save_for_backward(dpred)
+        count = float(n * px)
+        w = torch.tensor([w_lo, w_hi, w_mse], dtype=torch.float64, device=pred.device)
+        return ((parts / count) * w).sum().to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpred,) = ctx.saved_tensors
+        return dpred * g, None, None, None, None, None, None
+
+
+def native_quantile_loss(pred, target, params):
+    """quantile_regression_loss_fn on the fused kernel (pred (B,3,C,H,W) fp32 CUDA, target (B,C,H,W))."""
+    return _QuantileLossFn.apply(pred, target, float(params["q_lo"]), float(params["q_hi"]),
+                                 float(params["q_lo_weight"]), float(params["q_hi_weight"]), float(params["mse_weight"]))
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (defaults of core/scripts/train.py:120) with ONE kernel over a flat fp32 buffer.
+
+    Parameters are re-pointed at views of one contiguous buffer (as DDP-style flat buckets), gradients likewise, so the
+    data-parallel all-reduce is a single NCCL call on ``flat_grad`` and the update a single launch."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        params = [p for p in params]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        ps = [p for g in self.param_groups for p in g["params"]]
+        dev = ps[0].device
+        n = sum(p.numel() for p in ps)
+        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        off = 0
+        for p in ps:
+            k = p.numel()
+            self.flat_param[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + k].view_as(p.data)
+            p.grad = self.flat_grad[off:off + k].view_as(p.data)
+            off += k
+        self._params = ps
+        self._step = 0
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.flat_grad.zero_()
+        off = 0
+        for p in self._params:  # autograd may have replaced .grad with a fresh tensor; point it back at the flat view
+            k = p.numel()
+            p.grad = self.flat_grad[off:off + k].view_as(p.data)
+            off += k
+
+    def gather_grads(self):
+        """Copy gradients that autograd left outside the flat buffer into it (no-op when they already are views)."""
+        off = 0
+        for p in self._params:
+            k = p.numel()
+            view = self.flat_grad[off:off + k]
+            if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad.reshape(-1))
+            off += k
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        self.gather_grads()
+        self._step += 1
+        g = self.param_groups[0]
+        lib = _lib.load()
+        with torch.cuda.device(self.flat_param.device):
+            _lib.check(lib.im2im_adam_step_f32(self.flat_param.data_ptr(), self.flat_grad.data_ptr(),
+                                               self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                               self.flat_param.numel(), g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                                               self._step, grad_scale, _st(self.flat_param.device)), "adam_step")

@@ -175,6 +175,50 @@ int im2im_upsample2x_bilinear_bf16(const void* d_x, int32_t B, int32_t h, int32_
 int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W,
                            int32_t c_mid, int32_t n_out, float* d_out, void* stream);
 
+/*
+ * Training-side passes of the UNet path (autograd of core/scripts/train.py:152-162 through the modules of
+ * core/models/trunks/unet_parts.py and core/models/finallayers/quantile_layer.py).  NHWC bf16 activations, fp32 params.
+ *
+ *   im2im_channel_stats_bf16     sums[c] += sum_p z[p,c], sums[C+c] += sum_p z[p,c]^2            (BatchNorm batch statistics)
+ *   im2im_bn_finalize            sums -> scale/shift for y = relu(z*scale+shift), saved mean/rstd, running-stat update
+ *                                (nn.BatchNorm2d train mode, unet_parts.py:17,20; conv_bias only enters running_mean)
+ *   im2im_bn_apply_relu_bf16     y = relu(z*scale + shift)                                       (unet_parts.py:17-18)
+ *   im2im_bn_relu_bwd_bf16       ReLU + BatchNorm backward from dy and the saved pre-normalisation z:
+ *                                sums[c] = dbeta, sums[C+c] = dgamma, dz written
+ *   im2im_maxpool2x2_bwd_bf16    gradient of nn.MaxPool2d(2) (first maximal element, optional accumulate)
+ *   im2im_upsample2x_bilinear_bwd_bf16  gradient of Upsample(x2, bilinear, align_corners=True) + F.pad
+ *   im2im_quantile_loss_f32      quantile_regression_loss_fn (quantile_layer.py:23-32, pinball.py:12-24): loss_parts[3]
+ *                                (double: sum pinball_lo, sum pinball_hi, sum squared error) and d loss / d pred
+ *   im2im_adam_step_f32          torch.optim.Adam step on a flat fp32 buffer (train.py:120,162); grad_scale multiplies
+ *                                the gradient first (1/world_size after the NCCL all-reduce)
+ *   im2im_head_bwd               QuantileRegressionLayer backward: dm (bf16, row stride c_stride, zero padded),
+ *                                dW [n_out,c_mid,3,3] and db [n_out] accumulated
+ *   im2im_conv_first_wgrad       weight gradient of the first 3x3 conv (x fp32 NCHW, dz bf16 NHWC), accumulated
+ */
+int im2im_channel_stats_bf16(const void* d_z, int64_t n_pix, int32_t C, float* d_sums, void* stream);
+int im2im_bn_finalize(const float* d_sums, int64_t count, const float* d_conv_bias, const float* d_gamma,
+                      const float* d_beta, float eps, float momentum, int32_t C, float* d_running_mean,
+                      float* d_running_var, float* d_scale, float* d_shift, float* d_save_mean, float* d_save_rstd,
+                      void* stream);
+int im2im_bn_apply_relu_bf16(const void* d_z, const float* d_scale, const float* d_shift, int64_t n_pix, int32_t C,
+                             void* d_y, void* stream);
+int im2im_bn_relu_bwd_bf16(const void* d_dy, const void* d_z, const float* d_gamma, const float* d_beta,
+                           const float* d_mean, const float* d_rstd, int64_t n_pix, int32_t C, float* d_sums, void* d_dz,
+                           void* stream);
+int im2im_maxpool2x2_bwd_bf16(const void* d_x, const void* d_dy, int32_t B, int32_t H, int32_t W, int32_t C,
+                              int32_t accumulate, void* d_dx, void* stream);
+int im2im_upsample2x_bilinear_bwd_bf16(const void* d_du, int32_t B, int32_t h, int32_t w, int32_t C, int32_t H_out,
+                                       int32_t W_out, void* d_dx, void* stream);
+int im2im_quantile_loss_f32(const float* d_pred, const float* d_target, int64_t n_images, int64_t px, float q_lo,
+                            float q_hi, float w_lo, float w_hi, float w_mse, float* d_dpred, double* d_loss_parts,
+                            void* stream);
+int im2im_adam_step_f32(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n, float lr,
+                        float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+int im2im_head_bwd(const float* d_dout, const void* d_m, const float* d_weight, int32_t B, int32_t H, int32_t W,
+                   int32_t c_mid, int32_t c_stride, int32_t n_out, void* d_dm, float* d_dw, float* d_db, void* stream);
+int im2im_conv_first_wgrad(const float* d_x, const void* d_dz, int32_t B, int32_t c_in, int32_t H, int32_t W,
+                           int32_t c_out, float* d_dw, void* stream);
+
 /* Number of kernel launches this library has enqueued in this process (bench.py's `gpu_launches`). */
 unsigned long long im2im_launch_count(void);
 
