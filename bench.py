@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=192, help="images in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-unet", action="store_true", help="skip the UNet forward / train-step sub-benchmark")
+    ap.add_argument("--unet-batch", type=int, default=16, help="images per GPU per UNet step")
+    ap.add_argument("--unet-steps", type=int, default=10)
     return ap.parse_args()
 
 
@@ -191,6 +194,81 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+# --------------------------------------------------------------------------------------------- UNet sub-benchmark
+def run_unet_bench(args, world, rank, dev, group):
+    """Second half of BASELINE.json's metric: UNet(1,1)+quantile-head images/s at 320x320, forward (inference engine)
+    and full train step (forward, fused loss, backward, NCCL all-reduce of the flat fp32 gradients, fused Adam) on the
+    native sm_100a kernels.  Per-GPU batch is fixed (weak scaling); images/s is the whole-job aggregate."""
+    import torch
+    import torch.distributed as dist
+    from im2im_uq_b200.models.add_uncertainty import add_uncertainty
+    from im2im_uq_b200.models.unet import UNet
+    from im2im_uq_b200.models.unet_train import FusedAdam
+    params = dict(uncertainty_type="quantiles", q_lo=0.05, q_hi=0.95, q_lo_weight=1.0, q_hi_weight=1.0, mse_weight=1.0)
+    torch.manual_seed(0)
+    model = add_uncertainty(UNet(1, 1), params).to(dev)
+    B, side = args.unet_batch, args.side
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    x = torch.randn(B, 1, side, side, device=dev, generator=g)
+    y = x + 0.3 * torch.randn(B, 1, side, side, device=dev, generator=g)
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / iters], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    model.eval()
+    with torch.no_grad():
+        fwd_ms = timed(lambda: model(x), args.unet_steps)
+    model.train()
+    opt = FusedAdam(model.parameters(), lr=1e-4)
+    last = {}
+
+    def train_step():
+        opt.zero_grad()
+        loss = model.loss_fn(model(x), y)
+        loss.backward()
+        if world > 1:
+            opt.gather_grads()
+            dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.SUM, group=group)  # 69 MB fp32 over NCCL
+        opt.step(grad_scale=1.0 / world)
+        last["loss"] = loss.item()  # the reference reads the loss every step (train.py:155)
+
+    train_ms = timed(train_step, args.unet_steps)
+    fwd_flop, train_flop = 125.29e9, 375.87e9  # conv 2*MACs per 320x320 image (SURVEY.md §2.1); train = 3x forward
+    scale = (side / 320.0) ** 2
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        src = "MEASURED_PEAKS.json bf16_tflops (burst, of measured)"
+    except Exception:
+        peak, src = 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
+    fwd_tf = B * fwd_flop * scale / (fwd_ms * 1e-3) / 1e12
+    train_tf = B * train_flop * scale / (train_ms * 1e-3) / 1e12
+    return {"model": "UNet(1,1)+quantile head, 17.27M params", "image": f"1x{side}x{side}", "batch_per_gpu": B,
+            "scaling": "weak", "dtype": "bf16 operands, fp32 accumulate/params",
+            "forward_images_per_s": world * B / (fwd_ms * 1e-3), "forward_ms": fwd_ms,
+            "train_images_per_s": world * B / (train_ms * 1e-3), "train_ms_per_step": train_ms,
+            "train_step": "forward + fused pinball/MSE loss + backward + " +
+                          ("NCCL all-reduce of 69 MB fp32 grads + " if world > 1 else "") + "fused Adam + loss.item()",
+            "final_loss": last.get("loss"),
+            "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak, "peak_source": src,
+                         "forward_achieved": fwd_tf, "forward_frac": fwd_tf / peak,
+                         "train_achieved": train_tf, "train_frac": train_tf / peak,
+                         "flops": "conv 2*MACs only: 125.29 GFLOP fwd, 375.87 GFLOP train per 320x320 image"}}
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def main():
     args = parse_args()
@@ -329,6 +407,15 @@ def main():
                "d2h_bytes_per_step": args.images * L * 4 + L * 8 * world, "steps": args.e2e_steps,
                "api": "im2im_uq_b200.calibration.calibrate_model.calibrate_from_outputs(model, outputs_cpu, labels_cpu, config)"}
 
+    unet = None
+    if not args.no_unet:
+        try:
+            del host_out, host_lab
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        unet = run_unet_bench(args, world, rank, dev, group)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         alg_bytes = n_local * px * 16 + n_local * L * 4
@@ -352,7 +439,7 @@ def main():
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": float(kernel_ms),
                              "peak_source": peak_src},
-                "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches_t)}
+                "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches_t), "unet": unet}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import rcps_oracle as orc
             orc.build()

@@ -85,6 +85,8 @@ def _declare_more(lib):
     lib.im2im_conv_igemm_bf16.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.im2im_conv_wgrad_bf16.restype = c.c_int
     lib.im2im_conv_wgrad_bf16.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.im2im_pack_conv_weights.restype = c.c_int
+    lib.im2im_pack_conv_weights.argtypes = [vp, i32, i32, i32, vp, vp, vp]
     lib.im2im_conv_first_bf16.restype = c.c_int
     lib.im2im_conv_first_bf16.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.im2im_maxpool2x2_bf16.restype = c.c_int
@@ -92,7 +94,7 @@ def _declare_more(lib):
     lib.im2im_upsample2x_bilinear_bf16.restype = c.c_int
     lib.im2im_upsample2x_bilinear_bf16.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.im2im_head_conv3x3_f32.restype = c.c_int
-    lib.im2im_head_conv3x3_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.im2im_head_conv3x3_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
 
 
 def _declare_train(lib):
@@ -119,7 +121,7 @@ def _declare_train(lib):
 EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im_rcps_miss_counts",
            "im2im_rcps_loss_table", "im2im_quantile_nested_sets", "im2im_rcps_miss_map",
            "im2im_fraction_missed_counts", "im2im_rcps_loss_table_dev", "im2im_rcps_decide",
-           "im2im_conv_igemm_bf16", "im2im_conv_wgrad_bf16", "im2im_conv_first_bf16",
+           "im2im_conv_igemm_bf16", "im2im_conv_wgrad_bf16", "im2im_pack_conv_weights", "im2im_conv_first_bf16",
            "im2im_maxpool2x2_bf16", "im2im_upsample2x_bilinear_bf16", "im2im_head_conv3x3_f32",
            "im2im_channel_stats_bf16", "im2im_bn_finalize", "im2im_bn_apply_relu_bf16", "im2im_bn_relu_bwd_bf16",
            "im2im_maxpool2x2_bwd_bf16", "im2im_upsample2x_bilinear_bwd_bf16", "im2im_quantile_loss_f32",

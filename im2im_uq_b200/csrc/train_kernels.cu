@@ -394,12 +394,14 @@ __global__ void __launch_bounds__(128) head_dgrad_kernel(const float* __restrict
 }
 
 // (b) weight/bias gradient: dW[o, c, t] += sum_p dOut[o, p] * m[p + shift(t), c];  db[o] += sum_p dOut[o, p].
-// lane = channel c (c_mid <= 32), each of the 4 warps walks its own pixels, 9*N_OUT accumulators per lane.
+// lane = channel c (c_mid <= 32); each of the 4 warps walks its own pixels, kUnroll at a time so that 9*kUnroll
+// independent 64-byte loads are in flight per warp (the kernel is latency-bound otherwise); 9*N_OUT accumulators per lane.
 template <int N_OUT>
 __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict__ dout,
                                                          const __nv_bfloat16* __restrict__ m, int B, int H, int W,
                                                          int c_mid, int c_stride, float* __restrict__ dw,
                                                          float* __restrict__ db) {
+    constexpr int kUnroll = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long hw = static_cast<long long>(H) * W;
     const long long total = static_cast<long long>(B) * hw;
@@ -410,24 +412,35 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict
         for (int o = 0; o < N_OUT; ++o) acc[t][o] = 0.f;
 #pragma unroll
     for (int o = 0; o < N_OUT; ++o) accb[o] = 0.f;
-    for (long long pix = static_cast<long long>(blockIdx.x) * 4 + warp; pix < total;
-         pix += static_cast<long long>(gridDim.x) * 4) {
-        const int xw = static_cast<int>(pix % W);
-        const int yh = static_cast<int>((pix / W) % H);
-        const long long b = pix / hw;
-        float d[N_OUT];
+    const long long n_warps = static_cast<long long>(gridDim.x) * 4;
+    for (long long base = (static_cast<long long>(blockIdx.x) * 4 + warp) * kUnroll; base < total;
+         base += n_warps * kUnroll) {
+        float d[kUnroll][N_OUT], v[kUnroll][9];
 #pragma unroll
-        for (int o = 0; o < N_OUT; ++o) {
-            d[o] = __ldg(dout + (b * N_OUT + o) * hw + static_cast<long long>(yh) * W + xw);
-            accb[o] += d[o];
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long pix = base + u;
+            const bool ok = pix < total;
+            const int xw = static_cast<int>(pix % W);
+            const int yh = static_cast<int>((pix / W) % H);
+            const long long b = pix / hw;
+#pragma unroll
+            for (int o = 0; o < N_OUT; ++o)
+                d[u][o] = ok ? __ldg(dout + (b * N_OUT + o) * hw + static_cast<long long>(yh) * W + xw) : 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
+                const bool in = ok && yy >= 0 && yy < H && xx >= 0 && xx < W && lane < c_mid;
+                v[u][t] = in ? __bfloat162float(m[((b * H + yy) * W + xx) * c_stride + lane]) : 0.f;
+            }
         }
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const float v = lane < c_mid ? __bfloat162float(m[((b * H + yy) * W + xx) * c_stride + lane]) : 0.f;
+        for (int u = 0; u < kUnroll; ++u) {
 #pragma unroll
-            for (int o = 0; o < N_OUT; ++o) acc[t][o] = fmaf(d[o], v, acc[t][o]);
+            for (int o = 0; o < N_OUT; ++o) accb[o] += d[u][o];
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int o = 0; o < N_OUT; ++o) acc[t][o] = fmaf(d[u][o], v[u][t], acc[t][o]);
         }
     }
     __shared__ float s_acc[4][9 * N_OUT][32 + 1];
@@ -448,35 +461,62 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict
         for (int o = 0; o < N_OUT; ++o) atomicAdd(&db[o], accb[o]);
 }
 
-// First convolution's weight gradient: dW[co, ci, t] += sum_p dz[p, co] * x[b, ci, p + shift(t)]   (x fp32 NCHW)
-// thread = output channel co (64 per pixel stream), 4 pixel streams per block.
+// First convolution's weight gradient: dW[co, ci, t] += sum_p dz[p, co] * x[b, ci, p + shift(t)]   (x fp32 NCHW).
+// thread = (pixel stream, group of 8 output channels): one 16-byte load of dz feeds 8*9*c_in FMAs; the streams of a
+// block are reduced in shared memory so that each block issues one atomicAdd per weight.  c_in == 1 is specialised
+// (accumulators in registers); larger c_in loops over the input channels.
 __global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __restrict__ x,
                                                                const __nv_bfloat16* __restrict__ dz, int B, int c_in,
                                                                int H, int W, int c_out, float* __restrict__ dw) {
-    const int co = threadIdx.x % c_out;
-    const int stream = threadIdx.x / c_out;
-    const int n_streams = blockDim.x / c_out;
+    extern __shared__ float s_red[];  // [streams][c_out * 9]
+    const int groups = c_out / 8;
+    const int g = threadIdx.x % groups;
+    const int stream = threadIdx.x / groups;
+    const int n_streams = blockDim.x / groups;
     const long long hw = static_cast<long long>(H) * W;
     const long long total = static_cast<long long>(B) * hw;
-    float acc[8 * 9];
-    for (int i = 0; i < c_in * 9; ++i) acc[i] = 0.f;
-    for (long long pix = static_cast<long long>(blockIdx.x) * n_streams + stream; pix < total;
-         pix += static_cast<long long>(gridDim.x) * n_streams) {
-        const int xw = static_cast<int>(pix % W);
-        const int yh = static_cast<int>((pix / W) % H);
-        const long long b = pix / hw;
-        const float d = __bfloat162float(dz[pix * c_out + co]);
-        for (int ci = 0; ci < c_in; ++ci) {
+    for (int ci = 0; ci < c_in; ++ci) {
+        float acc[8][9];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
+        for (long long pix = static_cast<long long>(blockIdx.x) * n_streams + stream; pix < total;
+             pix += static_cast<long long>(gridDim.x) * n_streams) {
+            const int xw = static_cast<int>(pix % W);
+            const int yh = static_cast<int>((pix / W) % H);
+            const long long b = pix / hw;
+            Bf16x8 vd;
+            vd.u = *reinterpret_cast<const uint4*>(dz + pix * c_out + g * 8);
+            float d[8];
+            unpack8(vd, d);
             const float* xp = x + (b * c_in + ci) * hw;
+            float v[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
-                const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + static_cast<long long>(yy) * W + xx) : 0.f;
-                acc[ci * 9 + t] = fmaf(d, v, acc[ci * 9 + t]);
+                v[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + static_cast<long long>(yy) * W + xx) : 0.f;
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(d[j], v[t], acc[j][t]);
         }
+        // block reduction over the pixel streams
+        float* mine = s_red + static_cast<size_t>(stream) * c_out * 9;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) mine[(g * 8 + j) * 9 + t] = acc[j][t];
+        __syncthreads();
+        for (int i = threadIdx.x; i < c_out * 9; i += blockDim.x) {
+            float s = 0.f;
+            for (int st = 0; st < n_streams; ++st) s += s_red[static_cast<size_t>(st) * c_out * 9 + i];
+            const int co = i / 9, t = i % 9;
+            atomicAdd(&dw[(static_cast<long long>(co) * c_in + ci) * 9 + t], s);
+        }
+        __syncthreads();
     }
-    for (int i = 0; i < c_in * 9; ++i) atomicAdd(&dw[static_cast<long long>(co) * c_in * 9 + i], acc[i]);
 }
 
 }  // namespace
@@ -595,7 +635,7 @@ extern "C" int im2im_head_bwd(const float* d_dout, const void* d_m, const float*
     const long long pixels = static_cast<long long>(B) * H * W;
     const size_t smem = sizeof(float) * 9 * n_out * c_mid;
     const unsigned g1 = grid_for(pixels, 128, 8);
-    const unsigned g2 = static_cast<unsigned>(8 * sm_count());
+    const unsigned g2 = static_cast<unsigned>(4 * sm_count());
     switch (n_out) {
         case 3:
             head_dgrad_kernel<3><<<g1, 128, smem, ST(stream)>>>(d_dout, d_weight, B, H, W, c_mid, c_stride, BFW(d_dm));
@@ -615,10 +655,14 @@ extern "C" int im2im_head_bwd(const float* d_dout, const void* d_m, const float*
 
 extern "C" int im2im_conv_first_wgrad(const float* d_x, const void* d_dz, int32_t B, int32_t c_in, int32_t H, int32_t W,
                                       int32_t c_out, float* d_dw, void* stream) {
-    if (B <= 0 || H <= 0 || W <= 0 || c_in <= 0 || c_in > 8 || c_out <= 0 || 256 % c_out)
+    if (B <= 0 || H <= 0 || W <= 0 || c_in <= 0 || c_in > 8 || c_out <= 0 || c_out % 8 || 256 % (c_out / 8))
         return fail(IM2IM_ERANGE, "conv_first_wgrad: bad shape (c_in=%d c_out=%d)", c_in, c_out);
     if (!d_x || !d_dz || !d_dw) return fail(IM2IM_EINVAL, "conv_first_wgrad: null tensor");
-    conv_first_wgrad_kernel<<<static_cast<unsigned>(4 * sm_count()), 256, 0, ST(stream)>>>(d_x, BF(d_dz), B, c_in, H, W,
-                                                                                          c_out, d_dw);
+    const int n_streams = 256 / (c_out / 8);
+    const size_t smem = sizeof(float) * n_streams * c_out * 9;
+    if (smem > 200 * 1024) return fail(IM2IM_ERANGE, "conv_first_wgrad: c_out=%d too large", c_out);
+    IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_first_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_first_wgrad_kernel<<<static_cast<unsigned>(2 * sm_count()), 256, smem, ST(stream)>>>(d_x, BF(d_dz), B, c_in, H,
+                                                                                             W, c_out, d_dw);
     return check_launch("conv_first_wgrad_kernel");
 }

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
 template <int N_OUT>
 __global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, int B, int H, int W, int c_mid,
-                                                        float* __restrict__ y) {
+                                                        int c_stride, float* __restrict__ y) {
     extern __shared__ float s_w[];  // [tap][c_mid][N_OUT]
     for (int i = threadIdx.x; i < 9 * c_mid * N_OUT; i += blockDim.x) {
         const int o = i % N_OUT, c = (i / N_OUT) % c_mid, t = i / (N_OUT * c_mid);
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __r
         for (int t = 0; t < 9; ++t) {
             const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
             if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const __nv_bfloat16* p = x + ((b * H + yy) * W + xx) * c_mid;
+            const __nv_bfloat16* p = x + ((b * H + yy) * W + xx) * c_stride;
             const float* wt = s_w + t * c_mid * N_OUT;
             for (int c = 0; c < c_mid; c += 8) {
                 Bf16x8 v;
@@ -178,6 +178,30 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __r
         const long long hw = static_cast<long long>(H) * W;
 #pragma unroll
         for (int o = 0; o < N_OUT; ++o) y[(b * N_OUT + o) * hw + static_cast<long long>(yh) * W + xw] = acc[o];
+    }
+}
+
+// fp32 Conv2d weight [c_out, c_in, k, k] -> bf16 [c_out, taps, c_in] (forward GEMM operand, K-major rows) and, when
+// out_bwd != null, bf16 [c_in, taps, c_out] with the taps reversed (180 degree rotation) = the data-gradient operand.
+__global__ void __launch_bounds__(256) pack_conv_weights_kernel(const float* __restrict__ w, int c_out, int c_in,
+                                                                int taps, __nv_bfloat16* __restrict__ out_fwd,
+                                                                __nv_bfloat16* __restrict__ out_bwd) {
+    const long long n = static_cast<long long>(c_out) * taps * c_in;
+    const long long total = out_bwd ? 2 * n : n;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        if (e < n) {  // out_fwd[co][t][ci]
+            const int ci = static_cast<int>(e % c_in);
+            const int t = static_cast<int>((e / c_in) % taps);
+            const int co = static_cast<int>(e / (static_cast<long long>(c_in) * taps));
+            out_fwd[e] = __float2bfloat16_rn(w[(static_cast<long long>(co) * c_in + ci) * taps + t]);
+        } else {      // out_bwd[ci][t'][co] = w[co][ci][taps-1-t']
+            const long long f = e - n;
+            const int co = static_cast<int>(f % c_out);
+            const int t = static_cast<int>((f / c_out) % taps);
+            const int ci = static_cast<int>(f / (static_cast<long long>(c_out) * taps));
+            out_bwd[f] = __float2bfloat16_rn(w[(static_cast<long long>(co) * c_in + ci) * taps + (taps - 1 - t)]);
+        }
     }
 }
 
@@ -232,8 +256,10 @@ extern "C" int im2im_upsample2x_bilinear_bf16(const void* d_x, int32_t B, int32_
 }
 
 extern "C" int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias, int32_t B,
-                                      int32_t H, int32_t W, int32_t c_mid, int32_t n_out, float* d_out, void* stream) {
-    if (B <= 0 || H <= 0 || W <= 0 || c_mid <= 0 || c_mid % 8) return fail(IM2IM_ERANGE, "head: bad shape");
+                                      int32_t H, int32_t W, int32_t c_mid, int32_t c_stride, int32_t n_out,
+                                      float* d_out, void* stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || c_mid <= 0 || c_mid % 8 || c_stride < c_mid || c_stride % 8)
+        return fail(IM2IM_ERANGE, "head: bad shape");
     if (!d_x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "null tensor");
     const size_t smem = sizeof(float) * 9 * c_mid * n_out;
     if (smem > 48 * 1024) return fail(IM2IM_ERANGE, "head: weights do not fit shared memory");
@@ -242,10 +268,20 @@ extern "C" int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, co
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(d_x);
     switch (n_out) {
-        case 3: head_conv_kernel<3><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, d_out); break;
-        case 6: head_conv_kernel<6><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, d_out); break;
-        case 9: head_conv_kernel<9><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, d_out); break;
+        case 3: head_conv_kernel<3><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, c_stride, d_out); break;
+        case 6: head_conv_kernel<6><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, c_stride, d_out); break;
+        case 9: head_conv_kernel<9><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, c_stride, d_out); break;
         default: return fail(IM2IM_ENOTSUP, "head: n_out=%d (3*C_out with C_out in 1..3 supported)", n_out);
     }
     return check_launch("head_conv_kernel");
+}
+
+extern "C" int im2im_pack_conv_weights(const float* d_weight, int32_t c_out, int32_t c_in, int32_t taps, void* d_out_fwd,
+                                       void* d_out_bwd, void* stream) {
+    if (c_out <= 0 || c_in <= 0 || (taps != 9 && taps != 1)) return fail(IM2IM_EINVAL, "pack_conv_weights: bad shape");
+    if (!d_weight || !d_out_fwd) return fail(IM2IM_EINVAL, "pack_conv_weights: null tensor");
+    const long long n = static_cast<long long>(c_out) * c_in * taps * (d_out_bwd ? 2 : 1);
+    pack_conv_weights_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_weight, c_out, c_in, taps, static_cast<__nv_bfloat16*>(d_out_fwd), static_cast<__nv_bfloat16*>(d_out_bwd));
+    return check_launch("pack_conv_weights_kernel");
 }

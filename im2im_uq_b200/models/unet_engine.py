@@ -108,7 +108,7 @@ class UNetInferenceEngine:
         hw, hb = self.head
         n_out = hw.shape[0]
         y = torch.empty((B, n_out, H, W), dtype=torch.float32, device=x.device)
-        _lib.check(lib.im2im_head_conv3x3_f32(x.data_ptr(), hw.data_ptr(), hb.data_ptr(), B, H, W, C, n_out,
+        _lib.check(lib.im2im_head_conv3x3_f32(x.data_ptr(), hw.data_ptr(), hb.data_ptr(), B, H, W, C, C, n_out,
                                               y.data_ptr(), _stream(x.device)), "im2im_head_conv3x3_f32")
         return y.view(B, 3, self.c_out, H, W)
 

@@ -41,8 +41,15 @@ class _ConvBN:
         self.c_out, self.c_in = conv.weight.shape[0], conv.weight.shape[1]
 
     def pack(self):
-        self.w_fwd = pack_conv_weight(self.conv.weight)
-        self.w_bwd = pack_dgrad_weight(self.conv.weight)
+        """fp32 master weight -> the two bf16 GEMM operands, one kernel (buffers are reused across steps)."""
+        w = self.conv.weight.detach()
+        if getattr(self, "w_fwd", None) is None or self.w_fwd.device != w.device:
+            self.w_fwd = torch.empty((self.c_out, 9, self.c_in), dtype=torch.bfloat16, device=w.device)
+            self.w_bwd = torch.empty((self.c_in, 9, self.c_out), dtype=torch.bfloat16, device=w.device)
+        wc = w if w.is_contiguous() else w.contiguous()
+        with torch.cuda.device(w.device):
+            _lib.check(_lib.load().im2im_pack_conv_weights(wc.data_ptr(), self.c_out, self.c_in, 9, self.w_fwd.data_ptr(),
+                                                           self.w_bwd.data_ptr(), _st(w.device)), "pack_conv_weights")
 
 
 class UNetTrainEngine:
@@ -178,15 +185,14 @@ class UNetTrainEngine:
             b_pad[:self.c_mid] = self.out_conv.bias.detach().float()
             m = conv_igemm(y, w_pad, b_pad, relu=False)
             ctx["y_last"], ctx["m"], ctx["w_out_pad"] = y, m, w_pad
-            # head (CUDA cores): weights zero-padded to the 64-channel row stride of m
-            hw_ = torch.cat([self.head.lower.weight, self.head.prediction.weight, self.head.upper.weight], 0).detach().float()
-            hw_pad = torch.zeros((self.n_out, 64, 3, 3), dtype=torch.float32, device=dev)
-            hw_pad[:, :self.c_mid] = hw_
+            # head (CUDA cores)
+            hw_ = torch.cat([self.head.lower.weight, self.head.prediction.weight, self.head.upper.weight], 0).detach().float().contiguous()
             hb = torch.cat([self.head.lower.bias, self.head.prediction.bias, self.head.upper.bias], 0).detach().float().contiguous()
             out = torch.empty((B, self.n_out, H, W), dtype=torch.float32, device=dev)
-            _lib.check(lib.im2im_head_conv3x3_f32(m.data_ptr(), hw_pad.data_ptr(), hb.data_ptr(), B, H, W, 64,
+            # m has a 64-channel row stride (upper 32 are zero padding); the head reads only the 32 real channels
+            _lib.check(lib.im2im_head_conv3x3_f32(m.data_ptr(), hw_.data_ptr(), hb.data_ptr(), B, H, W, self.c_mid, 64,
                                                   self.n_out, out.data_ptr(), _st(dev)), "head_conv")
-            ctx["head_w"] = hw_.contiguous()
+            ctx["head_w"] = hw_
         return out.view(B, 3, self.n_out // 3, H, W), ctx
 
     # ------------------------------------------------------------------------------------------- backward

@@ -1,0 +1,96 @@
+"""GPU (-m gpu): the native training step (tcgen05 forward/dgrad/wgrad + fused BN/loss/Adam) end to end, driven through the
+reference's own loop shape (forward -> loss_fn -> backward -> optimizer.step, core/scripts/train.py:152-162), against
+PyTorch fp32 autograd through the same modules.
+
+Tolerance rationale: operands/activations are bf16.  At random init the pinball loss has sign-valued gradients, so even
+torch's own bf16 autocast deviates from its fp32 gradients by ~0.4 (median relative error) - that run is used as the
+yardstick: the native engine must be at least as close to fp32 as autocast is, its loss must match to 1e-3, and the loss
+trajectory over Adam steps must track torch's within 3 %."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PARAMS = dict(uncertainty_type="quantiles", q_lo=0.05, q_hi=0.95, q_lo_weight=1.0, q_hi_weight=1.0, mse_weight=1.0)
+
+
+def _build():
+    from core.models.add_uncertainty import add_uncertainty
+    from core.models.trunks.unet import UNet
+    torch.manual_seed(0)
+    return add_uncertainty(UNet(1, 1), PARAMS).to("cuda:0").train()
+
+
+def _grads(model, x, y, native, autocast=False):
+    model.use_native_training = native
+    model.zero_grad(set_to_none=True)
+    if autocast:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = model(x)
+        pred = pred.float()
+    else:
+        pred = model(x)
+    loss = model.loss_fn(pred, y)
+    loss.backward()
+    return pred.detach(), loss.item(), {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+
+
+def _rel(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def test_native_step_is_as_close_to_fp32_as_bf16_autocast():
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = torch.Generator(device="cuda:0").manual_seed(1)
+        x = torch.randn(8, 1, 96, 96, device="cuda:0", generator=g)
+        y = x + 0.3 * torch.randn(8, 1, 96, 96, device="cuda:0", generator=g)
+        p_ref, l_ref, g_ref = _grads(_build(), x, y, native=False)
+        p_ac, l_ac, g_ac = _grads(_build(), x, y, native=False, autocast=True)
+        model = _build()
+        p_nat, l_nat, g_nat = _grads(model, x, y, native=True)
+        assert "_native_train_engine" in model.__dict__            # the CUDA path ran, not the module graph
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert abs(l_nat - l_ref) <= 1e-3 * abs(l_ref)
+    assert _rel(p_nat, p_ref) <= max(6e-2, 1.2 * _rel(p_ac, p_ref))
+    names = [n for n in g_ref if g_ref[n].norm() > 1e-6]
+    err_nat = np.array([_rel(g_nat[n], g_ref[n]) for n in names])
+    err_ac = np.array([_rel(g_ac[n], g_ref[n]) for n in names])
+    assert np.median(err_nat) <= max(0.25, 1.2 * np.median(err_ac)), (np.median(err_nat), np.median(err_ac))
+    assert err_nat.max() <= max(0.8, 1.5 * err_ac.max())
+    # exactly-zero gradient for conv biases that feed a BatchNorm (documented deviation); torch has ~1e-9 noise there
+    for n, gr in g_nat.items():
+        if n.endswith("double_conv.0.bias") or n.endswith("double_conv.3.bias"):
+            assert float(gr.abs().max()) == 0.0 and float(g_ref[n].abs().max()) < 1e-5
+
+
+def test_loss_trajectory_tracks_torch_adam():
+    from im2im_uq_b200.models.unet_train import FusedAdam
+    g = torch.Generator(device="cuda:0").manual_seed(2)
+    x = torch.randn(4, 1, 64, 64, device="cuda:0", generator=g)
+    y = x + 0.3 * torch.randn(4, 1, 64, 64, device="cuda:0", generator=g)
+    m_ref, m_nat = _build(), _build()
+    m_ref.use_native_training = False
+    opt_ref = torch.optim.Adam(m_ref.parameters(), lr=1e-3)
+    opt_nat = FusedAdam(m_nat.parameters(), lr=1e-3)
+    for it in range(6):
+        losses = []
+        for model, opt in ((m_ref, opt_ref), (m_nat, opt_nat)):
+            opt.zero_grad()
+            loss = model.loss_fn(model(x), y)   # the reference's loop: train.py:152-153
+            loss.backward()                     # train.py:160
+            opt.step()                          # train.py:162
+            losses.append(loss.item())
+        assert abs(losses[1] - losses[0]) <= 3e-2 * abs(losses[0]), (it, losses)
+    assert losses[1] < 0.5 * 2.1                # and it actually learns
+    # BatchNorm running statistics advanced like torch's
+    for (n1, b1), (n2, b2) in zip(m_ref.named_buffers(), m_nat.named_buffers()):
+        # exact parity of the update rule is in test_train_kernels_gpu; here the bf16 and fp32 trajectories have drifted
+        # apart for 6 optimizer steps, so only the variances (positive, O(1) scale) are compared, loosely
+        if b1 is not None and "running_var" in n1:
+            assert _rel(b2, b1) <= 0.3, (n1, _rel(b2, b1))
+        if b1 is not None and "num_batches" in n1:
+            assert int(b1) == int(b2) == 6
