@@ -248,6 +248,73 @@ def device_decide_fn(px: int, config: dict, result: Optional[torch.Tensor] = Non
     return decide
 
 
+class RcpsGraph:
+    """The device side of one calibration captured ONCE into a CUDA graph and replayed: zero the outputs, the one-pass
+    miss-count kernel, (multi-GPU) the NCCL all-reduce of the per-lambda totals, the device-side stop decision and the
+    fp32 loss-table kernel.  Replaying removes the ~10 host launches per calibration, which matters once the kernel
+    itself takes a fraction of a millisecond (8 GPUs on a 10k-image set).  Scores must stay resident and unchanged in
+    shape; their contents may change between replays.
+
+        plan = RcpsGraph(outputs, labels, config, group=None, n_total=None)
+        lhat, stop, decided = plan.run()        # decided False -> a column fell in the guard band, call plan.replay_on_host()
+    """
+
+    def __init__(self, outputs: torch.Tensor, labels: torch.Tensor, config: dict, group=None, n_total=None):
+        assert outputs.is_cuda and labels.is_cuda
+        self.config, self.group = config, group
+        self.outputs, self.labels = outputs, labels
+        dev = outputs.device
+        self.lambdas, self.dlambda, lam_prime, self.default_lhat = sweep.lambda_grid(config)
+        if not bool((lam_prime[1:] >= lam_prime[:-1]).all()) or not bool(torch.isfinite(lam_prime).all()):
+            raise ValueError("RcpsGraph needs a finite ascending lambda grid")
+        self.lam_dev = lam_prime.to(dev)
+        n, L = outputs.shape[0], lam_prime.numel()
+        self.px = labels[0].numel()
+        self.n_total = n_total if n_total is not None else n
+        self.counts = torch.empty((n, L), dtype=torch.int32, device=dev)
+        self.totals = torch.empty((L,), dtype=torch.int64, device=dev)
+        self.table = torch.empty((n, L), dtype=torch.float32, device=dev)
+        self.result = torch.empty(4, dtype=torch.int32, device=dev)
+        self.result_host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+        self._decide = device_decide_fn(self.px, config, result=self.result)
+        self._enqueue()                      # warm-up outside capture (lazy module loads, NCCL channel setup)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+        self.kernels_per_replay = _lib.launch_count() - before  # libim2im_uq kernels inside one replay
+
+    def _enqueue(self):
+        rcps.miss_counts(self.outputs, self.labels, self.lam_dev, counts=self.counts, totals=self.totals, zero=True)
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.totals, op=dist.ReduceOp.SUM, group=self.group)
+        self._decide(self.totals, self.n_total, read=False)
+        rcps.loss_table(self.counts, self.px, out=self.table, first_visited_dev=self.result[3:])
+
+    def run(self):
+        self.graph.replay()
+        self.result_host.copy_(self.result, non_blocking=True)
+        torch.cuda.current_stream(self.result.device).synchronize()
+        stop, decided = int(self.result_host[0]), bool(self.result_host[1])
+        lhat = self.lambdas[stop] if stop >= 0 else self.default_lhat
+        return lhat, stop, decided
+
+    def replay_on_host(self, stats: Optional[dict] = None):
+        """Guard-band case: the reference's own expression on the ambiguous columns (sweep.find_stop_index)."""
+        px = self.px
+
+        def column_to_losses(col):
+            return rcps.loss_table(col.reshape(-1, 1).contiguous(), px)[:, 0]
+
+        lhat, stop, visited = sweep.sweep_from_counts(self.counts, self.totals, px, self.config, column_to_losses,
+                                                      ascending=True, group=self.group, stats=stats,
+                                                      n_total=self.n_total, totals_already_reduced=True)
+        rcps.loss_table(self.counts, px, first_visited_col=max(stop, 0), out=self.table)
+        return lhat, stop
+
+
 def rcps_sweep(outputs: torch.Tensor, labels: torch.Tensor, config: dict, device=None, group=None,
                verbose: bool = False, stats: Optional[dict] = None, n_total: Optional[int] = None):
     """lambda-hat and the loss table from head outputs (N,3,C,H,W) + labels (N,C,H,W), CPU- or CUDA-resident.

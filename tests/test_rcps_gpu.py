@@ -324,3 +324,24 @@ def test_two_rank_nccl_sweep():
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "NCCL_SWEEP_OK" in res.stdout
+
+
+def test_rcps_graph_replay_matches_reference(golden):
+    """The CUDA-graph plan (capture once, replay) gives the same lhat / table as the reference, replay after replay."""
+    cfg = dict(golden["config"], device="cuda:0")
+    out, lab = _dev(golden["outputs"]), _dev(golden["labels"])
+    plan = cm.RcpsGraph(out, lab, cfg)
+    for _ in range(3):
+        lhat, stop, decided = plan.run()
+        if not decided:
+            lhat, stop = plan.replay_on_host()
+        assert stop == int(golden["stop_idx"]) and np.float32(lhat.numpy()) == golden["lhat"]
+        assert np.array_equal(plan.table.cpu().numpy(), golden["calib_loss_table"])
+        assert np.array_equal(plan.counts.cpu().numpy(), golden["counts_prime"])
+    # new scores in the same buffers -> new answer from the same graph
+    out.copy_(out.flip(0)); lab.copy_(lab.flip(0))
+    lhat2, stop2, decided2 = plan.run()
+    if not decided2:
+        lhat2, stop2 = plan.replay_on_host()
+    assert stop2 == int(golden["stop_idx"])          # the stopping rule is permutation invariant
+    assert np.array_equal(plan.counts.cpu().numpy(), golden["counts_prime"][::-1])
