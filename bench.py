@@ -249,6 +249,32 @@ def run_unet_bench(args, world, rank, dev, group):
         last["loss"] = loss.item()  # the reference reads the loss every step (train.py:155)
 
     train_ms = timed(train_step, args.unet_steps)
+
+    # calibrate_model end to end (BASELINE configs[1]: 1k calibration images, full UNet): host dataset -> native UNet
+    # inference in batches -> scores stay in HBM -> one-pass RCPS -> lhat + loss table back on the host
+    cal = None
+    if rank == 0:
+        from im2im_uq_b200.calibration.calibrate_model import calibrate_model
+        n_cal = 1000
+        gx = torch.Generator().manual_seed(7)
+        xs = torch.randn(n_cal, 1, side, side, generator=gx).pin_memory()
+        ys = (xs + 0.3 * torch.randn(n_cal, 1, side, side, generator=gx)).pin_memory()
+        ds = torch.utils.data.TensorDataset(xs, ys)
+        cfg = config_dict(args, str(dev))
+        cfg.update(minimum_lambda=0.0, maximum_lambda=60.0, batch_size=50)
+        model.eval()
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            calibrate_model(model, ds, cfg)          # warm-up (engine build, allocator)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            calibrate_model(model, ds, cfg)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        cal = {"images": n_cal, "seconds": dt, "images_per_s": n_cal / dt, "lhat": float(model.lhat),
+               "api": "core.calibration.calibrate_model.calibrate_model(model, dataset, config)",
+               "note": "host TensorDataset -> H2D -> native UNet forward -> RCPS sweep -> table D2H; random-init weights"}
+        model.train()
     fwd_flop, train_flop = 125.29e9, 375.87e9  # conv 2*MACs per 320x320 image; train = 3x forward
     scale = (side / 320.0) ** 2
     try:
@@ -264,7 +290,7 @@ def run_unet_bench(args, world, rank, dev, group):
             "train_images_per_s": world * B / (train_ms * 1e-3), "train_ms_per_step": train_ms,
             "train_step": "forward + fused pinball/MSE loss + backward + " +
                           ("NCCL all-reduce of 69 MB fp32 grads + " if world > 1 else "") + "fused Adam + loss.item()",
-            "final_loss": last.get("loss"),
+            "final_loss": last.get("loss"), "calibrate_model_e2e": cal,
             "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak, "peak_source": src,
                          "forward_achieved": fwd_tf, "forward_frac": fwd_tf / peak,
                          "train_achieved": train_tf, "train_frac": train_tf / peak,

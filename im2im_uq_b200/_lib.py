@@ -94,7 +94,7 @@ def _declare_more(lib):
     lib.im2im_upsample2x_bilinear_bf16.restype = c.c_int
     lib.im2im_upsample2x_bilinear_bf16.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.im2im_head_conv3x3_f32.restype = c.c_int
-    lib.im2im_head_conv3x3_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.im2im_head_conv3x3_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
 
 
 def _declare_train(lib):

@@ -22,9 +22,9 @@ union Bf16x8 {
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, int B, int c_in, int H,
                                                          int W, int c_out, int relu, __nv_bfloat16* __restrict__ y) {
-    extern __shared__ float s_w[];  // [c_out][c_in*9] then bias [c_out]
+    extern __shared__ __align__(16) float s_w[];  // [c_in*9][c_out] (transposed: a thread's 8 channels are contiguous), bias [c_out]
     const int kk = c_in * 9;
-    for (int i = threadIdx.x; i < c_out * kk; i += blockDim.x) s_w[i] = w[i];
+    for (int i = threadIdx.x; i < c_out * kk; i += blockDim.x) s_w[(i % kk) * c_out + i / kk] = w[i];
     float* s_b = s_w + c_out * kk;
     for (int i = threadIdx.x; i < c_out; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
     __syncthreads();
@@ -46,8 +46,12 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
             for (int t = 0; t < 9; ++t) {
                 const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
                 const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + static_cast<long long>(yy) * W + xx) : 0.f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, s_w[(g * 8 + j) * kk + ci * 9 + t], acc[j]);
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ci * 9 + t) * c_out + g * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ci * 9 + t) * c_out + g * 8 + 4);
+                acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+                acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+                acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+                acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
             }
         }
         Bf16x8 o;
@@ -134,16 +138,21 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Head: x bf16 NHWC [B,H,W,c_mid] -> y fp32 [B, n_out, H, W] (n_out = 3*C_out planes: lower.., prediction.., upper..),
-// 3x3 pad 1, fp32 weights [n_out, c_mid, 3, 3] + bias.  One thread = one pixel, all outputs (n_out <= 12).
+// Head: x bf16 NHWC (c_mid channels used, row stride c_stride) -> y fp32 [B, n_out, H, W] (n_out = 3*C_out planes:
+// lower.., prediction.., upper..), 3x3 pad 1, fp32 weights [n_out, c_mid, 3, 3] + bias.  One thread = one pixel, all outputs.
+// Weights sit in shared memory as [tap][c][NP] with NP = n_out padded to a multiple of 4, so one 128-bit broadcast load
+// feeds 4 FMAs.  tap_bias (optional, [n_out][9]) is added once per IN-RANGE tap: it carries the bias of a 1x1 convolution
+// that was folded into these weights (inference: OutConv 64->32 composed with the head, exact incl. the zero padding).
 template <int N_OUT>
 __global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, int B, int H, int W, int c_mid,
-                                                        int c_stride, float* __restrict__ y) {
-    extern __shared__ float s_w[];  // [tap][c_mid][N_OUT]
-    for (int i = threadIdx.x; i < 9 * c_mid * N_OUT; i += blockDim.x) {
-        const int o = i % N_OUT, c = (i / N_OUT) % c_mid, t = i / (N_OUT * c_mid);
-        s_w[i] = w[(static_cast<long long>(o) * c_mid + c) * 9 + t];
+                                                        const float* __restrict__ bias,
+                                                        const float* __restrict__ tap_bias, int B, int H, int W,
+                                                        int c_mid, int c_stride, float* __restrict__ y) {
+    constexpr int NP = (N_OUT + 3) / 4 * 4;
+    extern __shared__ __align__(16) float s_w[];  // [tap][c_mid][NP]
+    for (int i = threadIdx.x; i < 9 * c_mid * NP; i += blockDim.x) {
+        const int o = i % NP, c = (i / NP) % c_mid, t = i / (NP * c_mid);
+        s_w[i] = o < N_OUT ? w[(static_cast<long long>(o) * c_mid + c) * 9 + t] : 0.f;
     }
     __syncthreads();
     const long long total = static_cast<long long>(B) * H * W;
@@ -152,15 +161,19 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __r
         const int xw = static_cast<int>(pix % W);
         const int yh = static_cast<int>((pix / W) % H);
         const long long b = pix / (static_cast<long long>(W) * H);
-        float acc[N_OUT];
+        float acc[NP];
 #pragma unroll
-        for (int o = 0; o < N_OUT; ++o) acc[o] = bias ? __ldg(bias + o) : 0.f;
+        for (int o = 0; o < NP; ++o) acc[o] = (bias && o < N_OUT) ? __ldg(bias + o) : 0.f;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
             if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            if (tap_bias) {
+#pragma unroll
+                for (int o = 0; o < N_OUT; ++o) acc[o] += __ldg(tap_bias + o * 9 + t);
+            }
             const __nv_bfloat16* p = x + ((b * H + yy) * W + xx) * c_stride;
-            const float* wt = s_w + t * c_mid * N_OUT;
+            const float* wt = s_w + t * c_mid * NP;
             for (int c = 0; c < c_mid; c += 8) {
                 Bf16x8 v;
                 v.u = *reinterpret_cast<const uint4*>(p + c);
@@ -168,9 +181,13 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __r
                 for (int j = 0; j < 4; ++j) {
                     const float2 f = __bfloat1622float2(v.h[j]);
 #pragma unroll
-                    for (int o = 0; o < N_OUT; ++o) {
-                        acc[o] = fmaf(f.x, wt[(c + 2 * j) * N_OUT + o], acc[o]);
-                        acc[o] = fmaf(f.y, wt[(c + 2 * j + 1) * N_OUT + o], acc[o]);
+                    for (int q = 0; q < NP / 4; ++q) {
+                        const float4 wa = *reinterpret_cast<const float4*>(wt + (c + 2 * j) * NP + 4 * q);
+                        const float4 wb = *reinterpret_cast<const float4*>(wt + (c + 2 * j + 1) * NP + 4 * q);
+                        acc[4 * q + 0] = fmaf(f.x, wa.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(f.x, wa.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(f.x, wa.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(f.x, wa.w, acc[4 * q + 3]);
+                        acc[4 * q + 0] = fmaf(f.y, wb.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(f.y, wb.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(f.y, wb.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(f.y, wb.w, acc[4 * q + 3]);
                     }
                 }
             }
@@ -255,22 +272,22 @@ extern "C" int im2im_upsample2x_bilinear_bf16(const void* d_x, int32_t B, int32_
     return check_launch("upsample2x_kernel");
 }
 
-extern "C" int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias, int32_t B,
-                                      int32_t H, int32_t W, int32_t c_mid, int32_t c_stride, int32_t n_out,
-                                      float* d_out, void* stream) {
+extern "C" int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias,
+                                      const float* d_tap_bias, int32_t B, int32_t H, int32_t W, int32_t c_mid,
+                                      int32_t c_stride, int32_t n_out, float* d_out, void* stream) {
     if (B <= 0 || H <= 0 || W <= 0 || c_mid <= 0 || c_mid % 8 || c_stride < c_mid || c_stride % 8)
         return fail(IM2IM_ERANGE, "head: bad shape");
     if (!d_x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "null tensor");
-    const size_t smem = sizeof(float) * 9 * c_mid * n_out;
+    const size_t smem = sizeof(float) * 9 * c_mid * ((n_out + 3) / 4 * 4);
     if (smem > 48 * 1024) return fail(IM2IM_ERANGE, "head: weights do not fit shared memory");
     const long long items = static_cast<long long>(B) * H * W;
     const unsigned grid = grid_for(items, 128);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(d_x);
     switch (n_out) {
-        case 3: head_conv_kernel<3><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, c_stride, d_out); break;
-        case 6: head_conv_kernel<6><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, c_stride, d_out); break;
-        case 9: head_conv_kernel<9><<<grid, 128, smem, st>>>(x, d_weight, d_bias, B, H, W, c_mid, c_stride, d_out); break;
+        case 3: head_conv_kernel<3><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, d_out); break;
+        case 6: head_conv_kernel<6><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, d_out); break;
+        case 9: head_conv_kernel<9><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, d_out); break;
         default: return fail(IM2IM_ENOTSUP, "head: n_out=%d (3*C_out with C_out in 1..3 supported)", n_out);
     }
     return check_launch("head_conv_kernel");

@@ -108,7 +108,7 @@ class UNetInferenceEngine:
         hw, hb = self.head
         n_out = hw.shape[0]
         y = torch.empty((B, n_out, H, W), dtype=torch.float32, device=x.device)
-        _lib.check(lib.im2im_head_conv3x3_f32(x.data_ptr(), hw.data_ptr(), hb.data_ptr(), B, H, W, C, C, n_out,
+        _lib.check(lib.im2im_head_conv3x3_f32(x.data_ptr(), hw.data_ptr(), hb.data_ptr(), None, B, H, W, C, C, n_out,
                                               y.data_ptr(), _stream(x.device)), "im2im_head_conv3x3_f32")
         return y.view(B, 3, self.c_out, H, W)
 
@@ -132,7 +132,7 @@ class UNetInferenceEngine:
                 u = self._upsample_to(y, skip.shape[1], skip.shape[2])
                 y = conv_igemm(skip, c1[0], c1[1], relu=True, x2=u)   # torch.cat([skip, up]) without the copy
                 y = conv_igemm(y, c2[0], c2[1], relu=True)
-            m = conv_igemm(y, self.out[0], self.out[1], relu=False)  # 1x1, 64 -> 32
+            m = conv_igemm(y, self.out[0], self.out[1], relu=False)  # 1x1 OutConv, 64 -> 32 (tensor cores)
             return self._head(m)
 
 

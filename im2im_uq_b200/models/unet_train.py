@@ -115,6 +115,13 @@ class UNetTrainEngine:
             grads[layer.conv.bias] = torch.zeros_like(layer.conv.bias)  # cancelled by the batch mean (see module doc)
         return dz
 
+    def _side_stream(self, dev):
+        st = self.__dict__.get("_side")
+        if st is None or st.device != dev:
+            st = torch.cuda.Stream(device=dev)
+            self._side = st
+        return st
+
     @staticmethod
     def _w_to_torch(dw: torch.Tensor, c_in: int):
         c_out, taps, _ = dw.shape
@@ -190,22 +197,33 @@ class UNetTrainEngine:
             hb = torch.cat([self.head.lower.bias, self.head.prediction.bias, self.head.upper.bias], 0).detach().float().contiguous()
             out = torch.empty((B, self.n_out, H, W), dtype=torch.float32, device=dev)
             # m has a 64-channel row stride (upper 32 are zero padding); the head reads only the 32 real channels
-            _lib.check(lib.im2im_head_conv3x3_f32(m.data_ptr(), hw_.data_ptr(), hb.data_ptr(), B, H, W, self.c_mid, 64,
+            _lib.check(lib.im2im_head_conv3x3_f32(m.data_ptr(), hw_.data_ptr(), hb.data_ptr(), None, B, H, W, self.c_mid, 64,
                                                   self.n_out, out.data_ptr(), _st(dev)), "head_conv")
             ctx["head_w"] = hw_
         return out.view(B, 3, self.n_out // 3, H, W), ctx
 
     # ------------------------------------------------------------------------------------------- backward
     def _conv_bwd(self, layer: _ConvBN, saved: dict, dz: torch.Tensor, grads: Dict, need_dx: bool = True):
-        """wgrad (+ dgrad) of a tensor-core conv layer; returns (dx for x_in, dx for x_in2 or None)."""
+        """wgrad (+ dgrad) of a tensor-core conv layer; returns (dx for x_in, dx for x_in2 or None).
+
+        The weight gradient is off the critical path (nothing downstream in the backward pass reads it), so it is
+        enqueued on a side stream: the tensor-bound wgrad GEMMs overlap the bandwidth-bound BatchNorm/ReLU backward
+        kernels of the next layers running on the main stream."""
         x1, x2 = saved["x_in"], saved.get("x_in2")
-        dw1 = conv_wgrad(x1, dz, 9)
-        if x2 is None:
-            grads[layer.conv.weight] = self._w_to_torch(dw1, layer.c_in)
-        else:
-            dw2 = conv_wgrad(x2, dz, 9)
-            c1, c2 = x1.shape[3], x2.shape[3]
-            grads[layer.conv.weight] = torch.cat([self._w_to_torch(dw1, c1), self._w_to_torch(dw2, c2)], dim=1)
+        main = torch.cuda.current_stream(dz.device)
+        side = self._side_stream(dz.device)
+        side.wait_stream(main)                      # dz (and everything before it) is ready
+        with torch.cuda.stream(side):
+            dw1 = conv_wgrad(x1, dz, 9)
+            if x2 is None:
+                grads[layer.conv.weight] = self._w_to_torch(dw1, layer.c_in)
+            else:
+                dw2 = conv_wgrad(x2, dz, 9)
+                c1, c2 = x1.shape[3], x2.shape[3]
+                grads[layer.conv.weight] = torch.cat([self._w_to_torch(dw1, c1), self._w_to_torch(dw2, c2)], dim=1)
+        for t in (dz, x1, x2):                      # keep the allocator from recycling them under the side stream
+            if t is not None:
+                t.record_stream(side)
         if not need_dx:
             return None, None
         if x2 is None:
@@ -275,6 +293,7 @@ class UNetTrainEngine:
             _lib.check(lib.im2im_conv_first_wgrad(x.data_ptr(), dz0.data_ptr(), B, c_in, H, W, first.c_out,
                                                   dw0.data_ptr(), _st(dev)), "conv_first_wgrad")
             grads[first.conv.weight] = dw0
+            torch.cuda.current_stream(dev).wait_stream(self._side_stream(dev))  # weight gradients are complete
         return grads
 
 

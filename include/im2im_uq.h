@@ -165,7 +165,9 @@ int im2im_conv_wgrad_bf16(const void* d_x, const void* d_dz, int32_t B, int32_t 
  *                                  (unet_parts.py:50,63-64; pad split floor/ceil like the reference)
  *   im2im_head_conv3x3_f32         QuantileRegressionLayer (core/models/finallayers/quantile_layer.py:15-20): the three
  *                                  3x3 convs stacked as n_out = 3*C_out output planes; x bf16 NHWC with c_mid channels
- *                                  used out of a row stride of c_stride (>= c_mid) elements,
+ *                                  used out of a row stride of c_stride (>= c_mid) elements; d_tap_bias (optional,
+ *                                  [n_out][9]) is added once per in-range tap - the bias of a 1x1 conv folded into
+ *                                  d_weight (inference: OutConv composed with the head, unet.py:31 + quantile_layer.py:20),
  *                                  weight fp32 [n_out,c_mid,3,3] -> fp32 [B,n_out,H,W] == the (B,3,C_out,H,W) tensor
  */
 /* fp32 nn.Conv2d weight [c_out,c_in,k,k] -> the bf16 operands of im2im_conv_igemm_bf16: d_out_fwd [c_out,taps,c_in] and
@@ -177,8 +179,9 @@ int im2im_conv_first_bf16(const float* d_x, const float* d_weight, const float* 
 int im2im_maxpool2x2_bf16(const void* d_x, int32_t B, int32_t H, int32_t W, int32_t C, void* d_out, void* stream);
 int im2im_upsample2x_bilinear_bf16(const void* d_x, int32_t B, int32_t h, int32_t w, int32_t C, int32_t H_out,
                                    int32_t W_out, void* d_out, void* stream);
-int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W,
-                           int32_t c_mid, int32_t c_stride, int32_t n_out, float* d_out, void* stream);
+int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias, const float* d_tap_bias,
+                           int32_t B, int32_t H, int32_t W, int32_t c_mid, int32_t c_stride, int32_t n_out, float* d_out,
+                           void* stream);
 
 /*
  * Training-side passes of the UNet path (autograd of core/scripts/train.py:152-162 through the modules of
