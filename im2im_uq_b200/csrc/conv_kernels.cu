@@ -437,6 +437,213 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------ halo kernel
+// For the wide, shallow layers (64/128 channels at 320x320 / 160x160) the persistent kernel above is bound by L2->SM
+// traffic, not by the tensor pipe: every 128-pixel tile re-fetches its activation box once per tap (9 x 16 KB) plus the
+// weight slab.  Here a tile is 8 x 16 output pixels and ONE halo box (16 wide x 18 tall pixel rows of 64 channels,
+// 36 KB, origin (w0-1, h0-1), TMA zero fill = padding) is loaded per 64-channel block; the nine taps are nine UMMA
+// descriptors into that same box: start = base + ((dy+1)*16 + (dx+1)) * 128 B, 8-row core groups = one output row
+// (8 consecutive pixels), SBO = 16 rows * 128 B = 2048 B.  The hardware applies the 128B swizzle on absolute shared-memory
+// address bits, so the shifted (not 1024-byte aligned) starts read the TMA-written box correctly with base_offset = 0.  The layer's weights (9 * c_in * bn * 2 B <= 144 KB)
+// are loaded ONCE per CTA and stay resident in shared memory across the persistent tile loop.
+struct HaloParams {
+    int c_in1, c_in2, c_out;
+    int B, H, W;
+    int tiles_w, tiles_h;   // 8-wide, 16-tall tiles
+    int bn;
+    int a_stages;
+    int relu;
+    const float* bias;
+    __nv_bfloat16* out_bf16;
+    float* out_f32;
+};
+
+constexpr int kHaloW = 16, kHaloH = 18, kHaloTileW = 8, kHaloTileH = 16;
+constexpr int kHaloBytes = kHaloW * kHaloH * kKStep * 2;  // 36864
+
+__device__ __forceinline__ uint64_t make_sw128_desc_halo(const void* smem_ptr) {
+    const uint32_t addr = smem_u32(smem_ptr);
+    uint64_t desc = 0;
+    desc |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+    desc |= static_cast<uint64_t>(1) << 16;                       // LBO (ignored, swizzled K-major)
+    desc |= static_cast<uint64_t>((kHaloW * 128) >> 4) << 32;     // SBO: next output row = 16 pixel rows further
+    desc |= static_cast<uint64_t>(1) << 46;                       // descriptor version
+    // base_offset stays 0: measured on B200 (tools/halo_debug.py) - the 128B swizzle is applied on absolute shared-memory
+    // address bits, so a start that is not 1024-byte aligned reads TMA-written data correctly as is; setting
+    // base_offset = (addr >> 7) & 7 breaks every tap with dx != -1.
+    desc |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
+    return desc;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
+                 const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int c_in = p.c_in1 + p.c_in2;
+    const int cblocks = c_in / kKStep;
+    const int b_tile_bytes = p.bn * kKStep * 2;
+    const int w_bytes = 9 * cblocks * b_tile_bytes;           // resident weights: [tap][cblock][bn rows x 128 B]
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* w_smem = base;
+    unsigned char* a_ring = base + w_bytes;                    // a_stages x 36 KB halo boxes
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_ring + static_cast<size_t>(p.a_stages) * kHaloBytes);
+    uint64_t* empty_bar = full_bar + p.a_stages;
+    uint64_t* w_bar = empty_bar + p.a_stages;
+    uint64_t* tmem_full = w_bar + 1;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t acc_cols = p.bn < 32 ? 32u : static_cast<uint32_t>(p.bn);
+    const uint32_t tmem_cols = 2 * acc_cols;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_x1);
+        if (p.c_in2 > 0) prefetch_tmap(&map_x2);
+        prefetch_tmap(&map_w);
+        for (int s = 0; s < p.a_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(w_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_smem, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int n_tiles_n = p.c_out / p.bn;
+    const int n_tiles_m = p.tiles_w * p.tiles_h * p.B;
+    // tiles of one N block are contiguous for a CTA so that the resident weights are loaded once: CTAs are split over
+    // the N blocks first (blockIdx.y), then stride over the pixel tiles
+    const int tn = blockIdx.y;
+    const int n0 = tn * p.bn;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // resident weights, once
+            mbar_arrive_expect_tx(w_bar, static_cast<unsigned>(w_bytes));
+            for (int tap = 0; tap < 9; ++tap)
+                for (int cb = 0; cb < cblocks; ++cb)
+                    tma_load_2d(w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes, &map_w, w_bar,
+                                tap * c_in + cb * kKStep, n0);
+            int stage = 0;
+            unsigned phase = 1;
+            for (int tile = blockIdx.x; tile < n_tiles_m; tile += gridDim.x) {
+                int t = tile;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                const int w0 = tw * kHaloTileW - 1, h0 = th * kHaloTileH - 1, b0 = t;
+                for (int cb = 0; cb < cblocks; ++cb) {
+                    mbar_wait(&empty_bar[stage], phase);
+                    unsigned char* dst = a_ring + static_cast<size_t>(stage) * kHaloBytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(kHaloBytes));
+                    const int c0 = cb * kKStep;
+                    if (c0 < p.c_in1) tma_load_4d(dst, &map_x1, &full_bar[stage], c0, w0, h0, b0);
+                    else tma_load_4d(dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0, h0, b0);
+                    if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(p.bn);
+            mbar_wait(w_bar, 0);
+            int stage = 0;
+            unsigned phase = 0;
+            unsigned acc_phase = 3u;
+            int buf = 0;
+            for (int tile = blockIdx.x; tile < n_tiles_m; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[buf], (acc_phase >> buf) & 1u);
+                acc_phase ^= 1u << buf;
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf) * acc_cols;
+                for (int cb = 0; cb < cblocks; ++cb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const unsigned char* a_src = a_ring + static_cast<size_t>(stage) * kHaloBytes;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3, dx = tap % 3;  // already offset by +1 (halo origin is (w0-1, h0-1))
+                        const uint64_t desc_a = make_sw128_desc_halo(a_src + (dy * kHaloW + dx) * 128);
+                        const uint64_t desc_b = make_sw128_desc(w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes);
+#pragma unroll
+                        for (int k = 0; k < kKStep / kUmmaK; ++k)
+                            umma_bf16(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
+                                      idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tmem_full[buf]);
+                buf ^= 1;
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int iw = row % kHaloTileW, ih = row / kHaloTileW;
+        unsigned full_phase = 0u;
+        int buf = 0;
+        for (int tile = blockIdx.x; tile < n_tiles_m; tile += gridDim.x) {
+            int t = tile;
+            const int tw = t % p.tiles_w; t /= p.tiles_w;
+            const int th = t % p.tiles_h; t /= p.tiles_h;
+            const int w = tw * kHaloTileW + iw, h = th * kHaloTileH + ih, b = t;
+            const bool in_range = (w < p.W) && (h < p.H);
+            const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
+            mbar_wait(&tmem_full[buf], (full_phase >> buf) & 1u);
+            full_phase ^= 1u << buf;
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(buf) * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
+            for (int c = 0; c < p.bn; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_acc + static_cast<uint32_t>(c), v);
+                tmem_ld_wait();
+                if (c + 32 >= p.bn) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                }
+                if (in_range) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(v[j]);
+                        if (p.bias) x += __ldg(p.bias + n0 + c + j);
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        f[j] = x;
+                    }
+                    if (p.out_bf16) {
+                        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.c_out + n0 + c);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 pk;
+                            __nv_bfloat162 h0_ = __floats2bfloat162_rn(f[8 * q + 0], f[8 * q + 1]);
+                            __nv_bfloat162 h1_ = __floats2bfloat162_rn(f[8 * q + 2], f[8 * q + 3]);
+                            __nv_bfloat162 h2_ = __floats2bfloat162_rn(f[8 * q + 4], f[8 * q + 5]);
+                            __nv_bfloat162 h3_ = __floats2bfloat162_rn(f[8 * q + 6], f[8 * q + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0_); pk.y = *reinterpret_cast<uint32_t*>(&h1_);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2_); pk.w = *reinterpret_cast<uint32_t*>(&h3_);
+                            dst[q] = pk;
+                        }
+                    }
+                    if (p.out_f32) {
+                        float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.c_out + n0 + c);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                    }
+                }
+            }
+            buf ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[co, tap, ci] = sum over pixels p of dZ[p, co] * X[p + shift(tap), ci]        (autograd of the conv above)
 // GEMM per CTA:  D[128 co][up to 256 (tap,ci) columns] += A * B^T with K = pixels.  Both operands are consumed
@@ -673,6 +880,43 @@ extern "C" int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void
     else m2 = m1;
     rc = make_weight_map(&mw, d_weight, c_out, taps * (c_in1 + c_in2), p.bn);
     if (rc) return rc;
+    // wide shallow layers: halo kernel (one activation box per channel block, taps via shifted descriptors, resident weights)
+    static const bool no_halo = (getenv("IM2IM_CONV_NO_HALO") != nullptr);
+    if (!no_halo && taps == 9 && W % kHaloTileW == 0 && H % kHaloTileH == 0) {
+        const int c_in = c_in1 + c_in2;
+        int hbn = 0;
+        for (int cand : {128, 64})
+            if (hbn == 0 && c_out % cand == 0 && 9ll * c_in * cand * 2 <= 147456) hbn = cand;
+        if (hbn != 0) {
+            HaloParams h;
+            h.c_in1 = c_in1; h.c_in2 = c_in2; h.c_out = c_out; h.B = B; h.H = H; h.W = W;
+            h.tiles_w = W / kHaloTileW; h.tiles_h = H / kHaloTileH; h.bn = hbn; h.relu = relu; h.bias = d_bias;
+            h.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16); h.out_f32 = d_out_f32;
+            const int w_bytes = 9 * c_in * hbn * 2;
+            h.a_stages = (220 * 1024 - w_bytes) / kHaloBytes;
+            if (h.a_stages > 4) h.a_stages = 4;
+            if (h.a_stages >= 2) {
+                CUtensorMap h1, h2, hw;
+                rc = make_act_map(&h1, d_x1, B, H, W, c_in1, kHaloW, kHaloH, 1);
+                if (rc) return rc;
+                if (c_in2 > 0) { rc = make_act_map(&h2, d_x2, B, H, W, c_in2, kHaloW, kHaloH, 1); if (rc) return rc; }
+                else h2 = h1;
+                rc = make_weight_map(&hw, d_weight, c_out, taps * c_in, hbn);
+                if (rc) return rc;
+                const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * kHaloBytes +
+                                     (2 * h.a_stages + 5) * sizeof(uint64_t) + 16 + 1024;
+                IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+                const int n_blocks_n = c_out / hbn;
+                const long long m_tiles = static_cast<long long>(h.tiles_w) * h.tiles_h * B;
+                long long gx = sm_count() / n_blocks_n;
+                if (gx < 1) gx = 1;
+                if (gx > m_tiles) gx = m_tiles;
+                dim3 hgrid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks_n));
+                conv_halo_kernel<<<hgrid, kConvThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h2, hw, h);
+                return check_launch("conv_halo_kernel");
+            }
+        }
+    }
     const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + (2 * p.stages + 4) * sizeof(uint64_t) + 16 + 1024;
     static const bool use_v1 = (getenv("IM2IM_CONV_V1") != nullptr);  // bring-up switch: one tile per CTA
     if (use_v1) {

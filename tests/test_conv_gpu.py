@@ -45,6 +45,9 @@ def _ref_and_got(B, H, W, c1, c2, cout, taps, relu, bias, out_dtype, seed=0):
     (2, 16, 8, 64, 0, 32, 1),        # 1x1 OutConv (64 -> 32)
     (1, 320, 320, 64, 0, 64, 9),     # the reference's full-resolution layer
     (5, 20, 20, 512, 512, 512, 9),   # up1 first conv (1024 -> 512), batch not a multiple of the box
+    (2, 48, 40, 64, 0, 128, 9),      # halo kernel, resident 64x128 weights (bn = 128)
+    (1, 32, 16, 128, 0, 128, 9),     # halo kernel, two N blocks of 64 (weights of one block resident per CTA)
+    (3, 16, 8, 64, 64, 64, 9),       # halo kernel with concatenated inputs, single tile per image
 ])
 def test_conv_matches_fp32_reference(shape):
     B, H, W, c1, c2, cout, taps = shape

@@ -18,7 +18,11 @@ def step():
     opt.zero_grad(); loss = model.loss_fn(model(x), y); loss.backward(); opt.step(); return loss
 for _ in range(2): step()
 torch.cuda.synchronize(); t = time.perf_counter()
-for _ in range(steps): l = step()
-l.item(); torch.cuda.synchronize()
+per = []
+for _ in range(steps):
+    t1 = time.perf_counter(); l = step(); l.item(); per.append((time.perf_counter() - t1) * 1e3)
+torch.cuda.synchronize()
 dt = (time.perf_counter() - t) / steps
+print("per-step ms:", " ".join(f"{p:.1f}" for p in per), "| max mem GB", round(torch.cuda.max_memory_allocated() / 1e9, 2),
+      "reserved", round(torch.cuda.memory_reserved() / 1e9, 2))
 print(f"native train step B={B} {side}x{side}: {dt * 1e3:.2f} ms  {B / dt:.0f} img/s  loss {l.item():.4f}")
