@@ -20,7 +20,11 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 IM2IM_RCPS_ZERO_OUTPUTS = 1
 IM2IM_RCPS_FORCE_GENERIC = 2
-IM2IM_HEAD_QUANTILES = 0
+IM2IM_HEAD_QUANTILES = 0      # (lower, pred, upper): quantiles, quantiles_l1, inn
+IM2IM_HEAD_RESIDUAL = 1       # (pred, |residual|): residual_magnitude, residual_magnitude_l1
+IM2IM_HEAD_GAUSSIAN = 2       # (mean, variance)
+IM2IM_HEAD_SOFTMAX_SETS = 3   # (lower quantile, argmax, upper quantile) from im2im_softmax_sets
+THREE_PLANE_HEADS = (IM2IM_HEAD_QUANTILES, IM2IM_HEAD_SOFTMAX_SETS)
 IM2IM_RCPS_MAX_LAMBDAS = 8192
 
 _lib = None
@@ -66,6 +70,10 @@ def _declare(lib):
     lib.im2im_rcps_loss_table.argtypes = [vp, i64, i32, i64, i32, vp, vp]
     lib.im2im_quantile_nested_sets.restype = c.c_int
     lib.im2im_quantile_nested_sets.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, f32, i32, vp, vp, vp]
+    lib.im2im_nested_sets.restype = c.c_int
+    lib.im2im_nested_sets.argtypes = [i32, vp, vp, vp, i64, i64, i64, i64, i64, f32, i32, vp, vp, vp]
+    lib.im2im_softmax_sets.restype = c.c_int
+    lib.im2im_softmax_sets.argtypes = [vp, i64, i32, i64, i64, i64, vp, vp]
     lib.im2im_rcps_miss_map.restype = c.c_int
     lib.im2im_rcps_miss_map.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32, i32, vp, u32, vp]
 
@@ -125,7 +133,8 @@ EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im
            "im2im_maxpool2x2_bf16", "im2im_upsample2x_bilinear_bf16", "im2im_head_conv3x3_f32",
            "im2im_channel_stats_bf16", "im2im_bn_finalize", "im2im_bn_apply_relu_bf16", "im2im_bn_relu_bwd_bf16",
            "im2im_maxpool2x2_bwd_bf16", "im2im_upsample2x_bilinear_bwd_bf16", "im2im_quantile_loss_f32",
-           "im2im_adam_step_f32", "im2im_head_bwd", "im2im_conv_first_wgrad"]
+           "im2im_adam_step_f32", "im2im_head_bwd", "im2im_conv_first_wgrad", "im2im_nested_sets",
+           "im2im_softmax_sets"]
 
 
 def load():

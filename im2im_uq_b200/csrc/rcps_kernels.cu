@@ -56,15 +56,37 @@ struct PixelQuery {
     bool active;
 };
 
-__device__ __forceinline__ PixelQuery make_query(float l, float p, float u, float y) {
+// torch.relu semantics (NaN propagates; clamp_min)
+__device__ __forceinline__ float t_relu(float x) { return (x != x) ? x : fmaxf(x, 0.f); }
+
+// Head kinds (include/im2im_uq.h).  Every head of the reference has the same shape after the outer clamp of
+// add_uncertainty.py:35-36:  upper = max(fl(fl(lam*d_up) + p), p+1e-6),  lower = min(fl(p - fl(lam*d_lo)), p-1e-6)
+// (fl(fl(-lam*d)+p) == fl(p - fl(lam*d)) bit for bit), only the widths differ:
+//   QUANTILES      (a,p,b) = (lower, pred, upper):  d_up = max(b, p+1e-6) - p,  d_lo = p - min(a, p-1e-6)
+//                  quantile_layer.py:39-42, quantile_l1_layer.py:39-42, inn_layer.py:35-38
+//   RESIDUAL       (p,b) = (pred, |residual|):      d_up = d_lo = b                residual_magnitude_layer.py:33-34
+//   GAUSSIAN       (p,b) = (mean, variance):        d_up = d_lo = sqrt(b)          gaussian_layer.py:31-32
+//   SOFTMAX_SETS   (a,p,b) = (lower quantile, argmax, upper quantile): d_up = relu(b-p), d_lo = relu(p-a)
+//                  softmax_layer.py:50-51
+template <int HEAD>
+__device__ __forceinline__ PixelQuery make_query(float a, float p, float b, float y) {
     const bool up = y > p;
-    const float U = up ? u : -l;
     PixelQuery q;
     q.P = up ? p : -p;
     q.Y = up ? y : -y;
     const float PP = __fadd_rn(q.P, 1e-6f);
-    q.active = (PP < q.Y) && (U == U);
-    q.d = __fsub_rn(fmaxf(U, PP), q.P);  // du or dl, >= 0 (NaN only when inactive)
+    if (HEAD == IM2IM_HEAD_QUANTILES) {
+        const float U = up ? b : -a;
+        q.active = (PP < q.Y) && (U == U);
+        q.d = __fsub_rn(fmaxf(U, PP), q.P);  // du or dl, >= 0 (NaN only when inactive)
+    } else if (HEAD == IM2IM_HEAD_SOFTMAX_SETS) {
+        const float U = up ? b : -a;
+        q.d = t_relu(__fsub_rn(U, q.P));
+        q.active = (PP < q.Y) && (q.d == q.d);
+    } else {
+        q.d = (HEAD == IM2IM_HEAD_GAUSSIAN) ? __fsqrt_rn(b) : b;  // torch.sqrt is correctly rounded; sqrt(<0) = NaN
+        q.active = (PP < q.Y) && (q.d == q.d);
+    }
     return q;
 }
 
@@ -82,6 +104,17 @@ __device__ __noinline__ int rank_bisect(float d, float P, float Y, const float* 
     return lo;
 }
 
+// Negative width (only reachable with the RESIDUAL head when a caller hands in a width plane that did not go through
+// abs()): the predicate is non-DEcreasing in lambda, i.e. true on a suffix of the grid.  Returns the first missed index.
+__device__ __noinline__ int rank_bisect_rising(float d, float P, float Y, const float* s_lam, int L) {
+    int lo = 0, hi = L;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__fadd_rn(__fmul_rn(s_lam[mid], d), P) < Y) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
 // Number of grid points at which the pixel is missed = index of the first lambda that covers it.
 // guess_scale/guess_bias map the real-valued crossing lam* = (Y-P)/d onto the (uniform) grid:
 // #{lam_j < lam*} = ceil((lam*-lam0)/dlam).  The guess g is then verified with the exact predicate at g-1 and g;
@@ -89,6 +122,7 @@ __device__ __noinline__ int rank_bisect(float d, float P, float Y, const float* 
 // shared load.
 // Returns the guess and sets `ok` when the verification passed (or the pixel can never miss); branch-free so that
 // the pixels of a thread interleave.  A failed verification is resolved by rank_bisect (rare).
+template <int HEAD>
 __device__ __forceinline__ int rank_guess(const PixelQuery& q, const float2* __restrict__ s_pair, int L,
                                           float guess_scale, float guess_bias, bool& ok) {
     float rcp;
@@ -109,17 +143,31 @@ __device__ __forceinline__ int rank_guess(const PixelQuery& q, const float2* __r
     const bool below_ok = missed(q, nb.x);   // missed at every grid point below g
     const bool above_ok = !missed(q, nb.y);  // covered from g upwards
     ok = !q.active || (below_ok && above_ok);
+    if (HEAD == IM2IM_HEAD_RESIDUAL) ok = ok && !(q.active && q.d < 0.f);  // negative width: resolve_slow
     return q.active ? g : 0;
+}
+
+// Slow path for a pixel whose guess failed verification.  Returns the rank for the falling histogram; a pixel with a
+// negative width is booked into the rising histogram instead (rise[k] = #pixels missed from index k upwards).
+template <int HEAD>
+__device__ __forceinline__ int resolve_slow(const PixelQuery& q, const float* s_lam, int L, unsigned* rise) {
+    if (HEAD == IM2IM_HEAD_RESIDUAL && q.d < 0.f) {
+        const int k2 = rank_bisect_rising(q.d, q.P, q.Y, s_lam, L);
+        if (k2 < L) { atomicAdd(&rise[k2], 1u); atomicAdd(&rise[L], 1u); }  // rise[L] = number of booked pixels
+        return 0;
+    }
+    return rank_bisect(q.d, q.P, q.Y, s_lam, L);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // hist[1..L] -> counts row (suffix sums), accumulate per-CTA totals, zero the histogram.  Consumer threads only.
-__device__ __forceinline__ void flush_image(unsigned* hist, unsigned long long* tot, unsigned* warp_sums, int L,
-                                            int* counts_row, bool exclusive, int ctid) {
+__device__ __forceinline__ void flush_image(unsigned* hist, unsigned* rise, unsigned long long* tot,
+                                            unsigned* warp_sums, int L, int* counts_row, bool exclusive, int ctid) {
     named_bar_sync(kFlushBarrier, kConsumerThreads);  // all histogram atomics of this image have landed
     const int per_thread = (L + kConsumerThreads - 1) / kConsumerThreads;
     const int r0 = ctid * per_thread;  // r = L-1-j : position counted from the top of the grid
     const int lane = ctid & 31, warp = ctid >> 5;
+    const bool any_rise = rise != nullptr && rise[L] != 0u;  // uniform: read after the barrier, reset after the next
     unsigned local = 0;
     for (int e = 0; e < per_thread; ++e) {
         const int r = r0 + e;
@@ -141,22 +189,31 @@ __device__ __forceinline__ void flush_image(unsigned* hist, unsigned long long* 
             run += hist[L - r];
             hist[L - r] = 0;
             const int j = L - 1 - r;
-            if (run != 0) {
-                if (exclusive) counts_row[j] = static_cast<int>(run);
-                else atomicAdd(&counts_row[j], static_cast<int>(run));
-                tot[j] += run;
+            unsigned val = run;
+            if (any_rise) {  // rare: pixels with a negative width are missed from rise-index k upwards
+                for (int k = 0; k <= j; ++k) val += rise[k];
+            }
+            if (val != 0) {
+                if (exclusive) counts_row[j] = static_cast<int>(val);
+                else atomicAdd(&counts_row[j], static_cast<int>(val));
+                tot[j] += val;
             }
         }
     }
     named_bar_sync(kFlushBarrier, kConsumerThreads);  // histogram is clean, warp_sums reusable
+    if (any_rise) {
+        for (int k = ctid; k <= L; k += kConsumerThreads) rise[k] = 0u;
+        named_bar_sync(kFlushBarrier, kConsumerThreads);
+    }
 }
 
-template <bool STAGED>
+template <bool STAGED, int HEAD>
 __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(const RcpsParams prm) {
+    constexpr int kFirstPlane = (HEAD == IM2IM_HEAD_RESIDUAL || HEAD == IM2IM_HEAD_GAUSSIAN) ? 1 : 0;  // 2-plane heads
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int L = prm.n_lambdas;
     // layout: [stage ring | STAGED only] [tot u64 x L] [mbarriers] [lambda pairs f32x2 x (L+1)] [lambda f32 x L]
-    //         [hist u32 x (L+1)] [warp sums]
+    //         [hist u32 x (L+1)] [warp sums] [rise u32 x (L+1) | RESIDUAL head only]
     unsigned char* cursor = smem_raw;
     float* ring = reinterpret_cast<float*>(cursor);
     if (STAGED) cursor += sizeof(float) * kStages * 4 * kTilePx;
@@ -172,6 +229,8 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
     unsigned* hist = reinterpret_cast<unsigned*>(cursor);
     cursor += sizeof(unsigned) * (L + 1);
     unsigned* warp_sums = reinterpret_cast<unsigned*>(cursor);
+    cursor += sizeof(unsigned) * kConsumerWarps;
+    unsigned* rise = (HEAD == IM2IM_HEAD_RESIDUAL) ? reinterpret_cast<unsigned*>(cursor) : nullptr;
 
     const int tid = threadIdx.x;
     for (int j = tid; j < L; j += kThreads) {
@@ -180,6 +239,7 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
     }
     for (int j = tid; j <= L; j += kThreads) {
         hist[j] = 0u;
+        if (HEAD == IM2IM_HEAD_RESIDUAL) rise[j] = 0u;
         s_pair[j] = make_float2(j > 0 ? prm.lambdas[j - 1] : -INFINITY, j < L ? prm.lambdas[j] : INFINITY);
     }
     if (STAGED && tid == 0) {
@@ -208,9 +268,9 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
                 const long long off = r * kTilePx;
                 const long long rem = prm.px - off;
                 const unsigned bytes = static_cast<unsigned>(rem < kTilePx ? rem : kTilePx) * 4u;
-                mbar_arrive_expect_tx(&full_bar[stage], 4u * bytes);
+                mbar_arrive_expect_tx(&full_bar[stage], (4u - kFirstPlane) * bytes);
 #pragma unroll
-                for (int pl = 0; pl < 4; ++pl)
+                for (int pl = kFirstPlane; pl < 4; ++pl)
                     bulk_g2s(ring + (stage * 4 + pl) * kTilePx, prm.plane[pl] + img * prm.stride[pl] + off, bytes,
                              &full_bar[stage]);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -243,10 +303,10 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
             mbar_wait(&full_bar[stage], phase);
             const int e0 = ctid * kPxPerThread;
             const bool have = e0 < npx;  // npx % 4 == 0 on this path: all four pixels or none
-            float4 vl, vp, vu, vy;
+            float4 vl = make_float4(0.f, 0.f, 0.f, 0.f), vp, vu, vy;
             if (have) {
                 const float* base = ring + stage * 4 * kTilePx + e0;
-                vl = *reinterpret_cast<const float4*>(base);
+                if (kFirstPlane == 0) vl = *reinterpret_cast<const float4*>(base);
                 vp = *reinterpret_cast<const float4*>(base + kTilePx);
                 vu = *reinterpret_cast<const float4*>(base + 2 * kTilePx);
                 vy = *reinterpret_cast<const float4*>(base + 3 * kTilePx);
@@ -262,13 +322,13 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
                 bool ok[4];
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                    q[m] = make_query(l[m], p[m], u[m], y[m]);
-                    k[m] = rank_guess(q[m], s_pair, L, guess_scale, guess_bias, ok[m]);
+                    q[m] = make_query<HEAD>(l[m], p[m], u[m], y[m]);
+                    k[m] = rank_guess<HEAD>(q[m], s_pair, L, guess_scale, guess_bias, ok[m]);
                 }
                 if (!(ok[0] && ok[1] && ok[2] && ok[3])) {  // rare: guess off by more than the checked window
 #pragma unroll
                     for (int m = 0; m < 4; ++m)
-                        if (!ok[m]) k[m] = rank_bisect(q[m].d, q[m].P, q[m].Y, s_lam, L);
+                        if (!ok[m]) k[m] = resolve_slow<HEAD>(q[m], s_lam, L, rise);
                 }
 #pragma unroll
                 for (int m = 0; m < 4; ++m)
@@ -276,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
             }
         } else {
             const long long off = static_cast<long long>(r) * kTilePx;
-            const float* gl = prm.plane[0] + img * prm.stride[0] + off;
+            const float* gl = prm.plane[kFirstPlane] + img * prm.stride[kFirstPlane] + off;  // 2-plane heads: unused
             const float* gp = prm.plane[1] + img * prm.stride[1] + off;
             const float* gu = prm.plane[2] + img * prm.stride[2] + off;
             const float* gy = prm.plane[3] + img * prm.stride[3] + off;
@@ -285,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
             for (int m = 0; m < kPxPerThread; ++m) {
                 const int e = m * kConsumerThreads + ctid;  // coalesced 4-byte loads
                 if (e < npx) {
-                    l[m] = ldg_stream_f32(gl + e); p[m] = ldg_stream_f32(gp + e);
+                    l[m] = kFirstPlane == 0 ? ldg_stream_f32(gl + e) : 0.f; p[m] = ldg_stream_f32(gp + e);
                     u[m] = ldg_stream_f32(gu + e); y[m] = ldg_stream_f32(gy + e);
                 } else {
                     l[m] = p[m] = u[m] = y[m] = 0.f;  // y == p: inactive, rank 0
@@ -296,17 +356,18 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
             bool ok[kPxPerThread];
 #pragma unroll
             for (int m = 0; m < kPxPerThread; ++m) {
-                q[m] = make_query(l[m], p[m], u[m], y[m]);
-                k[m] = rank_guess(q[m], s_pair, L, guess_scale, guess_bias, ok[m]);
+                q[m] = make_query<HEAD>(l[m], p[m], u[m], y[m]);
+                k[m] = rank_guess<HEAD>(q[m], s_pair, L, guess_scale, guess_bias, ok[m]);
             }
 #pragma unroll
             for (int m = 0; m < kPxPerThread; ++m) {
-                if (!ok[m]) k[m] = rank_bisect(q[m].d, q[m].P, q[m].Y, s_lam, L);
+                if (!ok[m]) k[m] = resolve_slow<HEAD>(q[m], s_lam, L, rise);
                 if (k[m] > 0) atomicAdd(&hist[k[m]], 1u);
             }
         }
         if (image_ends_here || it == n_my_tiles - 1) {
-            flush_image(hist, tot, warp_sums, L, prm.counts + img * L, image_started_here && image_ends_here, ctid);
+            flush_image(hist, rise, tot, warp_sums, L, prm.counts + img * L, image_started_here && image_ends_here,
+                        ctid);
         }
         if (++r == tpi32) { r = 0; ++img; image_started_here = true; }
     }
@@ -377,31 +438,49 @@ __global__ void __launch_bounds__(256) rcps_decide_kernel(const unsigned long lo
 __device__ __forceinline__ float t_min(float a, float b) { return (a != a) ? a : ((b != b) ? b : fminf(a, b)); }
 __device__ __forceinline__ float t_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
 
-__device__ __forceinline__ void nested_set(float l, float p, float u, float lam, float& lo2, float& up2, float& l1,
+// Endpoints of one pixel at one lambda, op for op as the reference computes them (head set function, then the outer
+// clamp of add_uncertainty.py:35-36).  l1/u1 are the in-place clamped planes of the quantile-type heads.
+template <int HEAD>
+__device__ __forceinline__ void nested_set(float a, float p, float b, float lam, float& lo2, float& up2, float& l1,
                                            float& u1) {
     const float pm = __fsub_rn(p, 1e-6f), pp = __fadd_rn(p, 1e-6f);
-    l1 = t_min(l, pm);
-    u1 = t_max(u, pp);
-    const float upper = __fadd_rn(__fmul_rn(lam, __fsub_rn(u1, p)), p);
-    const float lower = __fsub_rn(p, __fmul_rn(lam, __fsub_rn(p, l1)));
+    float upper, lower;
+    l1 = a;
+    u1 = b;
+    if (HEAD == IM2IM_HEAD_QUANTILES) {
+        l1 = t_min(a, pm);
+        u1 = t_max(b, pp);
+        upper = __fadd_rn(__fmul_rn(lam, __fsub_rn(u1, p)), p);
+        lower = __fsub_rn(p, __fmul_rn(lam, __fsub_rn(p, l1)));
+    } else if (HEAD == IM2IM_HEAD_SOFTMAX_SETS) {
+        lower = __fsub_rn(p, __fmul_rn(t_relu(__fsub_rn(p, a)), lam));   // softmax_layer.py:50
+        upper = __fadd_rn(p, __fmul_rn(t_relu(__fsub_rn(b, p)), lam));   // softmax_layer.py:51
+    } else {
+        const float w = (HEAD == IM2IM_HEAD_GAUSSIAN) ? __fsqrt_rn(b) : b;
+        upper = __fadd_rn(__fmul_rn(lam, w), p);                         // gaussian_layer.py:31 / residual :33
+        lower = __fadd_rn(__fmul_rn(-lam, w), p);                        // gaussian_layer.py:32 / residual :34
+    }
     up2 = t_max(upper, pp);
     lo2 = t_min(lower, pm);
 }
 
+template <int HEAD>
 __global__ void __launch_bounds__(256) nested_sets_kernel(float* lower, const float* __restrict__ pred, float* upper,
                                                           long long n_images, long long px, long long sl,
                                                           long long sp, long long su, float lam, int write_back,
                                                           float* __restrict__ lower_out,
                                                           float* __restrict__ upper_out) {
+    constexpr bool kThree = (HEAD == IM2IM_HEAD_QUANTILES || HEAD == IM2IM_HEAD_SOFTMAX_SETS);
     const long long total = n_images * px;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
         const long long i = e / px, k = e - i * px;
         float lo2, up2, l1, u1;
-        nested_set(lower[i * sl + k], ldg_stream_f32(pred + i * sp + k), upper[i * su + k], lam, lo2, up2, l1, u1);
+        nested_set<HEAD>(kThree ? lower[i * sl + k] : 0.f, ldg_stream_f32(pred + i * sp + k), upper[i * su + k], lam,
+                         lo2, up2, l1, u1);
         lower_out[e] = lo2;
         upper_out[e] = up2;
-        if (write_back) {  // the reference's in-place clamp of `output` (quantile_layer.py:39-40)
+        if (HEAD == IM2IM_HEAD_QUANTILES && write_back) {  // the reference's in-place clamp (quantile_layer.py:39-40)
             lower[i * sl + k] = l1;
             upper[i * su + k] = u1;
         }
@@ -409,12 +488,14 @@ __global__ void __launch_bounds__(256) nested_sets_kernel(float* lower, const fl
 }
 
 // map[k] += #{images in this block's slab whose pixel k is missed}; threads run along pixels (coalesced).
+template <int HEAD>
 __global__ void __launch_bounds__(256) miss_map_kernel(const float* __restrict__ lower, const float* __restrict__ pred,
                                                        const float* __restrict__ upper,
                                                        const float* __restrict__ label, long long n_images,
                                                        long long px, long long sl, long long sp, long long su,
                                                        long long sy, float lam, int images_per_slab,
                                                        int* __restrict__ map) {
+    constexpr bool kThree = (HEAD == IM2IM_HEAD_QUANTILES || HEAD == IM2IM_HEAD_SOFTMAX_SETS);
     const long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (k >= px) return;
     const long long i0 = static_cast<long long>(blockIdx.y) * images_per_slab;
@@ -422,8 +503,8 @@ __global__ void __launch_bounds__(256) miss_map_kernel(const float* __restrict__
     int acc = 0;
     for (long long i = i0; i < i1; ++i) {
         float lo2, up2, l1, u1;
-        nested_set(ldg_stream_f32(lower + i * sl + k), ldg_stream_f32(pred + i * sp + k),
-                   ldg_stream_f32(upper + i * su + k), lam, lo2, up2, l1, u1);
+        nested_set<HEAD>(kThree ? ldg_stream_f32(lower + i * sl + k) : 0.f, ldg_stream_f32(pred + i * sp + k),
+                         ldg_stream_f32(upper + i * su + k), lam, lo2, up2, l1, u1);
         const float y = ldg_stream_f32(label + i * sy + k);
         acc += ((lo2 > y) || (up2 < y)) ? 1 : 0;
     }
@@ -453,11 +534,102 @@ __global__ void __launch_bounds__(256) fraction_missed_kernel(const float* __res
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&counts[i], acc);
 }
 
-size_t hist_smem_bytes(bool staged, int L) {
+// Softmax head: logits -> (lower quantile, argmax prediction, upper quantile), the lambda-independent part of
+// softmax_nested_sets_from_output (softmax_layer.py:34-48); the lambda-dependent part (:50-51) is the SOFTMAX_SETS head
+// kind of the sweep / nested-set kernels.  One thread per pixel, classes strided by `sk` elements (coalesced across
+// pixels); K <= kMaxSoftmax values are held in registers so the logits are read from HBM once.
+constexpr int kMaxSoftmax = 64;
+
+template <int KMAX>
+__global__ void __launch_bounds__(256) softmax_sets_kernel(const float* __restrict__ logits, long long n_images, int K,
+                                                           long long inner, long long si, long long sk,
+                                                           float* __restrict__ sets) {
+    const long long total = n_images * inner;
+    const float fK = static_cast<float>(K);
+    const float step = static_cast<float>(1.0 / static_cast<double>(K));  // python float 1/K entering an fp32 op
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long i = e / inner, k0 = e - i * inner;
+        const float* src = logits + i * si + k0;
+        float v[KMAX];
+        float m = -INFINITY;
+        bool has_nan = false;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                v[k] = ldg_stream_f32(src + k * sk);
+                has_nan = has_nan || (v[k] != v[k]);
+                m = fmaxf(m, v[k]);
+            }
+        }
+        float ssum = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                v[k] = expf(__fsub_rn(v[k], m));
+                ssum = __fadd_rn(ssum, v[k]);
+            }
+        }
+        float cum = 0.f, best = -INFINITY;
+        int n_lo = 0, n_hi = 0, arg = 0;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                const float pk = __fdiv_rn(v[k], ssum);
+                cum = __fadd_rn(cum, pk);
+                n_lo += (cum <= 0.05f) ? 1 : 0;
+                n_hi += (cum <= 0.95f) ? 1 : 0;
+                if (pk > best) { best = pk; arg = k; }  // first maximal element, like torch.argmax
+            }
+        }
+        float lq, pr, uq;
+        if (has_nan) {
+            // a NaN logit makes the whole softmax row NaN: every `cumsum <= q` is false and torch.argmax returns the
+            // first NaN, i.e. class 0
+            lq = 0.f; uq = 0.f; pr = 0.f;
+        } else {
+            lq = __fdiv_rn(static_cast<float>(n_lo), fK);
+            uq = __fdiv_rn(static_cast<float>(n_hi), fK);
+            pr = __fdiv_rn(static_cast<float>(arg), fK);
+        }
+        if (pr == lq) lq = __fsub_rn(lq, step);   // softmax_layer.py:45
+        if (pr == uq) uq = __fadd_rn(uq, step);   // softmax_layer.py:46
+        lq = fminf(fmaxf(lq, 0.f), 1.f);          // :47-48
+        uq = fminf(fmaxf(uq, 0.f), 1.f);
+        float* dst = sets + i * 3 * inner + k0;
+        dst[0] = lq;
+        dst[inner] = pr;
+        dst[2 * inner] = uq;
+    }
+}
+
+size_t hist_smem_bytes(bool staged, int L, int head) {
     size_t b = staged ? sizeof(float) * kStages * 4 * kTilePx : 0;
     b += sizeof(unsigned long long) * L + sizeof(uint64_t) * 2 * kStages + sizeof(float2) * (L + 1) +
          sizeof(float) * L + sizeof(unsigned) * (L + 1) + sizeof(unsigned) * kConsumerWarps;
+    if (head == IM2IM_HEAD_RESIDUAL) b += sizeof(unsigned) * (L + 1);  // rising histogram (negative widths)
     return b;
+}
+
+bool head_known(int head) { return head >= IM2IM_HEAD_QUANTILES && head <= IM2IM_HEAD_SOFTMAX_SETS; }
+bool head_three_planes(int head) { return head == IM2IM_HEAD_QUANTILES || head == IM2IM_HEAD_SOFTMAX_SETS; }
+
+template <bool STAGED, int HEAD>
+int launch_hist(const RcpsParams& prm, size_t smem, long long grid, cudaStream_t st) {
+    IM2IM_CUDA_TRY(cudaFuncSetAttribute(rcps_hist_kernel<STAGED, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    rcps_hist_kernel<STAGED, HEAD><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(prm);
+    return check_launch(STAGED ? "rcps_hist_kernel<staged>" : "rcps_hist_kernel<generic>");
+}
+
+template <bool STAGED>
+int launch_hist_head(int head, const RcpsParams& prm, size_t smem, long long grid, cudaStream_t st) {
+    switch (head) {
+        case IM2IM_HEAD_QUANTILES: return launch_hist<STAGED, IM2IM_HEAD_QUANTILES>(prm, smem, grid, st);
+        case IM2IM_HEAD_RESIDUAL: return launch_hist<STAGED, IM2IM_HEAD_RESIDUAL>(prm, smem, grid, st);
+        case IM2IM_HEAD_GAUSSIAN: return launch_hist<STAGED, IM2IM_HEAD_GAUSSIAN>(prm, smem, grid, st);
+        default: return launch_hist<STAGED, IM2IM_HEAD_SOFTMAX_SETS>(prm, smem, grid, st);
+    }
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -473,7 +645,8 @@ extern "C" int im2im_rcps_miss_counts(const float* d_lower, const float* d_pred,
                                       const float* d_lambdas, int32_t n_lambdas, int32_t head_kind,
                                       int32_t* d_counts, unsigned long long* d_totals, uint32_t flags,
                                       void* stream) {
-    if (head_kind != IM2IM_HEAD_QUANTILES) return fail(IM2IM_ENOTSUP, "head_kind %d not implemented", head_kind);
+    if (!head_known(head_kind)) return fail(IM2IM_ENOTSUP, "head_kind %d not implemented", head_kind);
+    if (!head_three_planes(head_kind)) { d_lower = d_pred; stride_lower = stride_pred; }  // 2-plane heads: unused
     if (n_images < 0 || px < 0) return fail(IM2IM_EINVAL, "negative size (n_images=%lld px=%lld)",
                                             (long long)n_images, (long long)px);
     if (n_lambdas < 1 || n_lambdas > IM2IM_RCPS_MAX_LAMBDAS)
@@ -510,22 +683,16 @@ extern "C" int im2im_rcps_miss_counts(const float* d_lower, const float* d_pred,
     prm.counts = d_counts;
     prm.totals = d_totals;
 
-    if (fast && hist_smem_bytes(true, n_lambdas) > kMaxSmemOptin) fast = false;  // very long grids: no room for the ring
-    const size_t smem = hist_smem_bytes(fast, n_lambdas);
+    if (fast && hist_smem_bytes(true, n_lambdas, head_kind) > kMaxSmemOptin) fast = false;  // very long grids: no room for the ring
+    const size_t smem = hist_smem_bytes(fast, n_lambdas, head_kind);
     const int sms = sm_count();
     if (fast) {
-        IM2IM_CUDA_TRY(cudaFuncSetAttribute(rcps_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(smem)));
         const long long grid = prm.total_tiles < sms ? prm.total_tiles : sms;
-        rcps_hist_kernel<true><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(prm);
-        return check_launch("rcps_hist_kernel<staged>");
+        return launch_hist_head<true>(head_kind, prm, smem, grid, st);
     }
-    IM2IM_CUDA_TRY(cudaFuncSetAttribute(rcps_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
     const long long cap = 2ll * sms;
     const long long grid = prm.total_tiles < cap ? prm.total_tiles : cap;
-    rcps_hist_kernel<false><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(prm);
-    return check_launch("rcps_hist_kernel<generic>");
+    return launch_hist_head<false>(head_kind, prm, smem, grid, st);
 }
 
 extern "C" int im2im_rcps_loss_table(const int32_t* d_counts, int64_t n_images, int32_t n_lambdas, int64_t px,
@@ -567,28 +734,47 @@ extern "C" int im2im_rcps_decide(const unsigned long long* d_totals, int32_t n_l
     return check_launch("rcps_decide_kernel");
 }
 
-extern "C" int im2im_quantile_nested_sets(float* d_lower, const float* d_pred, float* d_upper, int64_t n_images,
-                                          int64_t px, int64_t stride_lower, int64_t stride_pred,
-                                          int64_t stride_upper, float lam, int32_t write_back_clamp,
-                                          float* d_lower_out, float* d_upper_out, void* stream) {
+extern "C" int im2im_nested_sets(int32_t head_kind, float* d_lower, const float* d_pred, float* d_upper,
+                                int64_t n_images, int64_t px, int64_t stride_lower, int64_t stride_pred,
+                                int64_t stride_upper, float lam, int32_t write_back_clamp, float* d_lower_out,
+                                float* d_upper_out, void* stream) {
+    if (!head_known(head_kind)) return fail(IM2IM_ENOTSUP, "head_kind %d not implemented", head_kind);
+    if (!head_three_planes(head_kind)) { d_lower = d_upper; stride_lower = stride_upper; }  // unused plane
     if (n_images < 0 || px < 0) return fail(IM2IM_EINVAL, "negative size");
     if (n_images == 0 || px == 0) return IM2IM_OK;
     if (!d_lower || !d_pred || !d_upper || !d_lower_out || !d_upper_out) return fail(IM2IM_EINVAL, "null plane");
     const long long n = static_cast<long long>(n_images) * px;
     const long long blocks = (n + 255) / 256;
     const long long cap = 16ll * sm_count();
-    nested_sets_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0,
-                         static_cast<cudaStream_t>(stream)>>>(d_lower, d_pred, d_upper, n_images, px, stride_lower,
-                                                              stride_pred, stride_upper, lam, write_back_clamp,
-                                                              d_lower_out, d_upper_out);
+    const unsigned grid = static_cast<unsigned>(blocks < cap ? blocks : cap);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define IM2IM_NS_LAUNCH(H)                                                                                          \
+    nested_sets_kernel<H><<<grid, 256, 0, st>>>(d_lower, d_pred, d_upper, n_images, px, stride_lower, stride_pred, \
+                                                stride_upper, lam, write_back_clamp, d_lower_out, d_upper_out)
+    switch (head_kind) {
+        case IM2IM_HEAD_QUANTILES: IM2IM_NS_LAUNCH(IM2IM_HEAD_QUANTILES); break;
+        case IM2IM_HEAD_RESIDUAL: IM2IM_NS_LAUNCH(IM2IM_HEAD_RESIDUAL); break;
+        case IM2IM_HEAD_GAUSSIAN: IM2IM_NS_LAUNCH(IM2IM_HEAD_GAUSSIAN); break;
+        default: IM2IM_NS_LAUNCH(IM2IM_HEAD_SOFTMAX_SETS); break;
+    }
+#undef IM2IM_NS_LAUNCH
     return check_launch("nested_sets_kernel");
+}
+
+extern "C" int im2im_quantile_nested_sets(float* d_lower, const float* d_pred, float* d_upper, int64_t n_images,
+                                          int64_t px, int64_t stride_lower, int64_t stride_pred,
+                                          int64_t stride_upper, float lam, int32_t write_back_clamp,
+                                          float* d_lower_out, float* d_upper_out, void* stream) {
+    return im2im_nested_sets(IM2IM_HEAD_QUANTILES, d_lower, d_pred, d_upper, n_images, px, stride_lower, stride_pred,
+                             stride_upper, lam, write_back_clamp, d_lower_out, d_upper_out, stream);
 }
 
 extern "C" int im2im_rcps_miss_map(const float* d_lower, const float* d_pred, const float* d_upper,
                                    const float* d_label, int64_t n_images, int64_t px, int64_t stride_lower,
                                    int64_t stride_pred, int64_t stride_upper, int64_t stride_label, float lam,
                                    int32_t head_kind, int32_t* d_map, uint32_t flags, void* stream) {
-    if (head_kind != IM2IM_HEAD_QUANTILES) return fail(IM2IM_ENOTSUP, "head_kind %d not implemented", head_kind);
+    if (!head_known(head_kind)) return fail(IM2IM_ENOTSUP, "head_kind %d not implemented", head_kind);
+    if (!head_three_planes(head_kind)) { d_lower = d_pred; stride_lower = stride_pred; }  // unused plane
     if (n_images < 0 || px < 0) return fail(IM2IM_EINVAL, "negative size");
     if (px == 0) return IM2IM_OK;
     if (!d_map) return fail(IM2IM_EINVAL, "null map");
@@ -604,8 +790,16 @@ extern "C" int im2im_rcps_miss_map(const float* d_lower, const float* d_pred, co
     if (slabs > 65535) slabs = 65535;
     const int per_slab = static_cast<int>((n_images + slabs - 1) / slabs);
     const unsigned by = static_cast<unsigned>((n_images + per_slab - 1) / per_slab);
-    miss_map_kernel<<<dim3(bx, by), 256, 0, st>>>(d_lower, d_pred, d_upper, d_label, n_images, px, stride_lower,
-                                                  stride_pred, stride_upper, stride_label, lam, per_slab, d_map);
+#define IM2IM_MM_LAUNCH(H)                                                                                     \
+    miss_map_kernel<H><<<dim3(bx, by), 256, 0, st>>>(d_lower, d_pred, d_upper, d_label, n_images, px, stride_lower, \
+                                                     stride_pred, stride_upper, stride_label, lam, per_slab, d_map)
+    switch (head_kind) {
+        case IM2IM_HEAD_QUANTILES: IM2IM_MM_LAUNCH(IM2IM_HEAD_QUANTILES); break;
+        case IM2IM_HEAD_RESIDUAL: IM2IM_MM_LAUNCH(IM2IM_HEAD_RESIDUAL); break;
+        case IM2IM_HEAD_GAUSSIAN: IM2IM_MM_LAUNCH(IM2IM_HEAD_GAUSSIAN); break;
+        default: IM2IM_MM_LAUNCH(IM2IM_HEAD_SOFTMAX_SETS); break;
+    }
+#undef IM2IM_MM_LAUNCH
     return check_launch("miss_map_kernel");
 }
 
@@ -628,4 +822,20 @@ extern "C" int im2im_fraction_missed_counts(const float* d_lower_edge, const flo
     fraction_missed_kernel<<<dim3(static_cast<unsigned>(bx), static_cast<unsigned>(n_images)), 256, 0, st>>>(
         d_lower_edge, d_upper_edge, d_label, px, stride_lower, stride_upper, stride_label, d_counts);
     return check_launch("fraction_missed_kernel");
+}
+
+extern "C" int im2im_softmax_sets(const float* d_logits, int64_t n_images, int32_t n_classes, int64_t inner,
+                                  int64_t stride_image, int64_t stride_class, float* d_sets, void* stream) {
+    if (n_images < 0 || inner < 0) return fail(IM2IM_EINVAL, "negative size");
+    if (n_classes < 1 || n_classes > kMaxSoftmax)
+        return fail(IM2IM_ERANGE, "n_classes=%d outside [1, %d]", n_classes, kMaxSoftmax);
+    if (n_images == 0 || inner == 0) return IM2IM_OK;
+    if (!d_logits || !d_sets) return fail(IM2IM_EINVAL, "null logits/sets");
+    const long long n = static_cast<long long>(n_images) * inner;
+    const long long blocks = (n + 255) / 256;
+    const long long cap = 8ll * sm_count();
+    softmax_sets_kernel<kMaxSoftmax><<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0,
+                                       static_cast<cudaStream_t>(stream)>>>(d_logits, n_images, n_classes, inner,
+                                                                            stride_image, stride_class, d_sets);
+    return check_launch("softmax_sets_kernel");
 }

@@ -31,8 +31,25 @@ extern "C" {
 #define IM2IM_ECUDA (-5)       /* a CUDA runtime call or launch failed; see im2im_last_error() */
 #define IM2IM_ENOTSUP (-95)    /* head kind / option not implemented */
 
-/* head kinds (core/models/add_uncertainty.py:56-85 `uncertainty_type`) */
-#define IM2IM_HEAD_QUANTILES 0 /* planes = (lower, prediction, upper); core/models/finallayers/quantile_layer.py */
+/* head kinds (core/models/add_uncertainty.py:56-85 `uncertainty_type`): what the score planes mean.  After the outer
+ * clamp of add_uncertainty.py:35-36 every head has the form
+ *     upper = max(fl(fl(lam*w_up) + pred), pred+1e-6),   lower = min(fl(pred - fl(lam*w_lo)), pred-1e-6)
+ * and only the widths differ:
+ *   QUANTILES     d_lower/d_pred/d_upper = (lower, prediction, upper); w_up = max(upper, pred+1e-6) - pred,
+ *                 w_lo = pred - min(lower, pred-1e-6).  uncertainty_type "quantiles", "quantiles_l1", "inn"
+ *                 (finallayers/quantile_layer.py:34-44, quantile_l1_layer.py:34-44, inn_layer.py:30-40)
+ *   RESIDUAL      d_pred/d_upper = (prediction, |residual| magnitude), d_lower ignored (may be NULL); w_up = w_lo = d_upper.
+ *                 "residual_magnitude", "residual_magnitude_l1" (residual_magnitude_layer.py:28-36)
+ *   GAUSSIAN      d_pred/d_upper = (mean, variance), d_lower ignored; w_up = w_lo = sqrt(variance).
+ *                 "gaussian" (gaussian_layer.py:26-34)
+ *   SOFTMAX_SETS  d_lower/d_pred/d_upper = (lower quantile, argmax prediction, upper quantile) as produced by
+ *                 im2im_softmax_sets; w_up = relu(upper - pred), w_lo = relu(pred - lower).  "softmax"
+ *                 (softmax_layer.py:27-53)
+ */
+#define IM2IM_HEAD_QUANTILES 0
+#define IM2IM_HEAD_RESIDUAL 1
+#define IM2IM_HEAD_GAUSSIAN 2
+#define IM2IM_HEAD_SOFTMAX_SETS 3
 
 /* flags for im2im_rcps_miss_counts */
 #define IM2IM_RCPS_ZERO_OUTPUTS 1u  /* memset d_counts and d_totals on `stream` before the pass */
@@ -111,6 +128,32 @@ int im2im_rcps_decide(const unsigned long long* d_totals, int32_t n_lambdas, dou
 int im2im_quantile_nested_sets(float* d_lower, const float* d_pred, float* d_upper, int64_t n_images, int64_t px,
                                int64_t stride_lower, int64_t stride_pred, int64_t stride_upper, float lam,
                                int32_t write_back_clamp, float* d_lower_out, float* d_upper_out, void* stream);
+
+/*
+ * The same for any head kind (planes as described at IM2IM_HEAD_*): the head's own set function
+ *   gaussian_layer.py:26-34, residual_magnitude_layer.py:28-36, residual_magnitude_l1_layer.py:28-36,
+ *   quantile_l1_layer.py:34-44, inn_layer.py:30-40, softmax_layer.py:50-51
+ * followed by the +/-1e-6 clamp of ModelWithUncertainty.nested_sets_from_output (add_uncertainty.py:35-36).
+ * write_back_clamp only applies to IM2IM_HEAD_QUANTILES (the only set functions that mutate their argument).
+ */
+int im2im_nested_sets(int32_t head_kind, float* d_lower, const float* d_pred, float* d_upper, int64_t n_images,
+                      int64_t px, int64_t stride_lower, int64_t stride_pred, int64_t stride_upper, float lam,
+                      int32_t write_back_clamp, float* d_lower_out, float* d_upper_out, void* stream);
+
+/*
+ * Softmax head, lambda-independent half of softmax_nested_sets_from_output (softmax_layer.py:34-48): per pixel
+ * softmax over the n_classes logits, cumulative sum, lower/upper quantile = #{cumsum <= 0.05 / 0.95}/n_classes,
+ * prediction = argmax/n_classes, the +/- 1/n_classes separation of :45-46 and the clamp to [0,1].
+ *   d_logits : DEVICE fp32; class k of pixel j of image i at d_logits[i*stride_image + k*stride_class + j]
+ *              (the head's (B, K, 1, H, W) tensor: stride_class = inner = H*W, stride_image = K*inner)
+ *   d_sets   : DEVICE fp32 [n_images, 3, inner] = (lower quantile, prediction, upper quantile), the planes of
+ *              IM2IM_HEAD_SOFTMAX_SETS.  The reference recomputes this for every lambda step; here it is computed once.
+ * Parity: the outputs are multiples of 1/n_classes; they equal the reference's except where a cumulative sum lies
+ * within rounding distance of 0.05 / 0.95 (exp and the summation order differ between torch's CPU, torch's CUDA and
+ * this kernel by an ulp).  1 <= n_classes <= 64.
+ */
+int im2im_softmax_sets(const float* d_logits, int64_t n_images, int32_t n_classes, int64_t inner, int64_t stride_image,
+                       int64_t stride_class, float* d_sets, void* stream);
 
 /*
  * Per-pixel miss map at one lambda, summed over images: map[k] = #{i : pixel k of image i is missed}

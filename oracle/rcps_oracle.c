@@ -2,7 +2,7 @@
  * ORACLE - TEST INFRASTRUCTURE ONLY.  Not part of the product path.
  *
  * CPU restatement, op for op in IEEE fp32 without contraction, of the reference's RCPS per-pixel chain for the
- * quantile head.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * quantile head and (oracle_head_* functions) the gaussian, residual-magnitude and softmax heads.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library, and only as the checker / the timed CPU baseline - never behind the product API.
  *
  * Parity status: PINNED.  Checked against tests/golden/rcps_*.npz, which were produced by running the unmodified
@@ -15,6 +15,10 @@
  *   core/models/add_uncertainty.py:35-36              upper = max(upper, p+1e-6) ; lower = min(lower, p-1e-6)
  *   core/calibration/calibrate_model.py:77-80         misses = (lower>y)+(upper<y); clip to 1; mean over pixels
  *   core/calibration/calibrate_model.py:134-136       one full pass over the data PER lambda step
+ *   core/models/finallayers/gaussian_layer.py:31-32   upper = lam*sqrt(var)+mean ; lower = -lam*sqrt(var)+mean
+ *   core/models/finallayers/residual_magnitude_layer.py:33-34 (and _l1_layer.py:33-34)  upper = lam*r+p ; lower = -lam*r+p
+ *   core/models/finallayers/softmax_layer.py:34-51    softmax, cumsum, quantile counts, argmax, separation, clamp, edges
+ *   (quantile_l1_layer.py:39-42 and inn_layer.py:35-38 are textually the quantile head's set function)
  *
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off, no -ffast-math, optional -fopenmp).
  */
@@ -118,6 +122,116 @@ void oracle_quantile_miss_map(const float* lower, const float* pred, const float
         const float* u = upper + i * stride_upper;
         const float* y = label + i * stride_label;
         for (int64_t k = 0; k < px; ++k) map_counts[k] += pixel_miss(l[k], p[k], u[k], y[k], lam);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Other heads.  kind: 0 quantiles (a,p,b = lower,pred,upper), 1 residual magnitude (p,b = pred,|residual|),
+ * 2 gaussian (p,b = mean,variance), 3 softmax sets (a,p,b = lower quantile, argmax prediction, upper quantile).
+ * Every head is followed by the outer clamp of add_uncertainty.py:35-36. */
+static inline float t_relu(float x) { return (x != x) ? x : (x > 0.0f ? x : 0.0f); } /* torch.relu keeps NaN */
+
+static inline void head_sets(int kind, float a, float p, float b, float lam, float* lo2, float* up2) {
+    float upper, lower;
+    if (kind == 0) { pixel_sets(a, p, b, lam, lo2, up2); return; }
+    if (kind == 3) {
+        lower = f_sub(p, f_mul(t_relu(f_sub(p, a)), lam));   /* softmax_layer.py:50 */
+        upper = f_add(p, f_mul(t_relu(f_sub(b, p)), lam));   /* softmax_layer.py:51 */
+    } else {
+        volatile float w = (kind == 2) ? sqrtf(b) : b;       /* gaussian_layer.py:31 .sqrt() ; residual: the plane */
+        upper = f_add(f_mul(lam, w), p);                     /* gaussian_layer.py:31, residual_magnitude_layer.py:33 */
+        lower = f_add(f_mul(-lam, w), p);                    /* gaussian_layer.py:32, residual_magnitude_layer.py:34 */
+    }
+    *up2 = t_max(upper, f_add(p, EPS));                      /* add_uncertainty.py:35 */
+    *lo2 = t_min(lower, f_sub(p, EPS));                      /* add_uncertainty.py:36 */
+}
+
+static inline int head_miss(int kind, float a, float p, float b, float y, float lam) {
+    float lo2, up2;
+    head_sets(kind, a, p, b, lam, &lo2, &up2);
+    float m = (float)(lo2 > y) + (float)(up2 < y);
+    if (m > 1.0f) m = 1.0f;
+    return (int)m;
+}
+
+/* (N, L) miss counts, one pass per lambda.  For the 2-plane heads pass a == p (ignored). */
+void oracle_head_miss_table(int32_t kind, const float* a, const float* p, const float* b, const float* label,
+                            int64_t n_images, int64_t px, int64_t stride_a, int64_t stride_p, int64_t stride_b,
+                            int64_t stride_label, const float* lams, int64_t n_lambdas, int32_t* counts) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) collapse(2)
+#endif
+    for (int64_t j = 0; j < n_lambdas; ++j) {
+        for (int64_t i = 0; i < n_images; ++i) {
+            const float* pa = a + i * stride_a;
+            const float* pp = p + i * stride_p;
+            const float* pb = b + i * stride_b;
+            const float* y = label + i * stride_label;
+            int32_t c = 0;
+            for (int64_t k = 0; k < px; ++k) c += head_miss(kind, pa[k], pp[k], pb[k], y[k], lams[j]);
+            counts[i * n_lambdas + j] = c;
+        }
+    }
+}
+
+void oracle_head_nested_sets(int32_t kind, const float* a, const float* p, const float* b, int64_t n_images, int64_t px,
+                             int64_t stride_a, int64_t stride_p, int64_t stride_b, float lam, float* lower_out,
+                             float* upper_out) {
+    for (int64_t i = 0; i < n_images; ++i)
+        for (int64_t k = 0; k < px; ++k)
+            head_sets(kind, a[i * stride_a + k], p[i * stride_p + k], b[i * stride_b + k], lam,
+                      &lower_out[i * px + k], &upper_out[i * px + k]);
+}
+
+void oracle_head_miss_map(int32_t kind, const float* a, const float* p, const float* b, const float* label,
+                          int64_t n_images, int64_t px, int64_t stride_a, int64_t stride_p, int64_t stride_b,
+                          int64_t stride_label, float lam, int32_t* map_counts) {
+    for (int64_t k = 0; k < px; ++k) map_counts[k] = 0;
+    for (int64_t i = 0; i < n_images; ++i)
+        for (int64_t k = 0; k < px; ++k)
+            map_counts[k] += head_miss(kind, a[i * stride_a + k], p[i * stride_p + k], b[i * stride_b + k],
+                                       label[i * stride_label + k], lam);
+}
+
+/* softmax_layer.py:34-48: logits (n, K, inner) -> sets (n, 3, inner) = (lower quantile, prediction, upper quantile).
+ * expf / summation order are libm's and sequential; torch's differ by an ulp, so this half of the oracle is pinned to
+ * the reference only up to threshold ties (see tests). */
+void oracle_softmax_sets(const float* logits, int64_t n_images, int64_t K, int64_t inner, float* sets) {
+    const float step = (float)(1.0 / (double)K);
+    for (int64_t i = 0; i < n_images; ++i) {
+        for (int64_t j = 0; j < inner; ++j) {
+            const float* x = logits + i * K * inner + j;
+            float m = -INFINITY;
+            int nan_at = -1;
+            for (int64_t k = 0; k < K; ++k) {
+                float v = x[k * inner];
+                if (v != v && nan_at < 0) nan_at = (int)k;
+                if (v > m) m = v;
+            }
+            float lq, pr, uq;
+            if (nan_at >= 0) {
+                lq = 0.0f; uq = 0.0f; pr = 0.0f; /* softmax makes the whole row NaN: counts 0, argmax = first NaN = 0 */
+            } else {
+                float ssum = 0.0f;
+                for (int64_t k = 0; k < K; ++k) ssum = f_add(ssum, expf(f_sub(x[k * inner], m)));
+                float cum = 0.0f, best = -INFINITY;
+                int n_lo = 0, n_hi = 0, arg = 0;
+                for (int64_t k = 0; k < K; ++k) {
+                    volatile float pk = expf(f_sub(x[k * inner], m)) / ssum;
+                    cum = f_add(cum, pk);
+                    n_lo += cum <= 0.05f;
+                    n_hi += cum <= 0.95f;
+                    if (pk > best) { best = pk; arg = (int)k; }
+                }
+                lq = (float)n_lo / (float)K; uq = (float)n_hi / (float)K; pr = (float)arg / (float)K;
+            }
+            if (pr == lq) lq = f_sub(lq, step);
+            if (pr == uq) uq = f_add(uq, step);
+            lq = lq < 0.0f ? 0.0f : (lq > 1.0f ? 1.0f : lq);
+            uq = uq < 0.0f ? 0.0f : (uq > 1.0f ? 1.0f : uq);
+            float* dst = sets + i * 3 * inner + j;
+            dst[0] = lq; dst[inner] = pr; dst[2 * inner] = uq;
+        }
     }
 }
 

@@ -47,6 +47,14 @@ def _lib():
         lib.oracle_quantile_miss_table.argtypes = [_F32P] * 4 + [i64] * 6 + [_F32P, i64, _I32P]
         lib.oracle_quantile_nested_sets.argtypes = [_F32P] * 3 + [i64] * 5 + [f32, _F32P, _F32P]
         lib.oracle_quantile_miss_map.argtypes = [_F32P] * 4 + [i64] * 6 + [f32, _I32P]
+        i32 = ctypes.c_int32
+        lib.oracle_head_miss_table.argtypes = [i32] + [_F32P] * 4 + [i64] * 6 + [_F32P, i64, _I32P]
+        lib.oracle_head_nested_sets.argtypes = [i32] + [_F32P] * 3 + [i64] * 5 + [f32, _F32P, _F32P]
+        lib.oracle_head_miss_map.argtypes = [i32] + [_F32P] * 4 + [i64] * 6 + [f32, _I32P]
+        lib.oracle_softmax_sets.argtypes = [_F32P, i64, i64, i64, _F32P]
+        for fn in (lib.oracle_head_miss_table, lib.oracle_head_nested_sets, lib.oracle_head_miss_map,
+                   lib.oracle_softmax_sets):
+            fn.restype = None
         lib.oracle_num_threads.restype = ctypes.c_int
         for fn in (lib.oracle_quantile_miss_counts, lib.oracle_quantile_miss_table,
                    lib.oracle_quantile_nested_sets, lib.oracle_quantile_miss_map):
@@ -114,6 +122,91 @@ def c_miss_map(outputs, labels, lam: float) -> np.ndarray:
     return m.reshape(outputs.shape[2:])
 
 
+# ----------------------------------------------------------------------------- other heads (C restatement)
+HEAD_KINDS = {"quantiles": 0, "quantiles_l1": 0, "inn": 0, "residual_magnitude": 1, "residual_magnitude_l1": 1,
+              "gaussian": 2, "softmax_sets": 3}
+
+
+def _head_planes(outputs: np.ndarray, head: str):
+    """(a, p, b) plane offsets (in elements) and image stride for the head's output tensor (N, 2 or 3, ...)."""
+    kind = HEAD_KINDS[head]
+    outputs = np.ascontiguousarray(outputs, dtype=np.float32)
+    n = outputs.shape[0]
+    px = int(np.prod(outputs.shape[2:]))
+    if kind in (0, 3):
+        assert outputs.shape[1] == 3
+        offs, stride = (0, px, 2 * px), 3 * px
+    else:
+        assert outputs.shape[1] == 2
+        offs, stride = (0, 0, px), 2 * px   # a is ignored for the 2-plane heads
+    return kind, outputs, n, px, offs, stride
+
+
+def head_miss_table(outputs, labels, lams, head: str) -> np.ndarray:
+    """(N, L) integer miss counts for any head, one pass per lambda."""
+    kind, outputs, n, px, offs, stride = _head_planes(outputs, head)
+    labels = np.ascontiguousarray(labels, dtype=np.float32)
+    lams = np.ascontiguousarray(np.atleast_1d(lams), dtype=np.float32)
+    counts = np.zeros((n, lams.shape[0]), dtype=np.int32)
+    _lib().oracle_head_miss_table(kind, _ptr(outputs, offs[0]), _ptr(outputs, offs[1]), _ptr(outputs, offs[2]),
+                                  _ptr(labels), n, px, stride, stride, stride, px, _ptr(lams), lams.shape[0],
+                                  counts.ctypes.data_as(_I32P))
+    return counts
+
+
+def head_nested_sets(outputs, lam: float, head: str):
+    kind, outputs, n, px, offs, stride = _head_planes(outputs, head)
+    lo = np.empty((n,) + outputs.shape[2:], dtype=np.float32)
+    up = np.empty_like(lo)
+    _lib().oracle_head_nested_sets(kind, _ptr(outputs, offs[0]), _ptr(outputs, offs[1]), _ptr(outputs, offs[2]), n, px,
+                                   stride, stride, stride, np.float32(lam), _ptr(lo), _ptr(up))
+    pred = outputs[:, 1] if kind in (0, 3) else outputs[:, 0]
+    return lo, pred.copy(), up
+
+
+def head_miss_map(outputs, labels, lam: float, head: str) -> np.ndarray:
+    kind, outputs, n, px, offs, stride = _head_planes(outputs, head)
+    labels = np.ascontiguousarray(labels, dtype=np.float32)
+    m = np.zeros(px, dtype=np.int32)
+    _lib().oracle_head_miss_map(kind, _ptr(outputs, offs[0]), _ptr(outputs, offs[1]), _ptr(outputs, offs[2]),
+                                _ptr(labels), n, px, stride, stride, stride, px, np.float32(lam),
+                                m.ctypes.data_as(_I32P))
+    return m.reshape(outputs.shape[2:])
+
+
+def softmax_sets(logits: np.ndarray) -> np.ndarray:
+    """softmax_layer.py:34-48: logits (N, K, ...) -> (N, 3, ...) = (lower quantile, prediction, upper quantile)."""
+    logits = np.ascontiguousarray(logits, dtype=np.float32)
+    n, k = logits.shape[:2]
+    inner = int(np.prod(logits.shape[2:]))
+    sets = np.empty((n, 3) + logits.shape[2:], dtype=np.float32)
+    _lib().oracle_softmax_sets(_ptr(logits), n, k, inner, _ptr(sets))
+    return sets
+
+
+def np_head_nested_sets(outputs: np.ndarray, lam, head: str):
+    """Literal numpy transcription of the other heads' set functions + add_uncertainty.py:35-36."""
+    kind = HEAD_KINDS[head]
+    if kind == 0:
+        return np_nested_sets(outputs, lam)
+    eps, lam = np.float32(1e-6), np.float32(lam)
+    out = np.asarray(outputs, dtype=np.float32)
+    with np.errstate(all="ignore"):
+        if kind == 3:
+            a, p, b = out[:, 0], out[:, 1], out[:, 2]
+            relu = lambda t: np.where(np.isnan(t), t, np.maximum(t, np.float32(0)))
+            lower = p - relu(p - a) * lam
+            upper = p + relu(b - p) * lam
+        else:
+            p = out[:, 0]
+            w = np.sqrt(out[:, 1]) if kind == 2 else out[:, 1]
+            upper = lam * w + p
+            lower = -lam * w + p
+        upper = np.maximum(upper, p + eps)
+        lower = np.minimum(lower, p - eps)
+    return lower, p, upper
+
+
 # ----------------------------------------------------------------------------- numpy transcription
 def np_nested_sets(outputs: np.ndarray, lam) -> tuple:
     """quantile_layer.py:39-42 then add_uncertainty.py:35-36; every numpy op rounds to fp32 like an ATen op."""
@@ -172,7 +265,8 @@ def hb_mu_plus(muhat, n, delta, maxiters=1000):
         return 1.0
 
 
-def calibrate_sweep(outputs, labels, lam_min, lam_max, num_lambdas, alpha, delta, miss_counts=c_miss_counts):
+def calibrate_sweep(outputs, labels, lam_min, lam_max, num_lambdas, alpha, delta, miss_counts=c_miss_counts,
+                    head=None):
     """calibrate_model.py:97-100,130-145 restated: reverse linear scan with early stop.
 
     Returns (lhat fp32 0-dim tensor, stop index or -1, (N,L) fp32 loss table with unvisited columns zero).
@@ -181,6 +275,8 @@ def calibrate_sweep(outputs, labels, lam_min, lam_max, num_lambdas, alpha, delta
     import torch
     import warnings
 
+    if head is not None:
+        miss_counts = lambda o, l, lam: head_miss_table(o, l, [lam], head)[:, 0]  # noqa: E731
     lambdas = torch.linspace(lam_min, lam_max, num_lambdas)
     n = outputs.shape[0]
     px = int(np.prod(outputs.shape[2:]))

@@ -35,9 +35,20 @@ def import_reference():
     import core.calibration.calibrate_model as calibrate_model
     import core.models.add_uncertainty as add_uncertainty
     import core.models.finallayers.quantile_layer as quantile_layer
+    import core.models.finallayers.gaussian_layer as gaussian_layer
+    import core.models.finallayers.inn_layer as inn_layer
+    import core.models.finallayers.quantile_l1_layer as quantile_l1_layer
+    import core.models.finallayers.residual_magnitude_l1_layer as residual_magnitude_l1_layer
+    import core.models.finallayers.residual_magnitude_layer as residual_magnitude_layer
+    import core.models.finallayers.softmax_layer as softmax_layer
+    import core.models.losses.inn as inn
     import core.models.losses.pinball as pinball
     import core.models.trunks.unet as unet
     assert bounds.__file__.startswith(REFERENCE_ROOT), bounds.__file__
     ns = types.SimpleNamespace(bounds=bounds, calibrate_model=calibrate_model, add_uncertainty=add_uncertainty,
-                               quantile_layer=quantile_layer, pinball=pinball, unet=unet)
+                               quantile_layer=quantile_layer, pinball=pinball, unet=unet, gaussian_layer=gaussian_layer,
+                               inn_layer=inn_layer, quantile_l1_layer=quantile_l1_layer,
+                               residual_magnitude_layer=residual_magnitude_layer,
+                               residual_magnitude_l1_layer=residual_magnitude_l1_layer, softmax_layer=softmax_layer,
+                               inn=inn)
     return ns
