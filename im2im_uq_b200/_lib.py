@@ -24,6 +24,7 @@ IM2IM_HEAD_QUANTILES = 0      # (lower, pred, upper): quantiles, quantiles_l1, i
 IM2IM_HEAD_RESIDUAL = 1       # (pred, |residual|): residual_magnitude, residual_magnitude_l1
 IM2IM_HEAD_GAUSSIAN = 2       # (mean, variance)
 IM2IM_HEAD_SOFTMAX_SETS = 3   # (lower quantile, argmax, upper quantile) from im2im_softmax_sets
+LOSS_QUANTILES, LOSS_QUANTILES_L1, LOSS_GAUSSIAN, LOSS_RESIDUAL, LOSS_RESIDUAL_L1, LOSS_INN = range(6)
 THREE_PLANE_HEADS = (IM2IM_HEAD_QUANTILES, IM2IM_HEAD_SOFTMAX_SETS)
 IM2IM_RCPS_MAX_LAMBDAS = 8192
 
@@ -103,6 +104,8 @@ def _declare_more(lib):
     lib.im2im_upsample2x_bilinear_bf16.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.im2im_head_conv3x3_f32.restype = c.c_int
     lib.im2im_head_conv3x3_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.im2im_head_conv3x3_act_f32.restype = c.c_int
+    lib.im2im_head_conv3x3_act_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
 
 
 def _declare_train(lib):
@@ -117,6 +120,7 @@ def _declare_train(lib):
         "im2im_upsample2x_bilinear_bwd_bf16": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
         "im2im_quantile_loss_f32": [vp, vp, i64, i64, f32, f32, f32, f32, f32, vp, vp, vp],
         "im2im_adam_step_f32": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
+        "im2im_head_loss_f32": [i32, vp, vp, i64, i64, f32, f32, f32, f32, f32, f32, vp, vp, vp],
         "im2im_head_bwd": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
         "im2im_conv_first_wgrad": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
     }
@@ -134,7 +138,7 @@ EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im
            "im2im_channel_stats_bf16", "im2im_bn_finalize", "im2im_bn_apply_relu_bf16", "im2im_bn_relu_bwd_bf16",
            "im2im_maxpool2x2_bwd_bf16", "im2im_upsample2x_bilinear_bwd_bf16", "im2im_quantile_loss_f32",
            "im2im_adam_step_f32", "im2im_head_bwd", "im2im_conv_first_wgrad", "im2im_nested_sets",
-           "im2im_softmax_sets"]
+           "im2im_softmax_sets", "im2im_head_conv3x3_act_f32", "im2im_head_loss_f32"]
 
 
 def load():

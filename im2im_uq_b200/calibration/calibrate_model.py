@@ -73,10 +73,33 @@ def _dataset_tensors(out_dataset) -> Tuple[torch.Tensor, torch.Tensor]:
     return torch.cat(xs, dim=0), torch.cat(ys, dim=0)
 
 
-def _is_fused_quantile(model, rcps_loss_fn) -> bool:
-    from ..models.quantile_layer import quantile_regression_nested_sets_from_output
-    return (rcps_loss_fn is fraction_missed_loss and
-            getattr(model, "in_nested_sets_from_output_fn", None) is quantile_regression_nested_sets_from_output)
+def _fused_head(model, rcps_loss_fn=None):
+    """(head kind, scores_from_output or None) when the model's set function is one of the built-in heads (each tags
+    itself with the head kind its kernel uses) and the loss is fraction_missed; None for user-supplied functions."""
+    if rcps_loss_fn is not None and rcps_loss_fn is not fraction_missed_loss:
+        return None
+    fn = getattr(model, "in_nested_sets_from_output_fn", None)
+    kind = getattr(fn, "im2im_head_kind", None)
+    if kind is None:
+        return None
+    return kind, getattr(fn, "im2im_scores_from_output", None)
+
+
+def _head_scores(model, outputs, device):
+    """Head kind + the score planes the sweep kernels read.  For the softmax head the lambda-independent half of the set
+    function (softmax, cumsum, quantiles; softmax_layer.py:34-48) is evaluated ONCE here, in chunks, on the device."""
+    fused = _fused_head(model)
+    if fused is None:
+        raise NotImplementedError("calibration needs one of the built-in heads (add_uncertainty) - a user-supplied "
+                                  "nested-set function has no one-pass kernel")
+    kind, to_scores = fused
+    if to_scores is None:
+        return kind, outputs
+    per_image = max(outputs[0].numel() * 4, 1) if outputs.shape[0] else 1
+    parts = [to_scores(outputs[lo:hi].to(device)) for lo, hi in _chunks(outputs.shape[0], per_image)]
+    if not parts:
+        return kind, torch.empty((0, 3) + tuple(outputs.shape[2:]), dtype=torch.float32, device=device)
+    return kind, parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
 
 
 def _resolve_lambda(model, lam):
@@ -93,7 +116,8 @@ def _chunks(n: int, bytes_per_image: int):
         yield lo, min(n, lo + step)
 
 
-def _miss_counts_any_device(outputs, labels, lam_sorted_dev, device, counts=None, totals=None):
+def _miss_counts_any_device(outputs, labels, lam_sorted_dev, device, counts=None, totals=None,
+                            head=_lib.IM2IM_HEAD_QUANTILES):
     """One-pass miss counts for scores that live on `device` already, or on the host (staged in pinned chunks)."""
     n = outputs.shape[0]
     n_lam = lam_sorted_dev.numel()
@@ -102,7 +126,7 @@ def _miss_counts_any_device(outputs, labels, lam_sorted_dev, device, counts=None
     if totals is None:
         totals = torch.zeros((n_lam,), dtype=torch.int64, device=device)
     if outputs.is_cuda and labels.is_cuda:
-        rcps.miss_counts(outputs, labels, lam_sorted_dev, counts=counts, totals=totals, zero=False)
+        rcps.miss_counts(outputs, labels, lam_sorted_dev, counts=counts, totals=totals, zero=False, head=head)
         return counts, totals
     per_image = (outputs[0].numel() + labels[0].numel()) * 4 if n else 1
     copy_stream = torch.cuda.Stream(device=device)
@@ -115,7 +139,7 @@ def _miss_counts_any_device(outputs, labels, lam_sorted_dev, device, counts=None
             ready = torch.cuda.Event()
             ready.record(copy_stream)
         main.wait_event(ready)
-        rcps.miss_counts(x, y, lam_sorted_dev, counts=counts[lo:hi], totals=totals, zero=False)
+        rcps.miss_counts(x, y, lam_sorted_dev, counts=counts[lo:hi], totals=totals, zero=False, head=head)
         x.record_stream(main)
         y.record_stream(main)
         prev = (x, y)
@@ -131,11 +155,12 @@ def get_rcps_losses_from_outputs(model, out_dataset, rcps_loss_fn, lam, device):
     outputs, labels = _dataset_tensors(out_dataset)
     lam = _resolve_lambda(model, lam)
     with torch.no_grad():
-        if _is_fused_quantile(model, rcps_loss_fn):
+        if _fused_head(model, rcps_loss_fn) is not None:
+            kind, scores = _head_scores(model, outputs, device)
             lam_dev = torch.as_tensor(lam, dtype=torch.float32).reshape(1).to(device)
-            counts, _ = _miss_counts_any_device(outputs, labels, lam_dev, device)
-            px = outputs[0, 0].numel() if outputs.shape[0] else 1
-            return rcps.loss_table(counts, px)[:, 0].cpu()
+            counts, _ = _miss_counts_any_device(scores, labels, lam_dev, device, head=kind)
+            px = labels[0].numel() if labels.shape[0] else 1
+            return rcps.loss_table(counts, max(px, 1))[:, 0].cpu()
         losses = []
         for lo in range(0, outputs.shape[0], 64):
             x = outputs[lo:lo + 64].to(device).clone()
@@ -157,12 +182,14 @@ def get_rcps_metrics_from_outputs(model, out_dataset, rcps_loss_fn, device):
     n = outputs.shape[0]
     px = labels[0].numel()
     with torch.no_grad():
-        if not _is_fused_quantile(model, rcps_loss_fn):
-            raise NotImplementedError("metrics are implemented for the quantile head + fraction_missed loss")
-        outputs_d = outputs if outputs.is_cuda else outputs.to(device)
+        if _fused_head(model, rcps_loss_fn) is None:
+            raise NotImplementedError("metrics are implemented for the built-in heads + fraction_missed loss")
+        kind, outputs_d = _head_scores(model, outputs, device)
+        planes = outputs_d.shape[1]
+        outputs_d = outputs_d if outputs_d.is_cuda else outputs_d.to(device)
         labels_d = labels if labels.is_cuda else labels.to(device)
         lam_dev = torch.as_tensor(lam, dtype=torch.float32).reshape(1).to(device)
-        counts, _ = rcps.miss_counts(outputs_d, labels_d, lam_dev)
+        counts, _ = rcps.miss_counts(outputs_d, labels_d, lam_dev, head=kind)
         losses = rcps.loss_table(counts, px)[:, 0]
         # one random pixel per image, drawn batch by batch like the reference
         idx_parts = []
@@ -171,11 +198,11 @@ def get_rcps_metrics_from_outputs(model, out_dataset, rcps_loss_fn, device):
             idx_parts.append(np.random.choice(px, size=b))
         idx = torch.from_numpy(np.concatenate(idx_parts)).to(device)
         rows = torch.arange(n, device=device)
-        picked = outputs_d.reshape(n, 3, px)[rows, :, idx].reshape(n, 3, 1).contiguous()
-        lo_e, pred_e, up_e = rcps.quantile_nested_sets(picked, float(lam), write_back_clamp=False)
+        picked = outputs_d.reshape(n, planes, px)[rows, :, idx].reshape(n, planes, 1).contiguous()
+        lo_e, pred_e, up_e = rcps.head_nested_sets(picked, float(lam), kind)
         sizes = (up_e - lo_e).reshape(n).cpu()
         residuals = (labels_d.reshape(n, px)[rows, idx] - pred_e.reshape(n)).abs()
-        miss_map = rcps.miss_map(outputs_d, labels_d, float(lam))
+        miss_map = rcps.miss_map(outputs_d, labels_d, float(lam), head=kind)
     sizes = sizes + torch.rand(size=sizes.shape).to(sizes.device) * 1e-6
     residuals = residuals.detach().cpu().numpy()
     spearman = spearmanr(residuals, sizes)[0]
@@ -205,6 +232,10 @@ def evaluate_from_loss_table(loss_table, n, alpha, delta):
         if idx_lambda is None:
             print("No rejections made!")
             idx_lambda = 0
+        else:
+            # the reference indexes with the 1-element tensor `nonzero()[0]` (:70,:74): an index_select copy of shape
+            # (N_val, 1), whose fp32 mean is summed in a different order than the strided view an int index gives
+            idx_lambda = torch.tensor([idx_lambda])
         return val_table[:, idx_lambda].mean()
 
 
@@ -259,9 +290,10 @@ class RcpsGraph:
         lhat, stop, decided = plan.run()        # decided False -> a column fell in the guard band, call plan.replay_on_host()
     """
 
-    def __init__(self, outputs: torch.Tensor, labels: torch.Tensor, config: dict, group=None, n_total=None):
+    def __init__(self, outputs: torch.Tensor, labels: torch.Tensor, config: dict, group=None, n_total=None,
+                 head: int = _lib.IM2IM_HEAD_QUANTILES):
         assert outputs.is_cuda and labels.is_cuda
-        self.config, self.group = config, group
+        self.config, self.group, self.head = config, group, head
         self.outputs, self.labels = outputs, labels
         dev = outputs.device
         self.lambdas, self.dlambda, lam_prime, self.default_lhat = sweep.lambda_grid(config)
@@ -286,7 +318,8 @@ class RcpsGraph:
         self.kernels_per_replay = _lib.launch_count() - before  # libim2im_uq kernels inside one replay
 
     def _enqueue(self):
-        rcps.miss_counts(self.outputs, self.labels, self.lam_dev, counts=self.counts, totals=self.totals, zero=True)
+        rcps.miss_counts(self.outputs, self.labels, self.lam_dev, counts=self.counts, totals=self.totals, zero=True,
+                         head=self.head)
         if self.group is not None:
             import torch.distributed as dist
             dist.all_reduce(self.totals, op=dist.ReduceOp.SUM, group=self.group)
@@ -316,8 +349,10 @@ class RcpsGraph:
 
 
 def rcps_sweep(outputs: torch.Tensor, labels: torch.Tensor, config: dict, device=None, group=None,
-               verbose: bool = False, stats: Optional[dict] = None, n_total: Optional[int] = None):
-    """lambda-hat and the loss table from head outputs (N,3,C,H,W) + labels (N,C,H,W), CPU- or CUDA-resident.
+               verbose: bool = False, stats: Optional[dict] = None, n_total: Optional[int] = None,
+               head: int = _lib.IM2IM_HEAD_QUANTILES):
+    """lambda-hat and the loss table from head score planes (N,3|2,C,H,W; see rcps.py) + labels (N,C,H,W), CPU- or
+    CUDA-resident; ``head`` is the IM2IM_HEAD_* kind of the planes.
 
     Returns (lhat 0-dim fp32 CPU tensor, stop index or -1, counts int32 CUDA (N_local, L), visited bool mask (L,)).
     With a torch.distributed ``group`` every rank passes its own contiguous shard of images; the per-lambda totals are
@@ -337,7 +372,7 @@ def rcps_sweep(outputs: torch.Tensor, labels: torch.Tensor, config: dict, device
     n_local = outputs.shape[0]
     px = labels[0].numel() if n_local else 0
     lam_dev = lam_sorted.to(device)
-    counts, totals = _miss_counts_any_device(outputs, labels, lam_dev, device)
+    counts, totals = _miss_counts_any_device(outputs, labels, lam_dev, device, head=head)
     if order is not None:
         inv = torch.empty_like(order)
         inv[order] = torch.arange(L)
@@ -361,7 +396,9 @@ def calibrate_from_outputs(model, outputs: torch.Tensor, labels: torch.Tensor, c
     """
     device = _cuda_device(config['device'])
     with torch.no_grad():
-        lhat, stop, counts, visited = rcps_sweep(outputs, labels, config, device=device, group=group, stats=stats)
+        kind, scores = _head_scores(model, outputs, device)
+        lhat, stop, counts, visited = rcps_sweep(scores, labels, config, device=device, group=group, stats=stats,
+                                                 head=kind)
         model.set_lhat(lhat)
         px = labels[0].numel()
         L = counts.shape[1]

@@ -327,6 +327,81 @@ __global__ void __launch_bounds__(256) quantile_loss_kernel(const float* __restr
     }
 }
 
+// Training losses of the other heads, value parts + d loss / d pred in one pass (pred (B, planes, px), target (B, px)).
+//   IM2IM_LOSS_QUANTILES_L1   quantile_l1_layer.py:23-32   w_lo*pinball(q_lo) + w_hi*pinball(q_hi) + w_mse*L1(pred)
+//   IM2IM_LOSS_GAUSSIAN       gaussian_layer.py:20-24      nn.GaussianNLLLoss(): 0.5*(log(max(var,1e-6)) + (mean-y)^2/max(var,1e-6));
+//                                                          torch clamps the variance on a detached copy, so the gradient
+//                                                          uses the clamped value and flows to var unchanged
+//   IM2IM_LOSS_RESIDUAL       residual_magnitude_layer.py:20-26     MSE(pred,y) + MSE(r, |y-pred|)
+//   IM2IM_LOSS_RESIDUAL_L1    residual_magnitude_l1_layer.py:20-26  L1(pred,y)  + MSE(r, |y-pred|)
+//   IM2IM_LOSS_INN            inn_layer.py:23-28, losses/inn.py:11-14   MSE(pred,y) + mean(relu(y-u)^2 + relu(l-y)^2 + beta*|u-l|)
+// part[k] are plain sums; the host forms sum_k w_k * part[k] / count.  w[] also scales the gradients.
+__device__ __forceinline__ float sgnf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+template <int KIND>
+__global__ void __launch_bounds__(256) head_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                        long long n_images, long long px, float q_lo, float q_hi,
+                                                        float w0, float w1, float w2, float beta, float inv_count,
+                                                        float* __restrict__ dpred, double* __restrict__ loss_parts) {
+    constexpr int kPlanes = (KIND == IM2IM_LOSS_QUANTILES_L1 || KIND == IM2IM_LOSS_INN) ? 3 : 2;
+    double part[3] = {0.0, 0.0, 0.0};
+    const long long total = n_images * px;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long i = e / px, k = e - i * px;
+        const float y = target[e];
+        const long long o = i * kPlanes * px + k;
+        float g[3] = {0.f, 0.f, 0.f};
+        if (KIND == IM2IM_LOSS_QUANTILES_L1) {
+            const float e_lo = pred[o] - y, e_mid = pred[o + px] - y, e_hi = pred[o + 2 * px] - y;
+            part[0] += e_lo < 0.f ? q_lo * fabsf(e_lo) : (e_lo > 0.f ? (1.f - q_lo) * fabsf(e_lo) : 0.f);
+            part[1] += e_hi < 0.f ? q_hi * fabsf(e_hi) : (e_hi > 0.f ? (1.f - q_hi) * fabsf(e_hi) : 0.f);
+            part[2] += fabsf(e_mid);
+            g[0] = w0 * (e_lo < 0.f ? -q_lo : (e_lo > 0.f ? 1.f - q_lo : 0.f));
+            g[1] = w2 * sgnf(e_mid);
+            g[2] = w1 * (e_hi < 0.f ? -q_hi : (e_hi > 0.f ? 1.f - q_hi : 0.f));
+        } else if (KIND == IM2IM_LOSS_GAUSSIAN) {
+            const float d = pred[o] - y, v = fmaxf(pred[o + px], 1e-6f);
+            part[0] += 0.5f * (logf(v) + d * d / v);
+            g[0] = w0 * d / v;
+            g[1] = w0 * 0.5f * (1.f / v - d * d / (v * v));
+        } else if (KIND == IM2IM_LOSS_RESIDUAL || KIND == IM2IM_LOSS_RESIDUAL_L1) {
+            const float p = pred[o], r = pred[o + px];
+            const float d = p - y, res = y - p, rd = r - fabsf(res);
+            part[0] += (KIND == IM2IM_LOSS_RESIDUAL) ? d * d : fabsf(d);
+            part[1] += rd * rd;
+            g[0] = w0 * ((KIND == IM2IM_LOSS_RESIDUAL) ? 2.f * d : sgnf(d)) + w1 * 2.f * rd * sgnf(res);
+            g[1] = w1 * 2.f * rd;
+        } else {  // INN
+            const float l = pred[o], p = pred[o + px], u = pred[o + 2 * px];
+            const float d = p - y, over = fmaxf(y - u, 0.f), under = fmaxf(l - y, 0.f), wd = u - l;
+            part[0] += d * d;
+            part[1] += over * over + under * under + beta * fabsf(wd);
+            g[0] = w1 * (2.f * under - beta * sgnf(wd));
+            g[1] = w0 * 2.f * d;
+            g[2] = w1 * (-2.f * over + beta * sgnf(wd));
+        }
+        if (dpred) {
+#pragma unroll
+            for (int q = 0; q < kPlanes; ++q) dpred[o + q * px] = g[q] * inv_count;
+        }
+    }
+    __shared__ double s_part[3][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double v = part[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[q][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int wv = 0; wv < 8; ++wv) v += s_part[threadIdx.x][wv];
+        atomicAdd(&loss_parts[threadIdx.x], v);
+    }
+}
+
 // torch.optim.Adam (single tensor semantics, no amsgrad / weight decay / maximize):
 //   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -612,6 +687,30 @@ extern "C" int im2im_quantile_loss_f32(const float* d_pred, const float* d_targe
     return check_launch("quantile_loss_kernel");
 }
 
+extern "C" int im2im_head_loss_f32(int32_t loss_kind, const float* d_pred, const float* d_target, int64_t n_images,
+                                   int64_t px, float q_lo, float q_hi, float w0, float w1, float w2, float beta,
+                                   float* d_dpred, double* d_loss_parts, void* stream) {
+    if (n_images <= 0 || px <= 0 || !d_pred || !d_target || !d_loss_parts) return fail(IM2IM_EINVAL, "head_loss: bad arguments");
+    if (loss_kind == IM2IM_LOSS_QUANTILES)
+        return im2im_quantile_loss_f32(d_pred, d_target, n_images, px, q_lo, q_hi, w0, w1, w2, d_dpred, d_loss_parts, stream);
+    IM2IM_CUDA_TRY(cudaMemsetAsync(d_loss_parts, 0, sizeof(double) * 3, ST(stream)));
+    const long long n = n_images * px;
+    const unsigned grid = grid_for(n, 256, 8);
+    const float inv = 1.f / static_cast<float>(n);
+#define IM2IM_LOSS_CASE(K)                                                                                          \
+    case K:                                                                                                         \
+        head_loss_kernel<K><<<grid, 256, 0, ST(stream)>>>(d_pred, d_target, n_images, px, q_lo, q_hi, w0, w1, w2, beta, \
+                                                          inv, d_dpred, d_loss_parts);                              \
+        break
+    switch (loss_kind) {
+        IM2IM_LOSS_CASE(IM2IM_LOSS_QUANTILES_L1); IM2IM_LOSS_CASE(IM2IM_LOSS_GAUSSIAN); IM2IM_LOSS_CASE(IM2IM_LOSS_RESIDUAL);
+        IM2IM_LOSS_CASE(IM2IM_LOSS_RESIDUAL_L1); IM2IM_LOSS_CASE(IM2IM_LOSS_INN);
+        default: return fail(IM2IM_ENOTSUP, "head_loss: loss_kind=%d", loss_kind);
+    }
+#undef IM2IM_LOSS_CASE
+    return check_launch("head_loss_kernel");
+}
+
 extern "C" int im2im_adam_step_f32(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
                                    int64_t n, float lr, float beta1, float beta2, float eps, int32_t step,
                                    float grad_scale, void* stream) {
@@ -636,20 +735,18 @@ extern "C" int im2im_head_bwd(const float* d_dout, const void* d_m, const float*
     const size_t smem = sizeof(float) * 9 * n_out * c_mid;
     const unsigned g1 = grid_for(pixels, 128, 8);
     const unsigned g2 = static_cast<unsigned>(4 * sm_count());
+#define IM2IM_HEAD_BWD_CASE(N)                                                                                        \
+    case N:                                                                                                          \
+        head_dgrad_kernel<N><<<g1, 128, smem, ST(stream)>>>(d_dout, d_weight, B, H, W, c_mid, c_stride, BFW(d_dm));  \
+        if (int rc = check_launch("head_dgrad_kernel")) return rc;                                                   \
+        head_wgrad_kernel<N><<<g2, 128, 0, ST(stream)>>>(d_dout, BF(d_m), B, H, W, c_mid, c_stride, d_dw, d_db);    \
+        break
     switch (n_out) {
-        case 3:
-            head_dgrad_kernel<3><<<g1, 128, smem, ST(stream)>>>(d_dout, d_weight, B, H, W, c_mid, c_stride, BFW(d_dm));
-            if (int rc = check_launch("head_dgrad_kernel")) return rc;
-            head_wgrad_kernel<3><<<g2, 128, 0, ST(stream)>>>(d_dout, BF(d_m), B, H, W, c_mid, c_stride, d_dw, d_db);
-            break;
-        case 6:
-            head_dgrad_kernel<6><<<g1, 128, smem, ST(stream)>>>(d_dout, d_weight, B, H, W, c_mid, c_stride, BFW(d_dm));
-            if (int rc = check_launch("head_dgrad_kernel")) return rc;
-            head_wgrad_kernel<6><<<g2, 128, 0, ST(stream)>>>(d_dout, BF(d_m), B, H, W, c_mid, c_stride, d_dw, d_db);
-            break;
+        IM2IM_HEAD_BWD_CASE(2); IM2IM_HEAD_BWD_CASE(3); IM2IM_HEAD_BWD_CASE(4); IM2IM_HEAD_BWD_CASE(6);
         default:
-            return fail(IM2IM_ENOTSUP, "head_bwd: n_out=%d (3 or 6 supported)", n_out);
+            return fail(IM2IM_ENOTSUP, "head_bwd: n_out=%d (2, 3, 4 or 6 supported)", n_out);
     }
+#undef IM2IM_HEAD_BWD_CASE
     return check_launch("head_wgrad_kernel");
 }
 

@@ -147,7 +147,8 @@ template <int N_OUT>
 __global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias,
                                                         const float* __restrict__ tap_bias, int B, int H, int W,
-                                                        int c_mid, int c_stride, float* __restrict__ y) {
+                                                        int c_mid, int c_stride, int act_kind, int act_from,
+                                                        float* __restrict__ y) {
     constexpr int NP = (N_OUT + 3) / 4 * 4;
     extern __shared__ __align__(16) float s_w[];  // [tap][c_mid][NP]
     for (int i = threadIdx.x; i < 9 * c_mid * NP; i += blockDim.x) {
@@ -194,7 +195,14 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __r
         }
         const long long hw = static_cast<long long>(H) * W;
 #pragma unroll
-        for (int o = 0; o < N_OUT; ++o) y[(b * N_OUT + o) * hw + static_cast<long long>(yh) * W + xw] = acc[o];
+        for (int o = 0; o < N_OUT; ++o) {
+            float v = acc[o];
+            if (o >= act_from) {  // gaussian head: relu on the variance planes; residual heads: abs on the magnitude
+                if (act_kind == 1) v = (v != v) ? v : fmaxf(v, 0.f);
+                else if (act_kind == 2) v = fabsf(v);
+            }
+            y[(b * N_OUT + o) * hw + static_cast<long long>(yh) * W + xw] = v;
+        }
     }
 }
 
@@ -272,25 +280,39 @@ extern "C" int im2im_upsample2x_bilinear_bf16(const void* d_x, int32_t B, int32_
     return check_launch("upsample2x_kernel");
 }
 
-extern "C" int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias,
-                                      const float* d_tap_bias, int32_t B, int32_t H, int32_t W, int32_t c_mid,
-                                      int32_t c_stride, int32_t n_out, float* d_out, void* stream) {
+extern "C" int im2im_head_conv3x3_act_f32(const void* d_x, const float* d_weight, const float* d_bias,
+                                          const float* d_tap_bias, int32_t B, int32_t H, int32_t W, int32_t c_mid,
+                                          int32_t c_stride, int32_t n_out, int32_t act_kind, int32_t act_from_plane,
+                                          float* d_out, void* stream) {
     if (B <= 0 || H <= 0 || W <= 0 || c_mid <= 0 || c_mid % 8 || c_stride < c_mid || c_stride % 8)
         return fail(IM2IM_ERANGE, "head: bad shape");
     if (!d_x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "null tensor");
+    if (act_kind < 0 || act_kind > 2) return fail(IM2IM_EINVAL, "head: act_kind=%d", act_kind);
+    if (act_kind == 0) act_from_plane = n_out;
     const size_t smem = sizeof(float) * 9 * c_mid * ((n_out + 3) / 4 * 4);
     if (smem > 48 * 1024) return fail(IM2IM_ERANGE, "head: weights do not fit shared memory");
     const long long items = static_cast<long long>(B) * H * W;
     const unsigned grid = grid_for(items, 128);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(d_x);
+#define IM2IM_HEAD_CASE(N)                                                                                              \
+    case N:                                                                                                             \
+        head_conv_kernel<N><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, act_kind, \
+                                                     act_from_plane, d_out);                                            \
+        break
     switch (n_out) {
-        case 3: head_conv_kernel<3><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, d_out); break;
-        case 6: head_conv_kernel<6><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, d_out); break;
-        case 9: head_conv_kernel<9><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, d_out); break;
-        default: return fail(IM2IM_ENOTSUP, "head: n_out=%d (3*C_out with C_out in 1..3 supported)", n_out);
+        IM2IM_HEAD_CASE(2); IM2IM_HEAD_CASE(3); IM2IM_HEAD_CASE(4); IM2IM_HEAD_CASE(6); IM2IM_HEAD_CASE(9);
+        default: return fail(IM2IM_ENOTSUP, "head: n_out=%d (supported: 2, 3, 4, 6, 9 output planes)", n_out);
     }
+#undef IM2IM_HEAD_CASE
     return check_launch("head_conv_kernel");
+}
+
+extern "C" int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias,
+                                      const float* d_tap_bias, int32_t B, int32_t H, int32_t W, int32_t c_mid,
+                                      int32_t c_stride, int32_t n_out, float* d_out, void* stream) {
+    return im2im_head_conv3x3_act_f32(d_x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, n_out, 0, 0, d_out,
+                                      stream);
 }
 
 extern "C" int im2im_pack_conv_weights(const float* d_weight, int32_t c_out, int32_t c_in, int32_t taps, void* d_out_fwd,

@@ -3,12 +3,14 @@
   ModelWithUncertainty   :15-49   forward / loss_fn / nested_sets_from_output / nested_sets / set_lhat, buffer lhat
   add_uncertainty        :51-87   trunk + head selected by params["uncertainty_type"]
 
-Only the quantile head (the one BASELINE.json's north_star names) is implemented natively; the reference's other six
-``uncertainty_type`` values raise NotImplementedError here (listed as "next" in SURVEY.md §8f).
+All seven ``uncertainty_type`` values of the reference are available; every head's set function and calibration run
+on the native kernels (heads.py), the quantile head also has the native UNet inference/training engines behind
+``forward``; the other heads' forwards use the engine for the trunk + stacked head convolution where it applies.
 """
 import torch
 import torch.nn as nn
 
+from . import heads
 from .quantile_layer import (QuantileRegressionLayer, quantile_regression_loss_fn,
                              quantile_regression_nested_sets_from_output)
 
@@ -45,8 +47,9 @@ class ModelWithUncertainty(nn.Module):
     # Always outputs [0,1] valued nested sets
     def nested_sets_from_output(self, output, lam=None):
         lower_edge, prediction, upper_edge = self.in_nested_sets_from_output_fn(self, output, lam)
-        if self.in_nested_sets_from_output_fn is not quantile_regression_nested_sets_from_output:
-            # heads without a fused kernel: apply the reference's lower bound on the set size (:35-36)
+        if getattr(self.in_nested_sets_from_output_fn, "im2im_head_kind", None) is None:
+            # user-supplied set functions: apply the reference's lower bound on the set size (:35-36); the built-in
+            # heads have it fused into their kernel (the clamp is idempotent)
             upper_edge = torch.maximum(upper_edge, prediction + 1e-6)
             lower_edge = torch.minimum(lower_edge, prediction - 1e-6)
         return lower_edge, prediction, upper_edge
@@ -63,11 +66,28 @@ class ModelWithUncertainty(nn.Module):
         self.lhat = lhat
 
 
+_OTHER_HEADS = {
+    "quantiles_l1": (heads.QuantileRegressionL1Layer, heads.quantile_regression_l1_loss_fn,
+                     heads.quantile_regression_l1_nested_sets_from_output),
+    "gaussian": (heads.GaussianRegressionLayer, heads.gaussian_regression_loss_fn,
+                 heads.gaussian_regression_nested_sets_from_output),
+    "residual_magnitude": (heads.ResidualMagnitudeLayer, heads.residual_magnitude_loss_fn,
+                           heads.residual_magnitude_nested_sets_from_output),
+    "residual_magnitude_l1": (heads.ResidualMagnitudeL1Layer, heads.residual_magnitude_l1_loss_fn,
+                              heads.residual_magnitude_l1_nested_sets_from_output),
+    "softmax": (heads.SoftmaxLayer, heads.softmax_loss_fn, heads.softmax_nested_sets_from_output),
+    "inn": (heads.INNLayer, heads.inn_loss_fn, heads.inn_nested_sets_from_output),
+}
+
+
 def add_uncertainty(model, params):
     if params["uncertainty_type"] == "quantiles":
         last_layer = QuantileRegressionLayer(model.n_channels_middle, model.n_channels_out, params)
         train_loss_fn = quantile_regression_loss_fn
         nested_sets_from_output_fn = quantile_regression_nested_sets_from_output
+    elif params["uncertainty_type"] in _OTHER_HEADS:
+        layer_cls, train_loss_fn, nested_sets_from_output_fn = _OTHER_HEADS[params["uncertainty_type"]]
+        last_layer = layer_cls(model.n_channels_middle, model.n_channels_out, params)
     else:
         raise NotImplementedError
     return ModelWithUncertainty(model, last_layer, train_loss_fn, nested_sets_from_output_fn, params)

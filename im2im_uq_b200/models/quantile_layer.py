@@ -58,3 +58,7 @@ def quantile_regression_nested_sets_from_output(model, output, lam=None):
         lam = model.lhat
     lower_edge, prediction, upper_edge = rcps.quantile_nested_sets(output, float(lam), write_back_clamp=True)
     return lower_edge, prediction, upper_edge
+
+
+quantile_regression_nested_sets_from_output.im2im_head_kind = 0        # _lib.IM2IM_HEAD_QUANTILES
+quantile_regression_nested_sets_from_output.im2im_scores_from_output = None

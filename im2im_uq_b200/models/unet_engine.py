@@ -67,10 +67,18 @@ class UNetInferenceEngine:
             a, b = double(blk.conv)
             self.up.append((packed(a), packed(b)))
         self.out = packed(_fold_bn(trunk.out.conv, None))
-        hw = torch.cat([head.lower.weight, head.prediction.weight, head.upper.weight], dim=0).detach().float().contiguous()
-        hb = torch.cat([head.lower.bias, head.prediction.bias, head.upper.bias], dim=0).detach().float().contiguous()
+        planes = head_plane_convs(head)
+        if planes is None or len(planes[0]) * planes[0][0].weight.shape[0] not in (2, 3, 4, 6, 9):
+            self.head = None            # e.g. the 50-plane softmax head: native trunk, library head conv (forward())
+            self._stamp = self._param_stamp()
+            return
+        convs, act, act_from = planes
+        hw = torch.cat([c.weight for c in convs], dim=0).detach().float().contiguous()
+        hb = torch.cat([c.bias for c in convs], dim=0).detach().float().contiguous()
         self.head = (hw, hb)
-        self.c_out = head.lower.weight.shape[0]
+        self.n_planes = len(convs)
+        self.c_out = convs[0].weight.shape[0]
+        self.head_act = ({None: 0, "relu": 1, "abs": 2}[act], act_from * self.c_out)
         self._stamp = self._param_stamp()
 
     # ---- single launches
@@ -108,9 +116,10 @@ class UNetInferenceEngine:
         hw, hb = self.head
         n_out = hw.shape[0]
         y = torch.empty((B, n_out, H, W), dtype=torch.float32, device=x.device)
-        _lib.check(lib.im2im_head_conv3x3_f32(x.data_ptr(), hw.data_ptr(), hb.data_ptr(), None, B, H, W, C, C, n_out,
-                                              y.data_ptr(), _stream(x.device)), "im2im_head_conv3x3_f32")
-        return y.view(B, 3, self.c_out, H, W)
+        _lib.check(lib.im2im_head_conv3x3_act_f32(x.data_ptr(), hw.data_ptr(), hb.data_ptr(), None, B, H, W, C, C, n_out,
+                                                  self.head_act[0], self.head_act[1], y.data_ptr(), _stream(x.device)),
+                   "im2im_head_conv3x3_act_f32")
+        return y.view(B, self.n_planes, self.c_out, H, W)
 
     # ---- the forward
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -133,14 +142,32 @@ class UNetInferenceEngine:
                 y = conv_igemm(skip, c1[0], c1[1], relu=True, x2=u)   # torch.cat([skip, up]) without the copy
                 y = conv_igemm(y, c2[0], c2[1], relu=True)
             m = conv_igemm(y, self.out[0], self.out[1], relu=False)  # 1x1 OutConv, 64 -> 32 (tensor cores)
+            if self.head is None:  # heads without a native kernel (softmax: 50 planes) run their own module on the features
+                return self.model.last_layer(m.permute(0, 3, 1, 2).float())
             return self._head(m)
 
 
-def native_forward_applicable(model, x) -> bool:
+def head_plane_convs(head):
+    """(convs in plane order, activation name or None, first activated plane) of a stacked-planes head, else None.
+
+    Covers QuantileRegressionLayer (quantile_layer.py:15-20) and the heads of heads.py that stack one 3x3 conv per
+    plane (gaussian: relu on the variance plane; residual magnitude: abs on the magnitude plane)."""
+    from .heads import _StackedPlanesHead
     from .quantile_layer import QuantileRegressionLayer
+    if type(head) is QuantileRegressionLayer:
+        return [head.lower, head.prediction, head.upper], None, 0
+    if isinstance(head, _StackedPlanesHead):
+        return head.plane_convs(), head.act, head.act_from
+    return None
+
+
+def native_forward_applicable(model, x) -> bool:
     from .unet import UNet
-    return (not model.training and torch.is_tensor(x) and x.is_cuda and not torch.is_grad_enabled()
+    if not (not model.training and torch.is_tensor(x) and x.is_cuda and not torch.is_grad_enabled()
             and type(model.baseModel) is UNet and model.baseModel.bilinear
-            and type(model.last_layer) is QuantileRegressionLayer and getattr(model, "use_native_inference", True)
-            and x.dim() == 4 and x.shape[1] <= 8 and min(x.shape[2], x.shape[3]) >= 16
-            and model.last_layer.lower.weight.shape[0] <= 3)
+            and getattr(model, "use_native_inference", True)
+            and x.dim() == 4 and x.shape[1] <= 8 and min(x.shape[2], x.shape[3]) >= 16):
+        return False
+    if not isinstance(model.last_layer, nn.Module):
+        return False
+    return True

@@ -54,9 +54,9 @@ class _ConvBN:
 
 class UNetTrainEngine:
     def __init__(self, model):
-        from .quantile_layer import QuantileRegressionLayer
         from .unet import UNet
-        assert type(model.baseModel) is UNet and type(model.last_layer) is QuantileRegressionLayer
+        from .unet_engine import head_plane_convs
+        assert type(model.baseModel) is UNet and head_plane_convs(model.last_layer) is not None
         self.model = model
         t, self.head = model.baseModel, model.last_layer
         self.lib = _lib.load()
@@ -70,7 +70,11 @@ class UNetTrainEngine:
         self.up = [dc(b.conv) for b in (t.up1, t.up2, t.up3, t.up4)]
         self.out_conv = t.out.conv
         self.c_mid = self.out_conv.weight.shape[0]      # 32
-        self.n_out = 3 * self.head.lower.weight.shape[0]
+        self.head_convs, self.head_act, act_from = head_plane_convs(self.head)   # plane order, relu/abs/None
+        self.c_head = self.head_convs[0].weight.shape[0]
+        self.n_planes = len(self.head_convs)
+        self.n_out = self.n_planes * self.c_head
+        self.act_from = act_from * self.c_head
 
     # ------------------------------------------------------------------------------------------- primitive launches
     def _bn_relu(self, z: torch.Tensor, layer: _ConvBN, saved: dict):
@@ -193,14 +197,20 @@ class UNetTrainEngine:
             m = conv_igemm(y, w_pad, b_pad, relu=False)
             ctx["y_last"], ctx["m"], ctx["w_out_pad"] = y, m, w_pad
             # head (CUDA cores)
-            hw_ = torch.cat([self.head.lower.weight, self.head.prediction.weight, self.head.upper.weight], 0).detach().float().contiguous()
-            hb = torch.cat([self.head.lower.bias, self.head.prediction.bias, self.head.upper.bias], 0).detach().float().contiguous()
+            hw_ = torch.cat([c.weight for c in self.head_convs], 0).detach().float().contiguous()
+            hb = torch.cat([c.bias for c in self.head_convs], 0).detach().float().contiguous()
             out = torch.empty((B, self.n_out, H, W), dtype=torch.float32, device=dev)
             # m has a 64-channel row stride (upper 32 are zero padding); the head reads only the 32 real channels
             _lib.check(lib.im2im_head_conv3x3_f32(m.data_ptr(), hw_.data_ptr(), hb.data_ptr(), None, B, H, W, self.c_mid, 64,
                                                   self.n_out, out.data_ptr(), _st(dev)), "head_conv")
             ctx["head_w"] = hw_
-        return out.view(B, 3, self.n_out // 3, H, W), ctx
+            if self.head_act is not None:
+                # gaussian: relu(variance conv), residual magnitude: |magnitude conv| (gaussian_layer.py:18,
+                # residual_magnitude_layer.py:18); the derivative (0/1 or sign) of the pre-activation is kept for backward
+                tail = out[:, self.act_from:]
+                ctx["act_grad"] = (tail > 0).float() if self.head_act == "relu" else torch.sign(tail)
+                tail.copy_(torch.relu(tail) if self.head_act == "relu" else tail.abs())
+        return out.view(B, self.n_planes, self.c_head, H, W), ctx
 
     # ------------------------------------------------------------------------------------------- backward
     def _conv_bwd(self, layer: _ConvBN, saved: dict, dz: torch.Tensor, grads: Dict, need_dx: bool = True):
@@ -237,6 +247,9 @@ class UNetTrainEngine:
         x = ctx["x"]
         B, c_in, H, W = x.shape
         dout = dout.contiguous().float().view(B, self.n_out, H, W)
+        if self.head_act is not None:
+            dout = dout.clone()
+            dout[:, self.act_from:] *= ctx["act_grad"]
         with torch.cuda.device(dev):
             m, y_last = ctx["m"], ctx["y_last"]
             dm = torch.empty_like(m)
@@ -245,8 +258,8 @@ class UNetTrainEngine:
             _lib.check(lib.im2im_head_bwd(dout.data_ptr(), m.data_ptr(), ctx["head_w"].data_ptr(), B, H, W, self.c_mid,
                                           64, self.n_out, dm.data_ptr(), dwh.data_ptr(), dbh.data_ptr(), _st(dev)),
                        "head_bwd")
-            co = self.n_out // 3
-            for i, conv in enumerate((self.head.lower, self.head.prediction, self.head.upper)):
+            co = self.c_head
+            for i, conv in enumerate(self.head_convs):
                 grads[conv.weight] = dwh[i * co:(i + 1) * co]
                 grads[conv.bias] = dbh[i * co:(i + 1) * co]
             # 1x1 out conv: wgrad, bias grad (channel sums of dm), dgrad
@@ -315,13 +328,15 @@ class _NativeTrainFn(torch.autograd.Function):
 
 
 def native_train_applicable(model, x) -> bool:
-    from .quantile_layer import QuantileRegressionLayer
     from .unet import UNet
-    return (model.training and torch.is_tensor(x) and x.is_cuda and torch.is_grad_enabled()
+    from .unet_engine import head_plane_convs
+    if not (model.training and torch.is_tensor(x) and x.is_cuda and torch.is_grad_enabled()
             and type(model.baseModel) is UNet and model.baseModel.bilinear
-            and type(model.last_layer) is QuantileRegressionLayer and getattr(model, "use_native_training", True)
-            and x.dim() == 4 and x.shape[1] <= 8 and min(x.shape[2], x.shape[3]) >= 16
-            and model.last_layer.lower.weight.shape[0] <= 2)
+            and getattr(model, "use_native_training", True)
+            and x.dim() == 4 and x.shape[1] <= 8 and min(x.shape[2], x.shape[3]) >= 16):
+        return False
+    planes = head_plane_convs(model.last_layer)   # quantile / gaussian / residual / quantile-l1 / inn heads
+    return planes is not None and len(planes[0]) * planes[0][0].weight.shape[0] in (2, 3, 4, 6)
 
 
 def native_train_forward(model, x):

@@ -1,7 +1,9 @@
 """Tensor-level wrappers over the RCPS entry points of the C ABI (include/im2im_uq.h).
 
-All tensors are CUDA fp32; outputs follow the reference's head layout (N, 3, C, H, W) = (lower, pred, upper)
-(core/models/finallayers/quantile_layer.py:19-21) and labels (N, C, H, W).
+All tensors are CUDA fp32; outputs follow the reference's head layouts and labels are (N, C, H, W):
+  head QUANTILES / SOFTMAX_SETS   (N, 3, C, H, W) = (lower, pred, upper)      quantile_layer.py:19-21
+  head RESIDUAL / GAUSSIAN        (N, 2, C, H, W) = (pred, width | variance)  residual_magnitude_layer.py:17-19,
+                                                                              gaussian_layer.py:17-19
 """
 from typing import Optional, Tuple
 
@@ -21,11 +23,14 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def _score_planes(outputs: torch.Tensor, labels: Optional[torch.Tensor]):
-    """Raw pointers/strides of the (lower, pred, upper[, label]) planes without copying when the layout allows."""
+def _score_planes(outputs: torch.Tensor, labels: Optional[torch.Tensor], head: int = _lib.IM2IM_HEAD_QUANTILES):
+    """Raw pointers/strides of the (lower, pred, upper[, label]) planes without copying when the layout allows.
+    For the two-plane heads the `lower` slot repeats the prediction plane (the ABI ignores it)."""
     _require_cuda(outputs, "outputs")
-    if outputs.dim() < 3 or outputs.shape[1] != 3:
-        raise _lib.Im2ImError(f"outputs must be (N, 3, ...) = (lower, pred, upper); got {tuple(outputs.shape)}")
+    three = head in _lib.THREE_PLANE_HEADS
+    if outputs.dim() < 3 or outputs.shape[1] != (3 if three else 2):
+        want = "(N, 3, ...) = (lower, pred, upper)" if three else "(N, 2, ...) = (pred, width)"
+        raise _lib.Im2ImError(f"outputs must be {want} for head kind {head}; got {tuple(outputs.shape)}")
     n = outputs.shape[0]
     px = 1
     for s in outputs.shape[2:]:
@@ -33,9 +38,9 @@ def _score_planes(outputs: torch.Tensor, labels: Optional[torch.Tensor]):
     inner_contig = outputs[0, 0].is_contiguous() if n > 0 and px > 0 else True
     if not inner_contig:
         outputs = outputs.contiguous()
-    s_img, s_plane = (outputs.stride(0), outputs.stride(1)) if n > 0 and px > 0 else (3 * px, px)
+    s_img, s_plane = (outputs.stride(0), outputs.stride(1)) if n > 0 and px > 0 else (outputs.shape[1] * px, px)
     base = outputs.data_ptr()
-    ptrs = [base, base + 4 * s_plane, base + 8 * s_plane]
+    ptrs = [base, base + 4 * s_plane, base + 8 * s_plane] if three else [base, base, base + 4 * s_plane]
     strides = [s_img, s_img, s_img]
     keep = [outputs]
     if labels is not None:
@@ -52,14 +57,15 @@ def _score_planes(outputs: torch.Tensor, labels: Optional[torch.Tensor]):
 
 def miss_counts(outputs: torch.Tensor, labels: torch.Tensor, lambdas_sorted: torch.Tensor,
                 counts: Optional[torch.Tensor] = None, totals: Optional[torch.Tensor] = None,
-                zero: bool = True, force_generic: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+                zero: bool = True, force_generic: bool = False,
+                head: int = _lib.IM2IM_HEAD_QUANTILES) -> Tuple[torch.Tensor, torch.Tensor]:
     """counts[i, j] = #pixels of image i missed at lambdas_sorted[j]; totals[j] += column sums (int64).
 
     One pass over HBM for the whole grid (im2im_rcps_miss_counts).  ``lambdas_sorted`` is a CUDA fp32 vector,
     finite and ascending.  ``counts``/``totals`` may be preallocated (e.g. to accumulate chunks with zero=False).
     """
     lib = _lib.load()
-    n, px, ptrs, strides, keep = _score_planes(outputs, labels)
+    n, px, ptrs, strides, keep = _score_planes(outputs, labels, head)
     _require_cuda(lambdas_sorted, "lambdas_sorted")
     lambdas_sorted = lambdas_sorted.contiguous()
     n_lam = lambdas_sorted.numel()
@@ -75,7 +81,7 @@ def miss_counts(outputs: torch.Tensor, labels: torch.Tensor, lambdas_sorted: tor
     flags = (_lib.IM2IM_RCPS_ZERO_OUTPUTS if zero else 0) | (_lib.IM2IM_RCPS_FORCE_GENERIC if force_generic else 0)
     with torch.cuda.device(dev):
         rc = lib.im2im_rcps_miss_counts(ptrs[0], ptrs[1], ptrs[2], ptrs[3], n, px, strides[0], strides[1], strides[2],
-                                        strides[3], lambdas_sorted.data_ptr(), n_lam, _lib.IM2IM_HEAD_QUANTILES,
+                                        strides[3], lambdas_sorted.data_ptr(), n_lam, head,
                                         counts.data_ptr(), totals.data_ptr(), flags, _stream_ptr(dev))
     _lib.check(rc, "im2im_rcps_miss_counts")
     del keep
@@ -126,14 +132,53 @@ def quantile_nested_sets(outputs: torch.Tensor, lam: float, write_back_clamp: bo
     return lower, src[:, 1], upper
 
 
-def miss_map(outputs: torch.Tensor, labels: torch.Tensor, lam: float) -> torch.Tensor:
+def head_nested_sets(outputs: torch.Tensor, lam: float, head: int):
+    """(lower_edge, prediction, upper_edge) at one lambda for any head kind (im2im_nested_sets): the head's set
+    function followed by the +/-1e-6 clamp of add_uncertainty.py:35-36.  prediction is a view of ``outputs``."""
+    if head == _lib.IM2IM_HEAD_QUANTILES:
+        return quantile_nested_sets(outputs, lam, write_back_clamp=False)
+    lib = _lib.load()
+    n, px, ptrs, strides, keep = _score_planes(outputs, None, head)
+    src = keep[0]
+    shape = tuple(outputs.shape[:1]) + tuple(outputs.shape[2:])
+    lower = torch.empty(shape, dtype=torch.float32, device=outputs.device)
+    upper = torch.empty(shape, dtype=torch.float32, device=outputs.device)
+    with torch.cuda.device(outputs.device):
+        rc = lib.im2im_nested_sets(head, ptrs[0], ptrs[1], ptrs[2], n, px, strides[0], strides[1], strides[2],
+                                   float(lam), 0, lower.data_ptr(), upper.data_ptr(), _stream_ptr(outputs.device))
+    _lib.check(rc, "im2im_nested_sets")
+    return lower, src[:, 1 if head in _lib.THREE_PLANE_HEADS else 0], upper
+
+
+def softmax_sets(logits: torch.Tensor) -> torch.Tensor:
+    """Softmax head logits (N, K, ...) -> (N, 3, ...) = (lower quantile, argmax prediction, upper quantile): the
+    lambda-independent half of softmax_nested_sets_from_output (softmax_layer.py:34-48), computed once."""
+    lib = _lib.load()
+    _require_cuda(logits, "logits")
+    if logits.dim() < 3:
+        raise _lib.Im2ImError(f"logits must be (N, K, ...); got {tuple(logits.shape)}")
+    logits = logits.contiguous()
+    n, k = logits.shape[:2]
+    inner = 1
+    for s_ in logits.shape[2:]:
+        inner *= s_
+    sets = torch.empty((n, 3) + tuple(logits.shape[2:]), dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        rc = lib.im2im_softmax_sets(logits.data_ptr(), n, k, inner, k * inner, inner, sets.data_ptr(),
+                                    _stream_ptr(logits.device))
+    _lib.check(rc, "im2im_softmax_sets")
+    return sets
+
+
+def miss_map(outputs: torch.Tensor, labels: torch.Tensor, lam: float,
+             head: int = _lib.IM2IM_HEAD_QUANTILES) -> torch.Tensor:
     """int32 map over (C,H,W): number of images whose pixel is missed at ``lam``."""
     lib = _lib.load()
-    n, px, ptrs, strides, keep = _score_planes(outputs, labels)
+    n, px, ptrs, strides, keep = _score_planes(outputs, labels, head)
     out = torch.empty(tuple(outputs.shape[2:]), dtype=torch.int32, device=outputs.device)
     with torch.cuda.device(outputs.device):
         rc = lib.im2im_rcps_miss_map(ptrs[0], ptrs[1], ptrs[2], ptrs[3], n, px, strides[0], strides[1], strides[2],
-                                     strides[3], float(lam), _lib.IM2IM_HEAD_QUANTILES, out.data_ptr(),
+                                     strides[3], float(lam), head, out.data_ptr(),
                                      _lib.IM2IM_RCPS_ZERO_OUTPUTS, _stream_ptr(outputs.device))
     _lib.check(rc, "im2im_rcps_miss_map")
     del keep

@@ -225,6 +225,12 @@ int im2im_upsample2x_bilinear_bf16(const void* d_x, int32_t B, int32_t h, int32_
 int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias, const float* d_tap_bias,
                            int32_t B, int32_t H, int32_t W, int32_t c_mid, int32_t c_stride, int32_t n_out, float* d_out,
                            void* stream);
+/* The same with the head's output activation fused: planes >= act_from_plane get act_kind (0 none, 1 relu, 2 abs) -
+ * GaussianRegressionLayer.forward (gaussian_layer.py:17-19: relu on the variance conv) and ResidualMagnitude(L1)Layer
+ * .forward (residual_magnitude_layer.py:17-19: abs on the magnitude conv).  n_out in {2, 3, 4, 6, 9}. */
+int im2im_head_conv3x3_act_f32(const void* d_x, const float* d_weight, const float* d_bias, const float* d_tap_bias,
+                               int32_t B, int32_t H, int32_t W, int32_t c_mid, int32_t c_stride, int32_t n_out,
+                               int32_t act_kind, int32_t act_from_plane, float* d_out, void* stream);
 
 /*
  * Training-side passes of the UNet path (autograd of core/scripts/train.py:152-162 through the modules of
@@ -263,6 +269,25 @@ int im2im_upsample2x_bilinear_bwd_bf16(const void* d_du, int32_t B, int32_t h, i
 int im2im_quantile_loss_f32(const float* d_pred, const float* d_target, int64_t n_images, int64_t px, float q_lo,
                             float q_hi, float w_lo, float w_hi, float w_mse, float* d_dpred, double* d_loss_parts,
                             void* stream);
+/*
+ * Training losses of every affine head in one fused pass (value parts + gradient), pred (B, planes, px) fp32:
+ *   IM2IM_LOSS_QUANTILES     quantile_layer.py:23-32      parts = (sum pinball_lo, sum pinball_hi, sum sq err); w = (w_lo, w_hi, w_mse)
+ *   IM2IM_LOSS_QUANTILES_L1  quantile_l1_layer.py:23-32   parts = (sum pinball_lo, sum pinball_hi, sum |err|);  w = (w_lo, w_hi, w_mse)
+ *   IM2IM_LOSS_GAUSSIAN      gaussian_layer.py:20-24      parts = (sum 0.5*(log v + d^2/v), 0, 0), v = max(var, 1e-6); w0 = 1
+ *   IM2IM_LOSS_RESIDUAL      residual_magnitude_layer.py:20-26     parts = (sum (p-y)^2, sum (r-|y-p|)^2, 0); w = (1, 1)
+ *   IM2IM_LOSS_RESIDUAL_L1   residual_magnitude_l1_layer.py:20-26  parts = (sum |p-y|,  sum (r-|y-p|)^2, 0); w = (1, 1)
+ *   IM2IM_LOSS_INN           inn_layer.py:23-28 + losses/inn.py:11-14  parts = (sum (p-y)^2, sum relu(y-u)^2+relu(l-y)^2+beta|u-l|, 0)
+ * loss = sum_k w_k * parts[k] / (n_images*px); d_dpred (may be NULL) receives d loss / d pred with the same weights.
+ */
+#define IM2IM_LOSS_QUANTILES 0
+#define IM2IM_LOSS_QUANTILES_L1 1
+#define IM2IM_LOSS_GAUSSIAN 2
+#define IM2IM_LOSS_RESIDUAL 3
+#define IM2IM_LOSS_RESIDUAL_L1 4
+#define IM2IM_LOSS_INN 5
+int im2im_head_loss_f32(int32_t loss_kind, const float* d_pred, const float* d_target, int64_t n_images, int64_t px,
+                        float q_lo, float q_hi, float w0, float w1, float w2, float beta, float* d_dpred,
+                        double* d_loss_parts, void* stream);
 int im2im_adam_step_f32(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n, float lr,
                         float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
 int im2im_head_bwd(const float* d_dout, const void* d_m, const float* d_weight, int32_t B, int32_t H, int32_t W,

@@ -214,10 +214,31 @@ def loss_kats():
     print(f"[golden] head losses: {len(fns) * 2} cases")
 
 
+def loss_table_trials():
+    """evaluate_from_loss_table (calibrate_model.py:62-74) as plot_risks drives it (experiments/*/plot.py:133-136):
+    seeded trials on saved dense tables; pins the RNG consumption and the `<= delta` column choice."""
+    import warnings
+    cases = {}
+    for name, n, delta, trials in (("fastmri_small", 24, 0.1, 6), ("temca_small", 40, 0.3, 6), ("bsbcm_grid", 12, 0.2, 3)):
+        table = torch.from_numpy(np.load(os.path.join(HERE, f"rcps_{name}.npz"))["dense_grid"])
+        torch.manual_seed(1234)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            risks = torch.stack([ref.calibrate_model.evaluate_from_loss_table(table, n, 0.1, delta) for _ in range(trials)])
+        cases[name + "_risks"] = risks.numpy()
+        cases[name + "_args"] = json.dumps(dict(n=n, alpha=0.1, delta=delta, trials=trials, seed=1234))
+    np.savez_compressed(os.path.join(HERE, "loss_table_trials.npz"), **cases)
+    print("[golden] loss-table trials:", {k: v.tolist() for k, v in cases.items() if k.endswith("_risks")})
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    if only == ["trials"]:
+        loss_table_trials()
+        sys.exit(0)
     if not only:
         loss_kats()
+        loss_table_trials()
     _run_case = run_case
     run_case = lambda name, *a, **k: _run_case(name, *a, **k) if (not only or name in only) else None  # noqa: E731
     #        name               head                     seed n   c  h   w   nasty  lmin lmax L     alpha delta

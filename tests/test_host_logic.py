@@ -165,3 +165,31 @@ def test_quantile_loss_matches_reference_kats():
         loss.backward()
         np.testing.assert_allclose(loss.detach().numpy(), g[f"{name}_loss"], rtol=1e-6)
         np.testing.assert_allclose(pred.grad.numpy(), g[f"{name}_grad"], rtol=1e-6, atol=1e-9)
+
+
+def test_loss_table_trials_match_reference_and_wire_format(tmp_path):
+    """plot_risks' trial loop over evaluate_from_loss_table against values produced by the unmodified reference
+    (tests/golden/make_golden_heads.py::loss_table_trials), and the router's .pth wire format round trip."""
+    import json
+    import warnings
+    from conftest import load_golden
+    from im2im_uq_b200.scripts import eval as ev
+    kats = np.load(os.path.join(GOLDEN, "loss_table_trials.npz"))
+    for name in ("fastmri_small", "temca_small", "bsbcm_grid"):
+        args = json.loads(str(kats[name + "_args"]))
+        table = torch.from_numpy(load_golden(name)["dense_grid"])
+        torch.manual_seed(args["seed"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            risks = ev.evaluate_loss_table_trials(table, args["n"], args["alpha"], args["delta"], args["trials"])
+        assert np.array_equal(risks.numpy(), kats[name + "_risks"]), name
+    g = load_golden("batch65")
+    calib, val = torch.from_numpy(g["calib_loss_table"]), torch.from_numpy(g["dense_grid"])
+    path = str(tmp_path / ev.loss_table_filename(dict(dataset="fastmri", uncertainty_type="quantiles", batch_size=78,
+                                                       lr=0.0001, input_normalization="standard",
+                                                       output_normalization="min-max")))
+    assert path.endswith("loss_table_fastmri_quantiles_78_0.0001_standard_min-max.pth")
+    ev.save_loss_tables(calib, val, path)
+    back = ev.load_loss_table(path)
+    assert back.shape == (calib.shape[0] + val.shape[0], calib.shape[1])
+    assert torch.equal(back[:calib.shape[0]], calib) and torch.equal(back[calib.shape[0]:], val)
