@@ -120,6 +120,7 @@ def _declare_train(lib):
         "im2im_upsample2x_bilinear_bwd_bf16": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
         "im2im_quantile_loss_f32": [vp, vp, i64, i64, f32, f32, f32, f32, f32, vp, vp, vp],
         "im2im_adam_step_f32": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
+        "im2im_adam_step_dev_f32": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp],
         "im2im_head_loss_f32": [i32, vp, vp, i64, i64, f32, f32, f32, f32, f32, f32, vp, vp, vp],
         "im2im_head_bwd": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp],
         "im2im_conv_first_wgrad": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
@@ -138,7 +139,8 @@ EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im
            "im2im_channel_stats_bf16", "im2im_bn_finalize", "im2im_bn_apply_relu_bf16", "im2im_bn_relu_bwd_bf16",
            "im2im_maxpool2x2_bwd_bf16", "im2im_upsample2x_bilinear_bwd_bf16", "im2im_quantile_loss_f32",
            "im2im_adam_step_f32", "im2im_head_bwd", "im2im_conv_first_wgrad", "im2im_nested_sets",
-           "im2im_softmax_sets", "im2im_head_conv3x3_act_f32", "im2im_head_loss_f32"]
+           "im2im_softmax_sets", "im2im_head_conv3x3_act_f32", "im2im_head_loss_f32",
+           "im2im_adam_step_dev_f32"]
 
 
 def load():

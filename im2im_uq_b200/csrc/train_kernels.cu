@@ -407,7 +407,8 @@ __global__ void __launch_bounds__(256) head_loss_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n, float lr,
                                                    float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                                                   float grad_scale) {
+                                                   float grad_scale, const float* __restrict__ bc_dev) {
+    if (bc_dev != nullptr) { bc1 = bc_dev[0]; bc2_sqrt = bc_dev[1]; }  // step counter lives on the device (CUDA graphs)
     for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n;
          e += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float gr = g[e] * grad_scale;
@@ -418,6 +419,14 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
         const float denom = sqrtf(vv) / bc2_sqrt + eps;
         p[e] -= (lr / bc1) * (mm / denom);
     }
+}
+
+// state[0] = step counter (as float, exact below 2^24), state[1] = 1 - b1^step, state[2] = sqrt(1 - b2^step)
+__global__ void adam_advance_kernel(float* __restrict__ state, float b1, float b2) {
+    const double step = static_cast<double>(state[0]) + 1.0;
+    state[0] = static_cast<float>(step);
+    state[1] = static_cast<float>(1.0 - pow(static_cast<double>(b1), step));
+    state[2] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), step)));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -721,7 +730,20 @@ extern "C" int im2im_adam_step_f32(float* d_param, const float* d_grad, float* d
     const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
     adam_kernel<<<grid_for(n, 256, 16), 256, 0, ST(stream)>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, lr, beta1,
                                                              beta2, eps, static_cast<float>(bc1),
-                                                             static_cast<float>(sqrt(bc2)), grad_scale);
+                                                             static_cast<float>(sqrt(bc2)), grad_scale, nullptr);
+    return check_launch("adam_kernel");
+}
+
+extern "C" int im2im_adam_step_dev_f32(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
+                                       int64_t n, float lr, float beta1, float beta2, float eps, float* d_state,
+                                       float grad_scale, void* stream) {
+    if (n < 0 || !d_state) return fail(IM2IM_EINVAL, "adam_dev: bad arguments");
+    if (n > 0 && (!d_param || !d_grad || !d_exp_avg || !d_exp_avg_sq)) return fail(IM2IM_EINVAL, "adam_dev: null tensor");
+    adam_advance_kernel<<<1, 1, 0, ST(stream)>>>(d_state, beta1, beta2);
+    if (int rc = check_launch("adam_advance_kernel")) return rc;
+    if (n == 0) return IM2IM_OK;
+    adam_kernel<<<grid_for(n, 256, 16), 256, 0, ST(stream)>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, lr, beta1,
+                                                             beta2, eps, 1.f, 1.f, grad_scale, d_state + 1);
     return check_launch("adam_kernel");
 }
 

@@ -138,8 +138,7 @@ class _HeadLossFn(torch.autograd.Function):
                                                beta, dpred.data_ptr(), parts.data_ptr(),
                                                torch.cuda.current_stream(pred.device).cuda_stream), "im2im_head_loss_f32")
         ctx.save_for_backward(dpred)
-        w = torch.tensor([w0, w1, w2], dtype=torch.float64, device=pred.device)
-        return ((parts / float(n * px)) * w).sum().to(torch.float32)
+        return ((parts[0] * w0 + parts[1] * w1 + parts[2] * w2) / float(n * px)).to(torch.float32)
 
     @staticmethod
     def backward(ctx, g):

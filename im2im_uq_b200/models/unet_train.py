@@ -364,8 +364,8 @@ class _QuantileLossFn(torch.autograd.Function):
                        "quantile_loss")
         ctx.save_for_backward(dpred)
         count = float(n * px)
-        w = torch.tensor([w_lo, w_hi, w_mse], dtype=torch.float64, device=pred.device)
-        return ((parts / count) * w).sum().to(torch.float32)
+        # python-scalar weights: no host->device copy, so the step can be captured into a CUDA graph
+        return ((parts[0] * w_lo + parts[1] * w_hi + parts[2] * w_mse) / count).to(torch.float32)
 
     @staticmethod
     def backward(ctx, g):
@@ -404,6 +404,9 @@ class FusedAdam(torch.optim.Optimizer):
             off += k
         self._params = ps
         self._step = 0
+        # {step, 1-b1^step, sqrt(1-b2^step)} in device memory: the step count advances on the device, so a captured
+        # CUDA graph of the whole training step replays with the right bias correction
+        self.state_dev = torch.zeros(3, dtype=torch.float32, device=dev)
 
     def zero_grad(self, set_to_none: bool = False):
         self.flat_grad.zero_()
@@ -430,7 +433,62 @@ class FusedAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         lib = _lib.load()
         with torch.cuda.device(self.flat_param.device):
-            _lib.check(lib.im2im_adam_step_f32(self.flat_param.data_ptr(), self.flat_grad.data_ptr(),
-                                               self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                               self.flat_param.numel(), g["lr"], g["betas"][0], g["betas"][1], g["eps"],
-                                               self._step, grad_scale, _st(self.flat_param.device)), "adam_step")
+            _lib.check(lib.im2im_adam_step_dev_f32(self.flat_param.data_ptr(), self.flat_grad.data_ptr(),
+                                                   self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                                   self.flat_param.numel(), g["lr"], g["betas"][0], g["betas"][1],
+                                                   g["eps"], self.state_dev.data_ptr(), grad_scale,
+                                                   _st(self.flat_param.device)), "adam_step")
+
+
+class GraphedTrainStep:
+    """The reference's training iteration (core/scripts/train.py:152-162: forward, loss_fn, zero_grad, backward,
+    optimizer.step) captured ONCE into a CUDA graph and replayed - ~400 kernel launches per step become one
+    cudaGraphLaunch, which removes the host launch overhead that otherwise bounds the step.  Data parallel: pass a
+    torch.distributed ``group``; the NCCL all-reduce of the flat gradient buffer is part of the graph.
+
+        step = GraphedTrainStep(model, FusedAdam(model.parameters(), lr=1e-4), x0, y0)
+        for x, y in loader: loss = step(x, y)          # 0-dim CUDA tensor; .item() it when you need the number
+
+    Shapes are fixed at capture (the reference's loader uses a fixed batch size; a ragged last batch should run the
+    eager path).  BatchNorm running statistics, ``num_batches_tracked`` and Adam's step counter all advance on the device.
+    """
+
+    def __init__(self, model, optimizer: "FusedAdam", x: torch.Tensor, y: torch.Tensor, group=None, warmup: int = 3):
+        assert x.is_cuda and y.is_cuda and model.training
+        self.model, self.opt, self.group = model, optimizer, group
+        self.world = 1
+        if group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(group)
+        self.x, self.y = x.clone(), y.clone()
+        dev = x.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):            # warm-up off the capture: lazy allocations, cuDNN-free, NCCL channels
+            for _ in range(warmup):
+                self._iteration()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._iteration()
+        self.kernels_per_replay = _lib.launch_count() - before
+        self.warmup_steps = warmup               # optimizer steps already taken on the example batch (capture runs none)
+
+    def _iteration(self):
+        self.opt.zero_grad()
+        loss = self.model.loss_fn(self.model(self.x), self.y)
+        loss.backward()
+        if self.group is not None:
+            import torch.distributed as dist
+            self.opt.gather_grads()
+            dist.all_reduce(self.opt.flat_grad, group=self.group)
+        self.opt.step(grad_scale=1.0 / self.world)
+        return loss.detach()
+
+    def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self.loss

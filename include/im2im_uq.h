@@ -290,6 +290,12 @@ int im2im_head_loss_f32(int32_t loss_kind, const float* d_pred, const float* d_t
                         double* d_loss_parts, void* stream);
 int im2im_adam_step_f32(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n, float lr,
                         float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+/* im2im_adam_step_f32 with the step counter in DEVICE memory, so the whole training step can be replayed from a CUDA
+ * graph: d_state is float[3] = {step, 1-beta1^step, sqrt(1-beta2^step)}; the call first advances it (step += 1), then
+ * applies the update.  Zero-initialise d_state before the first step. */
+int im2im_adam_step_dev_f32(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
+                            float lr, float beta1, float beta2, float eps, float* d_state, float grad_scale,
+                            void* stream);
 int im2im_head_bwd(const float* d_dout, const void* d_m, const float* d_weight, int32_t B, int32_t H, int32_t W,
                    int32_t c_mid, int32_t c_stride, int32_t n_out, void* d_dm, float* d_dw, float* d_db, void* stream);
 int im2im_conv_first_wgrad(const float* d_x, const void* d_dz, int32_t B, int32_t c_in, int32_t H, int32_t W,

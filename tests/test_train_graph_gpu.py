@@ -1,0 +1,50 @@
+"""GPU (-m gpu): the training iteration captured into a CUDA graph (GraphedTrainStep) follows the eager native loop."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PARAMS = dict(uncertainty_type="quantiles", q_lo=0.05, q_hi=0.95, q_lo_weight=1.0, q_hi_weight=1.0, mse_weight=1.0)
+
+
+def _build():
+    from core.models.add_uncertainty import add_uncertainty
+    from core.models.trunks.unet import UNet
+    torch.manual_seed(0)
+    return add_uncertainty(UNet(1, 1), PARAMS).to("cuda:0").train()
+
+
+def test_graphed_step_tracks_eager_step():
+    from im2im_uq_b200 import _lib
+    from im2im_uq_b200.models.unet_train import FusedAdam, GraphedTrainStep
+    g = torch.Generator(device="cuda:0").manual_seed(2)
+    xs = [torch.randn(4, 1, 64, 64, device="cuda:0", generator=g) for _ in range(3)]
+    ys = [x + 0.3 * torch.randn(4, 1, 64, 64, device="cuda:0", generator=g) for x in xs]
+    warm = 2
+    # eager native loop: `warm` steps on batch 0 (the graph's warm-up; capturing itself executes nothing), then the sequence
+    m_e = _build()
+    o_e = FusedAdam(m_e.parameters(), lr=1e-3)
+    eager = []
+    seq = [0] * warm + [1, 2, 0, 1, 2]
+    for i in seq:
+        o_e.zero_grad()
+        loss = m_e.loss_fn(m_e(xs[i]), ys[i])
+        loss.backward()
+        o_e.step()
+        eager.append(loss.item())
+    m_g = _build()
+    o_g = FusedAdam(m_g.parameters(), lr=1e-3)
+    step = GraphedTrainStep(m_g, o_g, xs[0], ys[0], warmup=warm)
+    assert step.kernels_per_replay > 100
+    before = _lib.launch_count()
+    graph_losses = [step(xs[i].cpu().pin_memory(), ys[i].cpu().pin_memory()).item() for i in [1, 2, 0, 1, 2]]
+    assert _lib.launch_count() == before         # replays launch nothing from the host side
+    # wgrad uses fp32 atomics (order varies run to run), so trajectories agree to rounding, not bit for bit
+    for a, b in zip(graph_losses, eager[warm:]):
+        assert abs(a - b) <= 2e-2 * abs(b), (graph_losses, eager)
+    assert graph_losses[-1] < graph_losses[0]
+    # device-side step counter advanced once per executed iteration: warm-up + 5 replays
+    assert int(o_g.state_dev[0].item()) == warm + 5
+    for (n1, b1), (n2, b2) in zip(m_e.named_buffers(), m_g.named_buffers()):
+        if b1 is not None and "num_batches" in n1:
+            assert int(b1) == int(b2) == len(seq)
