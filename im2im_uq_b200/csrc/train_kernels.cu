@@ -33,6 +33,15 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     return v.u;
 }
 
+// streaming 16-byte load / store (read once, written once: keep them out of L1)
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
 unsigned grid_for(long long work_items, int threads, int per_sm = 8) {
     long long blocks = (work_items + threads - 1) / threads;
     const long long cap = static_cast<long long>(per_sm) * sm_count();
@@ -72,25 +81,39 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
             sh[j] = beta[g * 8 + j] - mu[j] * sc[j];
         }
     }
-    for (long long p = static_cast<long long>(blockIdx.x) * lanes + lane_p; p < n_pix;
-         p += static_cast<long long>(gridDim.x) * lanes) {
-        Bf16x8 va;
-        va.u = *reinterpret_cast<const uint4*>(a + p * C + g * 8);
-        float fa[8];
-        unpack8(va, fa);
-        if (MODE == 0) {
+    // kUnroll pixels per thread and iteration: all their 16-byte loads are issued before the first use, so that enough
+    // bytes are in flight per SM to cover the HBM latency
+    constexpr int kUnroll = 4;
+    const long long stride = static_cast<long long>(gridDim.x) * lanes;
+    for (long long p0 = static_cast<long long>(blockIdx.x) * lanes + lane_p; p0 < n_pix; p0 += stride * kUnroll) {
+        Bf16x8 va[kUnroll], vz[kUnroll];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { acc0[j] += fa[j]; acc1[j] = fmaf(fa[j], fa[j], acc1[j]); }
-        } else {
-            Bf16x8 vz;
-            vz.u = *reinterpret_cast<const uint4*>(zt + p * C + g * 8);
-            float fz[8];
-            unpack8(vz, fz);
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long p = p0 + u * stride;
+            va[u].u = make_uint4(0u, 0u, 0u, 0u);
+            vz[u].u = make_uint4(0u, 0u, 0u, 0u);
+            if (p < n_pix) {
+                va[u].u = ld_stream_u4(a + p * C + g * 8);
+                if (MODE == 1) vz[u].u = ld_stream_u4(zt + p * C + g * 8);
+            }
+        }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float gj = fmaf(fz[j], sc[j], sh[j]) > 0.f ? fa[j] : 0.f;   // ReLU mask exactly as the forward saw it
-                acc0[j] += gj;
-                acc1[j] = fmaf(gj, (fz[j] - mu[j]) * rs[j], acc1[j]);
+        for (int u = 0; u < kUnroll; ++u) {
+            if (p0 + u * stride >= n_pix) break;
+            float fa[8];
+            unpack8(va[u], fa);
+            if (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { acc0[j] += fa[j]; acc1[j] = fmaf(fa[j], fa[j], acc1[j]); }
+            } else {
+                float fz[8];
+                unpack8(vz[u], fz);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float gj = fmaf(fz[j], sc[j], sh[j]) > 0.f ? fa[j] : 0.f;   // ReLU mask exactly as the forward saw it
+                    acc0[j] += gj;
+                    acc1[j] = fmaf(gj, (fz[j] - mu[j]) * rs[j], acc1[j]);
+                }
             }
         }
     }
@@ -134,23 +157,35 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, double count,
     }
 }
 
-// y = relu(z*scale + shift)
+// y = relu(z*scale + shift).  gridDim.x*256 is a multiple of groups = C/8 (a power of two <= 256 or a divisor of 256,
+// checked by the host), so a thread's channel group never changes: the per-channel constants live in registers.
 __global__ void __launch_bounds__(256) bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ z,
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift, long long n_pix, int C,
                                                             __nv_bfloat16* __restrict__ y) {
+    constexpr int kUnroll = 2;
     const int groups = C / 8;
     const long long total = n_pix * groups;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(e % groups);
-        Bf16x8 v;
-        v.u = *reinterpret_cast<const uint4*>(z + e * 8);
-        float f[8];
-        unpack8(v, f);
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long e0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int g = static_cast<int>(e0 % groups);
+    float sc[8], sh[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], __ldg(scale + g * 8 + j), __ldg(shift + g * 8 + j)), 0.f);
-        *reinterpret_cast<uint4*>(y + e * 8) = pack8(f);
+    for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
+    for (long long e = e0; e < total; e += stride * kUnroll) {
+        Bf16x8 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (e + u * stride < total) v[u].u = ld_stream_u4(z + (e + u * stride) * 8);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (e + u * stride >= total) break;
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+            *reinterpret_cast<uint4*>(y + (e + u * stride) * 8) = pack8(f);
+        }
     }
 }
 
@@ -163,27 +198,46 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const __nv_bfloa
                                                                 const float* __restrict__ rstd,
                                                                 const float* __restrict__ sums, float inv_count,
                                                                 long long n_pix, int C, __nv_bfloat16* __restrict__ dz) {
+    // a thread's channel group is loop-invariant (see bn_apply_relu_kernel): per-channel constants in registers.
+    //   dz = sc*g - k0 - (z - mu)*k1,   k0 = sc*sum(g)/M,  k1 = sc*rstd*sum(g*xhat)/M
+    constexpr int kUnroll = 4;
     const int groups = C / 8;
     const long long total = n_pix * groups;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(e % groups);
-        Bf16x8 vd, vz;
-        vd.u = *reinterpret_cast<const uint4*>(dy + e * 8);
-        vz.u = *reinterpret_cast<const uint4*>(z + e * 8);
-        float fd[8], fz[8], o[8];
-        unpack8(vd, fd);
-        unpack8(vz, fz);
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long e0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int g = static_cast<int>(e0 % groups);
+    float sc[8], sh[8], mu[8], k0[8], k1[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = g * 8 + j;
-            const float gm = __ldg(gamma + c), rs = __ldg(rstd + c), mu = __ldg(mean + c);
-            const float sc = gm * rs, sh = __ldg(beta + c) - mu * sc;
-            const float xhat = (fz[j] - mu) * rs;
-            const float gj = fmaf(fz[j], sc, sh) > 0.f ? fd[j] : 0.f;
-            o[j] = sc * (gj - __ldg(sums + c) * inv_count - xhat * __ldg(sums + C + c) * inv_count);
+    for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        const float rs = __ldg(rstd + c);
+        mu[j] = __ldg(mean + c);
+        sc[j] = __ldg(gamma + c) * rs;
+        sh[j] = __ldg(beta + c) - mu[j] * sc[j];
+        k0[j] = sc[j] * (__ldg(sums + c) * inv_count);
+        k1[j] = sc[j] * (rs * (__ldg(sums + C + c) * inv_count));
+    }
+    for (long long e = e0; e < total; e += stride * kUnroll) {
+        Bf16x8 vd[kUnroll], vz[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (e + u * stride < total) {
+                vd[u].u = ld_stream_u4(dy + (e + u * stride) * 8);
+                vz[u].u = ld_stream_u4(z + (e + u * stride) * 8);
+            }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (e + u * stride >= total) break;
+            float fd[8], fz[8], o[8];
+            unpack8(vd[u], fd);
+            unpack8(vz[u], fz);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gj = fmaf(fz[j], sc[j], sh[j]) > 0.f ? fd[j] : 0.f;
+                o[j] = fmaf(sc[j], gj, -k0[j]) - (fz[j] - mu[j]) * k1[j];
+            }
+            *reinterpret_cast<uint4*>(dz + (e + u * stride) * 8) = pack8(o);
         }
-        *reinterpret_cast<uint4*>(dz + e * 8) = pack8(o);
     }
 }
 
@@ -478,8 +532,10 @@ __global__ void __launch_bounds__(128) head_dgrad_kernel(const float* __restrict
 }
 
 // (b) weight/bias gradient: dW[o, c, t] += sum_p dOut[o, p] * m[p + shift(t), c];  db[o] += sum_p dOut[o, p].
-// lane = channel c (c_mid <= 32); each of the 4 warps walks its own pixels, kUnroll at a time so that 9*kUnroll
-// independent 64-byte loads are in flight per warp (the kernel is latency-bound otherwise); 9*N_OUT accumulators per lane.
+// Scatter form: a pixel q of m contributes m[q, c] * dOut[o, q - shift(t)] to all 9*N_OUT weights of channel c.
+// lane = channel c (c_mid <= 32), one warp per image row: m is read ONCE (one 64-byte load per pixel instead of nine),
+// the 3x3xN_OUT window of dOut neighbours slides along the row in registers (warp-uniform broadcast loads, four new
+// columns per iteration so 4 + 4*3*N_OUT independent loads are in flight); 9*N_OUT accumulators per lane.
 template <int N_OUT>
 __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict__ dout,
                                                          const __nv_bfloat16* __restrict__ m, int B, int H, int W,
@@ -488,7 +544,6 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict
     constexpr int kUnroll = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long hw = static_cast<long long>(H) * W;
-    const long long total = static_cast<long long>(B) * hw;
     float acc[9][N_OUT], accb[N_OUT];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
@@ -496,37 +551,72 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict
         for (int o = 0; o < N_OUT; ++o) acc[t][o] = 0.f;
 #pragma unroll
     for (int o = 0; o < N_OUT; ++o) accb[o] = 0.f;
-    const long long n_warps = static_cast<long long>(gridDim.x) * 4;
-    for (long long base = (static_cast<long long>(blockIdx.x) * 4 + warp) * kUnroll; base < total;
-         base += n_warps * kUnroll) {
-        float d[kUnroll][N_OUT], v[kUnroll][9];
+    const long long rows = static_cast<long long>(B) * H;
+    const bool ch_ok = lane < c_mid;
+    for (long long row = static_cast<long long>(blockIdx.x) * 4 + warp; row < rows;
+         row += static_cast<long long>(gridDim.x) * 4) {
+        const long long b = row / H;
+        const int y = static_cast<int>(row - b * H);
+        // window row r = 0..2 <-> output rows y+1, y, y-1 (tap ky = r needs output row y + 1 - ky)
+        const float* drow[N_OUT][3];
+        bool rok[3];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const long long pix = base + u;
-            const bool ok = pix < total;
-            const int xw = static_cast<int>(pix % W);
-            const int yh = static_cast<int>((pix / W) % H);
-            const long long b = pix / hw;
+        for (int r = 0; r < 3; ++r) {
+            const int yy = y + 1 - r;
+            rok[r] = yy >= 0 && yy < H;
+#pragma unroll
+            for (int o = 0; o < N_OUT; ++o) drow[o][r] = dout + (b * N_OUT + o) * hw + static_cast<long long>(rok[r] ? yy : 0) * W;
+        }
+#pragma unroll
+        for (int o = 0; o < N_OUT; ++o)
+            for (int x = lane; x < W; x += 32) accb[o] += __ldg(drow[o][1] + x);
+        const __nv_bfloat16* mrow = m + (b * H + y) * static_cast<long long>(W) * c_stride + lane;
+        // wnd[o][r][j]: output column x - 1 + j ... (j = 0..5 covers the four pixels x..x+3 of this iteration);
+        // tap kx of pixel x+u needs output column x + u + 1 - kx = wnd index u + 2 - kx
+        float wnd[N_OUT][3][kUnroll + 2];
+#pragma unroll
+        for (int o = 0; o < N_OUT; ++o)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                wnd[o][r][0] = 0.f;                                        // column -1
+                wnd[o][r][1] = rok[r] ? __ldg(drow[o][r]) : 0.f;           // column 0
+            }
+        for (int x = 0; x < W; x += kUnroll) {
+            float mv[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                mv[u] = (ch_ok && x + u < W) ? __bfloat162float(mrow[static_cast<long long>(x + u) * c_stride]) : 0.f;
 #pragma unroll
             for (int o = 0; o < N_OUT; ++o)
-                d[u][o] = ok ? __ldg(dout + (b * N_OUT + o) * hw + static_cast<long long>(yh) * W + xw) : 0.f;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
-                const bool in = ok && yy >= 0 && yy < H && xx >= 0 && xx < W && lane < c_mid;
-                v[u][t] = in ? __bfloat162float(m[((b * H + yy) * W + xx) * c_stride + lane]) : 0.f;
-            }
-        }
+                for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
+                    for (int u = 0; u < kUnroll; ++u) {
+                        const int col = x + 1 + u;
+                        wnd[o][r][2 + u] = (rok[r] && col < W) ? __ldg(drow[o][r] + col) : 0.f;
+                    }
 #pragma unroll
-            for (int o = 0; o < N_OUT; ++o) accb[o] += d[u][o];
+            for (int u = 0; u < kUnroll; ++u)
 #pragma unroll
-            for (int t = 0; t < 9; ++t)
+                for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int o = 0; o < N_OUT; ++o) acc[t][o] = fmaf(d[u][o], v[u][t], acc[t][o]);
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int o = 0; o < N_OUT; ++o)
+                            acc[ky * 3 + kx][o] = fmaf(wnd[o][ky][u + 2 - kx], mv[u], acc[ky * 3 + kx][o]);
+#pragma unroll
+            for (int o = 0; o < N_OUT; ++o)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    wnd[o][r][0] = wnd[o][r][kUnroll];
+                    wnd[o][r][1] = wnd[o][r][kUnroll + 1];
+                }
         }
     }
+#pragma unroll
+    for (int o = 0; o < N_OUT; ++o)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) accb[o] += __shfl_xor_sync(0xffffffffu, accb[o], off);
     __shared__ float s_acc[4][9 * N_OUT][32 + 1];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
@@ -621,7 +711,7 @@ extern "C" int im2im_channel_stats_bf16(const void* d_z, int64_t n_pix, int32_t 
     if (int rc = check_channels(C, "channel_stats")) return rc;
     if (n_pix <= 0 || !d_z || !d_sums) return fail(IM2IM_EINVAL, "channel_stats: bad arguments");
     const int lanes = 256 / (C / 8);
-    channel_reduce_kernel<0><<<grid_for(n_pix, lanes, 4), 256, 0, ST(stream)>>>(BF(d_z), nullptr, nullptr, nullptr, nullptr,
+    channel_reduce_kernel<0><<<grid_for((n_pix + 3) / 4, lanes, 4), 256, 0, ST(stream)>>>(BF(d_z), nullptr, nullptr, nullptr, nullptr,
                                                                                nullptr, n_pix, C, d_sums);
     return check_launch("channel_reduce_kernel<stats>");
 }
@@ -640,7 +730,8 @@ extern "C" int im2im_bn_finalize(const float* d_sums, int64_t count, const float
 
 extern "C" int im2im_bn_apply_relu_bf16(const void* d_z, const float* d_scale, const float* d_shift, int64_t n_pix,
                                         int32_t C, void* d_y, void* stream) {
-    if (C <= 0 || C % 8 || n_pix <= 0 || !d_z || !d_scale || !d_shift || !d_y) return fail(IM2IM_EINVAL, "bn_apply: bad arguments");
+    if (int rc = check_channels(C, "bn_apply")) return rc;   // also guarantees 256 % (C/8) == 0 (loop-invariant channel group)
+    if (n_pix <= 0 || !d_z || !d_scale || !d_shift || !d_y) return fail(IM2IM_EINVAL, "bn_apply: bad arguments");
     bn_apply_relu_kernel<<<grid_for(n_pix * (C / 8), 256, 16), 256, 0, ST(stream)>>>(BF(d_z), d_scale, d_shift, n_pix, C,
                                                                                     BFW(d_y));
     return check_launch("bn_apply_relu_kernel");
@@ -654,7 +745,7 @@ extern "C" int im2im_bn_relu_bwd_bf16(const void* d_dy, const void* d_z, const f
         return fail(IM2IM_EINVAL, "bn_relu_bwd: bad arguments");
     IM2IM_CUDA_TRY(cudaMemsetAsync(d_sums, 0, sizeof(float) * 2 * C, ST(stream)));
     const int lanes = 256 / (C / 8);
-    channel_reduce_kernel<1><<<grid_for(n_pix, lanes, 4), 256, 0, ST(stream)>>>(BF(d_dy), BF(d_z), d_gamma, d_beta, d_mean,
+    channel_reduce_kernel<1><<<grid_for((n_pix + 3) / 4, lanes, 4), 256, 0, ST(stream)>>>(BF(d_dy), BF(d_z), d_gamma, d_beta, d_mean,
                                                                                d_rstd, n_pix, C, d_sums);
     if (int rc = check_launch("channel_reduce_kernel<bn_bwd>")) return rc;
     bn_relu_bwd_apply_kernel<<<grid_for(n_pix * (C / 8), 256, 16), 256, 0, ST(stream)>>>(
@@ -756,7 +847,8 @@ extern "C" int im2im_head_bwd(const float* d_dout, const void* d_m, const float*
     const long long pixels = static_cast<long long>(B) * H * W;
     const size_t smem = sizeof(float) * 9 * n_out * c_mid;
     const unsigned g1 = grid_for(pixels, 128, 8);
-    const unsigned g2 = static_cast<unsigned>(4 * sm_count());
+    const long long row_blocks = (static_cast<long long>(B) * H + 3) / 4;
+    const unsigned g2 = static_cast<unsigned>(row_blocks < 8ll * sm_count() ? row_blocks : 8ll * sm_count());
 #define IM2IM_HEAD_BWD_CASE(N)                                                                                        \
     case N:                                                                                                          \
         head_dgrad_kernel<N><<<g1, 128, smem, ST(stream)>>>(d_dout, d_weight, B, H, W, c_mid, c_stride, BFW(d_dm));  \
