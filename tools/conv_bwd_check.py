@@ -36,6 +36,8 @@ ok &= check(3, 20, 20, 256, 512)
 ok &= check(1, 37, 29, 64, 256)
 ok &= check(2, 32, 32, 64, 64, taps=1)
 ok &= check(2, 64, 64, 128, 128)
+ok &= check(2, 48, 24, 128, 192)     # halo wgrad: several channel / c_out blocks, W not a multiple of 16
+ok &= check(3, 32, 40, 64, 64)
 print("BWD NUMERICS", "OK" if ok else "FAIL", flush=True)
 
 def bench(B, H, W, cin, cout, iters=10):
