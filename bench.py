@@ -310,6 +310,31 @@ def run_unet_bench(args, world, rank, dev, group):
                          "flops": "conv 2*MACs only: 125.29 GFLOP fwd, 375.87 GFLOP train per 320x320 image"}}
 
 
+def bind_to_gpu_numa_node(torch, index: int):
+    """Run this process on the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers (first touch) are
+    allocated next to the GPU's PCIe root: the host->device copies of the e2e leg then do not cross the socket link.
+    Best effort: returns a description of what was done, never raises."""
+    try:
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa node unknown (-1): not bound"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return f"numa node {node}: none of its cpus is allowed here: not bound"
+        os.sched_setaffinity(0, allowed)
+        return f"bound to numa node {node} ({len(allowed)} cpus)"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def main():
     args = parse_args()
@@ -447,9 +472,12 @@ def main():
                 return x
         model = ModelWithUncertainty(_Id(), _Id(), quantile_regression_loss_fn,
                                      quantile_regression_nested_sets_from_output, cfg)
+        all_cpus = os.sched_getaffinity(0)
+        numa = bind_to_gpu_numa_node(torch, local_rank)      # pinned pages land on the GPU's NUMA node (first touch)
         host_out = torch.empty(out.shape, dtype=torch.float32, pin_memory=True)
         host_lab = torch.empty(lab.shape, dtype=torch.float32, pin_memory=True)
         host_out.copy_(out); host_lab.copy_(lab)
+        os.sched_setaffinity(0, all_cpus)                    # the CPU baseline below uses every core again
         torch.cuda.synchronize()
         del out, lab
         torch.cuda.empty_cache()
@@ -471,6 +499,7 @@ def main():
         e2e = {"value": args.images * args.e2e_steps / float(dt), "unit": UNIT,
                "h2d_bytes_per_step": args.images * px * 16 + L * 4 * world,
                "d2h_bytes_per_step": args.images * L * 4 + L * 8 * world, "steps": args.e2e_steps,
+               "host_buffers": "pinned, " + numa,
                "api": "im2im_uq_b200.calibration.calibrate_model.calibrate_from_outputs(model, outputs_cpu, labels_cpu, config)"}
 
     unet = None
