@@ -260,6 +260,8 @@ def run_unet_bench(args, world, rank, dev, group):
         last["loss"] = graphed(x_host, y_host).item()
 
     train_ms = timed(train_step_graph, args.unet_steps)
+    kernels_per_step = graphed.kernels_per_replay
+    graphed.close()      # drop the captured graph (it holds NCCL kernels when data parallel) before anything else runs
 
     # calibrate_model end to end (BASELINE configs[1]: 1k calibration images, full UNet): host dataset -> native UNet
     # inference in batches -> scores stay in HBM -> one-pass RCPS -> lhat + loss table back on the host
@@ -302,7 +304,7 @@ def run_unet_bench(args, world, rank, dev, group):
             "train_step": "one CUDA graph per step: H2D of the batch from pinned memory + forward + fused pinball/MSE "
                           "loss + backward + " + ("NCCL all-reduce of 69 MB fp32 grads + " if world > 1 else "") +
                           "fused Adam, then loss.item()",
-            "train_ms_per_step_eager": train_eager_ms, "train_kernels_per_step": graphed.kernels_per_replay,
+            "train_ms_per_step_eager": train_eager_ms, "train_kernels_per_step": kernels_per_step,
             "final_loss": last.get("loss"), "calibrate_model_e2e": cal,
             "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak, "peak_source": src,
                          "forward_achieved": fwd_tf, "forward_frac": fwd_tf / peak,
@@ -353,6 +355,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ["NCCL_DEBUG"] = "WARN"   # NCCL logs to stdout ("NCCL version ..."): keep stdout to the one JSON line
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -547,9 +550,16 @@ def main():
                                     "sample": f"{args.cpu_sample} images x {visited} visited lambda steps (the steps the "
                                               f"full set visits; one full pass + fp32 mean + HB bound per step), "
                                               f"{dt:.1f} s; cost is linear in images"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: ncclCommDestroy waits for every CUDA graph that captured one of its collectives
+        # (RcpsGraph, GraphedTrainStep) and was observed to hang at exit on a 2-GPU box.  Everything is synchronised, the
+        # JSON line is out; exit code 0 is what torchrun needs.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

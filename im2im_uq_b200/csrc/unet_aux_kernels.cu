@@ -18,50 +18,72 @@ union Bf16x8 {
 
 // ---------------------------------------------------------------------------------------------------------------
 // x: fp32 NCHW [B, c_in, H, W] (c_in <= 8) -> y: bf16 NHWC [B, H, W, c_out], 3x3 pad 1, + bias, ReLU.
-// One thread = one pixel x 8 output channels.  Weights fp32 [c_out, c_in, 3, 3] staged in shared memory.
+// One thread = TWO horizontally adjacent pixels x 16 output channels: the 3x4 input window is loaded once (12 loads for
+// 2 pixels) and every 128-bit weight load from shared memory feeds 8 FMAs, so the kernel is FMA- rather than
+// load/address-bound.  Weights fp32 [c_out, c_in, 3, 3] are staged transposed in shared memory.
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, int B, int c_in, int H,
                                                          int W, int c_out, int relu, __nv_bfloat16* __restrict__ y) {
-    extern __shared__ __align__(16) float s_w[];  // [c_in*9][c_out] (transposed: a thread's 8 channels are contiguous), bias [c_out]
+    extern __shared__ __align__(16) float s_w[];  // [c_in*9][c_out] (a thread's 16 channels are contiguous), bias [c_out]
     const int kk = c_in * 9;
     for (int i = threadIdx.x; i < c_out * kk; i += blockDim.x) s_w[(i % kk) * c_out + i / kk] = w[i];
     float* s_b = s_w + c_out * kk;
     for (int i = threadIdx.x; i < c_out; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
     __syncthreads();
-    const int groups = c_out / 8;
-    const long long total = static_cast<long long>(B) * H * W * groups;
+    const int groups = c_out / 16;
+    const int wp = (W + 1) / 2;  // pixel pairs per row
+    const long long total = static_cast<long long>(B) * H * wp * groups;
     for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
          e += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int g = static_cast<int>(e % groups);
-        long long pix = e / groups;
-        const int xw = static_cast<int>(pix % W);
-        const int yh = static_cast<int>((pix / W) % H);
-        const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-        float acc[8];
+        long long pp = e / groups;
+        const int xw = 2 * static_cast<int>(pp % wp);
+        const int yh = static_cast<int>((pp / wp) % H);
+        const int b = static_cast<int>(pp / (static_cast<long long>(wp) * H));
+        float acc0[16], acc1[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = s_b[g * 8 + j];
+        for (int j = 0; j < 16; ++j) acc0[j] = acc1[j] = s_b[g * 16 + j];
         for (int ci = 0; ci < c_in; ++ci) {
             const float* xp = x + (static_cast<long long>(b) * c_in + ci) * H * W;
+            float v[3][4];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int yy = yh + r - 1, xx = xw + c - 1;
+                    v[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + static_cast<long long>(yy) * W + xx) : 0.f;
+                }
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-                const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
-                const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + static_cast<long long>(yy) * W + xx) : 0.f;
-                const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ci * 9 + t) * c_out + g * 8);
-                const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ci * 9 + t) * c_out + g * 8 + 4);
-                acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-                acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-                acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-                acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+                const float a0 = v[t / 3][t % 3], a1 = v[t / 3][t % 3 + 1];
+                const float* wt = s_w + (ci * 9 + t) * c_out + g * 16;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wq = *reinterpret_cast<const float4*>(wt + 4 * q);
+                    acc0[4 * q + 0] = fmaf(a0, wq.x, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(a1, wq.x, acc1[4 * q + 0]);
+                    acc0[4 * q + 1] = fmaf(a0, wq.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(a1, wq.y, acc1[4 * q + 1]);
+                    acc0[4 * q + 2] = fmaf(a0, wq.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(a1, wq.z, acc1[4 * q + 2]);
+                    acc0[4 * q + 3] = fmaf(a0, wq.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(a1, wq.w, acc1[4 * q + 3]);
+                }
             }
         }
-        Bf16x8 o;
+        const long long pix = (static_cast<long long>(b) * H + yh) * W + xw;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float a0 = acc[2 * j], a1 = acc[2 * j + 1];
-            if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-            o.h[j] = __floats2bfloat162_rn(a0, a1);
+        for (int px2 = 0; px2 < 2; ++px2) {
+            if (xw + px2 >= W) break;
+            const float* acc = px2 ? acc1 : acc0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                Bf16x8 o;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a0 = acc[8 * half + 2 * j], a1 = acc[8 * half + 2 * j + 1];
+                    if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                    o.h[j] = __floats2bfloat162_rn(a0, a1);
+                }
+                *reinterpret_cast<uint4*>(y + (pix + px2) * c_out + g * 16 + 8 * half) = o.u;
+            }
         }
-        *reinterpret_cast<uint4*>(y + pix * c_out + g * 8) = o.u;
     }
 }
 
@@ -247,11 +269,11 @@ extern "C" int im2im_conv_first_bf16(const float* d_x, const float* d_weight, co
                                      int32_t c_in, int32_t H, int32_t W, int32_t c_out, int32_t relu, void* d_out,
                                      void* stream) {
     if (B <= 0 || H <= 0 || W <= 0 || c_in <= 0 || c_in > 8) return fail(IM2IM_ERANGE, "conv_first: bad shape (c_in=%d)", c_in);
-    if (c_out <= 0 || c_out % 8) return fail(IM2IM_ERANGE, "conv_first: c_out must be a multiple of 8");
+    if (c_out <= 0 || c_out % 16) return fail(IM2IM_ERANGE, "conv_first: c_out must be a multiple of 16");
     if (!d_x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "null tensor");
     const size_t smem = sizeof(float) * (static_cast<size_t>(c_out) * c_in * 9 + c_out);
     if (smem > 48 * 1024) return fail(IM2IM_ERANGE, "conv_first: weights do not fit shared memory");
-    const long long items = static_cast<long long>(B) * H * W * (c_out / 8);
+    const long long items = static_cast<long long>(B) * H * ((W + 1) / 2) * (c_out / 16);
     conv_first_kernel<<<grid_for(items, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         d_x, d_weight, d_bias, B, c_in, H, W, c_out, relu, static_cast<__nv_bfloat16*>(d_out));
     return check_launch("conv_first_kernel");

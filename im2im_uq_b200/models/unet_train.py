@@ -487,6 +487,15 @@ class GraphedTrainStep:
         self.opt.step(grad_scale=1.0 / self.world)
         return loss.detach()
 
+    def close(self):
+        """Release the captured graph and its memory pool (do this before destroying a process group whose collectives
+        were captured: NCCL waits for such graphs at communicator teardown)."""
+        torch.cuda.synchronize(self.x.device)
+        if self.graph is not None:
+            self.graph.reset()
+            self.graph = None
+        self.loss = None
+
     def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
