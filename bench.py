@@ -166,8 +166,12 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is the reference on ALL the host cores it can use
+    n_threads = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(n_threads)      # read by libgomp when the oracle library is loaded below
     import numpy as np
     import torch
+    torch.set_num_threads(n_threads)
     from oracle import rcps_oracle as orc
     orc.build()
     cfg = config_dict(args, "cpu")
@@ -355,7 +359,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ["NCCL_DEBUG"] = "WARN"   # NCCL logs to stdout ("NCCL version ..."): keep stdout to the one JSON line
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"   # NCCL logs ("NCCL version ...") go to stdout by default: keep stdout
+                                                    # to the one JSON line
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)

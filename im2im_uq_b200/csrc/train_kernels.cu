@@ -307,30 +307,45 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int uy = max(0, 2 * iy - 2); uy <= min(uh - 1, 2 * iy + 2); ++uy) {
-            const float fy = sy * uy;
-            const int y0 = static_cast<int>(fy);
-            const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
-            const float ly = fy - y0;
-            float wy = 0.f;
-            if (y0 == iy) wy += 1.f - ly;
-            if (y1 == iy) wy += ly;
-            if (wy == 0.f) continue;
-            for (int ux = max(0, 2 * ix - 2); ux <= min(uw - 1, 2 * ix + 2); ++ux) {
+        // the (at most five) output rows / columns whose bilinear footprint contains iy / ix, with the forward's own
+        // fp32 weights; computed once per axis instead of once per (row, column) pair
+        float wy[5], wx[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            const int uy = 2 * iy - 2 + a, ux = 2 * ix - 2 + a;
+            wy[a] = 0.f;
+            wx[a] = 0.f;
+            if (uy >= 0 && uy < uh) {
+                const float fy = sy * uy;
+                const int y0 = static_cast<int>(fy);
+                const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+                const float ly = fy - y0;
+                if (y0 == iy) wy[a] += 1.f - ly;
+                if (y1 == iy) wy[a] += ly;
+            }
+            if (ux >= 0 && ux < uw) {
                 const float fx = sx * ux;
                 const int x0 = static_cast<int>(fx);
                 const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
                 const float lx = fx - x0;
-                float wx = 0.f;
-                if (x0 == ix) wx += 1.f - lx;
-                if (x1 == ix) wx += lx;
-                if (wx == 0.f) continue;
+                if (x0 == ix) wx[a] += 1.f - lx;
+                if (x1 == ix) wx[a] += lx;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            if (wy[a] == 0.f) continue;
+            const int uy = 2 * iy - 2 + a;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                if (wx[c] == 0.f) continue;
+                const int ux = 2 * ix - 2 + c;
                 Bf16x8 t;
                 t.u = *reinterpret_cast<const uint4*>(
                     du + ((static_cast<long long>(b) * Ho + uy + pad_top) * Wo + ux + pad_left) * C + g * 8);
                 float f[8];
                 unpack8(t, f);
-                const float wgt = wy * wx;
+                const float wgt = wy[a] * wx[c];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, f[j], acc[j]);
             }

@@ -52,6 +52,28 @@ class _ConvBN:
                                                            self.w_bwd.data_ptr(), _st(w.device)), "pack_conv_weights")
 
 
+class _ZeroPool:
+    """One zero-filled fp32 buffer per pass handed out in slices: a single fill kernel instead of one per small
+    accumulator (BatchNorm sums, weight-gradient buffers, ...) - the step is made of ~400 launches, the tiny ones count."""
+
+    def __init__(self, n_floats: int, device):
+        self.buf = torch.zeros(max(n_floats, 4), dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, *shape):
+        k = 1
+        for d in shape:
+            k *= d
+        assert self.off + k <= self.buf.numel(), "zero pool exhausted"
+        v = self.buf[self.off:self.off + k].view(*shape)
+        self.off += (k + 3) // 4 * 4   # keep every slice 16-byte aligned
+        return v
+
+    @staticmethod
+    def padded(k: int) -> int:
+        return (k + 3) // 4 * 4
+
+
 class UNetTrainEngine:
     def __init__(self, model):
         from .unet import UNet
@@ -75,6 +97,12 @@ class UNetTrainEngine:
         self.n_planes = len(self.head_convs)
         self.n_out = self.n_planes * self.c_head
         self.act_from = act_from * self.c_head
+        layers = [l for pair in [self.inc] + self.down + self.up for l in pair]
+        pad = _ZeroPool.padded
+        self._fwd_zero_floats = sum(pad(2 * l.c_out) for l in layers)
+        self._bwd_zero_floats = (sum(2 * pad(l.c_out * 9 * l.c_in) for l in layers[1:])   # concat layers: two buffers
+                                 + pad(64 * 64) + pad(self.n_out * self.c_mid * 9) + pad(self.n_out) + pad(128)
+                                 + pad(layers[0].c_out * 8 * 9))
 
     # ------------------------------------------------------------------------------------------- primitive launches
     def _bn_relu(self, z: torch.Tensor, layer: _ConvBN, saved: dict):
@@ -82,7 +110,8 @@ class UNetTrainEngine:
         B, H, W, C = z.shape
         n_pix = B * H * W
         bn = layer.bn
-        sums = torch.zeros(2 * C, dtype=torch.float32, device=dev)
+        pool = self.__dict__.get("_zero")     # set by forward(); a direct call (unit tests) allocates its own
+        sums = pool.take(2 * C) if pool is not None else torch.zeros(2 * C, dtype=torch.float32, device=dev)
         scale = torch.empty(C, dtype=torch.float32, device=dev)
         shift = torch.empty_like(scale)
         rstd = torch.empty_like(scale)
@@ -96,7 +125,10 @@ class UNetTrainEngine:
                                          _ptr(bn.running_var) if track else None, scale.data_ptr(), shift.data_ptr(),
                                          mean.data_ptr(), rstd.data_ptr(), _st(dev)), "bn_finalize")
         if track and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+            if self.__dict__.get("_tracked") is not None:
+                self._tracked.append(bn.num_batches_tracked)   # advanced together at the end of forward (one launch)
+            else:
+                bn.num_batches_tracked.add_(1)
         y = torch.empty_like(z)
         _lib.check(lib.im2im_bn_apply_relu_bf16(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), n_pix, C,
                                                 y.data_ptr(), _st(dev)), "bn_apply_relu")
@@ -115,8 +147,8 @@ class UNetTrainEngine:
                                               _st(dev)), "bn_relu_bwd")
         grads[layer.bn.bias] = sums[:C]
         grads[layer.bn.weight] = sums[C:]
-        if layer.conv.bias is not None:
-            grads[layer.conv.bias] = torch.zeros_like(layer.conv.bias)  # cancelled by the batch mean (see module doc)
+        # layer.conv.bias gets no entry: its gradient is exactly zero (cancelled by the batch mean, see module doc), and
+        # returning None to autograd leaves the zeroed .grad untouched instead of launching a fill and an add per layer
         return dz
 
     def _side_stream(self, dev):
@@ -155,6 +187,8 @@ class UNetTrainEngine:
             if a is not self.inc[0]:
                 a.pack()
         ctx = {"x": x, "layers": []}
+        self._zero = _ZeroPool(self._fwd_zero_floats, dev)
+        self._tracked = []
         with torch.cuda.device(dev):
             # first conv (CUDA cores), no bias (cancelled by BN), no ReLU: z0
             first = self.inc[0]
@@ -190,10 +224,14 @@ class UNetTrainEngine:
             # 1x1 out conv, output channels zero-padded 32 -> 64 so the result feeds the 64-channel kernels
             w_out = self.out_conv.weight.detach()
             c_feat = w_out.shape[1]
-            w_pad = torch.zeros((64, 1, c_feat), dtype=torch.bfloat16, device=dev)
-            w_pad[:self.c_mid, 0] = w_out.view(self.c_mid, c_feat).to(torch.bfloat16)
-            b_pad = torch.zeros(64, dtype=torch.float32, device=dev)
-            b_pad[:self.c_mid] = self.out_conv.bias.detach().float()
+            pads = self.__dict__.get("_out_pad")
+            if pads is None or pads[0].device != dev:   # rows c_mid..63 stay zero for the engine's lifetime
+                pads = (torch.zeros((64, 1, c_feat), dtype=torch.bfloat16, device=dev),
+                        torch.zeros(64, dtype=torch.float32, device=dev))
+                self._out_pad = pads
+            w_pad, b_pad = pads
+            w_pad[:self.c_mid, 0] = w_out.view(self.c_mid, c_feat)          # fp32 -> bf16 in the copy
+            b_pad[:self.c_mid] = self.out_conv.bias.detach()
             m = conv_igemm(y, w_pad, b_pad, relu=False)
             ctx["y_last"], ctx["m"], ctx["w_out_pad"] = y, m, w_pad
             # head (CUDA cores)
@@ -204,6 +242,10 @@ class UNetTrainEngine:
             _lib.check(lib.im2im_head_conv3x3_f32(m.data_ptr(), hw_.data_ptr(), hb.data_ptr(), None, B, H, W, self.c_mid, 64,
                                                   self.n_out, out.data_ptr(), _st(dev)), "head_conv")
             ctx["head_w"] = hw_
+            if self._tracked:
+                torch._foreach_add_(self._tracked, 1)
+            self._tracked = None
+            self._zero = None
             if self.head_act is not None:
                 # gaussian: relu(variance conv), residual magnitude: |magnitude conv| (gaussian_layer.py:18,
                 # residual_magnitude_layer.py:18); the derivative (0/1 or sign) of the pre-activation is kept for backward
@@ -223,12 +265,13 @@ class UNetTrainEngine:
         main = torch.cuda.current_stream(dz.device)
         side = self._side_stream(dz.device)
         side.wait_stream(main)                      # dz (and everything before it) is ready
+        c_out = dz.shape[3]
         with torch.cuda.stream(side):
-            dw1 = conv_wgrad(x1, dz, 9)
+            dw1 = conv_wgrad(x1, dz, 9, out=self._zero.take(c_out, 9, x1.shape[3]))
             if x2 is None:
                 grads[layer.conv.weight] = self._w_to_torch(dw1, layer.c_in)
             else:
-                dw2 = conv_wgrad(x2, dz, 9)
+                dw2 = conv_wgrad(x2, dz, 9, out=self._zero.take(c_out, 9, x2.shape[3]))
                 c1, c2 = x1.shape[3], x2.shape[3]
                 grads[layer.conv.weight] = torch.cat([self._w_to_torch(dw1, c1), self._w_to_torch(dw2, c2)], dim=1)
         for t in (dz, x1, x2):                      # keep the allocator from recycling them under the side stream
@@ -247,14 +290,16 @@ class UNetTrainEngine:
         x = ctx["x"]
         B, c_in, H, W = x.shape
         dout = dout.contiguous().float().view(B, self.n_out, H, W)
+        self._zero = _ZeroPool(self._bwd_zero_floats, dev)   # ONE fill for every accumulated-into gradient buffer
+        self._zero.buf.record_stream(self._side_stream(dev))  # its slices are written by the side-stream weight gradients
         if self.head_act is not None:
             dout = dout.clone()
             dout[:, self.act_from:] *= ctx["act_grad"]
         with torch.cuda.device(dev):
             m, y_last = ctx["m"], ctx["y_last"]
             dm = torch.empty_like(m)
-            dwh = torch.zeros((self.n_out, self.c_mid, 3, 3), dtype=torch.float32, device=dev)
-            dbh = torch.zeros(self.n_out, dtype=torch.float32, device=dev)
+            dwh = self._zero.take(self.n_out, self.c_mid, 3, 3)
+            dbh = self._zero.take(self.n_out)
             _lib.check(lib.im2im_head_bwd(dout.data_ptr(), m.data_ptr(), ctx["head_w"].data_ptr(), B, H, W, self.c_mid,
                                           64, self.n_out, dm.data_ptr(), dwh.data_ptr(), dbh.data_ptr(), _st(dev)),
                        "head_bwd")
@@ -263,9 +308,9 @@ class UNetTrainEngine:
                 grads[conv.weight] = dwh[i * co:(i + 1) * co]
                 grads[conv.bias] = dbh[i * co:(i + 1) * co]
             # 1x1 out conv: wgrad, bias grad (channel sums of dm), dgrad
-            dw_out = conv_wgrad(y_last, dm, 1)                       # [64 (32 real), 1, 64]
+            dw_out = conv_wgrad(y_last, dm, 1, out=self._zero.take(64, 1, 64))   # [64 (32 real), 1, 64]
             grads[self.out_conv.weight] = dw_out[:self.c_mid].view(self.c_mid, -1, 1, 1)
-            sums = torch.zeros(128, dtype=torch.float32, device=dev)
+            sums = self._zero.take(128)
             _lib.check(lib.im2im_channel_stats_bf16(dm.data_ptr(), B * H * W, 64, sums.data_ptr(), _st(dev)), "dbias")
             grads[self.out_conv.bias] = sums[:self.c_mid]
             w_out_bwd = ctx["w_out_pad"].permute(2, 1, 0).contiguous()  # [64 ci, 1, 64 co]
@@ -302,7 +347,7 @@ class UNetTrainEngine:
             d_y0, _ = self._conv_bwd(self.inc[1], s1, dz, grads)
             dz0 = self._bn_relu_bwd(d_y0, self.inc[0], s0, grads)
             first = self.inc[0]
-            dw0 = torch.zeros((first.c_out, c_in, 3, 3), dtype=torch.float32, device=dev)
+            dw0 = self._zero.take(first.c_out, c_in, 3, 3)
             _lib.check(lib.im2im_conv_first_wgrad(x.data_ptr(), dz0.data_ptr(), B, c_in, H, W, first.c_out,
                                                   dw0.data_ptr(), _st(dev)), "conv_first_wgrad")
             grads[first.conv.weight] = dw0

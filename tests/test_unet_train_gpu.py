@@ -33,7 +33,9 @@ def _grads(model, x, y, native, autocast=False):
         pred = model(x)
     loss = model.loss_fn(pred, y)
     loss.backward()
-    return pred.detach(), loss.item(), {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    # conv biases that feed a BatchNorm get no gradient from the native engine (exactly zero): None -> zeros
+    return pred.detach(), loss.item(), {n: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p))
+                                        for n, p in model.named_parameters()}
 
 
 def _rel(a, b):
