@@ -58,7 +58,7 @@ unsigned grid_for(long long work_items, int threads, int per_sm = 8) {
 //   MODE 1: xhat = (z-mean)*rstd;  g = dy * (xhat*gamma+beta > 0);  sums[c] += g, sums[C+c] += g*xhat  (BN+ReLU backward)
 // (a = z or dy; in MODE 1 `a` is dy and `zt` is the saved pre-normalisation convolution output z)
 template <int MODE>
-__global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16* __restrict__ a,
+__global__ void __launch_bounds__(256, 3) channel_reduce_kernel(const __nv_bfloat16* __restrict__ a,
                                                              const __nv_bfloat16* __restrict__ zt,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta,
@@ -70,15 +70,16 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
     const int g = threadIdx.x % groups;
     const int lane_p = threadIdx.x / groups;
     const int lanes = 256 / groups;
-    float acc0[8], acc1[8], sc[8], sh[8], mu[8], rs[8];
+    // MODE 1 accumulates sum(g) and sum(g*z) per thread; sum(g*xhat) = rstd*(sum(g*z) - mean*sum(g)) is formed once per
+    // block below, which keeps mean/rstd out of the loop (fewer live registers -> three resident blocks per SM)
+    float acc0[8], acc1[8], sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         acc0[j] = acc1[j] = 0.f;
         if (MODE == 1) {
-            mu[j] = mean[g * 8 + j];
-            rs[j] = rstd[g * 8 + j];
-            sc[j] = gamma[g * 8 + j] * rs[j];              // the forward's scale/shift, recomputed with the same ops
-            sh[j] = beta[g * 8 + j] - mu[j] * sc[j];
+            const float mu = mean[g * 8 + j];
+            sc[j] = gamma[g * 8 + j] * rstd[g * 8 + j];    // the forward's scale/shift, recomputed with the same ops
+            sh[j] = beta[g * 8 + j] - mu * sc[j];
         }
     }
     // kUnroll pixels per thread and iteration: all their 16-byte loads are issued before the first use, so that enough
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
                 for (int j = 0; j < 8; ++j) {
                     const float gj = fmaf(fz[j], sc[j], sh[j]) > 0.f ? fa[j] : 0.f;   // ReLU mask exactly as the forward saw it
                     acc0[j] += gj;
-                    acc1[j] = fmaf(gj, (fz[j] - mu[j]) * rs[j], acc1[j]);
+                    acc1[j] = fmaf(gj, fz[j], acc1[j]);
                 }
             }
         }
@@ -120,13 +121,14 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s_part[0][threadIdx.x][j] = acc0[j]; s_part[1][threadIdx.x][j] = acc1[j]; }
     __syncthreads();
-    // thread t < 2*C finalises (which, channel)
-    for (int t = threadIdx.x; t < 2 * C; t += 256) {
-        const int which = t / C, c = t % C;
+    // thread c < C finalises channel c
+    for (int c = threadIdx.x; c < C; c += 256) {
         const int gg = c / 8, j = c % 8;
-        float s = 0.f;
-        for (int l = 0; l < lanes; ++l) s += s_part[which][l * groups + gg][j];
-        atomicAdd(&sums[which * C + c], s);
+        float s0 = 0.f, s1 = 0.f;
+        for (int l = 0; l < lanes; ++l) { s0 += s_part[0][l * groups + gg][j]; s1 += s_part[1][l * groups + gg][j]; }
+        if (MODE == 1) s1 = rstd[c] * (s1 - mean[c] * s0);
+        atomicAdd(&sums[c], s0);
+        atomicAdd(&sums[C + c], s1);
     }
 }
 
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(const __nv_bfloat16*
 }
 
 // dz = gamma*rstd * (g - sum(g)/M - xhat * sum(g*xhat)/M),  xhat = (z-mean)*rstd,  g = dy * (xhat*gamma+beta > 0)
-__global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
+__global__ void __launch_bounds__(256, 3) bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
                                                                 const __nv_bfloat16* __restrict__ z,
                                                                 const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta,
@@ -199,23 +201,23 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const __nv_bfloa
                                                                 const float* __restrict__ sums, float inv_count,
                                                                 long long n_pix, int C, __nv_bfloat16* __restrict__ dz) {
     // a thread's channel group is loop-invariant (see bn_apply_relu_kernel): per-channel constants in registers.
-    //   dz = sc*g - k0 - (z - mu)*k1,   k0 = sc*sum(g)/M,  k1 = sc*rstd*sum(g*xhat)/M
-    constexpr int kUnroll = 4;
+    //   dz = sc*g - k0 - (z - mu)*k1 = sc*g + c0 - z*k1,   k0 = sc*sum(g)/M,  k1 = sc*rstd*sum(g*xhat)/M,  c0 = mu*k1 - k0
+    // three resident blocks per SM (<= 85 registers) x 3 pixel groups per thread: 768 threads x 96 B in flight per SM
+    constexpr int kUnroll = 3;
     const int groups = C / 8;
     const long long total = n_pix * groups;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const long long e0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int g = static_cast<int>(e0 % groups);
-    float sc[8], sh[8], mu[8], k0[8], k1[8];
+    float sc[8], sh[8], c0[8], k1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = g * 8 + j;
-        const float rs = __ldg(rstd + c);
-        mu[j] = __ldg(mean + c);
+        const float rs = __ldg(rstd + c), mu = __ldg(mean + c);
         sc[j] = __ldg(gamma + c) * rs;
-        sh[j] = __ldg(beta + c) - mu[j] * sc[j];
-        k0[j] = sc[j] * (__ldg(sums + c) * inv_count);
+        sh[j] = __ldg(beta + c) - mu * sc[j];
         k1[j] = sc[j] * (rs * (__ldg(sums + C + c) * inv_count));
+        c0[j] = mu * k1[j] - sc[j] * (__ldg(sums + c) * inv_count);   // dz = sc*g + c0 - z*k1
     }
     for (long long e = e0; e < total; e += stride * kUnroll) {
         Bf16x8 vd[kUnroll], vz[kUnroll];
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const __nv_bfloa
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float gj = fmaf(fz[j], sc[j], sh[j]) > 0.f ? fd[j] : 0.f;
-                o[j] = fmaf(sc[j], gj, -k0[j]) - (fz[j] - mu[j]) * k1[j];
+                o[j] = fmaf(-fz[j], k1[j], fmaf(sc[j], gj, c0[j]));
             }
             *reinterpret_cast<uint4*>(dz + (e + u * stride) * 8) = pack8(o);
         }
@@ -307,45 +309,30 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        // the (at most five) output rows / columns whose bilinear footprint contains iy / ix, with the forward's own
-        // fp32 weights; computed once per axis instead of once per (row, column) pair
-        float wy[5], wx[5];
-#pragma unroll
-        for (int a = 0; a < 5; ++a) {
-            const int uy = 2 * iy - 2 + a, ux = 2 * ix - 2 + a;
-            wy[a] = 0.f;
-            wx[a] = 0.f;
-            if (uy >= 0 && uy < uh) {
-                const float fy = sy * uy;
-                const int y0 = static_cast<int>(fy);
-                const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
-                const float ly = fy - y0;
-                if (y0 == iy) wy[a] += 1.f - ly;
-                if (y1 == iy) wy[a] += ly;
-            }
-            if (ux >= 0 && ux < uw) {
+        for (int uy = max(0, 2 * iy - 2); uy <= min(uh - 1, 2 * iy + 2); ++uy) {
+            const float fy = sy * uy;
+            const int y0 = static_cast<int>(fy);
+            const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+            const float ly = fy - y0;
+            float wy = 0.f;
+            if (y0 == iy) wy += 1.f - ly;
+            if (y1 == iy) wy += ly;
+            if (wy == 0.f) continue;
+            for (int ux = max(0, 2 * ix - 2); ux <= min(uw - 1, 2 * ix + 2); ++ux) {
                 const float fx = sx * ux;
                 const int x0 = static_cast<int>(fx);
                 const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
                 const float lx = fx - x0;
-                if (x0 == ix) wx[a] += 1.f - lx;
-                if (x1 == ix) wx[a] += lx;
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < 5; ++a) {
-            if (wy[a] == 0.f) continue;
-            const int uy = 2 * iy - 2 + a;
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                if (wx[c] == 0.f) continue;
-                const int ux = 2 * ix - 2 + c;
+                float wx = 0.f;
+                if (x0 == ix) wx += 1.f - lx;
+                if (x1 == ix) wx += lx;
+                if (wx == 0.f) continue;
                 Bf16x8 t;
                 t.u = *reinterpret_cast<const uint4*>(
                     du + ((static_cast<long long>(b) * Ho + uy + pad_top) * Wo + ux + pad_left) * C + g * 8);
                 float f[8];
                 unpack8(t, f);
-                const float wgt = wy[a] * wx[c];
+                const float wgt = wy * wx;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, f[j], acc[j]);
             }
@@ -726,7 +713,7 @@ extern "C" int im2im_channel_stats_bf16(const void* d_z, int64_t n_pix, int32_t 
     if (int rc = check_channels(C, "channel_stats")) return rc;
     if (n_pix <= 0 || !d_z || !d_sums) return fail(IM2IM_EINVAL, "channel_stats: bad arguments");
     const int lanes = 256 / (C / 8);
-    channel_reduce_kernel<0><<<grid_for((n_pix + 3) / 4, lanes, 4), 256, 0, ST(stream)>>>(BF(d_z), nullptr, nullptr, nullptr, nullptr,
+    channel_reduce_kernel<0><<<grid_for((n_pix + 3) / 4, lanes, 3), 256, 0, ST(stream)>>>(BF(d_z), nullptr, nullptr, nullptr, nullptr,
                                                                                nullptr, n_pix, C, d_sums);
     return check_launch("channel_reduce_kernel<stats>");
 }
@@ -760,10 +747,10 @@ extern "C" int im2im_bn_relu_bwd_bf16(const void* d_dy, const void* d_z, const f
         return fail(IM2IM_EINVAL, "bn_relu_bwd: bad arguments");
     IM2IM_CUDA_TRY(cudaMemsetAsync(d_sums, 0, sizeof(float) * 2 * C, ST(stream)));
     const int lanes = 256 / (C / 8);
-    channel_reduce_kernel<1><<<grid_for((n_pix + 3) / 4, lanes, 4), 256, 0, ST(stream)>>>(BF(d_dy), BF(d_z), d_gamma, d_beta, d_mean,
+    channel_reduce_kernel<1><<<grid_for((n_pix + 3) / 4, lanes, 3), 256, 0, ST(stream)>>>(BF(d_dy), BF(d_z), d_gamma, d_beta, d_mean,
                                                                                d_rstd, n_pix, C, d_sums);
     if (int rc = check_launch("channel_reduce_kernel<bn_bwd>")) return rc;
-    bn_relu_bwd_apply_kernel<<<grid_for(n_pix * (C / 8), 256, 16), 256, 0, ST(stream)>>>(
+    bn_relu_bwd_apply_kernel<<<grid_for(n_pix * (C / 8), 256, 12), 256, 0, ST(stream)>>>(
         BF(d_dy), BF(d_z), d_gamma, d_beta, d_mean, d_rstd, d_sums, 1.f / static_cast<float>(n_pix), n_pix, C, BFW(d_dz));
     return check_launch("bn_relu_bwd_apply_kernel");
 }

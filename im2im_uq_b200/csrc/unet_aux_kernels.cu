@@ -165,30 +165,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
 // Weights sit in shared memory as [tap][c][NP] with NP = n_out padded to a multiple of 4, so one 128-bit broadcast load
 // feeds 4 FMAs.  tap_bias (optional, [n_out][9]) is added once per IN-RANGE tap: it carries the bias of a 1x1 convolution
 // that was folded into these weights (inference: OutConv 64->32 composed with the head, exact incl. the zero padding).
-// acc[0..NP) += sum over the 8 channels in `v` of x[c] * w[c][0..NP)   (w: [8][NP] fp32 in shared memory)
-template <int NP>
-__device__ __forceinline__ void head_accum8(const uint4& raw, const float* __restrict__ wt, float* acc) {
-    Bf16x8 v;
-    v.u = raw;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(v.h[j]);
-#pragma unroll
-        for (int q = 0; q < NP / 4; ++q) {
-            const float4 wa = *reinterpret_cast<const float4*>(wt + (2 * j) * NP + 4 * q);
-            const float4 wb = *reinterpret_cast<const float4*>(wt + (2 * j + 1) * NP + 4 * q);
-            acc[4 * q + 0] = fmaf(f.x, wa.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(f.x, wa.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(f.x, wa.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(f.x, wa.w, acc[4 * q + 3]);
-            acc[4 * q + 0] = fmaf(f.y, wb.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(f.y, wb.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(f.y, wb.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(f.y, wb.w, acc[4 * q + 3]);
-        }
-    }
-}
-
-// C32 = the feature map has exactly 32 channels (the reference's n_channels_middle): the twelve 16-byte loads of a
-// tap row are issued before the first use, so a thread keeps 192 bytes in flight instead of 16 (the kernel was
-// latency-bound on its single outstanding load).
-template <int N_OUT, bool C32>
+template <int N_OUT>
 __global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias,
                                                         const float* __restrict__ tap_bias, int B, int H, int W,
@@ -211,46 +188,30 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __r
 #pragma unroll
         for (int o = 0; o < NP; ++o) acc[o] = (bias && o < N_OUT) ? __ldg(bias + o) : 0.f;
 #pragma unroll
-        for (int ty = 0; ty < 3; ++ty) {
-            const int yy = yh + ty - 1;
-            if (yy < 0 || yy >= H) continue;
-            const __nv_bfloat16* prow = x + ((b * H + yy) * W) * c_stride;
-            if (C32) {
-                uint4 v[3][4];
+        for (int t = 0; t < 9; ++t) {
+            const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            if (tap_bias) {
 #pragma unroll
-                for (int tx = 0; tx < 3; ++tx) {
-                    const int xx = xw + tx - 1;
-                    if (xx >= 0 && xx < W) {
+                for (int o = 0; o < N_OUT; ++o) acc[o] += __ldg(tap_bias + o * 9 + t);
+            }
+            const __nv_bfloat16* p = x + ((b * H + yy) * W + xx) * c_stride;
+            const float* wt = s_w + t * c_mid * NP;
+            for (int c = 0; c < c_mid; c += 8) {
+                Bf16x8 v;
+                v.u = *reinterpret_cast<const uint4*>(p + c);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            v[tx][q] = *reinterpret_cast<const uint4*>(prow + static_cast<long long>(xx) * c_stride + 8 * q);
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(v.h[j]);
+#pragma unroll
+                    for (int q = 0; q < NP / 4; ++q) {
+                        const float4 wa = *reinterpret_cast<const float4*>(wt + (c + 2 * j) * NP + 4 * q);
+                        const float4 wb = *reinterpret_cast<const float4*>(wt + (c + 2 * j + 1) * NP + 4 * q);
+                        acc[4 * q + 0] = fmaf(f.x, wa.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(f.x, wa.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(f.x, wa.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(f.x, wa.w, acc[4 * q + 3]);
+                        acc[4 * q + 0] = fmaf(f.y, wb.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(f.y, wb.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(f.y, wb.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(f.y, wb.w, acc[4 * q + 3]);
                     }
-                }
-#pragma unroll
-                for (int tx = 0; tx < 3; ++tx) {
-                    const int xx = xw + tx - 1;
-                    if (xx < 0 || xx >= W) continue;
-                    const int t = ty * 3 + tx;
-                    if (tap_bias) {
-#pragma unroll
-                        for (int o = 0; o < N_OUT; ++o) acc[o] += __ldg(tap_bias + o * 9 + t);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) head_accum8<NP>(v[tx][q], s_w + (t * 32 + 8 * q) * NP, acc);
-                }
-            } else {
-#pragma unroll
-                for (int tx = 0; tx < 3; ++tx) {
-                    const int xx = xw + tx - 1;
-                    if (xx < 0 || xx >= W) continue;
-                    const int t = ty * 3 + tx;
-                    if (tap_bias) {
-#pragma unroll
-                        for (int o = 0; o < N_OUT; ++o) acc[o] += __ldg(tap_bias + o * 9 + t);
-                    }
-                    const __nv_bfloat16* p = prow + static_cast<long long>(xx) * c_stride;
-                    for (int c = 0; c < c_mid; c += 8)
-                        head_accum8<NP>(*reinterpret_cast<const uint4*>(p + c), s_w + (t * c_mid + c) * NP, acc);
                 }
             }
         }
@@ -358,12 +319,8 @@ extern "C" int im2im_head_conv3x3_act_f32(const void* d_x, const float* d_weight
     const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(d_x);
 #define IM2IM_HEAD_CASE(N)                                                                                              \
     case N:                                                                                                             \
-        if (c_mid == 32)                                                                                                \
-            head_conv_kernel<N, true><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, \
-                                                               act_kind, act_from_plane, d_out);                        \
-        else                                                                                                            \
-            head_conv_kernel<N, false><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid,        \
-                                                                c_stride, act_kind, act_from_plane, d_out);             \
+        head_conv_kernel<N><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, act_kind, \
+                                                     act_from_plane, d_out);                                            \
         break
     switch (n_out) {
         IM2IM_HEAD_CASE(2); IM2IM_HEAD_CASE(3); IM2IM_HEAD_CASE(4); IM2IM_HEAD_CASE(6); IM2IM_HEAD_CASE(9);
