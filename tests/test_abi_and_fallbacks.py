@@ -40,6 +40,16 @@ def test_argument_validation_without_gpu():
     assert rc == -22
     with pytest.raises(_lib.Im2ImError):
         _lib.check(rc, "probe")
+    # entry points added for the other heads / the graphed training step: argument checks come before any CUDA call
+    assert lib.im2im_nested_sets(9, None, None, None, 1, 16, 16, 16, 16, 1.0, 0, None, None, None) == -95
+    assert lib.im2im_nested_sets(2, None, None, None, 1, 16, 16, 16, 16, 1.0, 0, None, None, None) == -22
+    assert lib.im2im_nested_sets(1, None, None, None, 0, 16, 16, 16, 16, 1.0, 0, None, None, None) == 0   # empty: no-op
+    assert lib.im2im_rcps_miss_map(None, None, None, None, 1, 16, 16, 16, 16, 16, 1.0, 5, None, 0, None) == -95
+    assert lib.im2im_softmax_sets(None, 1, 65, 16, 16, 16, None, None) == -34 and b"n_classes" in lib.im2im_last_error()
+    assert lib.im2im_softmax_sets(None, 1, 50, 16, 800, 16, None, None) == -22
+    assert lib.im2im_head_loss_f32(2, None, None, 1, 16, .05, .95, 1., 1., 1., .1, None, None, None) == -22
+    assert lib.im2im_head_conv3x3_act_f32(None, None, None, None, 1, 8, 8, 32, 32, 2, 7, 1, None, None) == -22
+    assert lib.im2im_adam_step_dev_f32(None, None, None, None, 10, 1e-3, .9, .999, 1e-8, None, 1.0, None) == -22
 
 
 def test_cpu_tensors_are_rejected_loudly():
@@ -53,6 +63,10 @@ def test_cpu_tensors_are_rejected_loudly():
         cm.calibrate_from_outputs(None, out, lab, dict(device="cpu"))
     with pytest.raises(_lib.Im2ImError):
         cm.fraction_missed_loss((lab, lab, lab), lab)
+    with pytest.raises(_lib.Im2ImError, match="no CPU path"):
+        rcps.head_nested_sets(torch.zeros(2, 2, 1, 4, 4), 1.0, _lib.IM2IM_HEAD_GAUSSIAN)
+    with pytest.raises(_lib.Im2ImError, match="no CPU path"):
+        rcps.softmax_sets(torch.zeros(2, 50, 1, 4, 4))
 
 
 def test_product_does_not_import_the_oracle():
