@@ -292,3 +292,51 @@ def test_eval_set_metrics_consistent_with_calibration(head_golden):
         mm = orc.head_miss_map(g["scores"], g["labels"], float(g["lhat"]), g["score_head"])
         assert np.array_equal(spatial, (mm.astype(np.float32) / np.float32(n)).mean(axis=0))
     assert sizes.shape == (n,) and strat.shape == (4,) and spatial.shape == g["labels"].shape[2:]
+
+
+# ------------------------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("head", ["residual_magnitude", "gaussian", "softmax_sets"])
+def test_head_full_size_properties(head):
+    """BASELINE config C2's size (1k x 320^2, L = 1000) for the other head kinds: size-independent invariants (nested
+    sets are monotone in lambda, checksum of checksums, both kernels agree, shard additivity, chunked accumulation,
+    idempotence) + random rows against the oracle at full L."""
+    n, h, w, L = 1000, 320, 320, 1000
+    g = torch.Generator(device=DEV).manual_seed(3)
+    shape = (n, 1, h, w)
+    pred = torch.rand(shape, generator=g, device=DEV)
+    sig = 0.02 + 0.1 * torch.rand(shape, generator=g, device=DEV)
+    lab = pred + sig * torch.randn(shape, generator=g, device=DEV)
+    width = sig * (0.5 + torch.rand(shape, generator=g, device=DEV))
+    if head == "softmax_sets":
+        k = 50
+        out = torch.stack([torch.floor((pred - width).clamp(0, 1) * k) / k, torch.floor(pred * k) / k,
+                           torch.floor((pred + width).clamp(0, 1) * k) / k], dim=1).contiguous()
+    else:
+        out = torch.stack([pred, width ** 2 if head == "gaussian" else width], dim=1).contiguous()
+    kind = KIND[head]
+    lam_cpu = torch.linspace(0.0, 6.0, L) - (torch.linspace(0.0, 6.0, L)[1] - torch.linspace(0.0, 6.0, L)[0])
+    lam = lam_cpu.to(DEV)
+    px = h * w
+    c, t = rcps.miss_counts(out, lab, lam, head=kind)
+    assert int(c.min()) >= 0 and int(c.max()) <= px
+    assert bool((c[:, 1:] <= c[:, :-1]).all())
+    assert torch.equal(t, c.sum(0, dtype=torch.int64))
+    cg, tg = rcps.miss_counts(out, lab, lam, force_generic=True, head=kind)
+    assert torch.equal(c, cg) and torch.equal(t, tg)
+    h1 = n // 3
+    ca, ta = rcps.miss_counts(out[:h1], lab[:h1], lam, head=kind)
+    cb, tb = rcps.miss_counts(out[h1:], lab[h1:], lam, head=kind)
+    assert torch.equal(torch.cat([ca, cb]), c) and torch.equal(ta + tb, t)
+    c2 = torch.zeros_like(c); t2 = torch.zeros_like(t)
+    rcps.miss_counts(out[:h1], lab[:h1], lam, counts=c2[:h1], totals=t2, zero=False, head=kind)
+    rcps.miss_counts(out[h1:], lab[h1:], lam, counts=c2[h1:], totals=t2, zero=False, head=kind)
+    assert torch.equal(c2, c) and torch.equal(t2, t)
+    c3, t3 = rcps.miss_counts(out, lab, lam, head=kind)
+    assert torch.equal(c3, c) and torch.equal(t3, t)
+    rows = torch.randperm(n)[:4].to(DEV)
+    want = orc.head_miss_table(out[rows].cpu().numpy(), lab[rows].cpu().numpy(), lam_cpu.numpy(), head)
+    assert np.array_equal(c[rows].cpu().numpy(), want)
+    # interval endpoints at one lambda, whole set, against the oracle on the same rows (bit-exact)
+    lo, pr, up = rcps.head_nested_sets(out[rows].contiguous(), float(lam_cpu[L // 3]), kind)
+    lo_w, _, up_w = orc.head_nested_sets(out[rows].cpu().numpy(), float(lam_cpu[L // 3]), head)
+    assert np.array_equal(lo.cpu().numpy(), lo_w) and np.array_equal(up.cpu().numpy(), up_w)
