@@ -468,7 +468,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc_halo(const void* smem_ptr) {
     desc |= static_cast<uint64_t>(1) << 16;                       // LBO (ignored, swizzled K-major)
     desc |= static_cast<uint64_t>((kHaloW * 128) >> 4) << 32;     // SBO: next output row = 16 pixel rows further
     desc |= static_cast<uint64_t>(1) << 46;                       // descriptor version
-    // base_offset stays 0: measured on B200 (tools/halo_debug.py) - the 128B swizzle is applied on absolute shared-memory
+    // base_offset stays 0: measured on B200 (both settings were run through tools/conv_check.py) - the 128B swizzle is applied on absolute shared-memory
     // address bits, so a start that is not 1024-byte aligned reads TMA-written data correctly as is; setting
     // base_offset = (addr >> 7) & 7 breaks every tap with dx != -1.
     desc |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
