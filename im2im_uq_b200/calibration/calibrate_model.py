@@ -439,15 +439,30 @@ def collect_outputs(model, dataset, config, device):
     return outputs, labels
 
 
-def calibrate_model(model, dataset, config):
-    """Drop-in for the reference's ``calibrate_model``: returns ``(model, calib_loss_table)`` with ``model.lhat`` set."""
+def rank_shard(dataset, group):
+    """This rank's contiguous block of a map-style calibration set (rank order = row order of the loss table)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = len(dataset)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    return torch.utils.data.Subset(dataset, range(lo, hi))
+
+
+def calibrate_model(model, dataset, config, group=None):
+    """Drop-in for the reference's ``calibrate_model``: returns ``(model, calib_loss_table)`` with ``model.lhat`` set.
+
+    ``group`` (optional, a torch.distributed process group, one process per GPU) shards the calibration set: every rank
+    runs the model over its contiguous block of a map-style ``dataset`` and keeps its rows of the table; the only
+    collective on the data path is the all-reduce of the per-lambda miss totals (int64[L]); all ranks get the same lhat."""
     with torch.no_grad():
         print(f"Calibrating...")
         model.eval()
         device = _cuda_device(config['device'])
         get_rcps_loss_fn(config)  # raises NotImplementedError for unknown losses, like the reference
         model = model.to(device)
+        if group is not None:
+            dataset = rank_shard(dataset, group)
         outputs, labels = collect_outputs(model, dataset, config, device)
-        model, calib_loss_table = calibrate_from_outputs(model, outputs, labels, config)
+        model, calib_loss_table = calibrate_from_outputs(model, outputs, labels, config, group=group)
         print(f"Model's lhat set to {model.lhat}")
         return model, calib_loss_table

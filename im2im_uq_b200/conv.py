@@ -69,3 +69,48 @@ def pack_dgrad_weight(weight: torch.Tensor) -> torch.Tensor:
     c_out, c_in, kh, kw = weight.shape
     w = weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(c_in, kh * kw, c_out)
     return w.contiguous().to(torch.bfloat16)
+
+
+def head_tc_applicable(H: int, W: int, n_out: int, c_mid: int) -> bool:
+    """The tensor-core head (im2im_head_conv3x3_tc_f32) needs 8x16-pixel tiles, <= 32 output planes, <= 64 features."""
+    return W % 8 == 0 and H % 16 == 0 and 1 <= n_out <= 32 and c_mid <= 64
+
+
+def pad_head_weight(weight: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stacked head weight fp32 [n_out, c_mid, 3, 3] -> fp32 [64, 64, 3, 3] with zero rows / input channels (``out`` is a
+    persistent zero-initialised buffer: only the live block is rewritten)."""
+    n_out, c_mid = weight.shape[:2]
+    if out is None:
+        out = torch.zeros((64, 64, 3, 3), dtype=torch.float32, device=weight.device)
+    out[:n_out, :c_mid].copy_(weight.detach())
+    return out
+
+
+def head_conv_tc(x: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[torch.Tensor], n_out: int,
+                 act_kind: int = 0, act_from: int = 0) -> torch.Tensor:
+    """Head on tensor cores: x NHWC bf16 [B,H,W,64], weight bf16 [64,9,64] (pad_head_weight + pack_conv_weight) ->
+    fp32 planes [B, n_out, H, W] with the head's activation fused."""
+    lib = _lib.load()
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[3] == 64
+    assert weight_packed.dtype == torch.bfloat16 and weight_packed.is_contiguous() and tuple(weight_packed.shape) == (64, 9, 64)
+    B, H, W, _ = x.shape
+    out = torch.empty((B, n_out, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.im2im_head_conv3x3_tc_f32(x.data_ptr(), weight_packed.data_ptr(),
+                                           bias.data_ptr() if bias is not None else None, B, H, W, n_out, act_kind,
+                                           act_from, out.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "im2im_head_conv3x3_tc_f32")
+    return out
+
+
+def planar_to_nhwc64(src: torch.Tensor) -> torch.Tensor:
+    """fp32 planes [B, n, H, W] -> bf16 NHWC [B, H, W, 64], channels >= n zero."""
+    lib = _lib.load()
+    assert src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 4 and src.shape[1] <= 64
+    B, n, H, W = src.shape
+    dst = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        rc = lib.im2im_planar_to_nhwc64_bf16(src.data_ptr(), n, B, H, W, dst.data_ptr(),
+                                             torch.cuda.current_stream(src.device).cuda_stream)
+    _lib.check(rc, "im2im_planar_to_nhwc64_bf16")
+    return dst

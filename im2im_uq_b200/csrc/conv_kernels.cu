@@ -456,6 +456,10 @@ struct HaloParams {
     const float* bias;
     __nv_bfloat16* out_bf16;
     float* out_f32;
+    // head mode: only the first n_real (<= 32) output channels are real; they are written as fp32 PLANES
+    // [B, n_real, H, W] (the reference's (B, planes, C, H, W) head tensor), planes >= act_from get act_kind (1 relu, 2 abs)
+    float* out_planar;
+    int n_real, act_kind, act_from;
 };
 
 constexpr int kHaloW = 16, kHaloH = 18, kHaloTileW = 8, kHaloTileH = 16;
@@ -597,6 +601,33 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             full_phase ^= 1u << buf;
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(buf) * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
+            if (p.out_planar != nullptr) {
+                // head mode: the real outputs live in the first 32 accumulator columns; one TMEM load, then the buffer is free
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_acc, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                if (in_range) {
+                    const size_t hw = static_cast<size_t>(p.H) * p.W;
+                    float* dst = p.out_planar + static_cast<size_t>(b) * p.n_real * hw + static_cast<size_t>(h) * p.W + w;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < p.n_real) {
+                            float x = __uint_as_float(v[j]);
+                            if (p.bias) x += __ldg(p.bias + j);
+                            if (j >= p.act_from) {
+                                if (p.act_kind == 1) x = (x != x) ? x : fmaxf(x, 0.f);
+                                else if (p.act_kind == 2) x = fabsf(x);
+                            }
+                            dst[static_cast<size_t>(j) * hw] = x;   // lanes = 8 consecutive pixels of a row: 32-byte runs
+                        }
+                    }
+                }
+                buf ^= 1;
+                continue;
+            }
             for (int c = 0; c < p.bn; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tmem_acc + static_cast<uint32_t>(c), v);
@@ -1040,6 +1071,7 @@ extern "C" int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void
             h.c_in1 = c_in1; h.c_in2 = c_in2; h.c_out = c_out; h.B = B; h.H = H; h.W = W;
             h.tiles_w = W / kHaloTileW; h.tiles_h = H / kHaloTileH; h.bn = hbn; h.relu = relu; h.bias = d_bias;
             h.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16); h.out_f32 = d_out_f32;
+            h.out_planar = nullptr; h.n_real = 0; h.act_kind = 0; h.act_from = 0;
             const int w_bytes = 9 * c_in * hbn * 2;
             h.a_stages = (220 * 1024 - w_bytes) / kHaloBytes;
             if (h.a_stages > 4) h.a_stages = 4;
@@ -1080,6 +1112,79 @@ extern "C" int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void
     const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
     conv_igemm_persistent_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(m1, m2, mw, p);
     return check_launch("conv_igemm_persistent_kernel");
+}
+
+// planar fp32 [B, n, H, W] -> NHWC bf16 [B, H, W, 64] with channels >= n zero: the head's output gradient as a tensor-core
+// operand (weight / data gradient of the head through the same halo kernels as every other layer)
+namespace im2im { namespace {
+__global__ void __launch_bounds__(256) planar_to_nhwc64_kernel(const float* __restrict__ src, int n, long long hw,
+                                                               long long total_pix, __nv_bfloat16* __restrict__ dst) {
+    // thread = (pixel, 8-channel group): 8 groups per pixel
+    const long long total = total_pix * 8;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(e & 7);
+        const long long pix = e >> 3;
+        const long long b = pix / hw, k = pix - b * hw;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            f[j] = c < n ? __ldg(src + (b * n + c) * hw + k) : 0.f;
+        }
+        uint4 pk;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst + pix * 64 + g * 8) = pk;
+    }
+}
+} }
+
+extern "C" int im2im_planar_to_nhwc64_bf16(const float* d_src, int32_t n_planes, int32_t B, int32_t H, int32_t W,
+                                           void* d_dst, void* stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || n_planes < 1 || n_planes > 64) return fail(IM2IM_EINVAL, "planar_to_nhwc64: bad shape");
+    if (!d_src || !d_dst) return fail(IM2IM_EINVAL, "planar_to_nhwc64: null tensor");
+    const long long hw = static_cast<long long>(H) * W, pix = hw * B;
+    long long blocks = (pix * 8 + 255) / 256;
+    const long long cap = 16ll * sm_count();
+    if (blocks > cap) blocks = cap;
+    planar_to_nhwc64_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_src, n_planes, hw, pix, static_cast<__nv_bfloat16*>(d_dst));
+    return check_launch("planar_to_nhwc64_kernel");
+}
+
+extern "C" int im2im_head_conv3x3_tc_f32(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H,
+                                         int32_t W, int32_t n_real, int32_t act_kind, int32_t act_from_plane,
+                                         float* d_out, void* stream) {
+    if (B <= 0 || H <= 0 || W <= 0) return fail(IM2IM_EINVAL, "head_tc: bad activation shape");
+    if (n_real < 1 || n_real > 32) return fail(IM2IM_ERANGE, "head_tc: n_real=%d outside [1, 32]", n_real);
+    if (act_kind < 0 || act_kind > 2) return fail(IM2IM_EINVAL, "head_tc: act_kind=%d", act_kind);
+    if (W % kHaloTileW || H % kHaloTileH)
+        return fail(IM2IM_ENOTSUP, "head_tc: needs W %% 8 == 0 and H %% 16 == 0 (got %dx%d); use im2im_head_conv3x3_act_f32", H, W);
+    if (!d_x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "head_tc: null tensor");
+    HaloParams h;
+    h.c_in1 = 64; h.c_in2 = 0; h.c_out = 64; h.B = B; h.H = H; h.W = W;
+    // N = 32: only the first n_real <= 32 weight rows are real, so half of the 64 packed rows are never loaded or multiplied
+    h.tiles_w = W / kHaloTileW; h.tiles_h = H / kHaloTileH; h.bn = 32; h.relu = 0; h.bias = d_bias;
+    h.out_bf16 = nullptr; h.out_f32 = nullptr;
+    h.out_planar = d_out; h.n_real = n_real; h.act_kind = act_kind; h.act_from = act_kind ? act_from_plane : n_real;
+    const int w_bytes = 9 * 64 * h.bn * 2;
+    h.a_stages = 4;
+    CUtensorMap h1, hw;
+    int rc = make_act_map(&h1, d_x, B, H, W, 64, kHaloW, kHaloH, 1);
+    if (rc) return rc;
+    rc = make_weight_map(&hw, d_weight, 64, 9 * 64, h.bn);
+    if (rc) return rc;
+    const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * kHaloBytes +
+                         (2 * h.a_stages + 5) * sizeof(uint64_t) + 16 + 1024;
+    IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+    const long long m_tiles = static_cast<long long>(h.tiles_w) * h.tiles_h * B;
+    long long gx = sm_count();
+    if (gx > m_tiles) gx = m_tiles;
+    conv_halo_kernel<<<dim3(static_cast<unsigned>(gx), 1), kConvThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h1, hw, h);
+    return check_launch("conv_halo_kernel<head>");
 }
 
 extern "C" int im2im_conv_wgrad_bf16(const void* d_x, const void* d_dz, int32_t B, int32_t H, int32_t W, int32_t c_in,

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..conv import conv_igemm, pack_conv_weight
+from ..conv import conv_igemm, head_conv_tc, head_tc_applicable, pack_conv_weight, pad_head_weight
 
 
 def _fold_bn(conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d]) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -79,6 +79,20 @@ class UNetInferenceEngine:
         self.n_planes = len(convs)
         self.c_out = convs[0].weight.shape[0]
         self.head_act = ({None: 0, "relu": 1, "abs": 2}[act], act_from * self.c_out)
+        # tensor-core head (8x16-pixel tiles): OutConv padded to 64 output channels (rows >= 32 zero) feeds a 64 -> 64 halo
+        # convolution whose first n_out outputs are the head's planes
+        ow, ob = _fold_bn(trunk.out.conv, None)
+        c_mid = ow.shape[0]
+        self.c_mid = c_mid
+        if c_mid <= 64 and hw.shape[0] <= 32 and ow.shape[1] % 64 == 0:
+            ow64 = torch.zeros((64,) + tuple(ow.shape[1:]), dtype=torch.float32, device=ow.device)
+            ob64 = torch.zeros(64, dtype=torch.float32, device=ow.device)
+            ow64[:c_mid] = ow
+            ob64[:c_mid] = ob
+            self.out64 = (pack_conv_weight(ow64), ob64)
+            self.head_tc = (pack_conv_weight(pad_head_weight(hw)), hb)
+        else:
+            self.out64 = self.head_tc = None
         self._stamp = self._param_stamp()
 
     # ---- single launches
@@ -141,6 +155,12 @@ class UNetInferenceEngine:
                 u = self._upsample_to(y, skip.shape[1], skip.shape[2])
                 y = conv_igemm(skip, c1[0], c1[1], relu=True, x2=u)   # torch.cat([skip, up]) without the copy
                 y = conv_igemm(y, c2[0], c2[1], relu=True)
+            if (self.head is not None and self.head_tc is not None
+                    and head_tc_applicable(y.shape[1], y.shape[2], self.head[0].shape[0], self.c_mid)):
+                m = conv_igemm(y, self.out64[0], self.out64[1], relu=False)   # 1x1 OutConv, 64 -> 32 (+32 zero channels)
+                n_out = self.head[0].shape[0]
+                out = head_conv_tc(m, self.head_tc[0], self.head_tc[1], n_out, self.head_act[0], self.head_act[1])
+                return out.view(x.shape[0], self.n_planes, self.c_out, y.shape[1], y.shape[2])
             m = conv_igemm(y, self.out[0], self.out[1], relu=False)  # 1x1 OutConv, 64 -> 32 (tensor cores)
             if self.head is None:  # heads without a native kernel (softmax: 50 planes) run their own module on the features
                 return self.model.last_layer(m.permute(0, 3, 1, 2).float())

@@ -22,7 +22,8 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..conv import conv_igemm, conv_wgrad, pack_conv_weight, pack_dgrad_weight
+from ..conv import (conv_igemm, conv_wgrad, head_conv_tc, head_tc_applicable, pack_conv_weight, pack_dgrad_weight,
+                    planar_to_nhwc64)
 
 
 def _st(dev):
@@ -102,6 +103,7 @@ class UNetTrainEngine:
         self._fwd_zero_floats = sum(pad(2 * l.c_out) for l in layers)
         self._bwd_zero_floats = (sum(2 * pad(l.c_out * 9 * l.c_in) for l in layers[1:])   # concat layers: two buffers
                                  + pad(64 * 64) + pad(self.n_out * self.c_mid * 9) + pad(self.n_out) + pad(128)
+                                 + pad(64 * 9 * 64)
                                  + pad(layers[0].c_out * 8 * 9))
 
     # ------------------------------------------------------------------------------------------- primitive launches
@@ -237,10 +239,26 @@ class UNetTrainEngine:
             # head (CUDA cores)
             hw_ = torch.cat([c.weight for c in self.head_convs], 0).detach().float().contiguous()
             hb = torch.cat([c.bias for c in self.head_convs], 0).detach().float().contiguous()
-            out = torch.empty((B, self.n_out, H, W), dtype=torch.float32, device=dev)
-            # m has a 64-channel row stride (upper 32 are zero padding); the head reads only the 32 real channels
-            _lib.check(lib.im2im_head_conv3x3_f32(m.data_ptr(), hw_.data_ptr(), hb.data_ptr(), None, B, H, W, self.c_mid, 64,
-                                                  self.n_out, out.data_ptr(), _st(dev)), "head_conv")
+            ctx["head_tc"] = head_tc_applicable(H, W, self.n_out, self.c_mid)
+            if ctx["head_tc"]:
+                # head on tensor cores: the stacked 3x3 convs as one 64 -> 64 halo convolution over the zero-padded features
+                # (weights bf16 [64, 9, 64], rows >= n_out and input channels >= c_mid zero), planes written directly
+                bufs = self.__dict__.get("_head_bufs")
+                if bufs is None or bufs[0].device != dev:
+                    bufs = (torch.zeros((64, 64, 3, 3), dtype=torch.float32, device=dev),
+                            torch.empty((64, 9, 64), dtype=torch.bfloat16, device=dev),
+                            torch.empty((64, 9, 64), dtype=torch.bfloat16, device=dev))
+                    self._head_bufs = bufs
+                w64, w_fwd, w_bwd = bufs
+                w64[:self.n_out, :self.c_mid].copy_(hw_)
+                w_fwd.copy_(w64.permute(0, 2, 3, 1).reshape(64, 9, 64))                  # [co, tap, ci]
+                w_bwd.copy_(w64.flip(2, 3).permute(1, 2, 3, 0).reshape(64, 9, 64))       # [ci, flipped tap, co]
+                out = head_conv_tc(m, w_fwd, hb, self.n_out)
+            else:
+                out = torch.empty((B, self.n_out, H, W), dtype=torch.float32, device=dev)
+                # m has a 64-channel row stride (upper 32 are zero padding); the head reads only the 32 real channels
+                _lib.check(lib.im2im_head_conv3x3_f32(m.data_ptr(), hw_.data_ptr(), hb.data_ptr(), None, B, H, W, self.c_mid,
+                                                      64, self.n_out, out.data_ptr(), _st(dev)), "head_conv")
             ctx["head_w"] = hw_
             if self._tracked:
                 torch._foreach_add_(self._tracked, 1)
@@ -297,12 +315,21 @@ class UNetTrainEngine:
             dout[:, self.act_from:] *= ctx["act_grad"]
         with torch.cuda.device(dev):
             m, y_last = ctx["m"], ctx["y_last"]
-            dm = torch.empty_like(m)
-            dwh = self._zero.take(self.n_out, self.c_mid, 3, 3)
-            dbh = self._zero.take(self.n_out)
-            _lib.check(lib.im2im_head_bwd(dout.data_ptr(), m.data_ptr(), ctx["head_w"].data_ptr(), B, H, W, self.c_mid,
-                                          64, self.n_out, dm.data_ptr(), dwh.data_ptr(), dbh.data_ptr(), _st(dev)),
-                       "head_bwd")
+            if ctx.get("head_tc"):
+                # head gradients on tensor cores: dOut as a 64-channel NHWC bf16 operand, weight gradient through the halo
+                # wgrad kernel, data gradient = the halo conv with the flipped / transposed head weights
+                dout_nhwc = planar_to_nhwc64(dout)
+                dw64 = conv_wgrad(m, dout_nhwc, 9, out=self._zero.take(64, 9, 64))          # [plane, tap, feature]
+                dwh = dw64[:self.n_out, :, :self.c_mid].permute(0, 2, 1).reshape(self.n_out, self.c_mid, 3, 3)
+                dbh = dout.sum(dim=(0, 2, 3))
+                dm = conv_igemm(dout_nhwc, self._head_bufs[2])                               # channels >= c_mid come out zero
+            else:
+                dm = torch.empty_like(m)
+                dwh = self._zero.take(self.n_out, self.c_mid, 3, 3)
+                dbh = self._zero.take(self.n_out)
+                _lib.check(lib.im2im_head_bwd(dout.data_ptr(), m.data_ptr(), ctx["head_w"].data_ptr(), B, H, W, self.c_mid,
+                                              64, self.n_out, dm.data_ptr(), dwh.data_ptr(), dbh.data_ptr(), _st(dev)),
+                           "head_bwd")
             co = self.c_head
             for i, conv in enumerate(self.head_convs):
                 grads[conv.weight] = dwh[i * co:(i + 1) * co]

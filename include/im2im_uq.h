@@ -231,6 +231,17 @@ int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* 
 int im2im_head_conv3x3_act_f32(const void* d_x, const float* d_weight, const float* d_bias, const float* d_tap_bias,
                                int32_t B, int32_t H, int32_t W, int32_t c_mid, int32_t c_stride, int32_t n_out,
                                int32_t act_kind, int32_t act_from_plane, float* d_out, void* stream);
+/* The same head on TENSOR CORES (tcgen05 halo kernel): x bf16 NHWC with exactly 64 channels per pixel (the reference's 32
+ * feature channels zero-padded), d_weight bf16 [64, 9, 64] = the stacked head convolutions packed like
+ * im2im_pack_conv_weights with rows >= n_real and input channels >= c_mid zero, d_bias fp32 [>= n_real] or NULL; output
+ * fp32 planes [B, n_real, H, W], n_real <= 32.  Needs W % 8 == 0 and H % 16 == 0 (IM2IM_ENOTSUP otherwise: use the
+ * CUDA-core entry points above).  The head's weights enter as bf16 here (fp32 above); accumulation is fp32. */
+int im2im_head_conv3x3_tc_f32(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W,
+                              int32_t n_real, int32_t act_kind, int32_t act_from_plane, float* d_out, void* stream);
+/* fp32 planes [B, n_planes, H, W] -> bf16 NHWC [B, H, W, 64] (channels >= n_planes zero): the head's output gradient as an
+ * operand of im2im_conv_wgrad_bf16 / im2im_conv_igemm_bf16 (head weight / data gradient on tensor cores). */
+int im2im_planar_to_nhwc64_bf16(const float* d_src, int32_t n_planes, int32_t B, int32_t H, int32_t W, void* d_dst,
+                                void* stream);
 
 /*
  * Training-side passes of the UNet path (autograd of core/scripts/train.py:152-162 through the modules of

@@ -27,6 +27,26 @@ def main():
         assert stop == int(g["stop_idx"]), (case, rank, stop)
         assert np.float32(lhat.numpy()) == g["lhat"]
         assert np.array_equal(counts.cpu().numpy(), g["counts_prime"][lo:hi])
+    # the drop-in entry point with a sharded dataset: identity model, so dataset inputs are the head outputs
+    from im2im_uq_b200.models.add_uncertainty import ModelWithUncertainty
+    from im2im_uq_b200.models.quantile_layer import (quantile_regression_loss_fn,
+                                                     quantile_regression_nested_sets_from_output)
+
+    class _Id(torch.nn.Module):
+        def forward(self, x):
+            return x
+
+    for case in ("fastmri_small", "batch65"):
+        g = load_golden(case)
+        n = g["outputs"].shape[0]
+        cfg = dict(g["config"], device=str(dev))
+        model = ModelWithUncertainty(_Id(), _Id(), quantile_regression_loss_fn,
+                                     quantile_regression_nested_sets_from_output, cfg)
+        ds = torch.utils.data.TensorDataset(torch.from_numpy(g["outputs"].copy()), torch.from_numpy(g["labels"].copy()))
+        model, table = cm.calibrate_model(model, ds, cfg, group=dist.group.WORLD)
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        assert np.float32(model.lhat.numpy()) == g["lhat"], (case, rank)
+        assert np.array_equal(table.numpy(), g["calib_loss_table"][lo:hi]), (case, rank)
     dist.barrier()
     if rank == 0:
         print("NCCL_SWEEP_OK")
