@@ -359,8 +359,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"   # NCCL logs ("NCCL version ...") go to stdout by default: keep stdout
-                                                    # to the one JSON line
+    # Native libraries write to fd 1 behind Python's back (NCCL prints "NCCL version ..." at communicator init): point fd 1
+    # at stderr for the whole run and keep the real stdout for the ONE JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -555,7 +558,8 @@ def main():
                                     "sample": f"{args.cpu_sample} images x {visited} visited lambda steps (the steps the "
                                               f"full set visits; one full pass + fp32 mean + HB bound per step), "
                                               f"{dt:.1f} s; cost is linear in images"}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         # Leave without tearing NCCL down: ncclCommDestroy waits for every CUDA graph that captured one of its collectives
         # (RcpsGraph, GraphedTrainStep) and was observed to hang at exit on a 2-GPU box.  Everything is synchronised, the
