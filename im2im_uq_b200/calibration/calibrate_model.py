@@ -414,6 +414,17 @@ def calibrate_from_outputs(model, outputs: torch.Tensor, labels: torch.Tensor, c
         return model, table
 
 
+def _tensor_pair(dataset):
+    """(inputs, labels) when `dataset` is a two-tensor TensorDataset or a Subset of one over a contiguous range."""
+    if isinstance(dataset, TensorDataset) and len(dataset.tensors) == 2:
+        return dataset.tensors
+    if isinstance(dataset, torch.utils.data.Subset) and isinstance(dataset.dataset, TensorDataset) \
+            and len(dataset.dataset.tensors) == 2 and isinstance(dataset.indices, range) and dataset.indices.step == 1:
+        r = dataset.indices
+        return tuple(t[r.start:r.stop] for t in dataset.dataset.tensors)
+    return None
+
+
 def collect_outputs(model, dataset, config, device):
     """Stage 1 of ``calibrate_model`` (reference :106-123): run the model over the calibration set.
 
@@ -422,6 +433,23 @@ def collect_outputs(model, dataset, config, device):
     if config['dataset'] == 'temca':
         labels = torch.cat([x[1].unsqueeze(0).to(device) for x in iter(dataset)], dim=0)
         outputs = torch.cat([model(x[0].unsqueeze(0).to(device)) for x in iter(dataset)])
+        return outputs, labels
+    pair = _tensor_pair(dataset)
+    if pair is not None:
+        # TensorDataset (or a contiguous Subset of one): slicing the tensors is what the DataLoader's default collate
+        # (torch.stack of the items) produces, without the per-item Python loop and the extra host copy
+        xs, ys = pair
+        n = xs.shape[0]
+        bs = int(config['batch_size'])
+        if n == 0:
+            raise IndexError("empty calibration set")         # the reference fails on dataset[0]
+        labels = ys.to(device, non_blocking=True).to(torch.get_default_dtype())   # reference: assigned into torch.zeros(...)
+        outputs = None
+        for lo in range(0, n, bs):
+            out = model(xs[lo:lo + bs].to(device, non_blocking=True))
+            if outputs is None:
+                outputs = torch.empty((n,) + tuple(out.shape[1:]), dtype=out.dtype, device=device)
+            outputs[lo:lo + out.shape[0]] = out
         return outputs, labels
     labels_shape = list(dataset[0][1].unsqueeze(0).shape)
     labels_shape[0] = len(dataset)
