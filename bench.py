@@ -542,6 +542,9 @@ def main():
                 "config": {"workload": workload_name(args), "images_per_gpu": n_local,
                            "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % (n_local * px * 16 / 1e9),
                            "cuda_graph": plan is not None,
+                           "totals_allreduce": ("fused with the decision over NVLink peer memory (im2im_rcps_decide_p2p)"
+                                                if plan is not None and getattr(plan, "peer", None) is not None
+                                                else ("NCCL" if world > 1 else "none (single GPU)")),
                            "lhat": result["lhat"], "lhat_index": result["stop"],
                            "replayed_columns": result["replayed"], "parallelism": f"image shards x{world}, "
                            "one NCCL all-reduce of int64[L] totals" if world > 1 else "single GPU"},

@@ -90,6 +90,8 @@ def _declare_more(lib):
     lib.im2im_rcps_loss_table_dev.argtypes = [vp, i64, i32, i64, vp, vp, vp]
     lib.im2im_rcps_decide.restype = c.c_int
     lib.im2im_rcps_decide.argtypes = [vp, i32, f64, f64, f64, f64, f64, f64, vp, vp]
+    lib.im2im_rcps_decide_p2p.restype = c.c_int
+    lib.im2im_rcps_decide_p2p.argtypes = [vp, vp, vp, vp, i32, i32, i32, f64, f64, f64, f64, f64, f64, vp, vp, vp]
     lib.im2im_conv_igemm_bf16.restype = c.c_int
     lib.im2im_conv_igemm_bf16.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.im2im_conv_wgrad_bf16.restype = c.c_int
@@ -144,7 +146,8 @@ EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im
            "im2im_maxpool2x2_bwd_bf16", "im2im_upsample2x_bilinear_bwd_bf16", "im2im_quantile_loss_f32",
            "im2im_adam_step_f32", "im2im_head_bwd", "im2im_conv_first_wgrad", "im2im_nested_sets",
            "im2im_softmax_sets", "im2im_head_conv3x3_act_f32", "im2im_head_loss_f32",
-           "im2im_adam_step_dev_f32", "im2im_head_conv3x3_tc_f32", "im2im_planar_to_nhwc64_bf16"]
+           "im2im_adam_step_dev_f32", "im2im_head_conv3x3_tc_f32", "im2im_planar_to_nhwc64_bf16",
+           "im2im_rcps_decide_p2p"]
 
 
 def load():

@@ -279,10 +279,35 @@ def device_decide_fn(px: int, config: dict, result: Optional[torch.Tensor] = Non
     return decide
 
 
+class PeerTotals:
+    """Peer-mapped buffers for ``im2im_rcps_decide_p2p``: every rank's mailbox uint64[2][world][L] and flag array
+    uint32[world] in torch symmetric memory (CUDA peer / fabric mappings over NVLink), plus this rank's device-side epoch.
+    Construction is collective over ``group``.  Raises when symmetric memory is not available (callers fall back to NCCL)."""
+
+    def __init__(self, n_lambdas: int, group, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.mailbox = symm.empty(2 * self.world * n_lambdas, dtype=torch.int64, device=device)
+        self.flags = symm.empty(max(self.world, 32), dtype=torch.int32, device=device)
+        self.mailbox.zero_()
+        self.flags.zero_()
+        name = group.group_name if hasattr(group, "group_name") else group
+        h_mail = symm.rendezvous(self.mailbox, name)
+        h_flag = symm.rendezvous(self.flags, name)
+        self.mail_ptrs = torch.tensor([int(p) for p in h_mail.buffer_ptrs], dtype=torch.int64, device=device)
+        self.flag_ptrs = torch.tensor([int(p) for p in h_flag.buffer_ptrs], dtype=torch.int64, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self._handles = (h_mail, h_flag)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                 # every rank's flags are zero before anyone publishes
+
+
 class RcpsGraph:
     """The device side of one calibration captured ONCE into a CUDA graph and replayed: zero the outputs, the one-pass
-    miss-count kernel, (multi-GPU) the NCCL all-reduce of the per-lambda totals, the device-side stop decision and the
-    fp32 loss-table kernel.  Replaying removes the ~10 host launches per calibration, which matters once the kernel
+    miss-count kernel, (multi-GPU) the all-reduce of the per-lambda totals - fused with the decision over NVLink peer
+    memory (``im2im_rcps_decide_p2p``) when symmetric memory is available, a NCCL all-reduce otherwise - the device-side
+    stop decision and the fp32 loss-table kernel.  Replaying removes the ~10 host launches per calibration, which matters once the kernel
     itself takes a fraction of a millisecond (8 GPUs on a 10k-image set).  Scores must stay resident and unchanged in
     shape; their contents may change between replays.
 
@@ -291,7 +316,7 @@ class RcpsGraph:
     """
 
     def __init__(self, outputs: torch.Tensor, labels: torch.Tensor, config: dict, group=None, n_total=None,
-                 head: int = _lib.IM2IM_HEAD_QUANTILES):
+                 head: int = _lib.IM2IM_HEAD_QUANTILES, p2p: bool = True):
         assert outputs.is_cuda and labels.is_cuda
         self.config, self.group, self.head = config, group, head
         self.outputs, self.labels = outputs, labels
@@ -309,6 +334,20 @@ class RcpsGraph:
         self.result = torch.empty(4, dtype=torch.int32, device=dev)
         self.result_host = torch.empty(4, dtype=torch.int32, pin_memory=True)
         self._decide = device_decide_fn(self.px, config, result=self.result)
+        self.peer = None
+        if group is not None and p2p:
+            import torch.distributed as dist
+            try:
+                self.peer = PeerTotals(L, group, dev)
+                self.local_totals = torch.empty((L,), dtype=torch.int64, device=dev)
+            except Exception as e:  # noqa: BLE001 - no symmetric memory on this system: NCCL path
+                self.peer = None
+                self.p2p_error = f"{type(e).__name__}: {e}"
+            # all ranks must take the same path
+            ok = torch.tensor([1 if self.peer is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok) == 0:
+                self.peer = None
         self._enqueue()                      # warm-up outside capture (lazy module loads, NCCL channel setup)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
@@ -318,12 +357,27 @@ class RcpsGraph:
         self.kernels_per_replay = _lib.launch_count() - before  # libim2im_uq kernels inside one replay
 
     def _enqueue(self):
-        rcps.miss_counts(self.outputs, self.labels, self.lam_dev, counts=self.counts, totals=self.totals, zero=True,
-                         head=self.head)
-        if self.group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(self.totals, op=dist.ReduceOp.SUM, group=self.group)
-        self._decide(self.totals, self.n_total, read=False)
+        if self.peer is not None:
+            # totals stay local; the reduction over ranks happens inside the decision kernel, over peer memory
+            rcps.miss_counts(self.outputs, self.labels, self.lam_dev, counts=self.counts, totals=self.local_totals,
+                             zero=True, head=self.head)
+            n_px, gamma, alpha32, r_lo, r_hi, slack = sweep.screening_constants(self.n_total, self.px,
+                                                                                self.config['alpha'], self.config['delta'])
+            dev = self.totals.device
+            with torch.cuda.device(dev):
+                rc = _lib.load().im2im_rcps_decide_p2p(
+                    self.local_totals.data_ptr(), self.peer.mail_ptrs.data_ptr(), self.peer.flag_ptrs.data_ptr(),
+                    self.peer.epoch.data_ptr(), self.peer.rank, self.peer.world, self.totals.numel(), n_px, gamma, alpha32,
+                    r_lo, r_hi, slack, self.totals.data_ptr(), self.result.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "im2im_rcps_decide_p2p")
+        else:
+            rcps.miss_counts(self.outputs, self.labels, self.lam_dev, counts=self.counts, totals=self.totals, zero=True,
+                             head=self.head)
+            if self.group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(self.totals, op=dist.ReduceOp.SUM, group=self.group)
+            self._decide(self.totals, self.n_total, read=False)
         rcps.loss_table(self.counts, self.px, out=self.table, first_visited_dev=self.result[3:])
 
     def run(self):

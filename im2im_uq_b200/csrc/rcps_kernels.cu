@@ -434,6 +434,86 @@ __global__ void __launch_bounds__(256) rcps_decide_kernel(const unsigned long lo
     }
 }
 
+// Multi-GPU: the all-reduce of the per-lambda totals FUSED with the stop decision, over NVLink peer memory (no NCCL call
+// on the data path).  One-shot "push" all-reduce: every rank stores its u64[L] totals into its slot of every peer's
+// mailbox (peer-mapped symmetric memory, 8 KB per peer at L = 1000), publishes a release-flag per peer, waits for the
+// flags of all peers, sums the world slots of its OWN mailbox and runs the decision of rcps_decide_kernel on the sum.
+//   mailbox layout (per rank)  u64[2][world][L]   (two epochs: a slot is rewritten two steps later, after every peer has
+//                                                   provably finished reading it - it has sent the flag of the step between)
+//   flags (per rank)           u32[world]          flag[r] = last epoch rank r has published to this rank (monotone)
+//   epoch (per rank, local)    u32                 incremented by the kernel, so a CUDA-graph replay needs no new arguments
+// All ranks must call this the same number of times (collective semantics).  One CTA; the spin is on local memory.
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) rcps_decide_p2p_kernel(const unsigned long long* __restrict__ local_totals,
+                                                               unsigned long long* const* __restrict__ peer_mailbox,
+                                                               unsigned* const* __restrict__ peer_flags,
+                                                               unsigned* __restrict__ epoch_dev, int rank, int world, int L,
+                                                               double n_px, double gamma, double alpha32, double r_lo,
+                                                               double r_hi, double slack,
+                                                               unsigned long long* __restrict__ totals_out,
+                                                               int* __restrict__ result) {
+    __shared__ int s_first, s_verdict;
+    const unsigned epoch = *epoch_dev + 1u;
+    const size_t slot = (static_cast<size_t>(epoch & 1u) * world + rank) * L;   // my slot in every mailbox
+    // 1. push my totals into every peer's mailbox (including my own)
+    for (int i = threadIdx.x; i < world * L; i += blockDim.x) {
+        const int r = i / L, j = i - r * L;
+        peer_mailbox[r][slot + j] = local_totals[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. publish: flag[rank] on every peer = epoch (release: the stores above are visible before the flag)
+    if (threadIdx.x < world) st_release_sys_u32(peer_flags[threadIdx.x] + rank, epoch);
+    // 3. wait for every peer's flag in MY flag array (local memory)
+    if (threadIdx.x < world) {
+        const unsigned* f = peer_flags[rank] + threadIdx.x;
+        while (static_cast<int>(ld_acquire_sys_u32(f) - epoch) < 0) { }
+    }
+    if (threadIdx.x == 0) { s_first = -1; s_verdict = 0; }
+    __syncthreads();
+    // 4. sum the world slots of my own mailbox and screen the stopping rule (same logic as rcps_decide_kernel)
+    const unsigned long long* mine = peer_mailbox[rank] + static_cast<size_t>(epoch & 1u) * world * L;
+    int best = -1, best_v = 0;
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        unsigned long long t = 0ull;
+        for (int r = 0; r < world; ++r) t += ld_relaxed_sys_u64(mine + static_cast<size_t>(r) * L + j);
+        totals_out[j] = t;
+        const double R = static_cast<double>(t) / n_px;
+        const double lo = R * (1.0 - gamma), hi = R * (1.0 + gamma);
+        bool sure_true = lo >= alpha32 * (1.0 + 1e-6);
+        if (isfinite(r_hi)) sure_true = sure_true || (lo > r_hi + slack);
+        bool sure_false = hi < alpha32 * (1.0 - 1e-6);
+        if (isfinite(r_lo)) sure_false = sure_false && (hi < r_lo - slack);
+        int v = sure_true ? 1 : (sure_false ? -1 : 0);
+        if (t == 0ull) v = 0;
+        if (v >= 0 && j > best) { best = j; best_v = v; }
+    }
+    if (best >= 0) atomicMax(&s_first, best);
+    __syncthreads();
+    if (best >= 0 && best == s_first) s_verdict = best_v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int first = s_first;
+        if (first < 0) { result[0] = -1; result[1] = 1; result[2] = -1; result[3] = 0; }
+        else if (s_verdict > 0) { result[0] = first; result[1] = 1; result[2] = -1; result[3] = first; }
+        else { result[0] = -1; result[1] = 0; result[2] = first; result[3] = 0; }
+        *epoch_dev = epoch;
+    }
+}
+
 // torch.minimum / torch.maximum semantics (NaN propagates)
 __device__ __forceinline__ float t_min(float a, float b) { return (a != a) ? a : ((b != b) ? b : fminf(a, b)); }
 __device__ __forceinline__ float t_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
@@ -838,4 +918,20 @@ extern "C" int im2im_softmax_sets(const float* d_logits, int64_t n_images, int32
                                        static_cast<cudaStream_t>(stream)>>>(d_logits, n_images, n_classes, inner,
                                                                             stride_image, stride_class, d_sets);
     return check_launch("softmax_sets_kernel");
+}
+
+extern "C" int im2im_rcps_decide_p2p(const unsigned long long* d_local_totals, unsigned long long* const* d_peer_mailboxes,
+                                     unsigned* const* d_peer_flags, unsigned* d_epoch, int32_t rank, int32_t world,
+                                     int32_t n_lambdas, double n_images_times_px, double gamma, double alpha32,
+                                     double r_lo, double r_hi, double slack, unsigned long long* d_totals_out,
+                                     int32_t* d_result, void* stream) {
+    if (n_lambdas < 1 || n_lambdas > IM2IM_RCPS_MAX_LAMBDAS) return fail(IM2IM_ERANGE, "n_lambdas=%d", n_lambdas);
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(IM2IM_EINVAL, "bad rank/world (%d/%d)", rank, world);
+    if (!d_local_totals || !d_peer_mailboxes || !d_peer_flags || !d_epoch || !d_totals_out || !d_result)
+        return fail(IM2IM_EINVAL, "decide_p2p: null pointer");
+    if (!(n_images_times_px > 0)) return fail(IM2IM_EINVAL, "empty calibration set");
+    rcps_decide_p2p_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_local_totals, d_peer_mailboxes, d_peer_flags, d_epoch, rank, world, n_lambdas, n_images_times_px, gamma, alpha32,
+        r_lo, r_hi, slack, d_totals_out, d_result);
+    return check_launch("rcps_decide_p2p_kernel");
 }

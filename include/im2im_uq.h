@@ -118,6 +118,24 @@ int im2im_rcps_decide(const unsigned long long* d_totals, int32_t n_lambdas, dou
                       double alpha32, double r_lo, double r_hi, double slack, int32_t* d_result, void* stream);
 
 /*
+ * Multi-GPU form of im2im_rcps_decide: the all-reduce of the per-lambda totals fused with the decision, over NVLink peer
+ * memory instead of a NCCL call (the reduction the reference does implicitly by holding the whole calibration set in one
+ * process, calibrate_model.py:136-138).  One-shot push all-reduce: this rank stores d_local_totals into its slot of every
+ * peer's mailbox, publishes a release flag per peer, waits for all peers' flags, sums its own mailbox, decides.
+ *   d_peer_mailboxes : DEVICE array [world] of pointers; entry r = rank r's mailbox uint64[2][world][n_lambdas] as mapped
+ *                      into THIS process (symmetric / peer memory; zero-initialised is not required)
+ *   d_peer_flags     : DEVICE array [world] of pointers; entry r = rank r's flag array uint32[world], zero before first use
+ *   d_epoch          : DEVICE uint32, local, zero before first use; advanced by the call (CUDA-graph replays need no new
+ *                      arguments).  Every rank must make the same sequence of calls.
+ *   d_totals_out     : DEVICE uint64[n_lambdas], the reduced totals (for the host replay of guard-band columns)
+ *   d_result         : as im2im_rcps_decide
+ */
+int im2im_rcps_decide_p2p(const unsigned long long* d_local_totals, unsigned long long* const* d_peer_mailboxes,
+                          unsigned* const* d_peer_flags, unsigned* d_epoch, int32_t rank, int32_t world, int32_t n_lambdas,
+                          double n_images_times_px, double gamma, double alpha32, double r_lo, double r_hi, double slack,
+                          unsigned long long* d_totals_out, int32_t* d_result, void* stream);
+
+/*
  * Interval endpoints at one lambda: ModelWithUncertainty.nested_sets_from_output
  * (core/models/add_uncertainty.py:33-38 over core/models/finallayers/quantile_layer.py:34-44).
  * Writes lower/upper as dense (n_images, px) fp32; the prediction plane is returned by the caller as a view.

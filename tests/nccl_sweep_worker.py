@@ -47,10 +47,34 @@ def main():
         lo, hi = n * rank // world, n * (rank + 1) // world
         assert np.float32(model.lhat.numpy()) == g["lhat"], (case, rank)
         assert np.array_equal(table.numpy(), g["calib_loss_table"][lo:hi]), (case, rank)
+    # the captured plan: all-reduce fused with the decision over peer memory when symmetric memory works here, NCCL otherwise;
+    # both must reproduce the reference's lhat / table rows, replay after replay
+    for p2p in (True, False):
+        for case in ("fastmri_small", "temca_small", "top_risk_zero", "never_stops"):
+            g = load_golden(case)
+            n = g["outputs"].shape[0]
+            cuts = [n * r // world for r in range(world + 1)]
+            lo, hi = cuts[rank], cuts[rank + 1]
+            cfg = dict(g["config"], device=str(dev))
+            out = torch.from_numpy(g["outputs"][lo:hi]).to(dev); lab = torch.from_numpy(g["labels"][lo:hi]).to(dev)
+            plan = cm.RcpsGraph(out, lab, cfg, group=dist.group.WORLD, n_total=n, p2p=p2p)
+            if p2p and rank == 0:
+                print("P2P_PATH", "peer-memory" if plan.peer is not None else "nccl-fallback: " + getattr(plan, "p2p_error", "?"))
+            for _ in range(3):
+                lhat, stop, decided = plan.run()
+                if not decided:
+                    lhat, stop = plan.replay_on_host()
+                assert stop == int(g["stop_idx"]), (case, p2p, rank, stop)
+                assert np.float32(lhat.numpy()) == g["lhat"]
+                assert np.array_equal(plan.table.cpu().numpy(), g["calib_loss_table"][lo:hi]), (case, p2p, rank)
+                assert np.array_equal(plan.totals.cpu().numpy(), g["counts_prime"].sum(0, dtype=np.int64)), (case, p2p)
+    del plan
+    torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
-        print("NCCL_SWEEP_OK")
-    dist.destroy_process_group()
+        print("NCCL_SWEEP_OK", flush=True)
+    sys.stdout.flush()
+    os._exit(0)   # skip NCCL teardown: ncclCommDestroy can wait on captured graphs (see bench.py)
 
 
 if __name__ == "__main__":
