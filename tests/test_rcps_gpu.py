@@ -345,3 +345,31 @@ def test_rcps_graph_replay_matches_reference(golden):
         lhat2, stop2 = plan.replay_on_host()
     assert stop2 == int(golden["stop_idx"])          # the stopping rule is permutation invariant
     assert np.array_equal(plan.counts.cpu().numpy(), golden["counts_prime"][::-1])
+
+
+def test_decide_p2p_single_rank_equals_decide(golden):
+    """im2im_rcps_decide_p2p with world = 1 (the mailbox and flags are this GPU's own buffers): same decision and totals
+    as im2im_rcps_decide, call after call (the epoch advances on the device).  The multi-rank exchange itself is covered
+    by tests/nccl_sweep_worker.py on a 2-GPU box."""
+    lib = _lib.load()
+    cfg = golden["config"]
+    n, L = golden["outputs"].shape[0], len(golden["lam_prime"])
+    px = int(np.prod(golden["labels"].shape[1:]))
+    _, totals = rcps.miss_counts(_dev(golden["outputs"]), _dev(golden["labels"]), _dev(golden["lam_prime"]))
+    n_px, gamma, alpha32, r_lo, r_hi, slack = sweep.screening_constants(n, px, cfg["alpha"], cfg["delta"])
+    want = torch.empty(4, dtype=torch.int32, device=DEV)
+    st = torch.cuda.current_stream(DEV).cuda_stream
+    _lib.check(lib.im2im_rcps_decide(totals.data_ptr(), L, n_px, gamma, alpha32, r_lo, r_hi, slack, want.data_ptr(), st))
+    mailbox = torch.full((2 * 1 * L,), -7, dtype=torch.int64, device=DEV)      # garbage: must be overwritten before use
+    flags = torch.zeros(32, dtype=torch.int32, device=DEV)
+    epoch = torch.zeros(1, dtype=torch.int32, device=DEV)
+    mail_ptrs = torch.tensor([mailbox.data_ptr()], dtype=torch.int64, device=DEV)
+    flag_ptrs = torch.tensor([flags.data_ptr()], dtype=torch.int64, device=DEV)
+    for call in range(1, 4):
+        got = torch.full((4,), -9, dtype=torch.int32, device=DEV)
+        out = torch.zeros(L, dtype=torch.int64, device=DEV)
+        _lib.check(lib.im2im_rcps_decide_p2p(totals.data_ptr(), mail_ptrs.data_ptr(), flag_ptrs.data_ptr(), epoch.data_ptr(),
+                                             0, 1, L, n_px, gamma, alpha32, r_lo, r_hi, slack, out.data_ptr(),
+                                             got.data_ptr(), st), "im2im_rcps_decide_p2p")
+        assert torch.equal(got, want) and torch.equal(out, totals)
+        assert int(epoch) == call and int(flags[0]) == call
