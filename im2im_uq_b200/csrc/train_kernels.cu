@@ -250,15 +250,13 @@ __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const __nv_bfloat16
                                                              const __nv_bfloat16* __restrict__ dy, int B, int H, int W,
                                                              int C, int accumulate, __nv_bfloat16* __restrict__ dx) {
     const int Ho = H / 2, Wo = W / 2, groups = C / 8;
-    // one thread per (input 2x2 window, channel group); odd trailing rows/columns get zero (handled by a second loop)
-    const long long total = static_cast<long long>(B) * Ho * Wo * groups;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(e % groups);
-        long long pix = e / groups;
-        const int ox = static_cast<int>(pix % Wo);
-        const int oy = static_cast<int>((pix / Wo) % Ho);
-        const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+    // one thread per (input 2x2 window, channel group); grid = (ceil(Wo*groups / 256), Ho, B) so that row and image come
+    // from the block index (one 32-bit division per thread instead of a 64-bit div/mod chain)
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < Wo * groups) {
+        const int g = idx % groups, ox = idx / groups;
+        const int oy = blockIdx.y, b = blockIdx.z;
+        const long long pix = (static_cast<long long>(b) * Ho + oy) * Wo + ox;
         const long long base = ((static_cast<long long>(b) * H + 2 * oy) * W + 2 * ox) * C + g * 8;
         const long long offs[4] = {0, C, static_cast<long long>(W) * C, static_cast<long long>(W) * C + C};
         float v[4][8], d[8], out[4][8];
@@ -298,14 +296,12 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16
     const int uh = 2 * h, uw = 2 * w, groups = C / 8;
     const float sy = uh > 1 ? static_cast<float>(h - 1) / static_cast<float>(uh - 1) : 0.f;
     const float sx = uw > 1 ? static_cast<float>(w - 1) / static_cast<float>(uw - 1) : 0.f;
-    const long long total = static_cast<long long>(B) * h * w * groups;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(e % groups);
-        long long pix = e / groups;
-        const int ix = static_cast<int>(pix % w);
-        const int iy = static_cast<int>((pix / w) % h);
-        const int b = static_cast<int>(pix / (static_cast<long long>(w) * h));
+    // grid = (ceil(w*groups / 256), h, B): row and image from the block index
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < w * groups) {
+        const int g = idx % groups, ix = idx / groups;
+        const int iy = blockIdx.y, b = blockIdx.z;
+        const long long pix = (static_cast<long long>(b) * h + iy) * w + ix;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -760,8 +756,9 @@ extern "C" int im2im_maxpool2x2_bwd_bf16(const void* d_x, const void* d_dy, int3
     if (B <= 0 || H < 2 || W < 2 || C <= 0 || C % 8 || !d_x || !d_dy || !d_dx) return fail(IM2IM_EINVAL, "maxpool_bwd: bad arguments");
     if ((H % 2 || W % 2) && !accumulate)  // trailing odd row/column never reaches the pool: its gradient is zero
         IM2IM_CUDA_TRY(cudaMemsetAsync(d_dx, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(B) * H * W * C, ST(stream)));
-    const long long items = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
-    maxpool2x2_bwd_kernel<<<grid_for(items, 256, 16), 256, 0, ST(stream)>>>(BF(d_x), BF(d_dy), B, H, W, C, accumulate,
+    if (B > 65535 || H / 2 > 65535) return fail(IM2IM_ERANGE, "maxpool_bwd: B and H/2 must be <= 65535");
+    const dim3 pgrid(static_cast<unsigned>(((W / 2) * (C / 8) + 255) / 256), static_cast<unsigned>(H / 2), static_cast<unsigned>(B));
+    maxpool2x2_bwd_kernel<<<pgrid, 256, 0, ST(stream)>>>(BF(d_x), BF(d_dy), B, H, W, C, accumulate,
                                                                            BFW(d_dx));
     return check_launch("maxpool2x2_bwd_kernel");
 }
@@ -771,8 +768,9 @@ extern "C" int im2im_upsample2x_bilinear_bwd_bf16(const void* d_du, int32_t B, i
     if (B <= 0 || h <= 0 || w <= 0 || C <= 0 || C % 8 || H_out < 2 * h || W_out < 2 * w || !d_du || !d_dx)
         return fail(IM2IM_EINVAL, "upsample_bwd: bad arguments");
     const int pad_top = (H_out - 2 * h) / 2, pad_left = (W_out - 2 * w) / 2;
-    const long long items = static_cast<long long>(B) * h * w * (C / 8);
-    upsample2x_bwd_kernel<<<grid_for(items, 256, 16), 256, 0, ST(stream)>>>(BF(d_du), B, h, w, C, H_out, W_out, pad_top,
+    if (B > 65535 || h > 65535) return fail(IM2IM_ERANGE, "upsample_bwd: B and h must be <= 65535");
+    const dim3 ugrid(static_cast<unsigned>((w * (C / 8) + 255) / 256), static_cast<unsigned>(h), static_cast<unsigned>(B));
+    upsample2x_bwd_kernel<<<ugrid, 256, 0, ST(stream)>>>(BF(d_du), B, h, w, C, H_out, W_out, pad_top,
                                                                            pad_left, BFW(d_dx));
     return check_launch("upsample2x_bwd_kernel");
 }

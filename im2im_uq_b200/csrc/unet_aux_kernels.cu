@@ -91,15 +91,14 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 // 2x2 max pool, stride 2 (floor), NHWC bf16.
 __global__ void __launch_bounds__(256) maxpool2x2_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W,
                                                          int C, __nv_bfloat16* __restrict__ y) {
-    const int Ho = H / 2, Wo = W / 2, groups = C / 8;
-    const long long total = static_cast<long long>(B) * Ho * Wo * groups;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(e % groups);
-        long long pix = e / groups;
-        const int ox = static_cast<int>(pix % Wo);
-        const int oy = static_cast<int>((pix / Wo) % Ho);
-        const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+    // grid = (ceil(Wo*groups / 256), Ho, B): row and image come from the block index, so the per-thread index math is one
+    // 32-bit division (the 64-bit div/mod chain of a flat index cost more instructions than the pooling itself)
+    const int Wo = W / 2, groups = C / 8;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < Wo * groups) {
+        const int g = idx % groups, ox = idx / groups;
+        const int oy = blockIdx.y, b = blockIdx.z;
+        const long long pix = (static_cast<long long>(b) * gridDim.y + oy) * Wo + ox;
         const __nv_bfloat16* p = x + ((static_cast<long long>(b) * H + 2 * oy) * W + 2 * ox) * C + g * 8;
         Bf16x8 a, c, d, f, o;
         a.u = *reinterpret_cast<const uint4*>(p);
@@ -122,14 +121,12 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
     const int uh = 2 * h, uw = 2 * w, groups = C / 8;
     const float sy = uh > 1 ? static_cast<float>(h - 1) / static_cast<float>(uh - 1) : 0.f;
     const float sx = uw > 1 ? static_cast<float>(w - 1) / static_cast<float>(uw - 1) : 0.f;
-    const long long total = static_cast<long long>(B) * Ho * Wo * groups;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(e % groups);
-        long long pix = e / groups;
-        const int ox = static_cast<int>(pix % Wo);
-        const int oy = static_cast<int>((pix / Wo) % Ho);
-        const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+    // grid = (ceil(Wo*groups / 256), Ho, B): see maxpool2x2_kernel (ncu: this kernel was instruction-bound, issue 76 %)
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < Wo * groups) {
+        const int g = idx % groups, ox = idx / groups;
+        const int oy = blockIdx.y, b = blockIdx.z;
+        const long long pix = (static_cast<long long>(b) * Ho + oy) * Wo + ox;
         const int uy = oy - pad_top, ux = ox - pad_left;
         Bf16x8 o;
         if (uy < 0 || uy >= uh || ux < 0 || ux >= uw) {
@@ -283,8 +280,9 @@ extern "C" int im2im_maxpool2x2_bf16(const void* d_x, int32_t B, int32_t H, int3
                                      void* stream) {
     if (B <= 0 || H < 2 || W < 2 || C <= 0 || C % 8) return fail(IM2IM_ERANGE, "maxpool: bad shape");
     if (!d_x || !d_out) return fail(IM2IM_EINVAL, "null tensor");
-    const long long items = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
-    maxpool2x2_kernel<<<grid_for(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    if (B > 65535 || H / 2 > 65535) return fail(IM2IM_ERANGE, "maxpool: B and H/2 must be <= 65535");
+    const dim3 pgrid(static_cast<unsigned>(((W / 2) * (C / 8) + 255) / 256), static_cast<unsigned>(H / 2), static_cast<unsigned>(B));
+    maxpool2x2_kernel<<<pgrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(d_x), B, H, W, C, static_cast<__nv_bfloat16*>(d_out));
     return check_launch("maxpool2x2_kernel");
 }
@@ -295,8 +293,9 @@ extern "C" int im2im_upsample2x_bilinear_bf16(const void* d_x, int32_t B, int32_
     if (H_out < 2 * h || W_out < 2 * w) return fail(IM2IM_ERANGE, "upsample: output smaller than 2x input");
     if (!d_x || !d_out) return fail(IM2IM_EINVAL, "null tensor");
     const int pad_top = (H_out - 2 * h) / 2, pad_left = (W_out - 2 * w) / 2;  // F.pad split of unet_parts.py:63-64
-    const long long items = static_cast<long long>(B) * H_out * W_out * (C / 8);
-    upsample2x_kernel<<<grid_for(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    if (B > 65535 || H_out > 65535) return fail(IM2IM_ERANGE, "upsample: B and H_out must be <= 65535");
+    const dim3 ugrid(static_cast<unsigned>((W_out * (C / 8) + 255) / 256), static_cast<unsigned>(H_out), static_cast<unsigned>(B));
+    upsample2x_kernel<<<ugrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(d_x), B, h, w, C, H_out, W_out, pad_top, pad_left,
         static_cast<__nv_bfloat16*>(d_out));
     return check_launch("upsample2x_kernel");
