@@ -650,16 +650,20 @@ __global__ void __launch_bounds__(256) softmax_sets_kernel(const float* __restri
                 ssum = __fadd_rn(ssum, v[k]);
             }
         }
+        // The reference compares cumsum(e_k / s) with 0.05 / 0.95; here the running sum of the UN-normalised e_k is compared
+        // with 0.05*s / 0.95*s - no division per class (50 IEEE divisions were a third of the kernel).  The two differ
+        // only by fp32 rounding, i.e. only where a cumulative probability lies within rounding distance of a threshold,
+        // which is the tolerance this half of the head has anyway (0 mismatches on the reference fixtures).
+        const float t_lo = __fmul_rn(0.05f, ssum), t_hi = __fmul_rn(0.95f, ssum);
         float cum = 0.f, best = -INFINITY;
         int n_lo = 0, n_hi = 0, arg = 0;
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             if (k < K) {
-                const float pk = __fdiv_rn(v[k], ssum);
-                cum = __fadd_rn(cum, pk);
-                n_lo += (cum <= 0.05f) ? 1 : 0;
-                n_hi += (cum <= 0.95f) ? 1 : 0;
-                if (pk > best) { best = pk; arg = k; }  // first maximal element, like torch.argmax
+                cum = __fadd_rn(cum, v[k]);
+                n_lo += (cum <= t_lo) ? 1 : 0;
+                n_hi += (cum <= t_hi) ? 1 : 0;
+                if (v[k] > best) { best = v[k]; arg = k; }  // first maximal element, like torch.argmax
             }
         }
         float lq, pr, uq;
