@@ -38,6 +38,14 @@ class ModelWithUncertainty(nn.Module):
         from .unet_train import native_train_applicable, native_train_forward
         if native_train_applicable(self, x):
             return native_train_forward(self, x)  # training step on the native engine, bridged into autograd
+        if torch.is_tensor(x) and x.is_cuda and not self.__dict__.get("_warned_module_path"):
+            # CUDA input that neither engine takes (eval mode with autograd on, a trunk that is not the UNet, a disabled
+            # engine ...): say so once instead of silently running the library convolutions
+            import warnings
+            self.__dict__["_warned_module_path"] = True
+            warnings.warn("ModelWithUncertainty.forward: this call runs through the torch module graph, not the native "
+                          "sm_100a engines (they need the reference's bilinear UNet trunk and either eval mode under "
+                          "torch.no_grad() or training mode with autograd enabled)", stacklevel=2)
         x = self.baseModel(x)
         return self.last_layer(x)
 
