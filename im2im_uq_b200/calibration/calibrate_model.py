@@ -526,6 +526,8 @@ def rank_shard(dataset, group):
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n = len(dataset)
+    if n < world:
+        raise ValueError(f"calibration set of {n} images cannot be sharded over {world} ranks")
     lo, hi = n * rank // world, n * (rank + 1) // world
     return torch.utils.data.Subset(dataset, range(lo, hi))
 

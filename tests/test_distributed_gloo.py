@@ -62,3 +62,43 @@ def test_two_ranks_agree_with_reference(case, split):
         assert np.float32(lhat) == g["lhat"]
         assert totals == g["counts_prime"].sum(0, dtype=np.int64).tolist()  # all-reduced totals are global
     assert results[0][3] == results[1][3]
+
+
+def _shard_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from im2im_uq_b200.calibration.calibrate_model import _tensor_pair, rank_shard
+        ds = torch.utils.data.TensorDataset(torch.arange(n).float().view(n, 1), torch.arange(n).float().view(n, 1) + 0.5)
+        try:
+            sub = rank_shard(ds, dist.group.WORLD)
+        except ValueError as e:
+            q.put((rank, "ValueError", str(e), None))
+            return
+        xs, ys = _tensor_pair(sub)                      # contiguous Subset of a TensorDataset -> tensor slices
+        q.put((rank, [int(sub[i][0]) for i in range(len(sub))], xs.view(-1).tolist(), ys.view(-1).tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 7, 2, 1])
+def test_rank_shard_partitions_the_calibration_set_in_row_order(n):
+    """calibrate_model(..., group=...): contiguous blocks in rank order, every image exactly once, the TensorDataset fast
+    path sees exactly that block; fewer images than ranks is refused on every rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if n < 2:
+        assert all(r[1] == "ValueError" and "cannot be sharded" in r[2] for r in results)
+        return
+    assert results[0][1] + results[1][1] == list(range(n))
+    for rank, idx, xs, ys in results:
+        assert xs == [float(i) for i in idx] and ys == [i + 0.5 for i in idx]
