@@ -384,6 +384,9 @@ class RcpsGraph:
         self.graph.replay()
         self.result_host.copy_(self.result, non_blocking=True)
         torch.cuda.current_stream(self.result.device).synchronize()
+        if int(self.result_host[1]) == -2:
+            raise _lib.Im2ImError("im2im_rcps_decide_p2p: a peer rank did not publish its totals within the timeout "
+                                  "(crashed or not calling in lockstep)")
         stop, decided = int(self.result_host[0]), bool(self.result_host[1])
         lhat = self.lambdas[stop] if stop >= 0 else self.default_lhat
         return lhat, stop, decided

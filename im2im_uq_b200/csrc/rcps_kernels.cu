@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(1024) rcps_decide_p2p_kernel(const unsigned lo
                                                                double r_hi, double slack,
                                                                unsigned long long* __restrict__ totals_out,
                                                                int* __restrict__ result) {
-    __shared__ int s_first, s_verdict;
+    __shared__ int s_first, s_verdict;   // result[1] == -2 reports a peer timeout (see the wait below)
     const unsigned epoch = *epoch_dev + 1u;
     const size_t slot = (static_cast<size_t>(epoch & 1u) * world + rank) * L;   // my slot in every mailbox
     // 1. push my totals into every peer's mailbox (including my own)
@@ -478,12 +478,22 @@ __global__ void __launch_bounds__(1024) rcps_decide_p2p_kernel(const unsigned lo
     // 2. publish: flag[rank] on every peer = epoch (release: the stores above are visible before the flag)
     if (threadIdx.x < world) st_release_sys_u32(peer_flags[threadIdx.x] + rank, epoch);
     // 3. wait for every peer's flag in MY flag array (local memory)
+    __shared__ int s_timeout;
+    if (threadIdx.x == 0) { s_first = -1; s_verdict = 0; s_timeout = 0; }
+    __syncthreads();
     if (threadIdx.x < world) {
         const unsigned* f = peer_flags[rank] + threadIdx.x;
-        while (static_cast<int>(ld_acquire_sys_u32(f) - epoch) < 0) { }
+        const long long t0 = clock64();
+        while (static_cast<int>(ld_acquire_sys_u32(f) - epoch) < 0) {
+            // a peer that never arrives (crashed process) must not hang this GPU: give up after ~2^35 cycles (~15 s)
+            if (clock64() - t0 > (1ll << 35)) { s_timeout = 1; break; }
+        }
     }
-    if (threadIdx.x == 0) { s_first = -1; s_verdict = 0; }
     __syncthreads();
+    if (s_timeout) {
+        if (threadIdx.x == 0) { result[0] = -2; result[1] = -2; result[2] = -2; result[3] = 0; *epoch_dev = epoch; }
+        return;
+    }
     // 4. sum the world slots of my own mailbox and screen the stopping rule (same logic as rcps_decide_kernel)
     const unsigned long long* mine = peer_mailbox[rank] + static_cast<size_t>(epoch & 1u) * world * L;
     int best = -1, best_v = 0;

@@ -128,7 +128,8 @@ int im2im_rcps_decide(const unsigned long long* d_totals, int32_t n_lambdas, dou
  *   d_epoch          : DEVICE uint32, local, zero before first use; advanced by the call (CUDA-graph replays need no new
  *                      arguments).  Every rank must make the same sequence of calls.
  *   d_totals_out     : DEVICE uint64[n_lambdas], the reduced totals (for the host replay of guard-band columns)
- *   d_result         : as im2im_rcps_decide
+ *   d_result         : as im2im_rcps_decide; {-2, -2, -2, 0} when a peer did not arrive within ~15 s (the kernel gives up
+ *                      instead of hanging the GPU)
  */
 int im2im_rcps_decide_p2p(const unsigned long long* d_local_totals, unsigned long long* const* d_peer_mailboxes,
                           unsigned* const* d_peer_flags, unsigned* d_epoch, int32_t rank, int32_t world, int32_t n_lambdas,
