@@ -47,3 +47,29 @@ def test_softmax_sets_match_reference_up_to_threshold_ties(head_golden):
     # the only admissible differences: a cumulative probability within rounding distance of 0.05 / 0.95
     assert (g["threshold_margin"][~same] < 2e-6).all()
     assert same.mean() > 0.995
+
+
+def test_c_and_numpy_restatements_agree_on_random_nasty_inputs():
+    """Two independent restatements (C, op-by-op; numpy array ops) of every head's chain agree bit for bit on inputs with
+    NaN / inf / signed zeros / negative widths / huge and tiny magnitudes, over grids that straddle zero."""
+    rng = np.random.default_rng(123)
+    special = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, -0.07, 1e-30, 1e30, -1e-3, 0.5], dtype=np.float32)
+    for head, planes in (("residual_magnitude", 2), ("gaussian", 2), ("softmax_sets", 3), ("quantiles_l1", 3)):
+        for trial in range(6):
+            shape = (5, planes, 2, 7, 9)
+            out = rng.random(shape, dtype=np.float32)
+            if head == "softmax_sets":
+                out = np.floor(out * 50) / np.float32(50)
+            lab = rng.random((5, 2, 7, 9), dtype=np.float32)
+            idx = rng.integers(0, out.size, 60)
+            out.reshape(-1)[idx] = special[rng.integers(0, special.size, 60)]
+            idx = rng.integers(0, lab.size, 20)
+            lab.reshape(-1)[idx] = special[rng.integers(0, special.size, 20)]
+            lams = np.linspace(-1.0 - trial, 4.0 + trial, 17).astype(np.float32)
+            table = orc.head_miss_table(out, lab, lams, head)
+            for j, lam in enumerate(lams):
+                counts = orc.np_fraction_missed(orc.np_head_nested_sets(out, lam, head), lab)[1]
+                assert np.array_equal(counts, table[:, j]), (head, trial, j)
+                lo_c, _, up_c = orc.head_nested_sets(out, float(lam), head)
+                lo_n, _, up_n = orc.np_head_nested_sets(out, lam, head)
+                assert np.array_equal(lo_c, lo_n, equal_nan=True) and np.array_equal(up_c, up_n, equal_nan=True)
