@@ -30,6 +30,20 @@ IM2IM_RCPS_MAX_LAMBDAS = 8192
 
 _lib = None
 
+# Bumped by every code path that writes model parameters / BatchNorm statistics through raw device pointers or a CUDA-graph
+# replay (FusedAdam.step, GraphedTrainStep, the native training forward): torch's tensor._version does not see those
+# writes, so caches of derived weights (UNetInferenceEngine's folded BatchNorm) include this counter in their stamp.
+_weights_generation = 0
+
+
+def weights_changed() -> None:
+    global _weights_generation
+    _weights_generation += 1
+
+
+def weights_generation() -> int:
+    return _weights_generation
+
 
 class Im2ImError(RuntimeError):
     """A C-ABI call returned a negative code."""

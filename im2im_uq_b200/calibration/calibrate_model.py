@@ -191,6 +191,9 @@ def get_rcps_metrics_from_outputs(model, out_dataset, rcps_loss_fn, device):
         lam_dev = torch.as_tensor(lam, dtype=torch.float32).reshape(1).to(device)
         counts, _ = rcps.miss_counts(outputs_d, labels_d, lam_dev, head=kind)
         losses = rcps.loss_table(counts, px)[:, 0]
+        # the reference iterates a DataLoader (:35-36); its iterator draws one int64 base seed from torch's default
+        # generator (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__), which shifts the torch.rand below
+        torch.empty((), dtype=torch.int64).random_()
         # one random pixel per image, drawn batch by batch like the reference
         idx_parts = []
         for lo in range(0, n, 64):

@@ -41,7 +41,9 @@ class UNetInferenceEngine:
 
     # ---- weights
     def _param_stamp(self):
-        return tuple((p.data_ptr(), p._version) for p in self.model.parameters()) + \
+        # _lib.weights_generation(): raw-pointer / graph-replay writes (FusedAdam, bn_finalize, GraphedTrainStep) that
+        # tensor._version cannot see
+        return (_lib.weights_generation(),) + tuple((p.data_ptr(), p._version) for p in self.model.parameters()) + \
             tuple((b.data_ptr(), b._version) for n, b in self.model.named_buffers() if b is not None and n != "lhat")
 
     def refresh(self):

@@ -189,6 +189,7 @@ class UNetTrainEngine:
             if a is not self.inc[0]:
                 a.pack()
         ctx = {"x": x, "layers": []}
+        _lib.weights_changed()          # bn_finalize updates the running statistics through raw pointers
         self._zero = _ZeroPool(self._fwd_zero_floats, dev)
         self._tracked = []
         with torch.cuda.device(dev):
@@ -502,6 +503,7 @@ class FusedAdam(torch.optim.Optimizer):
     def step(self, closure=None, grad_scale: float = 1.0):
         self.gather_grads()
         self._step += 1
+        _lib.weights_changed()          # parameters are rewritten through raw pointers: tensor._version does not move
         g = self.param_groups[0]
         lib = _lib.load()
         with torch.cuda.device(self.flat_param.device):
@@ -571,5 +573,6 @@ class GraphedTrainStep:
     def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
+        _lib.weights_changed()          # the replay rewrites parameters and BatchNorm statistics behind torch's back
         self.graph.replay()
         return self.loss

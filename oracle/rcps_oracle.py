@@ -297,3 +297,45 @@ def calibrate_sweep(outputs, labels, lam_min, lam_max, num_lambdas, alpha, delta
             lhat, stop = lam, j
             break
     return lhat, stop, table
+
+
+def np_metrics_at_lambda(outputs, labels, lam, seed=None):
+    """calibrate_model.py:31-60 (get_rcps_metrics_from_outputs) restated on numpy fp32 + the reference's own RNG calls.
+
+    Batches of 64 in order (:35), per batch one ``np.random.choice(px, size=b)`` (:44); then one ``torch.rand(N)`` (:51).
+    ``seed`` (optional) seeds both generators the way tests/golden/make_golden_metrics.py does.
+    Returns (losses (N,) fp32, sizes (N,) fp32 tensor, spearman, stratified_risks (4,) tensor, mse, spatial (H,W))."""
+    import torch
+    from scipy.stats import spearmanr
+    outputs = np.asarray(outputs, dtype=np.float32)
+    labels = np.asarray(labels, dtype=np.float32)
+    if seed is not None:
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+    n = outputs.shape[0]
+    losses, sizes, residuals, maps = [], [], [], []
+    # :35 iterates a DataLoader: its iterator draws one int64 "base seed" from torch's default generator before the first
+    # batch (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__), which shifts the torch.rand of :50
+    torch.empty((), dtype=torch.int64).random_()
+    for lo in range(0, n, 64):
+        x, y = outputs[lo:lo + 64], labels[lo:lo + 64]
+        lower, pred, upper = np_nested_sets(x, lam)                                   # :40 (lam = model.lhat)
+        losses.append(np_fraction_missed((lower, pred, upper), y)[0])                 # :41
+        b = x.shape[0]
+        full = (upper - lower).reshape(b, -1)                                         # :42
+        idx = np.random.choice(full.shape[1], size=b)                                 # :43
+        sizes.append(full[np.arange(b), idx])                                         # :44
+        with np.errstate(all="ignore"):
+            residuals.append(np.abs(y - pred).reshape(b, -1)[np.arange(b), idx])      # :45
+            maps.append((y > upper).astype(np.float32) + (y < lower).astype(np.float32))   # :46
+    losses = torch.from_numpy(np.concatenate(losses))
+    sizes = torch.from_numpy(np.concatenate(sizes))
+    sizes = sizes + torch.rand(size=sizes.shape) * 1e-6                               # :50
+    residuals = np.concatenate(residuals)
+    spearman = spearmanr(residuals, sizes)[0]                                         # :52
+    mse = (residuals * residuals).mean().item()                                       # :53
+    spatial = np.concatenate(maps, axis=0).mean(axis=0).mean(axis=0)                  # :54
+    size_bins = torch.tensor([0, torch.quantile(sizes, 0.25), torch.quantile(sizes, 0.5), torch.quantile(sizes, 0.75)])
+    buckets = torch.bucketize(sizes, size_bins) - 1                                   # :56
+    strat = torch.tensor([losses[buckets == bucket].mean() for bucket in range(size_bins.shape[0])])
+    return losses, sizes, spearman, strat, mse, spatial

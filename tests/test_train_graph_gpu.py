@@ -48,3 +48,45 @@ def test_graphed_step_tracks_eager_step():
     for (n1, b1), (n2, b2) in zip(m_e.named_buffers(), m_g.named_buffers()):
         if b1 is not None and "num_batches" in n1:
             assert int(b1) == int(b2) == len(seq)
+
+
+def test_eval_engine_sees_graph_replays_and_fused_adam_steps():
+    """train (graph replay) -> eval -> more replays -> eval: the cached inference engine must re-fold the weights every
+    time, although FusedAdam / bn_finalize / cudaGraphLaunch never bump a tensor._version."""
+    from im2im_uq_b200.models.unet_train import FusedAdam, GraphedTrainStep
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    x = torch.randn(4, 1, 64, 64, device="cuda:0", generator=g)
+    y = x + 0.3 * torch.randn(4, 1, 64, 64, device="cuda:0", generator=g)
+    model = _build()
+    opt = FusedAdam(model.parameters(), lr=1e-2)
+    step = GraphedTrainStep(model, opt, x, y, warmup=1)
+
+    def eval_pair():
+        model.eval()
+        with torch.no_grad():
+            native = model(x)
+            assert "_native_engine" in model.__dict__
+            model.use_native_inference = False
+            ref = model(x)                        # torch module graph on the CURRENT parameters / running statistics
+            model.use_native_inference = True
+        model.train()
+        return native, ref
+
+    outs = []
+    for _ in range(3):
+        for _ in range(2):
+            step(x, y)
+        native, ref = eval_pair()
+        assert ((native - ref).norm() / ref.norm()).item() <= 2e-2
+        outs.append(native)
+    # the model really moved between the evaluations (lr 1e-2): a stale engine would have returned the same tensor
+    assert ((outs[1] - outs[0]).norm() / outs[0].norm()).item() > 5e-2
+    assert ((outs[2] - outs[1]).norm() / outs[1].norm()).item() > 1e-2
+    # same for the eager native loop with FusedAdam
+    for _ in range(2):
+        opt.zero_grad()
+        model.loss_fn(model(x), y).backward()
+        opt.step()
+    native, ref = eval_pair()
+    assert ((native - ref).norm() / ref.norm()).item() <= 2e-2
+    step.close()
