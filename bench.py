@@ -27,6 +27,17 @@ if ROOT not in sys.path:
 METRIC = "calibration images/sec (320x320, 10k set)"
 UNIT = "images/s"
 
+# BASELINE.json `configs`.  C3 is the configuration the metric is quoted on and the default.  The lambda
+# grids are the reference's: fastmri [0,6]x1000 (experiments/fastmri_test/config.yml:29,37-39), temca [7,10]x100
+# (experiments/temca_test/config.yml:29,37-39); alpha = delta = 0.1 in both (:24-27).  `noise` scales the synthetic label
+# noise so that lambda-hat lands mid-grid on that grid.
+CONFIGS = {
+    "C2": dict(images=1000, side=320, lambdas=1000, lam_min=0.0, lam_max=6.0, noise=1.0, gpus=1, name="fastmri_test, 1k calibration images"),
+    "C3": dict(images=10000, side=320, lambdas=1000, lam_min=0.0, lam_max=6.0, noise=1.0, gpus=8, name="fastmri_test"),
+    "C4": dict(images=4000, side=512, lambdas=100, lam_min=7.0, lam_max=10.0, noise=4.6, gpus=4, name="temca_test"),
+    "C5": dict(images=50000, side=640, lambdas=1000, lam_min=0.0, lam_max=6.0, noise=1.0, gpus=8, name="stress"),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -34,9 +45,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images", type=int, default=10000, help="calibration images in the whole job")
-    ap.add_argument("--side", type=int, default=320)
-    ap.add_argument("--lambdas", type=int, default=1000)
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS), help="BASELINE.json configuration (default C3 = the "
+                    "one the metric is quoted on: 10k x 320x320, lambda grid [0,6]x1000)")
+    ap.add_argument("--images", type=int, default=None, help="calibration images in the whole job (default: the config's)")
+    ap.add_argument("--side", type=int, default=None)
+    ap.add_argument("--lambdas", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=192, help="images in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -44,24 +57,35 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch the calibration step kernel by kernel instead of "
                     "replaying its CUDA graph")
     ap.add_argument("--no-unet", action="store_true", help="skip the UNet forward / train-step sub-benchmark")
-    ap.add_argument("--unet-batch", type=int, default=16, help="images per GPU per UNet step")
-    ap.add_argument("--unet-steps", type=int, default=10)
-    return ap.parse_args()
+    ap.add_argument("--unet-batch", type=int, default=78, help="images per GPU per UNet step (78 = the reference's "
+                    "batch size, experiments/fastmri_test/config.yml:45)")
+    ap.add_argument("--unet-steps", type=int, default=6)
+    ap.add_argument("--no-unet-reference", action="store_true", help="skip the torch/cuDNN and CPU reference legs of the "
+                    "UNet sub-benchmark")
+    ap.add_argument("--e2e-images", type=int, default=None, help="images per GPU in the e2e (host buffers) leg; default: "
+                    "the whole shard, capped at 16 GB of pinned host memory per rank")
+    args = ap.parse_args()
+    c = CONFIGS[args.config]
+    args.images = args.images if args.images is not None else c["images"]
+    args.side = args.side if args.side is not None else c["side"]
+    args.lambdas = args.lambdas if args.lambdas is not None else c["lambdas"]
+    args.lam_min, args.lam_max, args.noise = c["lam_min"], c["lam_max"], c["noise"]
+    return args
 
 
 def config_dict(args, device):
-    return dict(alpha=0.1, delta=0.1, device=device, uncertainty_type="quantiles", minimum_lambda=0.0,
-                maximum_lambda=6.0, num_lambdas=args.lambdas, rcps_loss="fraction_missed", dataset="synthetic",
+    return dict(alpha=0.1, delta=0.1, device=device, uncertainty_type="quantiles", minimum_lambda=args.lam_min,
+                maximum_lambda=args.lam_max, num_lambdas=args.lambdas, rcps_loss="fraction_missed", dataset="synthetic",
                 batch_size=78, q_lo=0.05, q_hi=0.95, q_lo_weight=1.0, q_hi_weight=1.0, mse_weight=1.0)
 
 
 def workload_name(args):
-    return f"fastmri_test RCPS calibration: {args.images} x 1x{args.side}x{args.side} fp32 quantile-head outputs, " \
-           f"lambda grid [0,6]x{args.lambdas}, alpha=delta=0.1"
+    return f"{args.config} {CONFIGS[args.config]['name']} RCPS calibration: {args.images} x 1x{args.side}x{args.side} fp32 " \
+           f"quantile-head outputs, lambda grid [{args.lam_min:g},{args.lam_max:g}]x{args.lambdas}, alpha=delta=0.1"
 
 
-def synth(n, side, device, seed):
-    """SURVEY.md §8c probe recipe (lambda-hat lands mid-grid); generated on `device`."""
+def synth(n, side, device, seed, noise=1.0):
+    """SURVEY.md §8c probe recipe (lambda-hat lands mid-grid; `noise` moves it for the temca grid); generated on `device`."""
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
     shape = (n, 1, side, side)
@@ -76,7 +100,7 @@ def synth(n, side, device, seed):
         out[lo:hi, 0] = pred - sig * (0.5 + torch.rand(s, generator=g, device=device))
         out[lo:hi, 1] = pred
         out[lo:hi, 2] = pred + sig * (0.5 + torch.rand(s, generator=g, device=device))
-        lab[lo:hi] = pred + sig * torch.randn(s, generator=g, device=device)
+        lab[lo:hi] = pred + noise * sig * torch.randn(s, generator=g, device=device)
     return out, lab
 
 
@@ -94,7 +118,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.gpu_index)],
+                                          "-lms", "20", "-i", str(self.gpu_index)],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -187,7 +211,7 @@ def run_reference_arm(args):
     orc.build()
     cfg = config_dict(args, "cpu")
     s_max = max(8, args.cpu_sample // 4)
-    out, lab = synth(s_max, args.side, "cpu", 1234)
+    out, lab = synth(s_max, args.side, "cpu", 1234, args.noise)
     out, lab = out.numpy(), lab.numpy()
     stop_full = None  # early stop decided on the sample with the HB bound at the full set size
     for _ in range(max(args.warmup, 1)):
@@ -220,6 +244,130 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------- UNet sub-benchmark
+def _reference_quantile_loss(pred, target, params):
+    """The reference's training loss as it is written there (quantile_layer.py:23-32 over pinball.py:12-24): boolean-mask
+    assignment (each one a nonzero + host sync) - used ONLY by the torch reference legs below."""
+    import torch
+
+    def pinball(out, tgt, q):
+        err = out - tgt
+        loss = torch.zeros_like(tgt)
+        neg, pos = err < 0, err > 0
+        loss[neg] = q * err[neg].abs()
+        loss[pos] = (1 - q) * err[pos].abs()
+        return loss.mean()
+
+    t = target.squeeze()
+    return (params["q_lo_weight"] * pinball(pred[:, 0].squeeze(), t, params["q_lo"]) +
+            params["q_hi_weight"] * pinball(pred[:, 2].squeeze(), t, params["q_hi"]) +
+            params["mse_weight"] * torch.nn.functional.mse_loss(pred[:, 1].squeeze(), t))
+
+
+def run_unet_reference_legs(args, dev, params, B, side, with_cpu):
+    """What the reference's own code path costs on this box: its module graph (fp32 nn.Conv2d / BatchNorm2d / ReLU / MaxPool2d /
+    bilinear Upsample, the mask-assignment pinball loss, torch.optim.Adam - core/scripts/train.py:147-165) through the
+    libraries torch 2.11 dispatches to (cuDNN, TF32 convolutions by default), plus bf16 autocast + channels_last as the
+    strongest library configuration, plus (N = 1 only) the same step on the host cores.  None of our kernels run here."""
+    import torch
+    from im2im_uq_b200.models.add_uncertainty import add_uncertainty
+    from im2im_uq_b200.models.unet import UNet
+
+    def build(device):
+        torch.manual_seed(0)
+        m = add_uncertainty(UNet(1, 1), params).to(device)
+        m.use_native_inference = False        # the torch module graph, not our engines
+        m.use_native_training = False
+        return m
+
+    def timed(fn, iters, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    g = torch.Generator(device=dev).manual_seed(5)
+    out = {"what": "the reference's module graph through torch %s + cuDNN on the same GPU (library kernels only), batch %d, "
+                   "1x%dx%d" % (torch.__version__, B, side, side)}
+    import warnings
+    for name, autocast, channels_last in (("torch_cudnn_tf32", False, False), ("torch_bf16_channels_last", True, True)):
+        leg = {"precision": "bf16 autocast, channels_last" if autocast else
+               "fp32 modules, cuDNN TF32 convolutions (torch default: cudnn.allow_tf32=%s)" % torch.backends.cudnn.allow_tf32}
+        b = B
+        while b >= 1:
+            try:
+                x = torch.randn(b, 1, side, side, device=dev, generator=g)
+                y = x + 0.3 * torch.randn(b, 1, side, side, device=dev, generator=g)
+                model = build(dev)
+                if channels_last:
+                    model = model.to(memory_format=torch.channels_last)
+                    x = x.contiguous(memory_format=torch.channels_last)
+
+                def fwd():
+                    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                        return model(x)
+
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    model.eval()
+                    f_ms = timed(fwd, 3)
+                    model.train()
+                    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+
+                    def train():
+                        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                            pred = model(x)
+                        loss = _reference_quantile_loss(pred.float(), y, params)
+                        loss.item()
+                        opt.zero_grad()
+                        loss.backward()
+                        opt.step()
+
+                    t_ms = timed(train, 3)
+                leg.update(batch=b, forward_ms=f_ms, forward_images_per_s=b / (f_ms * 1e-3), train_ms_per_step=t_ms,
+                           train_images_per_s=b / (t_ms * 1e-3))
+                del model, opt, x, y
+                torch.cuda.empty_cache()
+                break
+            except torch.cuda.OutOfMemoryError:
+                leg.setdefault("oom_at_batch", []).append(b)
+                model = opt = x = y = None
+                torch.cuda.empty_cache()
+                b //= 2
+        out[name] = leg
+    if with_cpu:
+        n_threads = len(os.sched_getaffinity(0))
+        torch.set_num_threads(n_threads)
+        bc = 4
+        gc = torch.Generator().manual_seed(5)
+        x = torch.randn(bc, 1, side, side, generator=gc)
+        y = x + 0.3 * torch.randn(bc, 1, side, side, generator=gc)
+        model = build("cpu")
+        model.eval()
+        with torch.no_grad():
+            model(x)
+            t0 = time.perf_counter()
+            model(x)
+            f_s = time.perf_counter() - t0
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        t0 = time.perf_counter()
+        loss = _reference_quantile_loss(model(x), y, params)
+        loss.item()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        t_s = time.perf_counter() - t0
+        out["cpu"] = {"cores": n_threads, "batch": bc, "forward_images_per_s": bc / f_s, "train_images_per_s": bc / t_s,
+                      "sample": "one forward and one training step at batch %d on the host cores (torch CPU, fp32)" % bc}
+    return out
+
+
 def run_unet_bench(args, world, rank, dev, group):
     """Second half of BASELINE.json's metric: UNet(1,1)+quantile-head images/s at 320x320, forward (inference engine)
     and full train step (forward, fused loss, backward, NCCL all-reduce of the flat fp32 gradients, fused Adam) on the
@@ -314,13 +462,20 @@ def run_unet_bench(args, world, rank, dev, group):
                "api": "core.calibration.calibrate_model.calibrate_model(model, dataset, config)",
                "note": "host TensorDataset -> H2D -> native UNet forward -> RCPS sweep -> table D2H; random-init weights"}
         model.train()
+    reference = None
+    if rank == 0 and not args.no_unet_reference:
+        del graphed, opt
+        torch.cuda.empty_cache()
+        reference = run_unet_reference_legs(args, dev, params, B, side, with_cpu=(world == 1))
     fwd_flop, train_flop = 125.29e9, 375.87e9  # conv 2*MACs per 320x320 image; train = 3x forward
     scale = (side / 320.0) ** 2
     try:
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
-        src = "MEASURED_PEAKS.json bf16_tflops (burst, of measured)"
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak = float(peaks["bf16_tflops"])
+        peak_sus = float(peaks.get("bf16_tflops_sustained", peak))
+        src = "MEASURED_PEAKS.json bf16_tflops (burst) / bf16_tflops_sustained, of measured"
     except Exception:
-        peak, src = 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
+        peak, peak_sus, src = 1590.0, 1400.0, "fallback 1.59 PFLOP/s burst / 1.4 sustained (B200_PROFILING.md)"
     fwd_tf = B * fwd_flop * scale / (fwd_ms * 1e-3) / 1e12
     train_tf = B * train_flop * scale / (train_ms * 1e-3) / 1e12
     return {"model": "UNet(1,1)+quantile head, 17.27M params", "image": f"1x{side}x{side}", "batch_per_gpu": B,
@@ -331,10 +486,11 @@ def run_unet_bench(args, world, rank, dev, group):
                           "loss + backward + " + ("NCCL all-reduce of 69 MB fp32 grads + " if world > 1 else "") +
                           "fused Adam, then loss.item()",
             "train_ms_per_step_eager": train_eager_ms, "train_kernels_per_step": kernels_per_step,
-            "final_loss": last.get("loss"), "calibrate_model_e2e": cal,
-            "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak, "peak_source": src,
+            "final_loss": last.get("loss"), "calibrate_model_e2e": cal, "reference": reference,
+            "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak, "peak_sustained": peak_sus, "peak_source": src,
                          "forward_achieved": fwd_tf, "forward_frac": fwd_tf / peak,
                          "train_achieved": train_tf, "train_frac": train_tf / peak,
+                         "train_frac_of_sustained": train_tf / peak_sus, "forward_frac_of_sustained": fwd_tf / peak_sus,
                          "flops": "conv 2*MACs only: 125.29 GFLOP fwd, 375.87 GFLOP train per 320x320 image"}}
 
 
@@ -400,7 +556,7 @@ def main():
     cuts = [args.images * r // world for r in range(world + 1)]
     n_local = cuts[rank + 1] - cuts[rank]
     px = args.side * args.side
-    out, lab = synth(n_local, args.side, dev, 1000 + rank)
+    out, lab = synth(n_local, args.side, dev, 1000 + rank, args.noise)
     lambdas, dlambda, lam_prime, default_lhat = sweep.lambda_grid(cfg)
     lam_dev = lam_prime.to(dev)
     L = args.lambdas
@@ -443,7 +599,6 @@ def main():
     if not args.no_graph:
         # steady-state path: the step's device work captured once into a CUDA graph (cm.RcpsGraph) and replayed
         plan = cm.RcpsGraph(out, lab, cfg, group=group, n_total=args.images)
-        graph_events = (k_start, k_end)
 
         def step(i=None):  # noqa: F811 - replaces the kernel-by-kernel step above
             lhat_t, stop, decided = plan.run()
@@ -460,33 +615,55 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
+    # clocks / throttle reasons are sampled from before the warm-up to the end of the timed region; the warm-up is extended
+    # (same steps, untimed) until the sampler has seen >= 1.2 s of this load, so that a 50 ms timed region still comes with
+    # a meaningful clock record
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    sync_all()
+    t_probe = time.perf_counter()
+    for _ in range(5):
+        step()
+    sync_all()
+    per_step = max((time.perf_counter() - t_probe) / 5, 1e-6)
+    extra = torch.tensor([int(min(20000, 1.2 / per_step))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(extra, src=0)     # the step is collective: every rank runs the same number of them
+    for _ in range(int(extra)):
+        step()
+    done = warm + 5 + int(extra)
+    sync_all()
     launches0 = _lib.launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     t_start.record()
     for i in range(args.steps):
+        if plan is not None:
+            k_start[i].record()     # graph path: the events bracket the replay = the step's kernel(s), inside the timed region
         step(i)
+        if plan is not None:
+            k_end[i].record()
     t_end.record()
     sync_all()
     launches = _lib.launch_count() - launches0
     if plan is not None:
         launches += args.steps * plan.kernels_per_replay  # kernels replayed from the captured graph
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "extended warm-up (%d untimed steps) + timed region" % done
     ms_total = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+    plan_fused = plan is not None and plan.fused
+    plan_peer = plan is not None and plan.peer is not None
+    plan_launches = plan.kernels_per_replay if plan is not None else None
+    kernel_note = "CUDA events around rcps_hist_kernel in the kernel-by-kernel step, inside the timed region"
     if plan is not None:
-        # events cannot bracket a node inside a replayed graph: time the dominant kernel on its own, same stream, same
-        # inputs, right after the timed region (back-to-back launches, inputs >> L2)
-        for i in range(args.steps):
-            k_start[i].record()
-            rcps.miss_counts(out, lab, lam_dev, counts=counts, totals=totals, zero=False)
-            k_end[i].record()
-        torch.cuda.synchronize()
+        kernel_note = ("CUDA events around each graph replay inside the timed region; the replay is ONE kernel "
+                       "(rcps_hist_kernel<fused>: counts + totals exchange + decision + loss table)") if plan_fused else \
+                      "CUDA events around each graph replay inside the timed region (memsets + kernels of the multi-launch step)"
     kernel_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(k_start, k_end)) / args.steps],
                              dtype=torch.float64, device=dev)
     launches_t = torch.tensor([launches], dtype=torch.int64, device=dev)
@@ -505,13 +682,23 @@ def main():
                 return x
         model = ModelWithUncertainty(_Id(), _Id(), quantile_regression_loss_fn,
                                      quantile_regression_nested_sets_from_output, cfg)
+        # host buffers: the whole shard when it fits 16 GB of pinned memory per rank, else a leading block of it
+        per_image = px * 16
+        n_e2e = args.e2e_images if args.e2e_images is not None else min(n_local, max(1, (16 << 30) // per_image))
+        n_e2e = min(n_e2e, n_local)
+        cuts_e = torch.tensor([n_e2e], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(cuts_e, op=dist.ReduceOp.SUM)
+        n_e2e_total = int(cuts_e)
         all_cpus = os.sched_getaffinity(0)
         numa = bind_to_gpu_numa_node(torch, local_rank)      # pinned pages land on the GPU's NUMA node (first touch)
-        host_out = torch.empty(out.shape, dtype=torch.float32, pin_memory=True)
-        host_lab = torch.empty(lab.shape, dtype=torch.float32, pin_memory=True)
-        host_out.copy_(out); host_lab.copy_(lab)
+        host_out = torch.empty((n_e2e,) + tuple(out.shape[1:]), dtype=torch.float32, pin_memory=True)
+        host_lab = torch.empty((n_e2e,) + tuple(lab.shape[1:]), dtype=torch.float32, pin_memory=True)
+        host_out.copy_(out[:n_e2e]); host_lab.copy_(lab[:n_e2e])
         os.sched_setaffinity(0, all_cpus)                    # the CPU baseline below uses every core again
         torch.cuda.synchronize()
+        if plan is not None:
+            plan.close()                                     # releases its references to the score tensors
         del out, lab
         torch.cuda.empty_cache()
 
@@ -528,19 +715,30 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        assert abs(lh - result["lhat"]) == 0.0, (lh, result)
-        e2e = {"value": args.images * args.e2e_steps / float(dt), "unit": UNIT,
-               "h2d_bytes_per_step": args.images * px * 16 + L * 4 * world,
-               "d2h_bytes_per_step": args.images * L * 4 + L * 8 * world, "steps": args.e2e_steps,
+        if n_e2e_total == args.images:
+            assert abs(lh - result["lhat"]) == 0.0, (lh, result)
+        e2e = {"value": n_e2e_total * args.e2e_steps / float(dt), "unit": UNIT,
+               "h2d_bytes_per_step": n_e2e_total * px * 16 + L * 4 * world,
+               "d2h_bytes_per_step": n_e2e_total * L * 4 + L * 8 * world, "steps": args.e2e_steps,
+               "images": n_e2e_total,
+               "sample": None if n_e2e_total == args.images else
+               f"{n_e2e_total} of {args.images} images (pinned host memory capped at 16 GB per rank)",
                "host_buffers": "pinned, " + numa,
                "api": "im2im_uq_b200.calibration.calibrate_model.calibrate_from_outputs(model, outputs_cpu, labels_cpu, config)"}
 
     unet = None
     if not args.no_unet:
+        if plan is not None:
+            plan.close()
         try:
             del host_out, host_lab
         except NameError:
             pass
+        try:
+            del out, lab                     # --no-e2e: the score tensors are still alive
+        except NameError:
+            pass
+        del counts, table, totals
         torch.cuda.empty_cache()
         unet = run_unet_bench(args, world, rank, dev, group)
 
@@ -548,11 +746,13 @@ def main():
         peak, peak_src = measured_peak()
         alg_bytes = n_local * px * 16 + n_local * L * 4
         achieved = alg_bytes / (float(kernel_ms) * 1e-3) / 1e9
-        traffic = None
-        try:
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per launch are an ncu counter: read from the committed capture of this very shape, if there is one
             prof = json.load(open(os.path.join(ROOT, "profiles", "rcps_hist_ncu_summary.json")))
             if prof.get("images") == n_local and prof.get("side") == args.side:
                 traffic = prof.get("dram_bytes_per_launch")
+                traffic_src = "from profile: profiles/rcps_hist_ncu_summary.json (ncu --set full, dram__bytes_read.sum + " \
+                              "dram__bytes_write.sum of one launch at this shape; not measured in this run)"
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -561,21 +761,23 @@ def main():
                 "config": {"workload": workload_name(args), "images_per_gpu": n_local,
                            "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % (n_local * px * 16 / 1e9),
                            "cuda_graph": plan is not None,
-                           "totals_allreduce": ("fused with the decision over NVLink peer memory (im2im_rcps_decide_p2p)"
-                                                if plan is not None and getattr(plan, "peer", None) is not None
-                                                else ("NCCL" if world > 1 else "none (single GPU)")),
+                           "launches_per_step": plan_launches,
+                           "totals_allreduce": (("inside the one fused launch, over NVLink peer memory (im2im_rcps_calibrate_fused)"
+                                                 if plan_fused else
+                                                 "fused with the decision over NVLink peer memory (im2im_rcps_decide_p2p)")
+                                                if plan_peer else ("NCCL" if world > 1 else "none (single GPU)")),
                            "lhat": result["lhat"], "lhat_index": result["stop"],
                            "replayed_columns": result["replayed"], "parallelism": f"image shards x{world}, "
                            "one NCCL all-reduce of int64[L] totals" if world > 1 else "single GPU"},
-                "roofline": {"bound": "hbm", "kernel": "rcps_hist_kernel<staged>", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "roofline": {"bound": "hbm", "kernel": "rcps_hist_kernel<fused>" if plan_fused else "rcps_hist_kernel<staged>", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": float(kernel_ms),
-                             "peak_source": peak_src},
+                             "kernel_ms_how": kernel_note, "peak_source": peak_src},
                 "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches_t), "unet": unet}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import rcps_oracle as orc
             orc.build()
-            s_out, s_lab = synth(args.cpu_sample, args.side, "cpu", 1234)
+            s_out, s_lab = synth(args.cpu_sample, args.side, "cpu", 1234, args.noise)
             dt, visited, tb = cpu_reference_sweep(s_out.numpy(), s_lab.numpy(), config_dict(args, "cpu"),
                                                   result["stop"], args.images)
             line["cpu_baseline"] = {"value": full_job_images_per_s(dt, tb, args.cpu_sample, args.images), "unit": UNIT,
@@ -587,15 +789,12 @@ def main():
                                               f"counted once)"}
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    if plan is not None:
+        plan.close()           # graphs that captured NCCL kernels / peer mappings are destroyed before the communicator (idempotent)
     if world > 1:
-        # Leave without tearing NCCL down: ncclCommDestroy waits for every CUDA graph that captured one of its collectives
-        # (RcpsGraph, GraphedTrainStep) and was observed to hang at exit on a 2-GPU box.  Everything is synchronised, the
-        # JSON line is out; exit code 0 is what torchrun needs.
         torch.cuda.synchronize()
         dist.barrier()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

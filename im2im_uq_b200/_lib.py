@@ -106,6 +106,16 @@ def _declare_more(lib):
     lib.im2im_rcps_decide.argtypes = [vp, i32, f64, f64, f64, f64, f64, f64, vp, vp]
     lib.im2im_rcps_decide_p2p.restype = c.c_int
     lib.im2im_rcps_decide_p2p.argtypes = [vp, vp, vp, vp, i32, i32, i32, f64, f64, f64, f64, f64, f64, vp, vp, vp]
+    lib.im2im_rcps_fused_workspace_bytes.restype = c.c_size_t
+    lib.im2im_rcps_fused_workspace_bytes.argtypes = [i32]
+    lib.im2im_rcps_calibrate_fused.restype = c.c_int
+    lib.im2im_rcps_calibrate_fused.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, i32, i32, vp, vp, vp,
+                                               f64, f64, f64, f64, f64, f64, vp, c.c_size_t, vp, vp, i32, i32, f64, vp,
+                                               vp, vp]
+    lib.im2im_rcps_calibrate_fused_check.restype = c.c_int
+    lib.im2im_rcps_calibrate_fused_check.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i32, i32]
+    lib.im2im_host_wait_flag.restype = c.c_int
+    lib.im2im_host_wait_flag.argtypes = [vp, i32, i64]
     lib.im2im_conv_igemm_bf16.restype = c.c_int
     lib.im2im_conv_igemm_bf16.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.im2im_conv_wgrad_bf16.restype = c.c_int
@@ -161,7 +171,8 @@ EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im
            "im2im_adam_step_f32", "im2im_head_bwd", "im2im_conv_first_wgrad", "im2im_nested_sets",
            "im2im_softmax_sets", "im2im_head_conv3x3_act_f32", "im2im_head_loss_f32",
            "im2im_adam_step_dev_f32", "im2im_head_conv3x3_tc_f32", "im2im_planar_to_nhwc64_bf16",
-           "im2im_rcps_decide_p2p"]
+           "im2im_rcps_decide_p2p", "im2im_rcps_fused_workspace_bytes", "im2im_rcps_calibrate_fused",
+           "im2im_host_wait_flag", "im2im_rcps_calibrate_fused_check"]
 
 
 def load():

@@ -282,10 +282,31 @@ def device_decide_fn(px: int, config: dict, result: Optional[torch.Tensor] = Non
     return decide
 
 
+def _peer_timeout_s() -> float:
+    """Bound on the in-kernel wait for the peers' flags (seconds; 0 = wait for ever).  Generous by default: normal rank
+    skew (a slow data loader, a first-call JIT, a debugger) must not fail a healthy job; a dead peer is the host
+    watchdog's business.  Override with IM2IM_P2P_TIMEOUT_S."""
+    import os
+    return float(os.environ.get("IM2IM_P2P_TIMEOUT_S", "600"))
+
+
+def peer_memory_available(group) -> bool:
+    """Cheap LOCAL capability check made before any collective allocation / rendezvous: torch symmetric memory importable
+    and every device of the group peer-accessible.  Ranks agree on the outcome with one all-reduce (RcpsGraph)."""
+    try:
+        import torch.distributed._symmetric_memory as symm  # noqa: F401
+        dev = torch.cuda.current_device()
+        return all(d == dev or torch.cuda.can_device_access_peer(dev, d) for d in range(torch.cuda.device_count()))
+    except Exception:  # noqa: BLE001
+        return False
+
+
 class PeerTotals:
-    """Peer-mapped buffers for ``im2im_rcps_decide_p2p``: every rank's mailbox uint64[2][world][L] and flag array
-    uint32[world] in torch symmetric memory (CUDA peer / fabric mappings over NVLink), plus this rank's device-side epoch.
-    Construction is collective over ``group``.  Raises when symmetric memory is not available (callers fall back to NCCL)."""
+    """Peer-mapped buffers for the totals exchange: every rank's mailbox uint64[2][world][L] and flag array uint32[world]
+    in torch symmetric memory (CUDA peer / fabric mappings over NVLink), plus this rank's device-side epoch (used by
+    ``im2im_rcps_decide_p2p``; the fused kernel keeps its epoch in its own workspace).  Construction is collective over
+    ``group``: call it only after the ranks have AGREED that peer memory is available (``peer_memory_available`` + an
+    all-reduce) - an exception on one rank in here would leave the others waiting in the rendezvous."""
 
     def __init__(self, n_lambdas: int, group, device):
         import torch.distributed as dist
@@ -305,25 +326,36 @@ class PeerTotals:
         torch.cuda.synchronize(device)
         dist.barrier(group)                 # every rank's flags are zero before anyone publishes
 
+    def close(self):
+        self._handles = None
+        self.mailbox = self.flags = None
+
 
 class RcpsGraph:
-    """The device side of one calibration captured ONCE into a CUDA graph and replayed: zero the outputs, the one-pass
-    miss-count kernel, (multi-GPU) the all-reduce of the per-lambda totals - fused with the decision over NVLink peer
-    memory (``im2im_rcps_decide_p2p``) when symmetric memory is available, a NCCL all-reduce otherwise - the device-side
-    stop decision and the fp32 loss-table kernel.  Replaying removes the ~10 host launches per calibration, which matters once the kernel
-    itself takes a fraction of a millisecond (8 GPUs on a 10k-image set).  Scores must stay resident and unchanged in
-    shape; their contents may change between replays.
+    """The device side of one calibration, captured ONCE into a CUDA graph and replayed.
+
+    Fused path (default whenever the bulk-copy kernel applies): ONE kernel per calibration
+    (``im2im_rcps_calibrate_fused``): miss counts written without a memset, block totals reduced in a self-cleaning
+    workspace, the last block all-reduces them over NVLink peer memory (multi-GPU), screens the stopping rule, publishes the
+    16-byte result into mapped pinned host memory, and the loss table is written by the same launch.  The host spins on
+    the result's epoch tag instead of synchronising the stream.
+    Fallback path: memsets + ``im2im_rcps_miss_counts`` + (NCCL all-reduce | ``im2im_rcps_decide_p2p``) +
+    ``im2im_rcps_loss_table_dev`` + a 16-byte copy.
+
+    Scores must stay resident and unchanged in shape; their contents may change between replays.
 
         plan = RcpsGraph(outputs, labels, config, group=None, n_total=None)
         lhat, stop, decided = plan.run()        # decided False -> a column fell in the guard band, call plan.replay_on_host()
+        plan.close()                            # before destroying the process group
     """
 
     def __init__(self, outputs: torch.Tensor, labels: torch.Tensor, config: dict, group=None, n_total=None,
-                 head: int = _lib.IM2IM_HEAD_QUANTILES, p2p: bool = True):
+                 head: int = _lib.IM2IM_HEAD_QUANTILES, p2p: bool = True, fused: bool = True):
         assert outputs.is_cuda and labels.is_cuda
         self.config, self.group, self.head = config, group, head
         self.outputs, self.labels = outputs, labels
         dev = outputs.device
+        lib = _lib.load()
         self.lambdas, self.dlambda, lam_prime, self.default_lhat = sweep.lambda_grid(config)
         if not bool((lam_prime[1:] >= lam_prime[:-1]).all()) or not bool(torch.isfinite(lam_prime).all()):
             raise ValueError("RcpsGraph needs a finite ascending lambda grid")
@@ -335,38 +367,67 @@ class RcpsGraph:
         self.totals = torch.empty((L,), dtype=torch.int64, device=dev)
         self.table = torch.empty((n, L), dtype=torch.float32, device=dev)
         self.result = torch.empty(4, dtype=torch.int32, device=dev)
-        self.result_host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+        self.result_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self._result_np = self.result_host.numpy()      # same memory; numpy scalar reads cost ~0.1 us (tensor indexing ~3 us)
         self._decide = device_decide_fn(self.px, config, result=self.result)
         self.peer = None
-        if group is not None and p2p:
+        self.graph = None
+        self._launches = 0          # executions of the fused kernel so far = the epoch tag the host waits for
+        self._planes = rcps._score_planes(outputs, labels, head)
+        n_, px_, ptrs, strides, _keep = self._planes
+        self.fused = bool(fused) and n > 0 and lib.im2im_rcps_calibrate_fused_check(
+            ptrs[0], ptrs[1], ptrs[2], ptrs[3], n_, px_, strides[0], strides[1], strides[2], strides[3], L, head) == 0
+        world = 1
+        if group is not None:
             import torch.distributed as dist
-            try:
-                self.peer = PeerTotals(L, group, dev)
-                self.local_totals = torch.empty((L,), dtype=torch.int64, device=dev)
-            except Exception as e:  # noqa: BLE001 - no symmetric memory on this system: NCCL path
-                self.peer = None
-                self.p2p_error = f"{type(e).__name__}: {e}"
-            # all ranks must take the same path
-            ok = torch.tensor([1 if self.peer is not None else 0], dtype=torch.int32, device=dev)
+            world = dist.get_world_size(group)
+            # all ranks must take the same path: agree BEFORE any collective allocation or rendezvous
+            ok = torch.tensor([1 if (p2p and peer_memory_available(group)) else 0, 1 if self.fused else 0],
+                              dtype=torch.int32, device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-            if int(ok) == 0:
-                self.peer = None
+            use_peer, self.fused = bool(ok[0]), bool(ok[1])
+            if use_peer:
+                self.peer = PeerTotals(L, group, dev)      # collective; a failure in here is fatal for the job
+                self.local_totals = torch.empty((L,), dtype=torch.int64, device=dev)
+            else:
+                self.fused = False                         # the fused kernel exchanges over peer memory only
+        self.world = world
+        if self.fused:
+            ws_bytes = int(lib.im2im_rcps_fused_workspace_bytes(L))
+            self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)   # zero-filled ONCE
         self._enqueue()                      # warm-up outside capture (lazy module loads, NCCL channel setup)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
         with torch.cuda.graph(self.graph):
-            self._enqueue()
+            self._enqueue(count=False)
         self.kernels_per_replay = _lib.launch_count() - before  # libim2im_uq kernels inside one replay
 
-    def _enqueue(self):
+    def _enqueue(self, count: bool = True):
+        dev = self.totals.device
+        n_px, gamma, alpha32, r_lo, r_hi, slack = sweep.screening_constants(self.n_total, self.px,
+                                                                            self.config['alpha'], self.config['delta'])
+        if self.fused:
+            n_, px_, ptrs, strides, _keep = self._planes
+            peer = self.peer
+            with torch.cuda.device(dev):
+                rc = _lib.load().im2im_rcps_calibrate_fused(
+                    ptrs[0], ptrs[1], ptrs[2], ptrs[3], n_, px_, strides[0], strides[1], strides[2], strides[3],
+                    self.lam_dev.data_ptr(), self.lam_dev.numel(), self.head, self.counts.data_ptr(),
+                    self.table.data_ptr(), self.totals.data_ptr(), n_px, gamma, alpha32, r_lo, r_hi, slack,
+                    self.workspace.data_ptr(), self.workspace.numel(),
+                    peer.mail_ptrs.data_ptr() if peer is not None else None,
+                    peer.flag_ptrs.data_ptr() if peer is not None else None,
+                    peer.rank if peer is not None else 0, peer.world if peer is not None else 1, _peer_timeout_s(),
+                    self.result.data_ptr(), self.result_host.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "im2im_rcps_calibrate_fused")
+            if count:
+                self._launches += 1
+            return
         if self.peer is not None:
             # totals stay local; the reduction over ranks happens inside the decision kernel, over peer memory
             rcps.miss_counts(self.outputs, self.labels, self.lam_dev, counts=self.counts, totals=self.local_totals,
                              zero=True, head=self.head)
-            n_px, gamma, alpha32, r_lo, r_hi, slack = sweep.screening_constants(self.n_total, self.px,
-                                                                                self.config['alpha'], self.config['delta'])
-            dev = self.totals.device
             with torch.cuda.device(dev):
                 rc = _lib.load().im2im_rcps_decide_p2p(
                     self.local_totals.data_ptr(), self.peer.mail_ptrs.data_ptr(), self.peer.flag_ptrs.data_ptr(),
@@ -385,18 +446,43 @@ class RcpsGraph:
 
     def run(self):
         self.graph.replay()
-        self.result_host.copy_(self.result, non_blocking=True)
-        torch.cuda.current_stream(self.result.device).synchronize()
-        if int(self.result_host[1]) == -2:
-            raise _lib.Im2ImError("im2im_rcps_decide_p2p: a peer rank did not publish its totals within the timeout "
-                                  "(crashed or not calling in lockstep)")
-        stop, decided = int(self.result_host[0]), bool(self.result_host[1])
+        if self.fused:
+            # the kernel stores the result into mapped pinned memory and tags it with its launch epoch: spin on the tag
+            self._launches += 1
+            if _lib.load().im2im_host_wait_flag(self.result_host.data_ptr() + 16, self._launches, 2_000_000) != 0:
+                torch.cuda.current_stream(self.result.device).synchronize()   # slow or failed launch: surface CUDA errors
+                if int(self._result_np[4]) != self._launches:
+                    raise _lib.Im2ImError("im2im_rcps_calibrate_fused finished without publishing its result")
+        else:
+            self.result_host[:4].copy_(self.result, non_blocking=True)
+            torch.cuda.current_stream(self.result.device).synchronize()
+        res = self._result_np
+        if int(res[1]) == -3:
+            raise _lib.Im2ImError("im2im_rcps_calibrate_fused: a wait between thread blocks of one GPU gave up (blocks not "
+                                  "co-resident?); results of this launch are invalid - build a new RcpsGraph")
+        if int(res[1]) == -2:
+            raise _lib.Im2ImError("a peer rank did not publish its totals within IM2IM_P2P_TIMEOUT_S (crashed or not "
+                                  "calling in lockstep); the ranks are out of step - close() this RcpsGraph on every rank "
+                                  "and build a new one")
+        stop, decided = int(res[0]), bool(res[1])
         lhat = self.lambdas[stop] if stop >= 0 else self.default_lhat
         return lhat, stop, decided
+
+    def close(self):
+        """Destroy the captured graph (it may hold NCCL kernels and peer mappings) - call before
+        ``dist.destroy_process_group()``: NCCL waits at communicator teardown for graphs that captured its collectives."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.result.device)
+            self.graph.reset()
+            self.graph = None
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
     def replay_on_host(self, stats: Optional[dict] = None):
         """Guard-band case: the reference's own expression on the ambiguous columns (sweep.find_stop_index)."""
         px = self.px
+        torch.cuda.current_stream(self.result.device).synchronize()   # fused path: run() did not wait for the stream
 
         def column_to_losses(col):
             return rcps.loss_table(col.reshape(-1, 1).contiguous(), px)[:, 0]

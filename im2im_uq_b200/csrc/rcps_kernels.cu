@@ -13,6 +13,8 @@
 // with cp.async.bulk (UBLKCP) + mbarrier transaction counts; 16 consumer warps read the tile with LDS.128, rank the
 // pixels and bump a per-image shared-memory histogram; a block-wide suffix scan turns the histogram into the
 // image's row of counts.
+#include <ctime>
+
 #include "common.cuh"
 
 namespace im2im {
@@ -38,6 +40,32 @@ struct RcpsParams {
     int n_lambdas;
     int* counts;                  // [n_images, n_lambdas]
     unsigned long long* totals;   // [n_lambdas] or null
+};
+
+// Stop-rule screening constants (host twin: calibration/sweep.py::screening_constants)
+struct ScreenParams {
+    double n_px, gamma, alpha32, r_lo, r_hi, slack;
+};
+
+// Everything the fused single-launch calibration needs on top of RcpsParams (rcps_hist_kernel<true, HEAD, true>).
+// Workspace invariant: totals_acc[0..L) == 0 and ticket == 0 between launches (the last CTA restores it).
+struct FusedParams {
+    float* table;                       // [n_images, n_lambdas] fp32 loss table or null
+    unsigned long long* totals_acc;     // workspace u64[L]
+    unsigned* ticket;                   // workspace: CTAs finished so far
+    unsigned* go;                       // workspace u32[2]: {epoch of the published decision, first visited column}
+    unsigned* err;                      // workspace u32: set when an intra-GPU wait gave up (a bug or a lost block, never a peer)
+    unsigned* head_flag;                // workspace u32[grid]: epoch at which CTA b published its head-partial row
+    int* head_partial;                  // workspace i32[grid][L]: miss counts of the image a CTA starts in the middle of
+    unsigned* epoch;                    // device-side launch counter (incremented by the kernel: graph replays need no new args)
+    ScreenParams scr;
+    unsigned long long* const* peer_mailbox;   // multi-GPU (world > 1): see rcps_decide_p2p_kernel
+    unsigned* const* peer_flags;
+    int rank, world;
+    long long timeout_cycles;           // peer wait limit in clock64 cycles, 0 = wait for ever
+    unsigned long long* totals_out;     // [L] totals summed over ranks
+    int* result;                        // device int32[4], as rcps_decide_kernel
+    volatile int* result_host;          // mapped pinned int32[8] or null: {result[0..3], epoch tag}
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -161,8 +189,15 @@ __device__ __forceinline__ int resolve_slow(const PixelQuery& q, const float* s_
 
 // ---------------------------------------------------------------------------------------------------------------
 // hist[1..L] -> counts row (suffix sums), accumulate per-CTA totals, zero the histogram.  Consumer threads only.
+//   kFlushAtomic     row shared with another CTA, pre-zeroed: atomicAdd of the non-zero entries
+//   kFlushSparse     row owned by this CTA, pre-zeroed: plain stores of the non-zero entries
+//   kFlushFull       row owned by this CTA, NOT pre-zeroed: every entry is stored (fused path: no memset launch)
+//   kFlushFullPlus   as kFlushFull, plus `addend[j]` (the part of the image the next CTA counted)
+enum { kFlushAtomic = 0, kFlushSparse = 1, kFlushFull = 2, kFlushFullPlus = 3 };
+
 __device__ __forceinline__ void flush_image(unsigned* hist, unsigned* rise, unsigned long long* tot,
-                                            unsigned* warp_sums, int L, int* counts_row, bool exclusive, int ctid) {
+                                            unsigned* warp_sums, int L, int* counts_row, int mode,
+                                            const int* addend, int ctid) {
     named_bar_sync(kFlushBarrier, kConsumerThreads);  // all histogram atomics of this image have landed
     const int per_thread = (L + kConsumerThreads - 1) / kConsumerThreads;
     const int r0 = ctid * per_thread;  // r = L-1-j : position counted from the top of the grid
@@ -193,8 +228,13 @@ __device__ __forceinline__ void flush_image(unsigned* hist, unsigned* rise, unsi
             if (any_rise) {  // rare: pixels with a negative width are missed from rise-index k upwards
                 for (int k = 0; k <= j; ++k) val += rise[k];
             }
-            if (val != 0) {
-                if (exclusive) counts_row[j] = static_cast<int>(val);
+            if (mode >= kFlushFull) {
+                int out = static_cast<int>(val);
+                if (mode == kFlushFullPlus) out += __ldcg(addend + j);
+                counts_row[j] = out;
+                tot[j] += val;
+            } else if (val != 0) {
+                if (mode == kFlushSparse) counts_row[j] = static_cast<int>(val);
                 else atomicAdd(&counts_row[j], static_cast<int>(val));
                 tot[j] += val;
             }
@@ -207,8 +247,52 @@ __device__ __forceinline__ void flush_image(unsigned* hist, unsigned* rise, unsi
     }
 }
 
-template <bool STAGED, int HEAD>
-__global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(const RcpsParams prm) {
+// Verdict of the reference's stopping rule `Rhat >= alpha or HB(Rhat) > alpha` for a column with exact total t:
+// +1 certainly true, -1 certainly false, 0 unsure (the host replays the reference's own fp32 expression).
+__device__ __forceinline__ int screen_verdict(unsigned long long t, const ScreenParams& c) {
+    const double R = static_cast<double>(t) / c.n_px;
+    const double lo = R * (1.0 - c.gamma), hi = R * (1.0 + c.gamma);
+    bool sure_true = lo >= c.alpha32 * (1.0 + 1e-6);
+    if (isfinite(c.r_hi)) sure_true = sure_true || (lo > c.r_hi + c.slack);
+    bool sure_false = hi < c.alpha32 * (1.0 - 1e-6);
+    if (isfinite(c.r_lo)) sure_false = sure_false && (hi < c.r_lo - c.slack);
+    int v = sure_true ? 1 : (sure_false ? -1 : 0);
+    if (t == 0ull) v = 0;  // HB_mu_plus(0) takes the reference's exception path: never guessed
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// FUSED (staged only): the whole calibration step in this one launch - no memset of the outputs (every counts row is
+// written in full by the CTA that owns the image's first tile; the part of an image that the NEXT CTA counted travels
+// through a per-CTA "head partial" row + flag), per-CTA totals reduced with u64 atomics into a self-cleaning workspace,
+// and a last-CTA-done tail: the last CTA (ticket) optionally all-reduces the totals over NVLink peer memory, screens the
+// stopping rule, publishes the 16-byte result to device memory AND to mapped pinned host memory, then releases the other
+// CTAs, which turn the counts rows they own into the fp32 loss table (zero left of the first visited column).
+// Requires floor(total_tiles / gridDim.x) >= tiles_per_image (an image spans at most two CTAs) and all CTAs co-resident
+// (cooperative launch).
+template <bool STAGED, int HEAD, bool FUSED>
+__global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(const RcpsParams prm, const FusedParams fz) {
     constexpr int kFirstPlane = (HEAD == IM2IM_HEAD_RESIDUAL || HEAD == IM2IM_HEAD_GAUSSIAN) ? 1 : 0;  // 2-plane heads
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int L = prm.n_lambdas;
@@ -231,6 +315,8 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
     unsigned* warp_sums = reinterpret_cast<unsigned*>(cursor);
     cursor += sizeof(unsigned) * kConsumerWarps;
     unsigned* rise = (HEAD == IM2IM_HEAD_RESIDUAL) ? reinterpret_cast<unsigned*>(cursor) : nullptr;
+    __shared__ int s_tail[4];   // fused tail: {is last CTA, first visited column, stop verdict, timeout}
+    const unsigned epoch = FUSED ? (*fz.epoch + 1u) : 0u;   // read before anything can bump it (only the last CTA does, at the end)
 
     const int tid = threadIdx.x;
     for (int j = tid; j < L; j += kThreads) {
@@ -366,10 +452,147 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
             }
         }
         if (image_ends_here || it == n_my_tiles - 1) {
-            flush_image(hist, rise, tot, warp_sums, L, prm.counts + img * L, image_started_here && image_ends_here,
-                        ctid);
+            if (!FUSED) {
+                flush_image(hist, rise, tot, warp_sums, L, prm.counts + img * L,
+                            (image_started_here && image_ends_here) ? kFlushSparse : kFlushAtomic, nullptr, ctid);
+            } else if (image_ends_here && image_started_here) {          // whole image counted here
+                flush_image(hist, rise, tot, warp_sums, L, prm.counts + img * L, kFlushFull, nullptr, ctid);
+            } else if (image_ends_here) {                                 // head partial: the previous CTA owns the row
+                flush_image(hist, rise, tot, warp_sums, L, fz.head_partial + static_cast<long long>(blockIdx.x) * L,
+                            kFlushFull, nullptr, ctid);
+                __threadfence();
+                named_bar_sync(kFlushBarrier, kConsumerThreads);
+                if (ctid == 0) st_release_gpu_u32(fz.head_flag + blockIdx.x, epoch);
+            } else {                                                      // tail partial: add what the next CTA counted
+                if (ctid == 0) {
+                    // the next CTA publishes its partial row right after its first image: this wait is normally over before
+                    // it starts.  Bounded (~2^33 cycles) so that a lost block surfaces as an error instead of a hung GPU.
+                    const unsigned* f = fz.head_flag + blockIdx.x + 1;
+                    const long long t0 = clock64();
+                    while (static_cast<int>(ld_acquire_gpu_u32(f) - epoch) < 0) {
+                        if (clock64() - t0 > (1ll << 33)) { atomicExch(fz.err, 1u); break; }
+                    }
+                }
+                flush_image(hist, rise, tot, warp_sums, L, prm.counts + img * L, kFlushFullPlus,
+                            fz.head_partial + static_cast<long long>(blockIdx.x + 1) * L, ctid);
+            }
         }
         if (++r == tpi32) { r = 0; ++img; image_started_here = true; }
+    }
+    if (FUSED) {
+        // ---------------------------------------------------------------- fused tail
+        const int per_thread = (L + kConsumerThreads - 1) / kConsumerThreads;
+        for (int e = 0; e < per_thread; ++e) {
+            const int rr = ctid * per_thread + e;
+            if (rr < L) {
+                const int j = L - 1 - rr;
+                if (tot[j] != 0ull) atomicAdd(&fz.totals_acc[j], tot[j]);
+            }
+        }
+        __threadfence();
+        named_bar_sync(kFlushBarrier, kConsumerThreads);
+        if (ctid == 0) {
+            const unsigned t = atomicAdd(fz.ticket, 1u);
+            s_tail[0] = (t == gridDim.x - 1) ? 1 : 0;
+            s_tail[1] = -1; s_tail[2] = 0; s_tail[3] = 0;
+        }
+        named_bar_sync(kFlushBarrier, kConsumerThreads);
+        int first_visited = 0;
+        if (s_tail[0]) {
+            // ---- last CTA: totals are complete.  Read + clean the workspace, (multi-GPU) exchange, decide, publish.
+            __threadfence();
+            unsigned long long* sum = tot;   // reuse the per-CTA totals array as the reduced totals
+            for (int j = ctid; j < L; j += kConsumerThreads) {
+                sum[j] = __ldcg(fz.totals_acc + j);
+                fz.totals_acc[j] = 0ull;
+            }
+            if (ctid == 0) *fz.ticket = 0u;
+            named_bar_sync(kFlushBarrier, kConsumerThreads);
+            if (fz.world > 1) {
+                // one-shot push all-reduce over peer memory (protocol of rcps_decide_p2p_kernel)
+                const size_t slot = (static_cast<size_t>(epoch & 1u) * fz.world + fz.rank) * L;
+                for (int i = ctid; i < fz.world * L; i += kConsumerThreads) {
+                    const int pr = i / L, j = i - pr * L;
+                    fz.peer_mailbox[pr][slot + j] = sum[j];
+                }
+                __threadfence_system();
+                named_bar_sync(kFlushBarrier, kConsumerThreads);
+                if (ctid < fz.world) {
+                    st_release_sys_u32(fz.peer_flags[ctid] + fz.rank, epoch);
+                    const unsigned* f = fz.peer_flags[fz.rank] + ctid;
+                    const long long t0 = clock64();
+                    while (static_cast<int>(ld_acquire_sys_u32(f) - epoch) < 0) {
+                        if (fz.timeout_cycles > 0 && clock64() - t0 > fz.timeout_cycles) { s_tail[3] = 1; break; }
+                    }
+                }
+                named_bar_sync(kFlushBarrier, kConsumerThreads);
+                if (!s_tail[3]) {
+                    const unsigned long long* mine = fz.peer_mailbox[fz.rank] + static_cast<size_t>(epoch & 1u) * fz.world * L;
+                    for (int j = ctid; j < L; j += kConsumerThreads) {
+                        unsigned long long t = 0ull;
+                        for (int pr = 0; pr < fz.world; ++pr) t += ld_relaxed_sys_u64(mine + static_cast<size_t>(pr) * L + j);
+                        sum[j] = t;
+                    }
+                }
+                named_bar_sync(kFlushBarrier, kConsumerThreads);
+            }
+            int best = -1, best_v = 0;
+            for (int j = ctid; j < L; j += kConsumerThreads) {
+                const unsigned long long t = sum[j];
+                if (fz.totals_out != nullptr) fz.totals_out[j] = t;
+                const int v = screen_verdict(t, fz.scr);
+                if (v >= 0 && j > best) { best = j; best_v = v; }
+            }
+            if (best >= 0) atomicMax(&s_tail[1], best);
+            named_bar_sync(kFlushBarrier, kConsumerThreads);
+            if (best >= 0 && best == s_tail[1]) s_tail[2] = best_v;
+            named_bar_sync(kFlushBarrier, kConsumerThreads);
+            const int first = s_tail[1];
+            int r0_, r1_, r2_, r3_;
+            if (__ldcg(fz.err) != 0u) { r0_ = -3; r1_ = -3; r2_ = -3; r3_ = 0; }    // an intra-GPU wait gave up
+            else if (s_tail[3]) { r0_ = -2; r1_ = -2; r2_ = -2; r3_ = 0; }     // a peer never arrived
+            else if (first < 0) { r0_ = -1; r1_ = 1; r2_ = -1; r3_ = 0; }      // ran off the grid
+            else if (s_tail[2] > 0) { r0_ = first; r1_ = 1; r2_ = -1; r3_ = first; }
+            else { r0_ = -1; r1_ = 0; r2_ = first; r3_ = 0; }                  // unsure: the host replays from `first`
+            first_visited = r3_;
+            if (ctid == 0) {
+                fz.result[0] = r0_; fz.result[1] = r1_; fz.result[2] = r2_; fz.result[3] = r3_;
+                if (fz.result_host != nullptr) {
+                    fz.result_host[0] = r0_; fz.result_host[1] = r1_; fz.result_host[2] = r2_; fz.result_host[3] = r3_;
+                    __threadfence_system();
+                    fz.result_host[4] = static_cast<int>(epoch);               // tag last: the host polls this word
+                }
+                fz.go[1] = static_cast<unsigned>(r3_);
+                __threadfence();
+                st_release_gpu_u32(fz.go, epoch);
+                *fz.epoch = epoch;   // a peer timeout (result -2) leaves the ranks out of step: the caller must rebuild
+            }
+        } else if (fz.table != nullptr) {
+            if (ctid == 0) {
+                const long long t0 = clock64();
+                const long long limit = (1ll << 33) + 2 * fz.timeout_cycles;   // the last CTA may be waiting for peers
+                bool ok = true;
+                while (static_cast<int>(ld_acquire_gpu_u32(fz.go) - epoch) < 0) {
+                    if (fz.timeout_cycles > 0 && clock64() - t0 > limit) { atomicExch(fz.err, 1u); ok = false; break; }
+                    if (fz.world == 1 && clock64() - t0 > (1ll << 33)) { atomicExch(fz.err, 1u); ok = false; break; }
+                }
+                s_tail[1] = ok ? static_cast<int>(__ldcg(fz.go + 1)) : 0;
+            }
+            named_bar_sync(kFlushBarrier, kConsumerThreads);
+            first_visited = s_tail[1];
+        }
+        if (fz.table != nullptr) {
+            // loss-table rows of the images whose FIRST tile lies in this CTA's range (those rows were completed here)
+            const long long i_begin = (t_begin + tpi - 1) / tpi, i_end = (t_end + tpi - 1) / tpi;
+            const float fpx = static_cast<float>(prm.px);
+            for (long long i = i_begin; i < i_end; ++i) {
+                const int* crow = prm.counts + i * L;
+                float* trow = fz.table + i * L;
+                for (int j = ctid; j < L; j += kConsumerThreads)
+                    trow[j] = (j >= first_visited) ? __fdiv_rn(static_cast<float>(__ldcg(crow + j)), fpx) : 0.f;
+            }
+        }
+        return;
     }
     if (prm.totals != nullptr) {
         const int per_thread = (L + kConsumerThreads - 1) / kConsumerThreads;
@@ -443,20 +666,6 @@ __global__ void __launch_bounds__(256) rcps_decide_kernel(const unsigned long lo
 //   flags (per rank)           u32[world]          flag[r] = last epoch rank r has published to this rank (monotone)
 //   epoch (per rank, local)    u32                 incremented by the kernel, so a CUDA-graph replay needs no new arguments
 // All ranks must call this the same number of times (collective semantics).  One CTA; the spin is on local memory.
-__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
 __global__ void __launch_bounds__(1024) rcps_decide_p2p_kernel(const unsigned long long* __restrict__ local_totals,
                                                                unsigned long long* const* __restrict__ peer_mailbox,
                                                                unsigned* const* __restrict__ peer_flags,
@@ -710,10 +919,22 @@ bool head_three_planes(int head) { return head == IM2IM_HEAD_QUANTILES || head =
 
 template <bool STAGED, int HEAD>
 int launch_hist(const RcpsParams& prm, size_t smem, long long grid, cudaStream_t st) {
-    IM2IM_CUDA_TRY(cudaFuncSetAttribute(rcps_hist_kernel<STAGED, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    IM2IM_CUDA_TRY(cudaFuncSetAttribute(rcps_hist_kernel<STAGED, HEAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-    rcps_hist_kernel<STAGED, HEAD><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(prm);
+    FusedParams none{};
+    rcps_hist_kernel<STAGED, HEAD, false><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(prm, none);
     return check_launch(STAGED ? "rcps_hist_kernel<staged>" : "rcps_hist_kernel<generic>");
+}
+
+// cooperative launch: every CTA is guaranteed to be resident (the tail spins on flags set by other CTAs)
+template <int HEAD>
+int launch_fused(const RcpsParams& prm, const FusedParams& fz, size_t smem, long long grid, cudaStream_t st) {
+    IM2IM_CUDA_TRY(cudaFuncSetAttribute(rcps_hist_kernel<true, HEAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    void* args[2] = {const_cast<RcpsParams*>(&prm), const_cast<FusedParams*>(&fz)};
+    IM2IM_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&rcps_hist_kernel<true, HEAD, true>),
+                                               dim3(static_cast<unsigned>(grid)), dim3(kThreads), args, smem, st));
+    return check_launch("rcps_hist_kernel<fused>");
 }
 
 template <bool STAGED>
@@ -787,6 +1008,148 @@ extern "C" int im2im_rcps_miss_counts(const float* d_lower, const float* d_pred,
     const long long cap = 2ll * sms;
     const long long grid = prm.total_tiles < cap ? prm.total_tiles : cap;
     return launch_hist_head<false>(head_kind, prm, smem, grid, st);
+}
+
+
+namespace im2im { namespace {
+constexpr int kFusedMaxGrid = 256;
+struct FusedWorkspace {      // byte offsets inside the caller's workspace
+    static size_t head_flag() { return 32; }
+    static size_t totals_acc() { return 32 + sizeof(unsigned) * kFusedMaxGrid; }
+    static size_t head_partial(int L) { return totals_acc() + sizeof(unsigned long long) * L; }
+    static size_t bytes(int L) { return head_partial(L) + sizeof(int) * static_cast<size_t>(kFusedMaxGrid) * L; }
+};
+} }
+
+namespace im2im { namespace {
+bool fused_fast_path(const float* l, const float* p, const float* u, const float* y, int64_t px, int64_t sl, int64_t sp,
+                     int64_t su, int64_t sy, int n_lambdas, int head_kind) {
+    return (px % 4 == 0) && aligned16(l) && aligned16(p) && aligned16(u) && aligned16(y) && (sl % 4 == 0) && (sp % 4 == 0) &&
+           (su % 4 == 0) && (sy % 4 == 0) && hist_smem_bytes(true, n_lambdas, head_kind) <= kMaxSmemOptin;
+}
+} }
+
+extern "C" int im2im_rcps_calibrate_fused_check(const float* d_lower, const float* d_pred, const float* d_upper,
+                                                const float* d_label, int64_t n_images, int64_t px, int64_t stride_lower,
+                                                int64_t stride_pred, int64_t stride_upper, int64_t stride_label,
+                                                int32_t n_lambdas, int32_t head_kind) {
+    if (!head_known(head_kind)) return fail(IM2IM_ENOTSUP, "head_kind %d not implemented", head_kind);
+    if (!head_three_planes(head_kind)) { d_lower = d_pred; stride_lower = stride_pred; }
+    if (n_images <= 0 || px <= 0 || px >= (1ll << 24) || n_lambdas < 1 || n_lambdas > IM2IM_RCPS_MAX_LAMBDAS)
+        return fail(IM2IM_ENOTSUP, "calibrate_fused: shape outside the fused path");
+    if (!fused_fast_path(d_lower, d_pred, d_upper, d_label, px, stride_lower, stride_pred, stride_upper, stride_label,
+                         n_lambdas, head_kind))
+        return fail(IM2IM_ENOTSUP, "calibrate_fused: needs 16-byte aligned planes, px %% 4 == 0 and room for the staging ring");
+    return IM2IM_OK;
+}
+
+extern "C" size_t im2im_rcps_fused_workspace_bytes(int32_t n_lambdas) {
+    if (n_lambdas < 1 || n_lambdas > IM2IM_RCPS_MAX_LAMBDAS) return 0;
+    return FusedWorkspace::bytes(n_lambdas);
+}
+
+extern "C" int im2im_rcps_calibrate_fused(const float* d_lower, const float* d_pred, const float* d_upper,
+                                          const float* d_label, int64_t n_images, int64_t px, int64_t stride_lower,
+                                          int64_t stride_pred, int64_t stride_upper, int64_t stride_label,
+                                          const float* d_lambdas, int32_t n_lambdas, int32_t head_kind,
+                                          int32_t* d_counts, float* d_table, unsigned long long* d_totals_out,
+                                          double n_images_times_px, double gamma, double alpha32, double r_lo,
+                                          double r_hi, double slack, void* d_workspace, size_t workspace_bytes,
+                                          unsigned long long* const* d_peer_mailboxes, unsigned* const* d_peer_flags,
+                                          int32_t rank, int32_t world, double peer_timeout_s, int32_t* d_result,
+                                          int32_t* h_result_mapped, void* stream) {
+    if (!head_known(head_kind)) return fail(IM2IM_ENOTSUP, "head_kind %d not implemented", head_kind);
+    if (!head_three_planes(head_kind)) { d_lower = d_pred; stride_lower = stride_pred; }
+    if (n_images <= 0 || px <= 0) return fail(IM2IM_EINVAL, "calibrate_fused: empty calibration set");
+    if (n_lambdas < 1 || n_lambdas > IM2IM_RCPS_MAX_LAMBDAS)
+        return fail(IM2IM_ERANGE, "n_lambdas=%d outside [1, %d]", n_lambdas, IM2IM_RCPS_MAX_LAMBDAS);
+    if (px >= (1ll << 24)) return fail(IM2IM_ERANGE, "px=%lld >= 2^24: fp32 per-image mean is not exact", (long long)px);
+    if (!d_lower || !d_pred || !d_upper || !d_label || !d_lambdas || !d_counts || !d_result || !d_workspace)
+        return fail(IM2IM_EINVAL, "calibrate_fused: null pointer");
+    if (!(n_images_times_px > 0)) return fail(IM2IM_EINVAL, "calibrate_fused: empty calibration set");
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(IM2IM_EINVAL, "bad rank/world (%d/%d)", rank, world);
+    if (world > 1 && (!d_peer_mailboxes || !d_peer_flags)) return fail(IM2IM_EINVAL, "calibrate_fused: null peer tables");
+    if (workspace_bytes < FusedWorkspace::bytes(n_lambdas))
+        return fail(IM2IM_EINVAL, "calibrate_fused: workspace of %zu bytes, %zu needed", workspace_bytes,
+                    FusedWorkspace::bytes(n_lambdas));
+    const bool fast = fused_fast_path(d_lower, d_pred, d_upper, d_label, px, stride_lower, stride_pred, stride_upper,
+                                      stride_label, n_lambdas, head_kind);
+    if (!fast) return fail(IM2IM_ENOTSUP, "calibrate_fused: needs 16-byte aligned planes, px %% 4 == 0 and a lambda grid that "
+                                         "leaves room for the staging ring; use the multi-launch path");
+    RcpsParams prm;
+    prm.plane[0] = d_lower; prm.plane[1] = d_pred; prm.plane[2] = d_upper; prm.plane[3] = d_label;
+    prm.stride[0] = stride_lower; prm.stride[1] = stride_pred; prm.stride[2] = stride_upper; prm.stride[3] = stride_label;
+    prm.n_images = n_images;
+    prm.px = px;
+    prm.tiles_per_image = (px + kTilePx - 1) / kTilePx;
+    prm.total_tiles = prm.tiles_per_image * n_images;
+    prm.lambdas = d_lambdas;
+    prm.n_lambdas = n_lambdas;
+    prm.counts = d_counts;
+    prm.totals = nullptr;
+    int sms = sm_count();
+    if (sms > kFusedMaxGrid) sms = kFusedMaxGrid;
+    long long grid = prm.total_tiles < sms ? prm.total_tiles : sms;
+    // an image may span at most two CTAs: shrink the grid until every CTA owns at least one image worth of tiles
+    if (prm.total_tiles / grid < prm.tiles_per_image) grid = prm.total_tiles / prm.tiles_per_image;   // = n_images
+    if (grid < 1) grid = 1;
+    unsigned char* ws = static_cast<unsigned char*>(d_workspace);
+    FusedParams fz;
+    fz.table = d_table;
+    fz.epoch = reinterpret_cast<unsigned*>(ws);
+    fz.ticket = reinterpret_cast<unsigned*>(ws) + 1;
+    fz.go = reinterpret_cast<unsigned*>(ws) + 2;
+    fz.err = reinterpret_cast<unsigned*>(ws) + 4;
+    fz.head_flag = reinterpret_cast<unsigned*>(ws + FusedWorkspace::head_flag());
+    fz.totals_acc = reinterpret_cast<unsigned long long*>(ws + FusedWorkspace::totals_acc());
+    fz.head_partial = reinterpret_cast<int*>(ws + FusedWorkspace::head_partial(n_lambdas));
+    fz.scr.n_px = n_images_times_px; fz.scr.gamma = gamma; fz.scr.alpha32 = alpha32;
+    fz.scr.r_lo = r_lo; fz.scr.r_hi = r_hi; fz.scr.slack = slack;
+    fz.peer_mailbox = d_peer_mailboxes; fz.peer_flags = d_peer_flags; fz.rank = rank; fz.world = world;
+    fz.timeout_cycles = 0;
+    if (peer_timeout_s > 0) {
+        int dev = 0, khz = 0;
+        IM2IM_CUDA_TRY(cudaGetDevice(&dev));
+        IM2IM_CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+        fz.timeout_cycles = static_cast<long long>(peer_timeout_s * 1e3 * static_cast<double>(khz));
+    }
+    fz.totals_out = d_totals_out;
+    fz.result = d_result;
+    fz.result_host = nullptr;
+    if (h_result_mapped != nullptr) {   // pinned host memory as the device sees it (same address under unified addressing)
+        void* dptr = nullptr;
+        IM2IM_CUDA_TRY(cudaHostGetDevicePointer(&dptr, h_result_mapped, 0));
+        fz.result_host = static_cast<volatile int*>(dptr);
+    }
+    const size_t smem = hist_smem_bytes(true, n_lambdas, head_kind);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (head_kind) {
+        case IM2IM_HEAD_QUANTILES: return launch_fused<IM2IM_HEAD_QUANTILES>(prm, fz, smem, grid, st);
+        case IM2IM_HEAD_RESIDUAL: return launch_fused<IM2IM_HEAD_RESIDUAL>(prm, fz, smem, grid, st);
+        case IM2IM_HEAD_GAUSSIAN: return launch_fused<IM2IM_HEAD_GAUSSIAN>(prm, fz, smem, grid, st);
+        default: return launch_fused<IM2IM_HEAD_SOFTMAX_SETS>(prm, fz, smem, grid, st);
+    }
+}
+
+// Host side of the fused step: spin on the epoch tag the kernel writes into mapped pinned memory (h_result[4]) instead of
+// a cudaStreamSynchronize + 16-byte copy.  Returns 0 when the tag reached `expected`, 1 after `spin_us` microseconds
+// (the caller then falls back to synchronising the stream).
+extern "C" int im2im_host_wait_flag(const volatile int32_t* h_flag, int32_t expected, int64_t spin_us) {
+    if (!h_flag) return fail(IM2IM_EINVAL, "host_wait_flag: null flag");
+    timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (unsigned it = 0;; ++it) {
+        if (static_cast<int32_t>(*h_flag - expected) >= 0) return 0;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((it & 1023u) == 1023u) {
+            timespec t1;
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            const long long us = (t1.tv_sec - t0.tv_sec) * 1000000ll + (t1.tv_nsec - t0.tv_nsec) / 1000;
+            if (us > spin_us) return 1;
+        }
+    }
 }
 
 extern "C" int im2im_rcps_loss_table(const int32_t* d_counts, int64_t n_images, int32_t n_lambdas, int64_t px,

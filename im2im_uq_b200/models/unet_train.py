@@ -458,9 +458,15 @@ class FusedAdam(torch.optim.Optimizer):
     Parameters are re-pointed at views of one contiguous buffer (as DDP-style flat buckets), gradients likewise, so the
     data-parallel all-reduce is a single NCCL call on ``flat_grad`` and the update a single launch."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False):
         params = [p for p in params]
+        if weight_decay != 0.0 or amsgrad:
+            raise ValueError("FusedAdam implements torch.optim.Adam's defaults only (no weight decay, no amsgrad) - the "
+                             "configuration of core/scripts/train.py:120")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedAdam updates ONE flat buffer with one (lr, betas, eps): pass a single parameter group "
+                             f"(got {len(self.param_groups)})")
         ps = [p for g in self.param_groups for p in g["params"]]
         dev = ps[0].device
         n = sum(p.numel() for p in ps)
@@ -504,6 +510,8 @@ class FusedAdam(torch.optim.Optimizer):
         self.gather_grads()
         self._step += 1
         _lib.weights_changed()          # parameters are rewritten through raw pointers: tensor._version does not move
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedAdam: parameter groups were added after construction; one group is supported")
         g = self.param_groups[0]
         lib = _lib.load()
         with torch.cuda.device(self.flat_param.device):
@@ -527,7 +535,8 @@ class GraphedTrainStep:
     eager path).  BatchNorm running statistics, ``num_batches_tracked`` and Adam's step counter all advance on the device.
     """
 
-    def __init__(self, model, optimizer: "FusedAdam", x: torch.Tensor, y: torch.Tensor, group=None, warmup: int = 3):
+    def __init__(self, model, optimizer: "FusedAdam", x: torch.Tensor, y: torch.Tensor, group=None, warmup: int = 3,
+                 keep_warmup: bool = False):
         assert x.is_cuda and y.is_cuda and model.training
         self.model, self.opt, self.group = model, optimizer, group
         self.world = 1
@@ -536,6 +545,14 @@ class GraphedTrainStep:
             self.world = dist.get_world_size(group)
         self.x, self.y = x.clone(), y.clone()
         dev = x.device
+        # The warm-up iterations (lazy allocations, NCCL channel setup) are real optimizer steps on the example batch.  Unless
+        # the caller asks to keep them, parameters, Adam moments / step counter and BatchNorm buffers are put back afterwards,
+        # so that the first replay is the FIRST step of the trajectory, exactly as in the reference's loop (train.py:147-162).
+        snapshot = None
+        if not keep_warmup:
+            snapshot = ([t.clone() for t in (optimizer.flat_param, optimizer.exp_avg, optimizer.exp_avg_sq,
+                                             optimizer.state_dev)],
+                        [b.clone() for b in model.buffers() if b is not None], optimizer._step)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):            # warm-up off the capture: lazy allocations, cuDNN-free, NCCL channels
@@ -543,12 +560,23 @@ class GraphedTrainStep:
                 self._iteration()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        if snapshot is not None:
+            with torch.no_grad():
+                for dst, src in zip((optimizer.flat_param, optimizer.exp_avg, optimizer.exp_avg_sq, optimizer.state_dev),
+                                    snapshot[0]):
+                    dst.copy_(src)
+                for dst, src in zip([b for b in model.buffers() if b is not None], snapshot[1]):
+                    dst.copy_(src)
+            optimizer._step = snapshot[2]
+            _lib.weights_changed()
+            torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self.loss = self._iteration()
         self.kernels_per_replay = _lib.launch_count() - before
-        self.warmup_steps = warmup               # optimizer steps already taken on the example batch (capture runs none)
+        # optimizer steps already taken on the example batch when the first replay runs (capture itself executes nothing)
+        self.warmup_steps = warmup if keep_warmup else 0
 
     def _iteration(self):
         self.opt.zero_grad()

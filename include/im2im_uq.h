@@ -137,6 +137,50 @@ int im2im_rcps_decide_p2p(const unsigned long long* d_local_totals, unsigned lon
                           unsigned long long* d_totals_out, int32_t* d_result, void* stream);
 
 /*
+ * The WHOLE device side of one calibration (core/calibration/calibrate_model.py:130-145) in ONE kernel launch:
+ * im2im_rcps_miss_counts + the exchange of the per-lambda totals between GPUs + im2im_rcps_decide +
+ * im2im_rcps_loss_table_dev, with no memset of the outputs and no device->host copy.
+ *   - every row of d_counts is written in full by the thread block that owns the image's first tile (an image that
+ *     straddles two blocks travels through a per-block partial row in the workspace), so d_counts need not be zeroed;
+ *   - block totals are reduced with uint64 atomics into the workspace; the LAST block to finish (ticket) sums them, and
+ *     when world > 1 all-reduces them with the one-shot push protocol of im2im_rcps_decide_p2p over NVLink peer memory;
+ *   - it screens the stopping rule exactly like im2im_rcps_decide, writes d_result AND h_result_mapped (mapped pinned
+ *     host memory: int32[8] = {result[0..3], epoch tag, -, -, -}; the tag is stored last, after a system fence, so a host
+ *     thread spinning on h_result_mapped[4] (im2im_host_wait_flag) sees a complete result without a stream synchronize);
+ *   - the other blocks then convert the counts rows they own into d_table (0 left of the first visited column).
+ *   d_table, d_totals_out, h_result_mapped may be NULL.
+ *   d_workspace : DEVICE, im2im_rcps_fused_workspace_bytes(n_lambdas) bytes, ZERO-FILLED once by the caller before the
+ *                 first call and then left alone (the kernel restores its invariants; the first uint32 is the launch
+ *                 epoch, advanced by every call so that CUDA-graph replays need no new arguments).  With world > 1 every
+ *                 rank must make the same sequence of calls on a workspace of the same age.
+ *   peer tables : as im2im_rcps_decide_p2p (ignored when world == 1).  peer_timeout_s > 0 bounds the wait for the peers'
+ *                 flags (result = {-2,-2,-2,0}: the ranks are out of step, tear the peer buffers down and rebuild);
+ *                 0 waits for ever.
+ * Launched cooperatively (all blocks resident).  Returns IM2IM_ENOTSUP - before launching anything - when the bulk-copy
+ * fast path does not apply (unaligned planes, px % 4 != 0, lambda grid too long for the staging ring): callers then
+ * use the separate entry points above.
+ */
+size_t im2im_rcps_fused_workspace_bytes(int32_t n_lambdas);
+/* IM2IM_OK when im2im_rcps_calibrate_fused would take these planes, IM2IM_ENOTSUP otherwise; launches nothing (ranks of a
+ * multi-GPU job agree on the path with it before the first collective call). */
+int im2im_rcps_calibrate_fused_check(const float* d_lower, const float* d_pred, const float* d_upper, const float* d_label,
+                                     int64_t n_images, int64_t px, int64_t stride_lower, int64_t stride_pred,
+                                     int64_t stride_upper, int64_t stride_label, int32_t n_lambdas, int32_t head_kind);
+int im2im_rcps_calibrate_fused(const float* d_lower, const float* d_pred, const float* d_upper, const float* d_label,
+                               int64_t n_images, int64_t px, int64_t stride_lower, int64_t stride_pred,
+                               int64_t stride_upper, int64_t stride_label, const float* d_lambdas, int32_t n_lambdas,
+                               int32_t head_kind, int32_t* d_counts, float* d_table, unsigned long long* d_totals_out,
+                               double n_images_times_px, double gamma, double alpha32, double r_lo, double r_hi,
+                               double slack, void* d_workspace, size_t workspace_bytes,
+                               unsigned long long* const* d_peer_mailboxes, unsigned* const* d_peer_flags, int32_t rank,
+                               int32_t world, double peer_timeout_s, int32_t* d_result, int32_t* h_result_mapped,
+                               void* stream);
+
+/* HOST helper for the fused step: spin (pause loop) until *h_flag - expected >= 0 or spin_us microseconds have passed.
+ * Returns 0 when the flag arrived, 1 on timeout (the caller falls back to synchronising the stream). */
+int im2im_host_wait_flag(const volatile int32_t* h_flag, int32_t expected, int64_t spin_us);
+
+/*
  * Interval endpoints at one lambda: ModelWithUncertainty.nested_sets_from_output
  * (core/models/add_uncertainty.py:33-38 over core/models/finallayers/quantile_layer.py:34-44).
  * Writes lower/upper as dense (n_images, px) fp32; the prediction plane is returned by the caller as a view.

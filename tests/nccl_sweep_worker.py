@@ -49,7 +49,7 @@ def main():
         assert np.array_equal(table.numpy(), g["calib_loss_table"][lo:hi]), (case, rank)
     # the captured plan: all-reduce fused with the decision over peer memory when symmetric memory works here, NCCL otherwise;
     # both must reproduce the reference's lhat / table rows, replay after replay
-    for p2p in (True, False):
+    for p2p, fused in ((True, True), (True, False), (False, False)):
         for case in ("fastmri_small", "temca_small", "top_risk_zero", "never_stops"):
             g = load_golden(case)
             n = g["outputs"].shape[0]
@@ -57,9 +57,11 @@ def main():
             lo, hi = cuts[rank], cuts[rank + 1]
             cfg = dict(g["config"], device=str(dev))
             out = torch.from_numpy(g["outputs"][lo:hi]).to(dev); lab = torch.from_numpy(g["labels"][lo:hi]).to(dev)
-            plan = cm.RcpsGraph(out, lab, cfg, group=dist.group.WORLD, n_total=n, p2p=p2p)
-            if p2p and rank == 0:
-                print("P2P_PATH", "peer-memory" if plan.peer is not None else "nccl-fallback: " + getattr(plan, "p2p_error", "?"))
+            plan = cm.RcpsGraph(out, lab, cfg, group=dist.group.WORLD, n_total=n, p2p=p2p, fused=fused)
+            if rank == 0 and case == "fastmri_small":
+                print("PLAN_PATH", "fused single launch over peer memory" if plan.fused else
+                      ("decide_p2p over peer memory" if plan.peer is not None else "nccl all-reduce"),
+                      "kernels/replay", plan.kernels_per_replay, flush=True)
             for _ in range(3):
                 lhat, stop, decided = plan.run()
                 if not decided:
@@ -68,13 +70,31 @@ def main():
                 assert np.float32(lhat.numpy()) == g["lhat"]
                 assert np.array_equal(plan.table.cpu().numpy(), g["calib_loss_table"][lo:hi]), (case, p2p, rank)
                 assert np.array_equal(plan.totals.cpu().numpy(), g["counts_prime"].sum(0, dtype=np.int64)), (case, p2p)
-    del plan
+            plan.close()
+    # images that straddle thread blocks, sharded unevenly over the ranks: fused peer path vs the single-GPU separate kernels
+    from conftest import synth_scores
+    n = 301
+    out_all, lab_all = synth_scores(9, n, 1, 64, 64, device=dev)
+    cfg = dict(uncertainty_type="quantiles", minimum_lambda=0.0, maximum_lambda=6.0, num_lambdas=1000, alpha=0.1,
+               delta=0.1, device=str(dev), dataset="synthetic", rcps_loss="fraction_missed")
+    ref = cm.RcpsGraph(out_all, lab_all, cfg, fused=False)
+    want = ref.run()
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    plan = cm.RcpsGraph(out_all[lo:hi].contiguous(), lab_all[lo:hi].contiguous(), cfg, group=dist.group.WORLD, n_total=n)
+    for _ in range(4):
+        got = plan.run()
+        torch.cuda.synchronize()
+        assert got[1] == want[1] and got[2] == want[2], (rank, got, want)
+        assert torch.equal(plan.totals, ref.totals) and torch.equal(plan.counts, ref.counts[lo:hi])
+        assert torch.equal(plan.table, ref.table[lo:hi])
+    if rank == 0:
+        print("FUSED_MULTI_GPU", "fused" if plan.fused else "not fused", flush=True)
+    plan.close(); ref.close()
     torch.cuda.synchronize()
     dist.barrier()
+    dist.destroy_process_group()          # graphs that captured NCCL kernels are gone (close()): teardown returns
     if rank == 0:
         print("NCCL_SWEEP_OK", flush=True)
-    sys.stdout.flush()
-    os._exit(0)   # skip NCCL teardown: ncclCommDestroy can wait on captured graphs (see bench.py)
 
 
 if __name__ == "__main__":

@@ -326,11 +326,16 @@ def test_two_rank_nccl_sweep():
     assert "NCCL_SWEEP_OK" in res.stdout
 
 
-def test_rcps_graph_replay_matches_reference(golden):
-    """The CUDA-graph plan (capture once, replay) gives the same lhat / table as the reference, replay after replay."""
+@pytest.mark.parametrize("fused", [True, False])
+def test_rcps_graph_replay_matches_reference(golden, fused):
+    """The CUDA-graph plan (capture once, replay) gives the same lhat / table as the reference, replay after replay -
+    as ONE fused launch per calibration (im2im_rcps_calibrate_fused) and as the multi-launch sequence."""
     cfg = dict(golden["config"], device="cuda:0")
     out, lab = _dev(golden["outputs"]), _dev(golden["labels"])
-    plan = cm.RcpsGraph(out, lab, cfg)
+    plan = cm.RcpsGraph(out, lab, cfg, fused=fused)
+    aligned = golden["labels"][0].size % 4 == 0
+    assert plan.fused == (fused and aligned)
+    assert plan.kernels_per_replay == (1 if plan.fused else 3)
     for _ in range(3):
         lhat, stop, decided = plan.run()
         if not decided:
@@ -345,6 +350,68 @@ def test_rcps_graph_replay_matches_reference(golden):
         lhat2, stop2 = plan.replay_on_host()
     assert stop2 == int(golden["stop_idx"])          # the stopping rule is permutation invariant
     assert np.array_equal(plan.counts.cpu().numpy(), golden["counts_prime"][::-1])
+    plan.close()
+
+
+@pytest.mark.parametrize("head", ["quantiles", "residual_magnitude", "gaussian", "softmax_sets"])
+@pytest.mark.parametrize("shape,L", [((300, 64, 64), 1000), ((20, 320, 320), 1000), ((400, 96, 96), 100),
+                                     ((1000, 32, 32), 333), ((7, 640, 640), 1000), ((149, 128, 128), 64)])
+def test_fused_single_launch_equals_multi_launch(shape, L, head):
+    """One launch (no memset, head-partial rows between neighbouring blocks, last-block decision, in-kernel loss table,
+    result through mapped pinned memory) against the separate kernels, on shapes where images straddle thread blocks
+    (2 / 4.5 / 8 tiles per image), where the grid shrinks to one block per image, and where blocks own whole images only.
+    Garbage in the output buffers beforehand proves that nothing relies on a memset."""
+    if head != "quantiles" and shape[0] * shape[1] * shape[2] > 300 * 64 * 64 * 2:
+        pytest.skip("other head kinds: small shapes only (same code path, templated)")
+    n, h, w = shape
+    out, lab = synth_scores(5, n, 1, h, w, device=DEV)
+    kind = {"quantiles": _lib.IM2IM_HEAD_QUANTILES, "residual_magnitude": _lib.IM2IM_HEAD_RESIDUAL,
+            "gaussian": _lib.IM2IM_HEAD_GAUSSIAN, "softmax_sets": _lib.IM2IM_HEAD_SOFTMAX_SETS}[head]
+    if head in ("residual_magnitude", "gaussian"):
+        width = (out[:, 2] - out[:, 1])
+        out = torch.stack([out[:, 1], width if head == "residual_magnitude" else width * width], dim=1).contiguous()
+    cfg = dict(uncertainty_type="quantiles", minimum_lambda=0.0, maximum_lambda=6.0, num_lambdas=L, alpha=0.1,
+               delta=0.1, device="cuda:0", dataset="synthetic", rcps_loss="fraction_missed")
+    ref = cm.RcpsGraph(out, lab, cfg, head=kind, fused=False)
+    plan = cm.RcpsGraph(out, lab, cfg, head=kind, fused=True)
+    assert plan.fused and plan.kernels_per_replay == 1 and not ref.fused
+    want = ref.run()
+    torch.cuda.synchronize()
+    for rep in range(3):
+        plan.counts.fill_(-12345); plan.table.fill_(float("nan")); plan.totals.fill_(-1)
+        got = plan.run()
+        torch.cuda.synchronize()
+        assert (got[1], got[2]) == (want[1], want[2]) and torch.equal(got[0], want[0])
+        assert torch.equal(plan.counts, ref.counts)
+        assert torch.equal(plan.totals, ref.totals)
+        assert torch.equal(plan.table, ref.table)
+        assert torch.equal(plan.result, ref.result)
+    if head == "quantiles" and n * h * w <= 300 * 64 * 64:
+        _, _, lam_prime, _ = sweep.lambda_grid(cfg)
+        assert np.array_equal(plan.counts.cpu().numpy(), orc.c_miss_table(out.cpu().numpy(), lab.cpu().numpy(), lam_prime.numpy()))
+    # new contents, same buffers: the workspace cleaned itself
+    lab.add_(0.01)
+    want = ref.run(); got = plan.run()
+    torch.cuda.synchronize()
+    assert got[1] == want[1] and torch.equal(plan.counts, ref.counts) and torch.equal(plan.table, ref.table)
+    plan.close(); ref.close()
+
+
+def test_fused_rejects_what_it_cannot_take():
+    lib = _lib.load()
+    out, lab = synth_scores(1, 4, 1, 9, 7, device=DEV)          # 63 values per image: not a multiple of 4
+    cfg = dict(uncertainty_type="quantiles", minimum_lambda=0.0, maximum_lambda=6.0, num_lambdas=50, alpha=0.1,
+               delta=0.1, device="cuda:0", dataset="synthetic", rcps_loss="fraction_missed")
+    plan = cm.RcpsGraph(out, lab, cfg)
+    assert not plan.fused and plan.kernels_per_replay == 3      # fell back to the separate kernels
+    lhat, stop, decided = plan.run()
+    plan.close()
+    assert lib.im2im_rcps_fused_workspace_bytes(0) == 0 and lib.im2im_rcps_fused_workspace_bytes(1000) > 8000
+    assert lib.im2im_host_wait_flag(None, 1, 10) == _lib_einval()
+
+
+def _lib_einval():
+    return -22
 
 
 def test_decide_p2p_single_rank_equals_decide(golden):

@@ -21,11 +21,12 @@ def test_graphed_step_tracks_eager_step():
     xs = [torch.randn(4, 1, 64, 64, device="cuda:0", generator=g) for _ in range(3)]
     ys = [x + 0.3 * torch.randn(4, 1, 64, 64, device="cuda:0", generator=g) for x in xs]
     warm = 2
-    # eager native loop: `warm` steps on batch 0 (the graph's warm-up; capturing itself executes nothing), then the sequence
+    # eager native loop over the sequence; the graph's warm-up steps on batch 0 are rolled back before capture (parameters,
+    # Adam state, BatchNorm buffers), so the first replay is the first step of the trajectory
     m_e = _build()
     o_e = FusedAdam(m_e.parameters(), lr=1e-3)
     eager = []
-    seq = [0] * warm + [1, 2, 0, 1, 2]
+    seq = [1, 2, 0, 1, 2]
     for i in seq:
         o_e.zero_grad()
         loss = m_e.loss_fn(m_e(xs[i]), ys[i])
@@ -40,11 +41,12 @@ def test_graphed_step_tracks_eager_step():
     graph_losses = [step(xs[i].cpu().pin_memory(), ys[i].cpu().pin_memory()).item() for i in [1, 2, 0, 1, 2]]
     assert _lib.launch_count() == before         # replays launch nothing from the host side
     # wgrad uses fp32 atomics (order varies run to run), so trajectories agree to rounding, not bit for bit
-    for a, b in zip(graph_losses, eager[warm:]):
+    assert step.warmup_steps == 0
+    for a, b in zip(graph_losses, eager):
         assert abs(a - b) <= 2e-2 * abs(b), (graph_losses, eager)
     assert graph_losses[-1] < graph_losses[0]
-    # device-side step counter advanced once per executed iteration: warm-up + 5 replays
-    assert int(o_g.state_dev[0].item()) == warm + 5
+    # device-side step counter advanced once per replay (the warm-up was rolled back)
+    assert int(o_g.state_dev[0].item()) == 5
     for (n1, b1), (n2, b2) in zip(m_e.named_buffers(), m_g.named_buffers()):
         if b1 is not None and "num_batches" in n1:
             assert int(b1) == int(b2) == len(seq)
