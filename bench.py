@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--unet-batch", type=int, default=78, help="images per GPU per UNet step (78 = the reference's "
                     "batch size, experiments/fastmri_test/config.yml:45)")
     ap.add_argument("--unet-steps", type=int, default=6)
+    ap.add_argument("--soak-seconds", type=float, default=0.0, help="run untimed steps for this long before the timed region "
+                    "(power-capped steady state instead of the burst)")
     ap.add_argument("--no-unet-reference", action="store_true", help="skip the torch/cuDNN and CPU reference legs of the "
                     "UNet sub-benchmark")
     ap.add_argument("--e2e-images", type=int, default=None, help="images per GPU in the e2e (host buffers) leg; default: "
@@ -105,17 +107,53 @@ def synth(n, side, device, seed, noise=1.0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock, power and throttle reasons sampled DURING the timed region (B200_PROFILING.md) - through NVML in this process
+    (the library behind nvidia-smi) from a thread, every ~1 ms, so that even a 50 ms timed region is covered by dozens of
+    samples; `nvidia-smi -lms` (one sample per ~30 ms) is the fallback when pynvml cannot be used."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
         "clocks_event_reasons.sw_power_cap"
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index=0):
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         self.gpu_index = gpu_index
+        self.thread = None
+        self.rows = []
+        self._stop = threading.Event()
+
+    def _nvml_loop(self, nv, handle):
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(handle) / 1e3,
+                                  int(reasons_fn(handle))))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber: match by PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(self.gpu_index).pci_bus_id
+            handle = None
+            for i in range(nv.nvmlDeviceGetCount()):
+                hnd = nv.nvmlDeviceGetHandleByIndex(i)
+                if nv.nvmlDeviceGetPciInfo(hnd).bus == bus:
+                    handle = hnd
+            if handle is None:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(self.gpu_index)],
@@ -125,6 +163,19 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            rows = list(self.rows)
+            if rows:
+                sm = sorted(r[0] for r in rows)
+                mask = 0
+                for r in rows:
+                    mask |= r[2]
+                out = {"sm_mhz": float(sm[len(sm) // 2]), "sm_min_mhz": float(sm[0]), "sm_max_mhz": self.max_mhz,
+                       "reasons": [nm for nm, bit in self.REASONS if mask & bit], "samples": len(rows),
+                       "power_w_max": max(r[1] for r in rows), "source": "NVML in-process, ~1 ms period"}
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -138,7 +189,7 @@ class ClockSampler:
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
             reasons = [nm for k, nm in enumerate(names) if any("Active" in r[4 + k] and "Not" not in r[4 + k] for r in rows)]
             out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][2]) if rows else None,
-                   "reasons": reasons, "samples": len(rows),
+                   "reasons": reasons, "samples": len(rows), "source": "nvidia-smi -lms 20",
                    "power_w_max": max(float(r[3]) for r in rows) if rows else None}
         except Exception as e:  # never let monitoring break the benchmark
             out["error"] = repr(e)
@@ -615,27 +666,27 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # clocks / throttle reasons are sampled from before the warm-up to the end of the timed region; the warm-up is extended
-    # (same steps, untimed) until the sampler has seen >= 1.2 s of this load, so that a 50 ms timed region still comes with
-    # a meaningful clock record
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     warm = max(args.warmup, 3)
     for _ in range(warm):
         step()
+    if args.soak_seconds > 0:
+        # optional: keep stepping (untimed) for this long first, to measure the power-capped steady state instead of the
+        # burst a single calibration really is
+        sync_all()
+        t_probe = time.perf_counter()
+        for _ in range(5):
+            step()
+        sync_all()
+        per_step = max((time.perf_counter() - t_probe) / 5, 1e-6)
+        extra = torch.tensor([int(min(100000, args.soak_seconds / per_step))], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.broadcast(extra, src=0)     # the step is collective: every rank runs the same number of them
+        for _ in range(int(extra)):
+            step()
     sync_all()
-    t_probe = time.perf_counter()
-    for _ in range(5):
-        step()
-    sync_all()
-    per_step = max((time.perf_counter() - t_probe) / 5, 1e-6)
-    extra = torch.tensor([int(min(20000, 1.2 / per_step))], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.broadcast(extra, src=0)     # the step is collective: every rank runs the same number of them
-    for _ in range(int(extra)):
-        step()
-    done = warm + 5 + int(extra)
+    sampler = ClockSampler(local_rank)       # NVML thread, ~1 ms period: covers the timed region with dozens of samples
+    if rank == 0:
+        sampler.start()
     sync_all()
     launches0 = _lib.launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -654,7 +705,7 @@ def main():
         launches += args.steps * plan.kernels_per_replay  # kernels replayed from the captured graph
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks["window"] = "extended warm-up (%d untimed steps) + timed region" % done
+        clocks["window"] = "the timed region (%d steps, %.1f ms)" % (args.steps, t_start.elapsed_time(t_end))
     ms_total = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
     plan_fused = plan is not None and plan.fused
     plan_peer = plan is not None and plan.peer is not None

@@ -197,7 +197,7 @@ enum { kFlushAtomic = 0, kFlushSparse = 1, kFlushFull = 2, kFlushFullPlus = 3 };
 
 __device__ __forceinline__ void flush_image(unsigned* hist, unsigned* rise, unsigned long long* tot,
                                             unsigned* warp_sums, int L, int* counts_row, int mode,
-                                            const int* addend, int ctid) {
+                                            const int* addend, int ctid, float* table_row = nullptr, float fpx = 1.f) {
     named_bar_sync(kFlushBarrier, kConsumerThreads);  // all histogram atomics of this image have landed
     const int per_thread = (L + kConsumerThreads - 1) / kConsumerThreads;
     const int r0 = ctid * per_thread;  // r = L-1-j : position counted from the top of the grid
@@ -232,6 +232,9 @@ __device__ __forceinline__ void flush_image(unsigned* hist, unsigned* rise, unsi
                 int out = static_cast<int>(val);
                 if (mode == kFlushFullPlus) out += __ldcg(addend + j);
                 counts_row[j] = out;
+                // fused path: the loss-table entry while the count is in a register (columns left of the first visited one
+                // are zeroed after the decision, by stores only)
+                if (table_row != nullptr) table_row[j] = __fdiv_rn(static_cast<float>(out), fpx);
                 tot[j] += val;
             } else if (val != 0) {
                 if (mode == kFlushSparse) counts_row[j] = static_cast<int>(val);
@@ -456,7 +459,8 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
                 flush_image(hist, rise, tot, warp_sums, L, prm.counts + img * L,
                             (image_started_here && image_ends_here) ? kFlushSparse : kFlushAtomic, nullptr, ctid);
             } else if (image_ends_here && image_started_here) {          // whole image counted here
-                flush_image(hist, rise, tot, warp_sums, L, prm.counts + img * L, kFlushFull, nullptr, ctid);
+                flush_image(hist, rise, tot, warp_sums, L, prm.counts + img * L, kFlushFull, nullptr, ctid,
+                            fz.table ? fz.table + img * L : nullptr, static_cast<float>(prm.px));
             } else if (image_ends_here) {                                 // head partial: the previous CTA owns the row
                 flush_image(hist, rise, tot, warp_sums, L, fz.head_partial + static_cast<long long>(blockIdx.x) * L,
                             kFlushFull, nullptr, ctid);
@@ -474,7 +478,8 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
                     }
                 }
                 flush_image(hist, rise, tot, warp_sums, L, prm.counts + img * L, kFlushFullPlus,
-                            fz.head_partial + static_cast<long long>(blockIdx.x + 1) * L, ctid);
+                            fz.head_partial + static_cast<long long>(blockIdx.x + 1) * L, ctid,
+                            fz.table ? fz.table + img * L : nullptr, static_cast<float>(prm.px));
             }
         }
         if (++r == tpi32) { r = 0; ++img; image_started_here = true; }
@@ -581,15 +586,13 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
             named_bar_sync(kFlushBarrier, kConsumerThreads);
             first_visited = s_tail[1];
         }
-        if (fz.table != nullptr) {
-            // loss-table rows of the images whose FIRST tile lies in this CTA's range (those rows were completed here)
+        if (fz.table != nullptr && first_visited > 0) {
+            // the rows of the images whose FIRST tile lies in this CTA's range were written here (count/px in every
+            // column): zero the columns the early-stopped sweep never visits (calibrate_model.py:133) - stores only
             const long long i_begin = (t_begin + tpi - 1) / tpi, i_end = (t_end + tpi - 1) / tpi;
-            const float fpx = static_cast<float>(prm.px);
             for (long long i = i_begin; i < i_end; ++i) {
-                const int* crow = prm.counts + i * L;
                 float* trow = fz.table + i * L;
-                for (int j = ctid; j < L; j += kConsumerThreads)
-                    trow[j] = (j >= first_visited) ? __fdiv_rn(static_cast<float>(__ldcg(crow + j)), fpx) : 0.f;
+                for (int j = ctid; j < first_visited; j += kConsumerThreads) trow[j] = 0.f;
             }
         }
         return;

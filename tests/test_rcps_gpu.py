@@ -132,41 +132,9 @@ def test_get_rcps_losses_from_outputs(golden):
         cm.get_rcps_losses_from_outputs(model, ds, cm.fraction_missed_loss, None, "cuda:0")
 
 
-def test_metrics_from_outputs_vs_literal_restatement():
-    g = load_golden("fastmri_small")
-    cfg = dict(g["config"], device="cuda:0")
-    model = _identity_model(cfg)
-    model.set_lhat(torch.tensor(g["lhat"]))
-    out, lab = torch.from_numpy(g["outputs"]), torch.from_numpy(g["labels"])
-    ds = torch.utils.data.TensorDataset(out, lab)
-    np.random.seed(5); torch.manual_seed(5)
-    losses, sizes, spearman, strat, mse, spatial = cm.get_rcps_metrics_from_outputs(model, ds, cm.fraction_missed_loss, "cuda:0")
-    # literal CPU restatement of calibrate_model.py:31-60 on the oracle's endpoints, same RNG calls in the same order
-    from scipy.stats import spearmanr
-    np.random.seed(5); torch.manual_seed(5)
-    lo, pr, up = (torch.from_numpy(a) for a in orc.np_nested_sets(g["outputs"], g["lhat"]))
-    n = out.shape[0]
-    r_sizes, r_res = [], []
-    for s in range(0, n, 64):
-        full = (up[s:s + 64] - lo[s:s + 64]).flatten(start_dim=1).numpy()
-        idx = np.random.choice(full.shape[1], size=full.shape[0])
-        r_sizes.append(torch.tensor(full[range(full.shape[0]), idx]))
-        r_res.append((lab[s:s + 64] - pr[s:s + 64]).abs().flatten(start_dim=1)[range(full.shape[0]), idx])
-    r_sizes = torch.cat(r_sizes); r_sizes = r_sizes + torch.rand(size=r_sizes.shape) * 1e-6
-    r_res = torch.cat(r_res).numpy()
-    miss = ((lab > up).float() + (lab < lo).float()).numpy()
-    assert np.array_equal(losses.cpu().numpy(), g["dense_prime"][:, 0] * 0 + orc.np_fraction_missed((lo.numpy(), pr.numpy(), up.numpy()), g["labels"])[0])
-    assert torch.equal(sizes, r_sizes)
-    assert spearman == spearmanr(r_res, r_sizes)[0]
-    assert mse == (r_res * r_res).mean().item()
-    assert np.array_equal(spatial, miss.mean(axis=0).mean(axis=0))
-    bins = torch.tensor([0, torch.quantile(r_sizes, 0.25), torch.quantile(r_sizes, 0.5), torch.quantile(r_sizes, 0.75)])
-    buckets = torch.bucketize(r_sizes, bins) - 1
-    want = torch.tensor([losses.cpu()[buckets == b].mean() for b in range(4)])
-    assert torch.equal(torch.nan_to_num(strat), torch.nan_to_num(want))
+# get_rcps_metrics_from_outputs: see tests/test_metrics_golden.py (fixtures produced by the reference's own function)
 
 
-# ------------------------------------------------------------------------------------------- edge cases
 def test_empty_and_degenerate_sizes():
     lam = torch.linspace(0, 2, 5, device=DEV)
     c, t = rcps.miss_counts(torch.zeros(0, 3, 1, 4, 4, device=DEV), torch.zeros(0, 1, 4, 4, device=DEV), lam)
