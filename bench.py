@@ -818,8 +818,9 @@ def main():
                                                  "fused with the decision over NVLink peer memory (im2im_rcps_decide_p2p)")
                                                 if plan_peer else ("NCCL" if world > 1 else "none (single GPU)")),
                            "lhat": result["lhat"], "lhat_index": result["stop"],
-                           "replayed_columns": result["replayed"], "parallelism": f"image shards x{world}, "
-                           "one NCCL all-reduce of int64[L] totals" if world > 1 else "single GPU"},
+                           "replayed_columns": result["replayed"], "parallelism": (f"image shards x{world}, one exchange of the "
+                           "uint64[L] totals per calibration (" + ("NVLink peer memory" if plan_peer else "NCCL all-reduce") + ")")
+                           if world > 1 else "single GPU"},
                 "roofline": {"bound": "hbm", "kernel": "rcps_hist_kernel<fused>" if plan_fused else "rcps_hist_kernel<staged>", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": float(kernel_ms),

@@ -46,6 +46,40 @@ def conv_igemm(x1: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[tor
     return out
 
 
+def round_to_tf32(t: torch.Tensor) -> torch.Tensor:
+    """fp32 tensor rounded to nearest (ties away from zero, like cvt.rna.tf32.f32) onto the TF32 grid (10-bit mantissa)."""
+    bits = t.detach().float().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def pack_conv_weight_tf32(weight: torch.Tensor) -> torch.Tensor:
+    """torch Conv2d weight [c_out, c_in, kh, kw] -> fp32 [c_out, kh*kw, c_in] (tap-major K), TF32-rounded, contiguous."""
+    c_out, c_in, kh, kw = weight.shape
+    return round_to_tf32(weight.detach().float().permute(0, 2, 3, 1).reshape(c_out, kh * kw, c_in).contiguous())
+
+
+def conv_igemm_tf32(x1: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+                    x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Reference-precision convolution (im2im_conv_igemm_tf32): fp32 NHWC in, tcgen05 kind::tf32, fp32 NHWC out."""
+    lib = _lib.load()
+    assert x1.is_cuda and x1.dtype == torch.float32 and x1.is_contiguous() and x1.dim() == 4
+    B, H, W, c1 = x1.shape
+    c2 = 0
+    if x2 is not None:
+        assert x2.is_cuda and x2.dtype == torch.float32 and x2.is_contiguous() and tuple(x2.shape[:3]) == (B, H, W)
+        c2 = x2.shape[3]
+    c_out, taps, c_in = weight_packed.shape
+    assert weight_packed.dtype == torch.float32 and weight_packed.is_contiguous() and c_in == c1 + c2
+    out = torch.empty((B, H, W, c_out), dtype=torch.float32, device=x1.device)
+    with torch.cuda.device(x1.device):
+        rc = lib.im2im_conv_igemm_tf32(x1.data_ptr(), c1, x2.data_ptr() if x2 is not None else None, c2,
+                                       weight_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                       B, H, W, c_out, taps, 1 if relu else 0, out.data_ptr(),
+                                       torch.cuda.current_stream(x1.device).cuda_stream)
+    _lib.check(rc, "im2im_conv_igemm_tf32")
+    return out
+
+
 def conv_wgrad(x: torch.Tensor, dz: torch.Tensor, taps: int = 9, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 dW [c_out, taps, c_in] (+= when ``out`` is given) from NHWC bf16 input ``x`` and output gradient ``dz``."""
     lib = _lib.load()

@@ -38,6 +38,8 @@ struct ConvParams {
     int bn;            // N tile
     int stages;
     int relu;
+    int tf32;          // 1: fp32 activations / weights in shared memory, tcgen05 kind::tf32 (K step = 32 channels = 128 B)
+    int kstep;         // channels per K step: 64 (bf16) or 32 (tf32) - one 128-byte swizzle row either way
     const float* bias;       // [c_out] or null
     __nv_bfloat16* out_bf16; // NHWC [B,H,W,c_out] or null
     float* out_f32;          // NHWC fp32 or null
@@ -82,6 +84,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem], fp32 data read as TF32 (10-bit mantissa; low 13 bits ignored), fp32 accumulate.
+// K of one instruction = 8 elements = 32 bytes, so the descriptor arithmetic of a 128-byte K step is the bf16 one.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// round-to-nearest (ties away) onto the TF32 grid: what is stored is exactly what the next layer's MMA will read
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 // mbarrier arrives when all previously issued tcgen05 ops of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -117,6 +138,12 @@ __device__ __forceinline__ uint64_t make_sw128_desc(const void* smem_ptr) {
 // Instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = bn
 __device__ __forceinline__ uint32_t make_idesc_bf16(int bn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
+           (static_cast<uint32_t>(kTileM >> 4) << 24);
+}
+
+// Instruction descriptor for kind::tf32: D = F32, A = B = TF32 (format 2), both K-major, M = 128, N = bn
+__device__ __forceinline__ uint32_t make_idesc_tf32(int bn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
            (static_cast<uint32_t>(kTileM >> 4) << 24);
 }
 
@@ -164,7 +191,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_const
     const int w0 = tw * p.bw, h0 = th * p.bh, b0 = tb * p.bb;
     const int n0 = blockIdx.y * p.bn;
     const int c_in = p.c_in1 + p.c_in2;
-    const int kblocks_per_tap = c_in / kKStep;
+    const int kblocks_per_tap = c_in / p.kstep;
     const int n_k = p.taps * kblocks_per_tap;
 
     if (warp == 0) {
@@ -181,7 +208,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_const
                 unsigned char* a_dst = tiles + static_cast<size_t>(stage) * stage_bytes;
                 unsigned char* b_dst = a_dst + kATileBytes;
                 mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(stage_bytes));
-                const int c0 = cblk * kKStep;
+                const int c0 = cblk * p.kstep;
                 if (c0 < p.c_in1) tma_load_4d(a_dst, &map_x1, &full_bar[stage], c0, w0 + dx, h0 + dy, b0);
                 else tma_load_4d(a_dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0 + dx, h0 + dy, b0);
                 tma_load_2d(b_dst, &map_w, &full_bar[stage], tap * c_in + c0, n0);
@@ -191,7 +218,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_const
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(p.bn);
+            const uint32_t idesc = p.tf32 ? make_idesc_tf32(p.bn) : make_idesc_bf16(p.bn);
             int stage = 0;
             unsigned phase = 0;
             for (int it = 0; it < n_k; ++it) {
@@ -202,9 +229,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_const
                 const uint64_t desc_b = make_sw128_desc(a_src + kATileBytes);
 #pragma unroll
                 for (int k = 0; k < kKStep / kUmmaK; ++k) {
-                    // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
-                    umma_bf16(tmem_base, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
-                              idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    // advance 32 bytes (16 bf16 / 8 tf32 elements) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                    if (p.tf32) umma_tf32(tmem_base, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
+                                          idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    else umma_bf16(tmem_base, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
+                                   idesc, (it > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -235,6 +264,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_const
                     float x = __uint_as_float(v[j]);
                     if (p.bias) x += __ldg(p.bias + n0 + c + j);
                     if (p.relu) x = fmaxf(x, 0.f);
+                    if (p.tf32) x = round_tf32(x);
                     f[j] = x;
                 }
                 if (p.out_bf16) {
@@ -311,7 +341,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
     const int n_tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
     const int n_tiles = n_tiles_m * n_tiles_n;
     const int c_in = p.c_in1 + p.c_in2;
-    const int kblocks_per_tap = c_in / kKStep;
+    const int kblocks_per_tap = c_in / p.kstep;
     const int n_k = p.taps * kblocks_per_tap;
 
     if (warp == 0) {
@@ -332,7 +362,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
                     mbar_wait(&empty_bar[stage], phase);
                     unsigned char* a_dst = tiles + static_cast<size_t>(stage) * stage_bytes;
                     mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(stage_bytes));
-                    const int c0 = cblk * kKStep;
+                    const int c0 = cblk * p.kstep;
                     if (c0 < p.c_in1) tma_load_4d(a_dst, &map_x1, &full_bar[stage], c0, w0 + dx, h0 + dy, b0);
                     else tma_load_4d(a_dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0 + dx, h0 + dy, b0);
                     tma_load_2d(a_dst + kATileBytes, &map_w, &full_bar[stage], tap * c_in + c0, n0);
@@ -342,7 +372,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(p.bn);
+            const uint32_t idesc = p.tf32 ? make_idesc_tf32(p.bn) : make_idesc_bf16(p.bn);
             int stage = 0;
             unsigned phase = 0;
             unsigned acc_phase = 3u;  // bit b = parity to wait for on tmem_empty[b]; fresh barriers: parity 1 passes
@@ -358,10 +388,17 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
                     const unsigned char* a_src = tiles + static_cast<size_t>(stage) * stage_bytes;
                     const uint64_t desc_a = make_sw128_desc(a_src);
                     const uint64_t desc_b = make_sw128_desc(a_src + kATileBytes);
+                    if (p.tf32) {
 #pragma unroll
-                    for (int k = 0; k < kKStep / kUmmaK; ++k)
-                        umma_bf16(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
-                                  idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kKStep / kUmmaK; ++k)
+                            umma_tf32(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
+                                      idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kKStep / kUmmaK; ++k)
+                            umma_bf16(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
+                                      idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
                     umma_commit(&empty_bar[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
@@ -406,6 +443,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
                         float x = __uint_as_float(v[j]);
                         if (p.bias) x += __ldg(p.bias + n0 + c + j);
                         if (p.relu) x = fmaxf(x, 0.f);
+                        if (p.tf32) x = round_tf32(x);   // stored activations are exactly what the next kind::tf32 MMA reads
                         f[j] = x;
                     }
                     if (p.out_bf16) {
@@ -981,30 +1019,31 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// NHWC bf16 activation [B,H,W,C] with a (64 ch, bw, bh, bb) box
-int make_act_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int bw, int bh, int bb) {
+// NHWC activation [B,H,W,C] with a (128 bytes of channels, bw, bh, bb) box: 64 bf16 or (f32 = true) 32 fp32 channels
+int make_act_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int bw, int bh, int bb, bool f32 = false) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(IM2IM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t es = f32 ? 4 : 2;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kKStep, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+    cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+    cuuint32_t box[4] = {(cuuint32_t)(f32 ? kKStep / 2 : kKStep), (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(IM2IM_ECUDA, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
     return IM2IM_OK;
 }
 
-// weights [c_out, K] bf16 (K = taps*c_in contiguous) with a (64, bn) box
-int make_weight_map(CUtensorMap* map, const void* base, int c_out, int K, int bn) {
+// weights [c_out, K] (K = taps*c_in contiguous) with a (128 bytes, bn) box: bf16, or fp32 when f32 = true
+int make_weight_map(CUtensorMap* map, const void* base, int c_out, int K, int bn, bool f32 = false) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(IM2IM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)c_out};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kKStep, (cuuint32_t)bn};
+    cuuint64_t strides[1] = {(cuuint64_t)K * (f32 ? 4 : 2)};
+    cuuint32_t box[2] = {(cuuint32_t)(f32 ? kKStep / 2 : kKStep), (cuuint32_t)bn};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(IM2IM_ECUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
@@ -1050,7 +1089,7 @@ extern "C" int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void
     const int stage_bytes = kATileBytes + p.bn * kKStep * 2;
     p.stages = (200 * 1024) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
-    p.relu = relu; p.bias = d_bias;
+    p.relu = relu; p.bias = d_bias; p.tf32 = 0; p.kstep = kKStep;
     p.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16); p.out_f32 = d_out_f32;
     CUtensorMap m1, m2, mw;
     int rc = make_act_map(&m1, d_x1, B, H, W, c_in1, p.bw, p.bh, p.bb);
@@ -1112,6 +1151,47 @@ extern "C" int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void
     const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
     conv_igemm_persistent_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(m1, m2, mw, p);
     return check_launch("conv_igemm_persistent_kernel");
+}
+
+// Reference-precision mode (SURVEY.md §7 hard part 3): fp32 NHWC activations and fp32 weights [c_out, taps, c_in] staged by
+// TMA as they are, tcgen05 kind::tf32 (what torch's cuDNN convolutions do by default with the reference's fp32 modules),
+// fp32 accumulation, fp32 NHWC output rounded to TF32.  Same persistent kernel and tile math as the bf16 path; a K step is
+// 32 channels (128 bytes).
+extern "C" int im2im_conv_igemm_tf32(const float* d_x1, int32_t c_in1, const float* d_x2, int32_t c_in2,
+                                     const float* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W,
+                                     int32_t c_out, int32_t taps, int32_t relu, float* d_out, void* stream) {
+    if (taps != 9 && taps != 1) return fail(IM2IM_EINVAL, "taps must be 9 (3x3) or 1 (1x1), got %d", taps);
+    if (B <= 0 || H <= 0 || W <= 0) return fail(IM2IM_EINVAL, "bad activation shape %dx%dx%d", B, H, W);
+    constexpr int ks = kKStep / 2;
+    if (c_in1 <= 0 || c_in1 % ks || c_in2 < 0 || c_in2 % ks)
+        return fail(IM2IM_ERANGE, "tf32: input channels must be multiples of %d (got %d + %d)", ks, c_in1, c_in2);
+    if (c_out < 32 || c_out % 32) return fail(IM2IM_ERANGE, "c_out must be a multiple of 32 (got %d)", c_out);
+    if (!d_x1 || !d_weight || !d_out || (c_in2 > 0 && !d_x2)) return fail(IM2IM_EINVAL, "null tensor");
+    ConvParams p;
+    p.taps = taps; p.c_in1 = c_in1; p.c_in2 = c_in2; p.c_out = c_out; p.B = B; p.H = H; p.W = W;
+    pick_box(B, H, W, p.bw, p.bh, p.bb);
+    p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh; p.tiles_b = (B + p.bb - 1) / p.bb;
+    p.bn = (c_out % 256 == 0) ? 256 : (c_out % 128 == 0) ? 128 : (c_out % 64 == 0) ? 64 : 32;
+    const int stage_bytes = kATileBytes + p.bn * 128;
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    p.relu = relu; p.bias = d_bias; p.tf32 = 1; p.kstep = ks;
+    p.out_bf16 = nullptr; p.out_f32 = d_out;
+    CUtensorMap m1, m2, mw;
+    int rc = make_act_map(&m1, d_x1, B, H, W, c_in1, p.bw, p.bh, p.bb, true);
+    if (rc) return rc;
+    if (c_in2 > 0) { rc = make_act_map(&m2, d_x2, B, H, W, c_in2, p.bw, p.bh, p.bb, true); if (rc) return rc; }
+    else m2 = m1;
+    rc = make_weight_map(&mw, d_weight, c_out, taps * (c_in1 + c_in2), p.bn, true);
+    if (rc) return rc;
+    const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + (2 * p.stages + 4) * sizeof(uint64_t) + 16 + 1024;
+    IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    const long long n_tiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_b * (c_out / p.bn);
+    const int sms = sm_count();
+    const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
+    conv_igemm_persistent_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(m1, m2, mw, p);
+    return check_launch("conv_igemm_persistent_kernel<tf32>");
 }
 
 // planar fp32 [B, n, H, W] -> NHWC bf16 [B, H, W, 64] with channels >= n zero: the head's output gradient as a tensor-core

@@ -16,14 +16,59 @@ union Bf16x8 {
     __nv_bfloat162 h[4];
 };
 
+// Eight consecutive channels of an NHWC activation as fp32 registers, for both storage types of the UNet engines:
+// bf16 (16 bytes) and - reference-precision tf32 mode - fp32 (32 bytes, values rounded onto the TF32 grid on store,
+// so that what is stored is exactly what the next kind::tf32 MMA reads).
+template <typename T>
+struct Vec8;
+template <>
+struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
+        Bf16x8 v;
+        v.u = *reinterpret_cast<const uint4*>(p);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 t = __bfloat1622float2(v.h[j]);
+            f[2 * j] = t.x;
+            f[2 * j + 1] = t.y;
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* f) {
+        Bf16x8 v;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        *reinterpret_cast<uint4*>(p) = v.u;
+    }
+};
+__device__ __forceinline__ float aux_round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+template <>
+struct Vec8<float> {
+    static __device__ __forceinline__ void load(const float* p, float* f) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float* f) {
+        float4 a, b;
+        a.x = aux_round_tf32(f[0]); a.y = aux_round_tf32(f[1]); a.z = aux_round_tf32(f[2]); a.w = aux_round_tf32(f[3]);
+        b.x = aux_round_tf32(f[4]); b.y = aux_round_tf32(f[5]); b.z = aux_round_tf32(f[6]); b.w = aux_round_tf32(f[7]);
+        *reinterpret_cast<float4*>(p) = a;
+        *reinterpret_cast<float4*>(p + 4) = b;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // x: fp32 NCHW [B, c_in, H, W] (c_in <= 8) -> y: bf16 NHWC [B, H, W, c_out], 3x3 pad 1, + bias, ReLU.
 // One thread = TWO horizontally adjacent pixels x 16 output channels: the 3x4 input window is loaded once (12 loads for
 // 2 pixels) and every 128-bit weight load from shared memory feeds 8 FMAs, so the kernel is FMA- rather than
 // load/address-bound.  Weights fp32 [c_out, c_in, 3, 3] are staged transposed in shared memory.
+template <typename T>
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, int B, int c_in, int H,
-                                                         int W, int c_out, int relu, __nv_bfloat16* __restrict__ y) {
+                                                         int W, int c_out, int relu, T* __restrict__ y) {
     extern __shared__ __align__(16) float s_w[];  // [c_in*9][c_out] (a thread's 16 channels are contiguous), bias [c_out]
     const int kk = c_in * 9;
     for (int i = threadIdx.x; i < c_out * kk; i += blockDim.x) s_w[(i % kk) * c_out + i / kk] = w[i];
@@ -74,14 +119,10 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
             const float* acc = px2 ? acc1 : acc0;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                Bf16x8 o;
+                float o[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float a0 = acc[8 * half + 2 * j], a1 = acc[8 * half + 2 * j + 1];
-                    if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                    o.h[j] = __floats2bfloat162_rn(a0, a1);
-                }
-                *reinterpret_cast<uint4*>(y + (pix + px2) * c_out + g * 16 + 8 * half) = o.u;
+                for (int j = 0; j < 8; ++j) o[j] = relu ? fmaxf(acc[8 * half + j], 0.f) : acc[8 * half + j];
+                Vec8<T>::store(y + (pix + px2) * c_out + g * 16 + 8 * half, o);
             }
         }
     }
@@ -89,8 +130,9 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 
 // ---------------------------------------------------------------------------------------------------------------
 // 2x2 max pool, stride 2 (floor), NHWC bf16.
-__global__ void __launch_bounds__(256) maxpool2x2_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W,
-                                                         int C, __nv_bfloat16* __restrict__ y) {
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(const T* __restrict__ x, int B, int H, int W,
+                                                         int C, T* __restrict__ y) {
     // grid = (ceil(Wo*groups / 256), Ho, B): row and image come from the block index, so the per-thread index math is one
     // 32-bit division (the 64-bit div/mod chain of a flat index cost more instructions than the pooling itself)
     const int Wo = W / 2, groups = C / 8;
@@ -99,15 +141,15 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const __nv_bfloat16* __
         const int g = idx % groups, ox = idx / groups;
         const int oy = blockIdx.y, b = blockIdx.z;
         const long long pix = (static_cast<long long>(b) * gridDim.y + oy) * Wo + ox;
-        const __nv_bfloat16* p = x + ((static_cast<long long>(b) * H + 2 * oy) * W + 2 * ox) * C + g * 8;
-        Bf16x8 a, c, d, f, o;
-        a.u = *reinterpret_cast<const uint4*>(p);
-        c.u = *reinterpret_cast<const uint4*>(p + C);
-        d.u = *reinterpret_cast<const uint4*>(p + static_cast<long long>(W) * C);
-        f.u = *reinterpret_cast<const uint4*>(p + static_cast<long long>(W) * C + C);
+        const T* p = x + ((static_cast<long long>(b) * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+        float a[8], c[8], d[8], f[8], o[8];
+        Vec8<T>::load(p, a);
+        Vec8<T>::load(p + C, c);
+        Vec8<T>::load(p + static_cast<long long>(W) * C, d);
+        Vec8<T>::load(p + static_cast<long long>(W) * C + C, f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o.h[j] = __hmax2(__hmax2(a.h[j], c.h[j]), __hmax2(d.h[j], f.h[j]));
-        *reinterpret_cast<uint4*>(y + pix * C + g * 8) = o.u;
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaxf(a[j], c[j]), fmaxf(d[j], f[j]));   // exact in either storage type
+        Vec8<T>::store(y + pix * C + g * 8, o);
     }
 }
 
@@ -115,9 +157,10 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const __nv_bfloat16* __
 // Bilinear x2 upsample with align_corners=True of x [B,h,w,C], written into y [B,Ho,Wo,C] at offset (pad_top, pad_left)
 // with zeros elsewhere (F.pad to the skip connection's size).  Source index and weights follow ATen's
 // upsample_bilinear2d: src = dst * (in-1)/(out-1) in fp32, i0 = (int)src, frac = src - i0.
-__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int B, int h, int w,
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ x, int B, int h, int w,
                                                          int C, int Ho, int Wo, int pad_top, int pad_left,
-                                                         __nv_bfloat16* __restrict__ y) {
+                                                         T* __restrict__ y) {
     const int uh = 2 * h, uw = 2 * w, groups = C / 8;
     const float sy = uh > 1 ? static_cast<float>(h - 1) / static_cast<float>(uh - 1) : 0.f;
     const float sx = uw > 1 ? static_cast<float>(w - 1) / static_cast<float>(uw - 1) : 0.f;
@@ -128,31 +171,26 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
         const int oy = blockIdx.y, b = blockIdx.z;
         const long long pix = (static_cast<long long>(b) * Ho + oy) * Wo + ox;
         const int uy = oy - pad_top, ux = ox - pad_left;
-        Bf16x8 o;
+        float o[8];
         if (uy < 0 || uy >= uh || ux < 0 || ux >= uw) {
-            o.u = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = 0.f;
         } else {
             const float fy = sy * uy, fx = sx * ux;
             const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
             const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
             const float ly = fy - y0, lx = fx - x0;
             const float hy = 1.f - ly, hx = 1.f - lx;
-            const __nv_bfloat16* base = x + static_cast<long long>(b) * h * w * C + g * 8;
-            Bf16x8 v00, v01, v10, v11;
-            v00.u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * w + x0) * C);
-            v01.u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * w + x1) * C);
-            v10.u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * w + x0) * C);
-            v11.u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * w + x1) * C);
+            const T* base = x + static_cast<long long>(b) * h * w * C + g * 8;
+            float v00[8], v01[8], v10[8], v11[8];
+            Vec8<T>::load(base + (static_cast<long long>(y0) * w + x0) * C, v00);
+            Vec8<T>::load(base + (static_cast<long long>(y0) * w + x1) * C, v01);
+            Vec8<T>::load(base + (static_cast<long long>(y1) * w + x0) * C, v10);
+            Vec8<T>::load(base + (static_cast<long long>(y1) * w + x1) * C, v11);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 a = __bfloat1622float2(v00.h[j]), c = __bfloat1622float2(v01.h[j]);
-                const float2 d = __bfloat1622float2(v10.h[j]), f = __bfloat1622float2(v11.h[j]);
-                const float r0 = hy * (hx * a.x + lx * c.x) + ly * (hx * d.x + lx * f.x);
-                const float r1 = hy * (hx * a.y + lx * c.y) + ly * (hx * d.y + lx * f.y);
-                o.h[j] = __floats2bfloat162_rn(r0, r1);
-            }
+            for (int j = 0; j < 8; ++j) o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
         }
-        *reinterpret_cast<uint4*>(y + pix * C + g * 8) = o.u;
+        Vec8<T>::store(y + pix * C + g * 8, o);
     }
 }
 
@@ -162,8 +200,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
 // Weights sit in shared memory as [tap][c][NP] with NP = n_out padded to a multiple of 4, so one 128-bit broadcast load
 // feeds 4 FMAs.  tap_bias (optional, [n_out][9]) is added once per IN-RANGE tap: it carries the bias of a 1x1 convolution
 // that was folded into these weights (inference: OutConv 64->32 composed with the head, exact incl. the zero padding).
-template <int N_OUT>
-__global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+template <int N_OUT, typename T>
+__global__ void __launch_bounds__(128) head_conv_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias,
                                                         const float* __restrict__ tap_bias, int B, int H, int W,
                                                         int c_mid, int c_stride, int act_kind, int act_from,
@@ -192,14 +230,14 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const __nv_bfloat16* __r
 #pragma unroll
                 for (int o = 0; o < N_OUT; ++o) acc[o] += __ldg(tap_bias + o * 9 + t);
             }
-            const __nv_bfloat16* p = x + ((b * H + yy) * W + xx) * c_stride;
+            const T* p = x + ((b * H + yy) * W + xx) * c_stride;
             const float* wt = s_w + t * c_mid * NP;
             for (int c = 0; c < c_mid; c += 8) {
-                Bf16x8 v;
-                v.u = *reinterpret_cast<const uint4*>(p + c);
+                float v[8];
+                Vec8<T>::load(p + c, v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float2 f = __bfloat1622float2(v.h[j]);
+                    const float2 f = make_float2(v[2 * j], v[2 * j + 1]);
 #pragma unroll
                     for (int q = 0; q < NP / 4; ++q) {
                         const float4 wa = *reinterpret_cast<const float4*>(wt + (c + 2 * j) * NP + 4 * q);
@@ -262,52 +300,50 @@ unsigned grid_for(long long work_items, int threads) {
 
 using namespace im2im;
 
-extern "C" int im2im_conv_first_bf16(const float* d_x, const float* d_weight, const float* d_bias, int32_t B,
-                                     int32_t c_in, int32_t H, int32_t W, int32_t c_out, int32_t relu, void* d_out,
-                                     void* stream) {
+namespace im2im { namespace {
+template <typename T>
+int conv_first_launch(const float* d_x, const float* d_weight, const float* d_bias, int B, int c_in, int H, int W, int c_out,
+                      int relu, T* d_out, void* stream) {
     if (B <= 0 || H <= 0 || W <= 0 || c_in <= 0 || c_in > 8) return fail(IM2IM_ERANGE, "conv_first: bad shape (c_in=%d)", c_in);
     if (c_out <= 0 || c_out % 16) return fail(IM2IM_ERANGE, "conv_first: c_out must be a multiple of 16");
     if (!d_x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "null tensor");
     const size_t smem = sizeof(float) * (static_cast<size_t>(c_out) * c_in * 9 + c_out);
     if (smem > 48 * 1024) return fail(IM2IM_ERANGE, "conv_first: weights do not fit shared memory");
     const long long items = static_cast<long long>(B) * H * ((W + 1) / 2) * (c_out / 16);
-    conv_first_kernel<<<grid_for(items, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        d_x, d_weight, d_bias, B, c_in, H, W, c_out, relu, static_cast<__nv_bfloat16*>(d_out));
+    conv_first_kernel<T><<<grid_for(items, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        d_x, d_weight, d_bias, B, c_in, H, W, c_out, relu, d_out);
     return check_launch("conv_first_kernel");
 }
 
-extern "C" int im2im_maxpool2x2_bf16(const void* d_x, int32_t B, int32_t H, int32_t W, int32_t C, void* d_out,
-                                     void* stream) {
+template <typename T>
+int maxpool_launch(const T* d_x, int B, int H, int W, int C, T* d_out, void* stream) {
     if (B <= 0 || H < 2 || W < 2 || C <= 0 || C % 8) return fail(IM2IM_ERANGE, "maxpool: bad shape");
     if (!d_x || !d_out) return fail(IM2IM_EINVAL, "null tensor");
     if (B > 65535 || H / 2 > 65535) return fail(IM2IM_ERANGE, "maxpool: B and H/2 must be <= 65535");
     const dim3 pgrid(static_cast<unsigned>(((W / 2) * (C / 8) + 255) / 256), static_cast<unsigned>(H / 2), static_cast<unsigned>(B));
-    maxpool2x2_kernel<<<pgrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(d_x), B, H, W, C, static_cast<__nv_bfloat16*>(d_out));
+    maxpool2x2_kernel<T><<<pgrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, B, H, W, C, d_out);
     return check_launch("maxpool2x2_kernel");
 }
 
-extern "C" int im2im_upsample2x_bilinear_bf16(const void* d_x, int32_t B, int32_t h, int32_t w, int32_t C,
-                                              int32_t H_out, int32_t W_out, void* d_out, void* stream) {
+template <typename T>
+int upsample_launch(const T* d_x, int B, int h, int w, int C, int H_out, int W_out, T* d_out, void* stream) {
     if (B <= 0 || h <= 0 || w <= 0 || C <= 0 || C % 8) return fail(IM2IM_ERANGE, "upsample: bad shape");
     if (H_out < 2 * h || W_out < 2 * w) return fail(IM2IM_ERANGE, "upsample: output smaller than 2x input");
     if (!d_x || !d_out) return fail(IM2IM_EINVAL, "null tensor");
     const int pad_top = (H_out - 2 * h) / 2, pad_left = (W_out - 2 * w) / 2;  // F.pad split of unet_parts.py:63-64
     if (B > 65535 || H_out > 65535) return fail(IM2IM_ERANGE, "upsample: B and H_out must be <= 65535");
     const dim3 ugrid(static_cast<unsigned>((W_out * (C / 8) + 255) / 256), static_cast<unsigned>(H_out), static_cast<unsigned>(B));
-    upsample2x_kernel<<<ugrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(d_x), B, h, w, C, H_out, W_out, pad_top, pad_left,
-        static_cast<__nv_bfloat16*>(d_out));
+    upsample2x_kernel<T><<<ugrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, B, h, w, C, H_out, W_out, pad_top, pad_left,
+                                                                              d_out);
     return check_launch("upsample2x_kernel");
 }
 
-extern "C" int im2im_head_conv3x3_act_f32(const void* d_x, const float* d_weight, const float* d_bias,
-                                          const float* d_tap_bias, int32_t B, int32_t H, int32_t W, int32_t c_mid,
-                                          int32_t c_stride, int32_t n_out, int32_t act_kind, int32_t act_from_plane,
-                                          float* d_out, void* stream) {
+template <typename T>
+int head_conv_launch(const T* x, const float* d_weight, const float* d_bias, const float* d_tap_bias, int B, int H, int W,
+                     int c_mid, int c_stride, int n_out, int act_kind, int act_from_plane, float* d_out, void* stream) {
     if (B <= 0 || H <= 0 || W <= 0 || c_mid <= 0 || c_mid % 8 || c_stride < c_mid || c_stride % 8)
         return fail(IM2IM_ERANGE, "head: bad shape");
-    if (!d_x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "null tensor");
+    if (!x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "null tensor");
     if (act_kind < 0 || act_kind > 2) return fail(IM2IM_EINVAL, "head: act_kind=%d", act_kind);
     if (act_kind == 0) act_from_plane = n_out;
     const size_t smem = sizeof(float) * 9 * c_mid * ((n_out + 3) / 4 * 4);
@@ -315,11 +351,10 @@ extern "C" int im2im_head_conv3x3_act_f32(const void* d_x, const float* d_weight
     const long long items = static_cast<long long>(B) * H * W;
     const unsigned grid = grid_for(items, 128);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(d_x);
 #define IM2IM_HEAD_CASE(N)                                                                                              \
     case N:                                                                                                             \
-        head_conv_kernel<N><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, act_kind, \
-                                                     act_from_plane, d_out);                                            \
+        head_conv_kernel<N, T><<<grid, 128, smem, st>>>(x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, act_kind, \
+                                                        act_from_plane, d_out);                                         \
         break
     switch (n_out) {
         IM2IM_HEAD_CASE(2); IM2IM_HEAD_CASE(3); IM2IM_HEAD_CASE(4); IM2IM_HEAD_CASE(6); IM2IM_HEAD_CASE(9);
@@ -328,12 +363,63 @@ extern "C" int im2im_head_conv3x3_act_f32(const void* d_x, const float* d_weight
 #undef IM2IM_HEAD_CASE
     return check_launch("head_conv_kernel");
 }
+} }
+
+extern "C" int im2im_conv_first_bf16(const float* d_x, const float* d_weight, const float* d_bias, int32_t B,
+                                     int32_t c_in, int32_t H, int32_t W, int32_t c_out, int32_t relu, void* d_out,
+                                     void* stream) {
+    return conv_first_launch(d_x, d_weight, d_bias, B, c_in, H, W, c_out, relu, static_cast<__nv_bfloat16*>(d_out), stream);
+}
+
+extern "C" int im2im_maxpool2x2_bf16(const void* d_x, int32_t B, int32_t H, int32_t W, int32_t C, void* d_out,
+                                     void* stream) {
+    return maxpool_launch(static_cast<const __nv_bfloat16*>(d_x), B, H, W, C, static_cast<__nv_bfloat16*>(d_out), stream);
+}
+
+extern "C" int im2im_upsample2x_bilinear_bf16(const void* d_x, int32_t B, int32_t h, int32_t w, int32_t C,
+                                              int32_t H_out, int32_t W_out, void* d_out, void* stream) {
+    return upsample_launch(static_cast<const __nv_bfloat16*>(d_x), B, h, w, C, H_out, W_out,
+                           static_cast<__nv_bfloat16*>(d_out), stream);
+}
+
+extern "C" int im2im_head_conv3x3_act_f32(const void* d_x, const float* d_weight, const float* d_bias,
+                                          const float* d_tap_bias, int32_t B, int32_t H, int32_t W, int32_t c_mid,
+                                          int32_t c_stride, int32_t n_out, int32_t act_kind, int32_t act_from_plane,
+                                          float* d_out, void* stream) {
+    return head_conv_launch(static_cast<const __nv_bfloat16*>(d_x), d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride,
+                            n_out, act_kind, act_from_plane, d_out, stream);
+}
 
 extern "C" int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* d_bias,
                                       const float* d_tap_bias, int32_t B, int32_t H, int32_t W, int32_t c_mid,
                                       int32_t c_stride, int32_t n_out, float* d_out, void* stream) {
     return im2im_head_conv3x3_act_f32(d_x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, n_out, 0, 0, d_out,
                                       stream);
+}
+
+// ---- reference-precision (tf32) mode: the same kernels on fp32 NHWC activations (values rounded onto the TF32 grid)
+extern "C" int im2im_conv_first_nhwc_f32(const float* d_x, const float* d_weight, const float* d_bias, int32_t B,
+                                         int32_t c_in, int32_t H, int32_t W, int32_t c_out, int32_t relu, float* d_out,
+                                         void* stream) {
+    return conv_first_launch(d_x, d_weight, d_bias, B, c_in, H, W, c_out, relu, d_out, stream);
+}
+
+extern "C" int im2im_maxpool2x2_nhwc_f32(const float* d_x, int32_t B, int32_t H, int32_t W, int32_t C, float* d_out,
+                                         void* stream) {
+    return maxpool_launch(d_x, B, H, W, C, d_out, stream);
+}
+
+extern "C" int im2im_upsample2x_bilinear_nhwc_f32(const float* d_x, int32_t B, int32_t h, int32_t w, int32_t C,
+                                                  int32_t H_out, int32_t W_out, float* d_out, void* stream) {
+    return upsample_launch(d_x, B, h, w, C, H_out, W_out, d_out, stream);
+}
+
+extern "C" int im2im_head_conv3x3_act_nhwc_f32(const float* d_x, const float* d_weight, const float* d_bias,
+                                               const float* d_tap_bias, int32_t B, int32_t H, int32_t W, int32_t c_mid,
+                                               int32_t c_stride, int32_t n_out, int32_t act_kind, int32_t act_from_plane,
+                                               float* d_out, void* stream) {
+    return head_conv_launch(d_x, d_weight, d_bias, d_tap_bias, B, H, W, c_mid, c_stride, n_out, act_kind, act_from_plane,
+                            d_out, stream);
 }
 
 extern "C" int im2im_pack_conv_weights(const float* d_weight, int32_t c_out, int32_t c_in, int32_t taps, void* d_out_fwd,

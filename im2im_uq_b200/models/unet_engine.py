@@ -6,14 +6,22 @@ Replaces, for ``model.eval()`` forwards on CUDA under ``torch.no_grad()``, the l
 BatchNorm (running statistics) is folded into each convolution's weight/bias, activations are NHWC bf16, the 3x3 / 1x1
 convolutions run as implicit GEMMs on tcgen05 (fp32 accumulation), ReLU is fused, the skip concatenation is never
 materialised, and the head writes the reference's (B, 3, C_out, H, W) fp32 tensor directly.
+
+Two precisions (``model.native_precision`` or the environment variable IM2IM_UNET_PRECISION):
+  "bf16" (default)  bf16 operands / activations, tcgen05 kind::f16 - the fast mode (outputs within ~1e-2 of fp32)
+  "tf32"            the reference's precision: its modules are fp32 (unet_parts.py:16-21) and torch runs their cuDNN
+                    convolutions as TF32 on a GPU; fp32 NHWC activations, tcgen05 kind::tf32 (rel-L2 ~5e-4 vs fp32),
+                    about half the throughput.  SURVEY.md §7 hard part 3.
 """
+import os
 from typing import List, Optional, Tuple
 
 import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..conv import conv_igemm, head_conv_tc, head_tc_applicable, pack_conv_weight, pad_head_weight
+from ..conv import (conv_igemm, conv_igemm_tf32, head_conv_tc, head_tc_applicable, pack_conv_weight,
+                    pack_conv_weight_tf32, pad_head_weight)
 
 
 def _fold_bn(conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d]) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -39,15 +47,23 @@ class UNetInferenceEngine:
         self._stamp = None
         self.refresh()
 
+    def _precision(self) -> str:
+        p = getattr(self.model, "native_precision", None) or os.environ.get("IM2IM_UNET_PRECISION", "bf16")
+        if p not in ("bf16", "tf32"):
+            raise ValueError(f"native_precision must be 'bf16' or 'tf32', got {p!r}")
+        return p
+
     # ---- weights
     def _param_stamp(self):
         # _lib.weights_generation(): raw-pointer / graph-replay writes (FusedAdam, bn_finalize, GraphedTrainStep) that
         # tensor._version cannot see
-        return (_lib.weights_generation(),) + tuple((p.data_ptr(), p._version) for p in self.model.parameters()) + \
+        return (_lib.weights_generation(), self._precision()) + tuple((p.data_ptr(), p._version) for p in self.model.parameters()) + \
             tuple((b.data_ptr(), b._version) for n, b in self.model.named_buffers() if b is not None and n != "lhat")
 
     def refresh(self):
         trunk, head = self.model.baseModel, self.model.last_layer
+        self.precision = self._precision()
+        tf32 = self.precision == "tf32"
 
         def double(dc):
             seq = dc.double_conv
@@ -55,7 +71,7 @@ class UNetInferenceEngine:
 
         def packed(wb):
             w, b = wb
-            return pack_conv_weight(w), b
+            return (pack_conv_weight_tf32(w) if tf32 else pack_conv_weight(w)), b
 
         (w0, b0), second = double(trunk.inc)
         self.first = (w0.contiguous(), b0)  # fp32 [64, c_in, 3, 3]
@@ -86,7 +102,7 @@ class UNetInferenceEngine:
         ow, ob = _fold_bn(trunk.out.conv, None)
         c_mid = ow.shape[0]
         self.c_mid = c_mid
-        if c_mid <= 64 and hw.shape[0] <= 32 and ow.shape[1] % 64 == 0:
+        if not tf32 and c_mid <= 64 and hw.shape[0] <= 32 and ow.shape[1] % 64 == 0:
             ow64 = torch.zeros((64,) + tuple(ow.shape[1:]), dtype=torch.float32, device=ow.device)
             ob64 = torch.zeros(64, dtype=torch.float32, device=ow.device)
             ow64[:c_mid] = ow
@@ -144,6 +160,8 @@ class UNetInferenceEngine:
         if not x.is_cuda:
             raise _lib.Im2ImError("native UNet forward needs a CUDA tensor")
         x = x.contiguous().float()
+        if self.precision == "tf32":
+            return self._forward_tf32(x)
         with torch.cuda.device(x.device):
             a = self._conv_first(x, *self.first)
             skips: List[torch.Tensor] = [conv_igemm(a, self.inc2[0], self.inc2[1], relu=True)]
@@ -167,6 +185,59 @@ class UNetInferenceEngine:
             if self.head is None:  # heads without a native kernel (softmax: 50 planes) run their own module on the features
                 return self.model.last_layer(m.permute(0, 3, 1, 2).float())
             return self._head(m)
+
+
+def _forward_tf32(self, x: torch.Tensor) -> torch.Tensor:
+    """The same launch sequence on fp32 NHWC activations with kind::tf32 convolutions (the reference's precision)."""
+    lib = _lib.load()
+    dev = x.device
+    st = _stream(dev)
+    B, c_in, H, W = x.shape
+
+    def first(x):
+        w, b = self.first
+        y = torch.empty((B, H, W, w.shape[0]), dtype=torch.float32, device=dev)
+        _lib.check(lib.im2im_conv_first_nhwc_f32(x.data_ptr(), w.data_ptr(), b.data_ptr(), B, c_in, H, W, w.shape[0], 1,
+                                                 y.data_ptr(), st), "im2im_conv_first_nhwc_f32")
+        return y
+
+    def pool(t):
+        b_, h, w_, c = t.shape
+        y = torch.empty((b_, h // 2, w_ // 2, c), dtype=torch.float32, device=dev)
+        _lib.check(lib.im2im_maxpool2x2_nhwc_f32(t.data_ptr(), b_, h, w_, c, y.data_ptr(), st), "im2im_maxpool2x2_nhwc_f32")
+        return y
+
+    def upsample(t, ho, wo):
+        b_, h, w_, c = t.shape
+        y = torch.empty((b_, ho, wo, c), dtype=torch.float32, device=dev)
+        _lib.check(lib.im2im_upsample2x_bilinear_nhwc_f32(t.data_ptr(), b_, h, w_, c, ho, wo, y.data_ptr(), st),
+                   "im2im_upsample2x_bilinear_nhwc_f32")
+        return y
+
+    with torch.cuda.device(dev):
+        skips: List[torch.Tensor] = [conv_igemm_tf32(first(x), self.inc2[0], self.inc2[1], relu=True)]
+        for (c1, c2) in self.down:
+            p = conv_igemm_tf32(pool(skips[-1]), c1[0], c1[1], relu=True)
+            skips.append(conv_igemm_tf32(p, c2[0], c2[1], relu=True))
+        y = skips.pop()
+        for (c1, c2) in self.up:
+            skip = skips.pop()
+            u = upsample(y, skip.shape[1], skip.shape[2])
+            y = conv_igemm_tf32(skip, c1[0], c1[1], relu=True, x2=u)
+            y = conv_igemm_tf32(y, c2[0], c2[1], relu=True)
+        m = conv_igemm_tf32(y, self.out[0], self.out[1], relu=False)           # 1x1 OutConv, 64 -> 32
+        if self.head is None:
+            return self.model.last_layer(m.permute(0, 3, 1, 2))
+        hw, hb = self.head
+        n_out, c_mid = hw.shape[0], m.shape[3]
+        out = torch.empty((B, n_out, H, W), dtype=torch.float32, device=dev)
+        _lib.check(lib.im2im_head_conv3x3_act_nhwc_f32(m.data_ptr(), hw.data_ptr(), hb.data_ptr(), None, B, H, W, c_mid, c_mid,
+                                                       n_out, self.head_act[0], self.head_act[1], out.data_ptr(), st),
+                   "im2im_head_conv3x3_act_nhwc_f32")
+        return out.view(B, self.n_planes, self.c_out, H, W)
+
+
+UNetInferenceEngine._forward_tf32 = _forward_tf32
 
 
 def head_plane_convs(head):

@@ -253,6 +253,19 @@ int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void* d_x2, int
                           int32_t relu, void* d_out_bf16, float* d_out_f32, void* stream);
 
 /*
+ * The same convolution in the REFERENCE'S PRECISION: the reference's modules are fp32 (unet_parts.py:16-21, no autocast
+ * anywhere) and torch's cuDNN convolutions run them as TF32 on the GPU; here fp32 NHWC activations and fp32 weights are
+ * staged by TMA as they are and multiplied with tcgen05 kind::tf32 (fp32 accumulation), output fp32 NHWC with every value
+ * rounded (to nearest) onto the TF32 grid, so that the next layer's MMA reads exactly what was stored.
+ *   d_x1 / d_x2 : DEVICE fp32 [B,H,W,c_in1] / [B,H,W,c_in2]; channel counts multiples of 32
+ *   d_weight    : DEVICE fp32 [c_out, taps, c_in1+c_in2];  d_bias fp32 [c_out] or NULL;  d_out fp32 NHWC, c_out % 32 == 0
+ * About half the bf16 path's throughput (the TF32 tensor rate); it is the parity mode of the inference engine.
+ */
+int im2im_conv_igemm_tf32(const float* d_x1, int32_t c_in1, const float* d_x2, int32_t c_in2, const float* d_weight,
+                          const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps,
+                          int32_t relu, float* d_out, void* stream);
+
+/*
  * Weight gradient of the convolution above (autograd of nn.Conv2d inside core/models/trunks/unet_parts.py:16-21, as
  * driven by core/scripts/train.py:160 `loss.backward()`):  dW[co, tap, ci] += sum_p dZ[p, co] * X[p + shift(tap), ci].
  *   d_x  : DEVICE bf16 NHWC [B,H,W,c_in]  (the conv's input);   d_dz : DEVICE bf16 NHWC [B,H,W,c_out] (grad of its output)
@@ -294,6 +307,17 @@ int im2im_head_conv3x3_f32(const void* d_x, const float* d_weight, const float* 
 int im2im_head_conv3x3_act_f32(const void* d_x, const float* d_weight, const float* d_bias, const float* d_tap_bias,
                                int32_t B, int32_t H, int32_t W, int32_t c_mid, int32_t c_stride, int32_t n_out,
                                int32_t act_kind, int32_t act_from_plane, float* d_out, void* stream);
+/* fp32 NHWC (tf32 mode) forms of the four CUDA-core kernels above: same arithmetic, activations stored as fp32 rounded onto
+ * the TF32 grid.  unet.py:20 first conv, unet_parts.py:34 max pool, :50,:63 bilinear x2 + pad, quantile_layer.py:15-20 head. */
+int im2im_conv_first_nhwc_f32(const float* d_x, const float* d_weight, const float* d_bias, int32_t B, int32_t c_in,
+                              int32_t H, int32_t W, int32_t c_out, int32_t relu, float* d_out, void* stream);
+int im2im_maxpool2x2_nhwc_f32(const float* d_x, int32_t B, int32_t H, int32_t W, int32_t C, float* d_out, void* stream);
+int im2im_upsample2x_bilinear_nhwc_f32(const float* d_x, int32_t B, int32_t h, int32_t w, int32_t C, int32_t H_out,
+                                       int32_t W_out, float* d_out, void* stream);
+int im2im_head_conv3x3_act_nhwc_f32(const float* d_x, const float* d_weight, const float* d_bias, const float* d_tap_bias,
+                                    int32_t B, int32_t H, int32_t W, int32_t c_mid, int32_t c_stride, int32_t n_out,
+                                    int32_t act_kind, int32_t act_from_plane, float* d_out, void* stream);
+
 /* The same head on TENSOR CORES (tcgen05 halo kernel): x bf16 NHWC with exactly 64 channels per pixel (the reference's 32
  * feature channels zero-padded), d_weight bf16 [64, 9, 64] = the stacked head convolutions packed like
  * im2im_pack_conv_weights with rows >= n_real and input channels >= c_mid zero, d_bias fp32 [>= n_real] or NULL; output
