@@ -118,6 +118,9 @@ def _declare_more(lib):
     lib.im2im_host_wait_flag.argtypes = [vp, i32, i64]
     lib.im2im_conv_igemm_bf16.restype = c.c_int
     lib.im2im_conv_igemm_bf16.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.im2im_conv_igemm_bf16_stats.restype = c.c_int
+    lib.im2im_conv_igemm_bf16_stats.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp,
+                                                vp, vp, vp]
     lib.im2im_conv_igemm_tf32.restype = c.c_int
     lib.im2im_conv_igemm_tf32.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.im2im_conv_first_nhwc_f32.restype = c.c_int
@@ -156,6 +159,7 @@ def _declare_train(lib):
         "im2im_bn_finalize": [vp, i64, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp],
         "im2im_bn_apply_relu_bf16": [vp, vp, vp, i64, i32, vp, vp],
         "im2im_bn_relu_bwd_bf16": [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp],
+        "im2im_bn_relu_bwd_apply_bf16": [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp, vp],
         "im2im_maxpool2x2_bwd_bf16": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
         "im2im_upsample2x_bilinear_bwd_bf16": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
         "im2im_quantile_loss_f32": [vp, vp, i64, i64, f32, f32, f32, f32, f32, vp, vp, vp],
@@ -184,7 +188,7 @@ EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im
            "im2im_rcps_decide_p2p", "im2im_rcps_fused_workspace_bytes", "im2im_rcps_calibrate_fused",
            "im2im_host_wait_flag", "im2im_rcps_calibrate_fused_check", "im2im_conv_igemm_tf32",
            "im2im_conv_first_nhwc_f32", "im2im_maxpool2x2_nhwc_f32", "im2im_upsample2x_bilinear_nhwc_f32",
-           "im2im_head_conv3x3_act_nhwc_f32"]
+           "im2im_head_conv3x3_act_nhwc_f32", "im2im_conv_igemm_bf16_stats", "im2im_bn_relu_bwd_apply_bf16"]
 
 
 def load():

@@ -46,6 +46,34 @@ def conv_igemm(x1: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[tor
     return out
 
 
+def conv_igemm_stats(x1: torch.Tensor, weight_packed: torch.Tensor, stat_mode: int, sums: torch.Tensor,
+                     x2: Optional[torch.Tensor] = None, bn=None):
+    """conv_igemm (no bias / ReLU, bf16 out) with per-channel statistics fused into the epilogue
+    (im2im_conv_igemm_bf16_stats).  ``bn`` = (z, gamma, beta, mean, rstd) for stat_mode 2.  Returns (out, fused)."""
+    import ctypes
+    lib = _lib.load()
+    assert x1.is_cuda and x1.dtype == torch.bfloat16 and x1.is_contiguous() and x1.dim() == 4
+    B, H, W, c1 = x1.shape
+    c2 = x2.shape[3] if x2 is not None else 0
+    c_out, taps, c_in = weight_packed.shape
+    assert weight_packed.dtype == torch.bfloat16 and weight_packed.is_contiguous() and c_in == c1 + c2
+    assert sums.dtype == torch.float32 and sums.numel() >= 2 * c_out and sums.is_contiguous()
+    out = torch.empty((B, H, W, c_out), dtype=torch.bfloat16, device=x1.device)
+    z = gamma = beta = mean = rstd = None
+    if stat_mode == 2:
+        z, gamma, beta, mean, rstd = bn
+        assert z.dtype == torch.bfloat16 and z.is_contiguous() and tuple(z.shape) == (B, H, W, c_out)
+    fused = ctypes.c_int32(0)
+    ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+    with torch.cuda.device(x1.device):
+        rc = lib.im2im_conv_igemm_bf16_stats(x1.data_ptr(), c1, ptr(x2), c2, weight_packed.data_ptr(), B, H, W, c_out, taps,
+                                             out.data_ptr(), stat_mode, sums.data_ptr(), ptr(z), ptr(gamma), ptr(beta),
+                                             ptr(mean), ptr(rstd), ctypes.byref(fused),
+                                             torch.cuda.current_stream(x1.device).cuda_stream)
+    _lib.check(rc, "im2im_conv_igemm_bf16_stats")
+    return out, bool(fused.value)
+
+
 def round_to_tf32(t: torch.Tensor) -> torch.Tensor:
     """fp32 tensor rounded to nearest (ties away from zero, like cvt.rna.tf32.f32) onto the TF32 grid (10-bit mantissa)."""
     bits = t.detach().float().contiguous().view(torch.int32)

@@ -199,7 +199,9 @@ __global__ void __launch_bounds__(256, 3) bn_relu_bwd_apply_kernel(const __nv_bf
                                                                 const float* __restrict__ mean,
                                                                 const float* __restrict__ rstd,
                                                                 const float* __restrict__ sums, float inv_count,
-                                                                long long n_pix, int C, __nv_bfloat16* __restrict__ dz) {
+                                                                long long n_pix, int C, int premasked,
+                                                                __nv_bfloat16* __restrict__ dz) {
+    // premasked != 0: `dy` already is g = dy * relu_mask (written by the data-gradient convolution's fused epilogue)
     // a thread's channel group is loop-invariant (see bn_apply_relu_kernel): per-channel constants in registers.
     //   dz = sc*g - k0 - (z - mu)*k1 = sc*g + c0 - z*k1,   k0 = sc*sum(g)/M,  k1 = sc*rstd*sum(g*xhat)/M,  c0 = mu*k1 - k0
     // three resident blocks per SM (<= 85 registers) x 3 pixel groups per thread: 768 threads x 96 B in flight per SM
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(256, 3) bn_relu_bwd_apply_kernel(const __nv_bf
             unpack8(vz[u], fz);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float gj = fmaf(fz[j], sc[j], sh[j]) > 0.f ? fd[j] : 0.f;
+                const float gj = (premasked || fmaf(fz[j], sc[j], sh[j]) > 0.f) ? fd[j] : 0.f;
                 o[j] = fmaf(-fz[j], k1[j], fmaf(sc[j], gj, c0[j]));
             }
             *reinterpret_cast<uint4*>(dz + (e + u * stride) * 8) = pack8(o);
@@ -288,8 +290,23 @@ __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const __nv_bfloat16
     }
 }
 
-// Bilinear x2 (align_corners=True) + pad backward, gather form: dx[b,iy,ix,:] = sum over the (<=4x4) output pixels whose
-// bilinear footprint contains (iy,ix), with the forward's own fp32 weights.
+// Bilinear x2 (align_corners=True) + pad backward, gather form: dx[b,iy,ix,:] = sum over the (<=5x5) output pixels whose
+// bilinear footprint contains (iy,ix), with the forward's own fp32 weights.  The per-axis weights of the five candidate
+// output rows / columns (2i-2 .. 2i+2) are computed once per thread; the 25 taps are then independent predicated 16-byte
+// loads (about 16 of them live), so many loads are in flight instead of a weight computation between every two.
+__device__ __forceinline__ float upsample_axis_weight(int u, int n_out, int n_in, float scale, int i) {
+    // weight with which input index i contributes to output index u (0 when u is out of range or i is not a neighbour)
+    if (u < 0 || u >= n_out) return 0.f;
+    const float f = scale * u;
+    const int i0 = static_cast<int>(f);
+    const int i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+    const float l = f - i0;
+    float w = 0.f;
+    if (i0 == i) w += 1.f - l;
+    if (i1 == i) w += l;
+    return w;
+}
+
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ du, int B, int h, int w,
                                                              int C, int Ho, int Wo, int pad_top, int pad_left,
                                                              __nv_bfloat16* __restrict__ dx) {
@@ -302,37 +319,36 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16
         const int g = idx % groups, ix = idx / groups;
         const int iy = blockIdx.y, b = blockIdx.z;
         const long long pix = (static_cast<long long>(b) * h + iy) * w + ix;
+        float wy[5], wx[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            wy[a] = upsample_axis_weight(2 * iy - 2 + a, uh, h, sy, iy);
+            wx[a] = upsample_axis_weight(2 * ix - 2 + a, uw, w, sx, ix);
+        }
+        const __nv_bfloat16* base = du + ((static_cast<long long>(b) * Ho + (2 * iy - 2 + pad_top)) * Wo + (2 * ix - 2 + pad_left)) * C + g * 8;
+        Bf16x8 t[5][5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                t[a][c].u = make_uint4(0u, 0u, 0u, 0u);
+                if (wy[a] != 0.f && wx[c] != 0.f)
+                    t[a][c].u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(a) * Wo + c) * C);
+            }
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int uy = max(0, 2 * iy - 2); uy <= min(uh - 1, 2 * iy + 2); ++uy) {
-            const float fy = sy * uy;
-            const int y0 = static_cast<int>(fy);
-            const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
-            const float ly = fy - y0;
-            float wy = 0.f;
-            if (y0 == iy) wy += 1.f - ly;
-            if (y1 == iy) wy += ly;
-            if (wy == 0.f) continue;
-            for (int ux = max(0, 2 * ix - 2); ux <= min(uw - 1, 2 * ix + 2); ++ux) {
-                const float fx = sx * ux;
-                const int x0 = static_cast<int>(fx);
-                const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
-                const float lx = fx - x0;
-                float wx = 0.f;
-                if (x0 == ix) wx += 1.f - lx;
-                if (x1 == ix) wx += lx;
-                if (wx == 0.f) continue;
-                Bf16x8 t;
-                t.u = *reinterpret_cast<const uint4*>(
-                    du + ((static_cast<long long>(b) * Ho + uy + pad_top) * Wo + ux + pad_left) * C + g * 8);
+        // same accumulation order as the forward-difference formulation: rows outer, columns inner, fp32 FMAs
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const float wgt = wy[a] * wx[c];
                 float f[8];
-                unpack8(t, f);
-                const float wgt = wy * wx;
+                unpack8(t[a][c], f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, f[j], acc[j]);
             }
-        }
         *reinterpret_cast<uint4*>(dx + pix * C + g * 8) = pack8(acc);
     }
 }
@@ -653,26 +669,37 @@ __global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __re
         for (int j = 0; j < 8; ++j)
 #pragma unroll
             for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
-        for (long long pix = static_cast<long long>(blockIdx.x) * n_streams + stream; pix < total;
-             pix += static_cast<long long>(gridDim.x) * n_streams) {
-            const int xw = static_cast<int>(pix % W);
-            const int yh = static_cast<int>((pix / W) % H);
-            const long long b = pix / hw;
-            Bf16x8 vd;
-            vd.u = *reinterpret_cast<const uint4*>(dz + pix * c_out + g * 8);
-            float d[8];
-            unpack8(vd, d);
+        // two horizontally adjacent pixels per iteration: one 3x4 window of x (12 loads) and two 16-byte loads of dz are
+        // issued before the first FMA, and feed 2 x 72 FMAs
+        const int wp = (W + 1) / 2;
+        const long long pairs = static_cast<long long>(B) * H * wp;
+        for (long long pp = static_cast<long long>(blockIdx.x) * n_streams + stream; pp < pairs;
+             pp += static_cast<long long>(gridDim.x) * n_streams) {
+            const int xw = 2 * static_cast<int>(pp % wp);
+            const int yh = static_cast<int>((pp / wp) % H);
+            const long long b = pp / (static_cast<long long>(wp) * H);
+            const long long pix = (b * H + yh) * W + xw;
+            const bool second = xw + 1 < W;
+            Bf16x8 vd0, vd1;
+            vd0.u = *reinterpret_cast<const uint4*>(dz + pix * c_out + g * 8);
+            vd1.u = second ? *reinterpret_cast<const uint4*>(dz + (pix + 1) * c_out + g * 8) : make_uint4(0u, 0u, 0u, 0u);
             const float* xp = x + (b * c_in + ci) * hw;
-            float v[9];
+            float v[3][4];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
-                v[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + static_cast<long long>(yy) * W + xx) : 0.f;
-            }
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int yy = yh + r - 1, xx = xw + c - 1;
+                    v[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + static_cast<long long>(yy) * W + xx) : 0.f;
+                }
+            float d0[8], d1[8];
+            unpack8(vd0, d0);
+            unpack8(vd1, d1);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
 #pragma unroll
-                for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(d[j], v[t], acc[j][t]);
+                for (int t = 0; t < 9; ++t)
+                    acc[j][t] = fmaf(d1[j], v[t / 3][t % 3 + 1], fmaf(d0[j], v[t / 3][t % 3], acc[j][t]));
         }
         // block reduction over the pixel streams
         float* mine = s_red + static_cast<size_t>(stream) * c_out * 9;
@@ -747,7 +774,19 @@ extern "C" int im2im_bn_relu_bwd_bf16(const void* d_dy, const void* d_z, const f
                                                                                d_rstd, n_pix, C, d_sums);
     if (int rc = check_launch("channel_reduce_kernel<bn_bwd>")) return rc;
     bn_relu_bwd_apply_kernel<<<grid_for(n_pix * (C / 8), 256, 12), 256, 0, ST(stream)>>>(
-        BF(d_dy), BF(d_z), d_gamma, d_beta, d_mean, d_rstd, d_sums, 1.f / static_cast<float>(n_pix), n_pix, C, BFW(d_dz));
+        BF(d_dy), BF(d_z), d_gamma, d_beta, d_mean, d_rstd, d_sums, 1.f / static_cast<float>(n_pix), n_pix, C, 0, BFW(d_dz));
+    return check_launch("bn_relu_bwd_apply_kernel");
+}
+
+extern "C" int im2im_bn_relu_bwd_apply_bf16(const void* d_g, const void* d_z, const float* d_gamma, const float* d_beta,
+                                            const float* d_mean, const float* d_rstd, const float* d_sums, int64_t n_pix,
+                                            int32_t C, int32_t premasked, void* d_dz, void* stream) {
+    if (int rc = check_channels(C, "bn_relu_bwd_apply")) return rc;
+    if (n_pix <= 0 || !d_g || !d_z || !d_gamma || !d_beta || !d_mean || !d_rstd || !d_sums || !d_dz)
+        return fail(IM2IM_EINVAL, "bn_relu_bwd_apply: bad arguments");
+    bn_relu_bwd_apply_kernel<<<grid_for(n_pix * (C / 8), 256, 12), 256, 0, ST(stream)>>>(
+        BF(d_g), BF(d_z), d_gamma, d_beta, d_mean, d_rstd, d_sums, 1.f / static_cast<float>(n_pix), n_pix, C,
+        premasked ? 1 : 0, BFW(d_dz));
     return check_launch("bn_relu_bwd_apply_kernel");
 }
 

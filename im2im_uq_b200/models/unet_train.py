@@ -22,8 +22,8 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..conv import (conv_igemm, conv_wgrad, head_conv_tc, head_tc_applicable, pack_conv_weight, pack_dgrad_weight,
-                    planar_to_nhwc64)
+from ..conv import (conv_igemm, conv_igemm_stats, conv_wgrad, head_conv_tc, head_tc_applicable, pack_conv_weight,
+                    pack_dgrad_weight, planar_to_nhwc64)
 
 
 def _st(dev):
@@ -102,23 +102,39 @@ class UNetTrainEngine:
         pad = _ZeroPool.padded
         self._fwd_zero_floats = sum(pad(2 * l.c_out) for l in layers)
         self._bwd_zero_floats = (sum(2 * pad(l.c_out * 9 * l.c_in) for l in layers[1:])   # concat layers: two buffers
+                                 + sum(pad(2 * l.c_out) for l in layers)   # BatchNorm-backward sums fused into dgrad epilogues
                                  + pad(64 * 64) + pad(self.n_out * self.c_mid * 9) + pad(self.n_out) + pad(128)
                                  + pad(64 * 9 * 64)
                                  + pad(layers[0].c_out * 8 * 9))
 
     # ------------------------------------------------------------------------------------------- primitive launches
-    def _bn_relu(self, z: torch.Tensor, layer: _ConvBN, saved: dict):
+    def _conv_bn_relu(self, x: torch.Tensor, layer: _ConvBN, saved: dict, x2: Optional[torch.Tensor] = None):
+        """conv3x3 on tensor cores -> BatchNorm (batch statistics) -> ReLU.  Where the layer runs on the halo kernel the
+        statistics come out of the convolution's epilogue (im2im_conv_igemm_bf16_stats): no separate pass over z."""
+        pool = self.__dict__.get("_zero")
+        C = layer.c_out
+        sums = pool.take(2 * C) if pool is not None else torch.zeros(2 * C, dtype=torch.float32, device=x.device)
+        if getattr(self, "fuse_stats", True):
+            z, fused = conv_igemm_stats(x, layer.w_fwd, 1, sums, x2=x2)
+        else:
+            z, fused = conv_igemm(x, layer.w_fwd, x2=x2), False
+        return self._bn_relu(z, layer, saved, sums=sums, have_stats=fused)
+
+    def _bn_relu(self, z: torch.Tensor, layer: _ConvBN, saved: dict, sums: Optional[torch.Tensor] = None,
+                 have_stats: bool = False):
         lib, dev = self.lib, z.device
         B, H, W, C = z.shape
         n_pix = B * H * W
         bn = layer.bn
         pool = self.__dict__.get("_zero")     # set by forward(); a direct call (unit tests) allocates its own
-        sums = pool.take(2 * C) if pool is not None else torch.zeros(2 * C, dtype=torch.float32, device=dev)
+        if sums is None:
+            sums = pool.take(2 * C) if pool is not None else torch.zeros(2 * C, dtype=torch.float32, device=dev)
         scale = torch.empty(C, dtype=torch.float32, device=dev)
         shift = torch.empty_like(scale)
         rstd = torch.empty_like(scale)
         mean = torch.empty_like(scale)
-        _lib.check(lib.im2im_channel_stats_bf16(z.data_ptr(), n_pix, C, sums.data_ptr(), _st(dev)), "channel_stats")
+        if not have_stats:
+            _lib.check(lib.im2im_channel_stats_bf16(z.data_ptr(), n_pix, C, sums.data_ptr(), _st(dev)), "channel_stats")
         momentum = bn.momentum if bn.momentum is not None else 0.1
         track = bn.track_running_stats and bn.running_mean is not None
         _lib.check(lib.im2im_bn_finalize(sums.data_ptr(), n_pix, _ptr(layer.conv.bias), bn.weight.data_ptr(),
@@ -202,16 +218,16 @@ class UNetTrainEngine:
             s0 = {}
             y0 = self._bn_relu(z, first, s0)
             s1 = {"x_in": y0}
-            x1 = self._bn_relu(conv_igemm(y0, self.inc[1].w_fwd), self.inc[1], s1)
+            x1 = self._conv_bn_relu(y0, self.inc[1], s1)
             ctx["inc"] = (s0, s1)
             skips = [x1]
             ctx["down"] = []
             for (a, b) in self.down:
                 p = self._pool(skips[-1])
                 sa = {"x_in": p}
-                ya = self._bn_relu(conv_igemm(p, a.w_fwd), a, sa)
+                ya = self._conv_bn_relu(p, a, sa)
                 sb = {"x_in": ya}
-                skips.append(self._bn_relu(conv_igemm(ya, b.w_fwd), b, sb))
+                skips.append(self._conv_bn_relu(ya, b, sb))
                 ctx["down"].append((sa, sb))
             ctx["skips"] = list(skips)
             y = skips.pop()
@@ -220,9 +236,9 @@ class UNetTrainEngine:
                 skip = skips.pop()
                 u = self._upsample_to(y, skip.shape[1], skip.shape[2])
                 sa = {"x_in": skip, "x_in2": u, "low_shape": tuple(y.shape)}
-                ya = self._bn_relu(conv_igemm(skip, a.w_fwd, x2=u), a, sa)
+                ya = self._conv_bn_relu(skip, a, sa, x2=u)
                 sb = {"x_in": ya}
-                y = self._bn_relu(conv_igemm(ya, b.w_fwd), b, sb)
+                y = self._conv_bn_relu(ya, b, sb)
                 ctx["up"].append((sa, sb))
             # 1x1 out conv, output channels zero-padded 32 -> 64 so the result feeds the 64-channel kernels
             w_out = self.out_conv.weight.detach()
@@ -274,8 +290,13 @@ class UNetTrainEngine:
         return out.view(B, self.n_planes, self.c_head, H, W), ctx
 
     # ------------------------------------------------------------------------------------------- backward
-    def _conv_bwd(self, layer: _ConvBN, saved: dict, dz: torch.Tensor, grads: Dict, need_dx: bool = True):
+    def _conv_bwd(self, layer: _ConvBN, saved: dict, dz: torch.Tensor, grads: Dict, need_dx: bool = True,
+                  bn_next=None):
         """wgrad (+ dgrad) of a tensor-core conv layer; returns (dx for x_in, dx for x_in2 or None).
+
+        ``bn_next`` = (layer, saved) of the BatchNorm+ReLU layer whose output is this conv's (single) input: its backward
+        is then folded in - the data gradient's epilogue applies the ReLU mask and accumulates the two per-channel sums
+        (im2im_conv_igemm_bf16_stats, stat_mode 2), one apply pass finishes - and the first return value is that layer's dz.
 
         The weight gradient is off the critical path (nothing downstream in the backward pass reads it), so it is
         enqueued on a side stream: the tensor-bound wgrad GEMMs overlap the bandwidth-bound BatchNorm/ReLU backward
@@ -298,6 +319,28 @@ class UNetTrainEngine:
                 t.record_stream(side)
         if not need_dx:
             return None, None
+        if x2 is None and bn_next is not None:
+            la, sa = bn_next
+            C = la.c_out
+            bn = la.bn
+            sums = self._zero.take(2 * C)
+            if getattr(self, "fuse_stats", True):
+                g, fused = conv_igemm_stats(dz, layer.w_bwd, 2, sums,
+                                            bn=(sa["z"], bn.weight.detach(), bn.bias.detach(), sa["mean"], sa["rstd"]))
+            else:
+                g, fused = conv_igemm(dz, layer.w_bwd), False
+            if not fused:
+                return self._bn_relu_bwd(g, la, sa, grads), None
+            z = sa["z"]
+            dza = torch.empty_like(z)
+            n_pix = z.shape[0] * z.shape[1] * z.shape[2]
+            _lib.check(self.lib.im2im_bn_relu_bwd_apply_bf16(g.data_ptr(), z.data_ptr(), bn.weight.data_ptr(),
+                                                             bn.bias.data_ptr(), sa["mean"].data_ptr(), sa["rstd"].data_ptr(),
+                                                             sums.data_ptr(), n_pix, C, 1, dza.data_ptr(), _st(dz.device)),
+                       "bn_relu_bwd_apply")
+            grads[bn.bias] = sums[:C]
+            grads[bn.weight] = sums[C:]
+            return dza, None
         if x2 is None:
             return conv_igemm(dz, layer.w_bwd), None
         c1 = x1.shape[3]
@@ -348,8 +391,7 @@ class UNetTrainEngine:
             for k in range(3, -1, -1):
                 (a, b), (sa, sb) = self.up[k], ctx["up"][k]
                 dz = self._bn_relu_bwd(dy, b, sb, grads)
-                d_ya, _ = self._conv_bwd(b, sb, dz, grads)
-                dz = self._bn_relu_bwd(d_ya, a, sa, grads)
+                dz, _ = self._conv_bwd(b, sb, dz, grads, bn_next=(a, sa))     # dz of layer a
                 d_skip, d_u = self._conv_bwd(a, sa, dz, grads)
                 skip_grads[3 - k] = d_skip                              # up1 uses x4, ..., up4 uses x1
                 lb, lh, lw, lc = sa["low_shape"]
@@ -361,8 +403,7 @@ class UNetTrainEngine:
             for k in range(3, -1, -1):
                 (a, b), (sa, sb) = self.down[k], ctx["down"][k]
                 dz = self._bn_relu_bwd(dy, b, sb, grads)
-                d_ya, _ = self._conv_bwd(b, sb, dz, grads)
-                dz = self._bn_relu_bwd(d_ya, a, sa, grads)
+                dz, _ = self._conv_bwd(b, sb, dz, grads, bn_next=(a, sa))     # dz of layer a
                 d_p, _ = self._conv_bwd(a, sa, dz, grads)
                 src = skips[k]                                          # input of this block's max-pool
                 dy = skip_grads[k]                                      # gradient from the up path, accumulated into
@@ -372,8 +413,7 @@ class UNetTrainEngine:
             # inc block
             s0, s1 = ctx["inc"]
             dz = self._bn_relu_bwd(dy, self.inc[1], s1, grads)
-            d_y0, _ = self._conv_bwd(self.inc[1], s1, dz, grads)
-            dz0 = self._bn_relu_bwd(d_y0, self.inc[0], s0, grads)
+            dz0, _ = self._conv_bwd(self.inc[1], s1, dz, grads, bn_next=(self.inc[0], s0))
             first = self.inc[0]
             dw0 = self._zero.take(first.c_out, c_in, 3, 3)
             _lib.check(lib.im2im_conv_first_wgrad(x.data_ptr(), dz0.data_ptr(), B, c_in, H, W, first.c_out,

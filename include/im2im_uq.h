@@ -253,6 +253,26 @@ int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void* d_x2, int
                           int32_t relu, void* d_out_bf16, float* d_out_f32, void* stream);
 
 /*
+ * im2im_conv_igemm_bf16 (no bias, no ReLU, bf16 output) with per-channel statistics accumulated in the convolution's
+ * epilogue, from the bf16 values it stores - one pass over the activations less per BatchNorm layer of the training step
+ * (core/models/trunks/unet_parts.py:17,20 in train mode; autograd of the same in core/scripts/train.py:160):
+ *   stat_mode 1 (forward)   d_stat_sums[c] += z, d_stat_sums[c_out + c] += z*z      = im2im_channel_stats_bf16 of the output
+ *   stat_mode 2 (backward)  the convolution is a data gradient whose output dy feeds BatchNorm+ReLU backward of the layer
+ *                           with saved pre-normalisation output d_bn_z [B,H,W,c_out] and (gamma, beta, mean, rstd):
+ *                           g = dy * (bn_z*gamma*rstd + beta - mean*gamma*rstd > 0) is stored INSTEAD of dy, and
+ *                           d_stat_sums[c] += g, d_stat_sums[c_out + c] += rstd*(sum(g*bn_z) - mean*sum(g))
+ *                           (the reduction half of im2im_bn_relu_bwd_bf16; finish with im2im_bn_relu_bwd_apply_bf16).
+ * d_stat_sums is ACCUMULATED into (zero it first).  *h_fused (HOST int) = 1 when the statistics were produced (the layer
+ * ran on the halo kernel); 0 means only the convolution ran - stored values are then plain dy / z and the caller runs the
+ * separate reduction.
+ */
+int im2im_conv_igemm_bf16_stats(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2, const void* d_weight,
+                                int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps, void* d_out_bf16,
+                                int32_t stat_mode, float* d_stat_sums, const void* d_bn_z, const float* d_bn_gamma,
+                                const float* d_bn_beta, const float* d_bn_mean, const float* d_bn_rstd, int32_t* h_fused,
+                                void* stream);
+
+/*
  * The same convolution in the REFERENCE'S PRECISION: the reference's modules are fp32 (unet_parts.py:16-21, no autocast
  * anywhere) and torch's cuDNN convolutions run them as TF32 on the GPU; here fp32 NHWC activations and fp32 weights are
  * staged by TMA as they are and multiplied with tcgen05 kind::tf32 (fp32 accumulation), output fp32 NHWC with every value
@@ -360,6 +380,11 @@ int im2im_bn_apply_relu_bf16(const void* d_z, const float* d_scale, const float*
 int im2im_bn_relu_bwd_bf16(const void* d_dy, const void* d_z, const float* d_gamma, const float* d_beta,
                            const float* d_mean, const float* d_rstd, int64_t n_pix, int32_t C, float* d_sums, void* d_dz,
                            void* stream);
+/* The second half of im2im_bn_relu_bwd_bf16 on its own: dz from sums that are already complete.  premasked != 0: d_g is
+ * g = dy * relu_mask as written by im2im_conv_igemm_bf16_stats(stat_mode 2), which also produced d_sums. */
+int im2im_bn_relu_bwd_apply_bf16(const void* d_g, const void* d_z, const float* d_gamma, const float* d_beta,
+                                 const float* d_mean, const float* d_rstd, const float* d_sums, int64_t n_pix, int32_t C,
+                                 int32_t premasked, void* d_dz, void* stream);
 int im2im_maxpool2x2_bwd_bf16(const void* d_x, const void* d_dy, int32_t B, int32_t H, int32_t W, int32_t C,
                               int32_t accumulate, void* d_dx, void* stream);
 int im2im_upsample2x_bilinear_bwd_bf16(const void* d_du, int32_t B, int32_t h, int32_t w, int32_t C, int32_t H_out,

@@ -173,3 +173,73 @@ def test_fused_adam_matches_torch_adam():
         ours.step(); ref.step()
         for p, q in zip(ps, qs):
             np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=2e-6, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------- statistics fused into conv epilogues
+@pytest.mark.parametrize("c1,c2,cout,shape", [(64, 0, 64, (2, 32, 48)), (64, 64, 64, (3, 16, 16)), (64, 0, 128, (2, 32, 16)),
+                                              (128, 0, 128, (1, 48, 40)), (128, 0, 256, (2, 16, 8))])
+def test_conv_epilogue_batch_statistics(c1, c2, cout, shape):
+    """im2im_conv_igemm_bf16_stats mode 1: output identical to the plain convolution; sums = channel sums / sums of squares
+    of the stored bf16 output (what im2im_channel_stats_bf16 would compute in a second pass)."""
+    from im2im_uq_b200.conv import conv_igemm, conv_igemm_stats, pack_conv_weight
+    B, H, W = shape
+    g = torch.Generator(device=DEV).manual_seed(4)
+    x1 = _nhwc(torch.randn(B, c1, H, W, device=DEV, generator=g))
+    x2 = _nhwc(torch.randn(B, c2, H, W, device=DEV, generator=g)) if c2 else None
+    w = pack_conv_weight(torch.randn(cout, c1 + c2, 3, 3, device=DEV, generator=g) / (9 * (c1 + c2)) ** 0.5)
+    sums = torch.zeros(2 * cout, device=DEV)
+    z, fused = conv_igemm_stats(x1, w, 1, sums, x2=x2)
+    assert fused                                           # every shape here is a halo-kernel layer
+    assert torch.equal(z, conv_igemm(x1, w, x2=x2))
+    zf = z.float().reshape(-1, cout)
+    _close(sums[:cout], zf.sum(0), 2e-5)
+    _close(sums[cout:], (zf * zf).sum(0), 2e-5)
+    # accumulates: a second call doubles the sums
+    conv_igemm_stats(x1, w, 1, sums, x2=x2)
+    _close(sums[:cout], 2 * zf.sum(0), 2e-5)
+
+
+def test_conv_epilogue_statistics_fall_back_off_the_halo_kernel():
+    from im2im_uq_b200.conv import conv_igemm, conv_igemm_stats, pack_conv_weight
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = _nhwc(torch.randn(2, 512, 20, 20, device=DEV, generator=g))     # 20x20: not an 8x16-tile shape
+    w = pack_conv_weight(torch.randn(512, 512, 3, 3, device=DEV, generator=g) / 70)
+    sums = torch.zeros(1024, device=DEV)
+    z, fused = conv_igemm_stats(x, w, 1, sums)
+    assert not fused and float(sums.abs().max()) == 0.0 and torch.equal(z, conv_igemm(x, w))
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(64, 64, (2, 32, 48)), (128, 64, (2, 32, 16)), (128, 128, (1, 48, 40))])
+def test_dgrad_epilogue_batchnorm_backward_sums(cin, cout, shape):
+    """stat_mode 2: the data-gradient convolution stores g = dy * relu_mask and the two BatchNorm-backward sums; followed by
+    the apply pass it must equal the unfused conv -> im2im_bn_relu_bwd_bf16 sequence."""
+    from im2im_uq_b200.conv import conv_igemm, conv_igemm_stats, pack_conv_weight
+    B, H, W = shape
+    g = torch.Generator(device=DEV).manual_seed(6)
+    dz_in = _nhwc(torch.randn(B, cin, H, W, device=DEV, generator=g))
+    w = pack_conv_weight(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) / (9 * cin) ** 0.5)
+    z = _nhwc(torch.randn(B, cout, H, W, device=DEV, generator=g) * 1.3 + 0.2)
+    gamma = torch.rand(cout, device=DEV, generator=g) + 0.5
+    beta = torch.rand(cout, device=DEV, generator=g) - 0.5
+    zf = z.float().reshape(-1, cout)
+    mean = zf.mean(0).contiguous()
+    rstd = (1.0 / torch.sqrt(zf.var(0, unbiased=False) + 1e-5)).contiguous()
+    n_pix = B * H * W
+    # unfused reference path
+    dy = conv_igemm(dz_in, w)
+    sums_ref = torch.empty(2 * cout, device=DEV)
+    dz_ref = torch.empty_like(z)
+    _lib.check(LIB.im2im_bn_relu_bwd_bf16(dy.data_ptr(), z.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
+                                          rstd.data_ptr(), n_pix, cout, sums_ref.data_ptr(), dz_ref.data_ptr(), _st()))
+    # fused path
+    sums = torch.zeros(2 * cout, device=DEV)
+    gm, fused = conv_igemm_stats(dz_in, w, 2, sums, bn=(z, gamma, beta, mean, rstd))
+    assert fused
+    sc = gamma * rstd
+    mask = (zf * sc + (beta - mean * sc)) > 0
+    assert torch.equal(gm.reshape(-1, cout), torch.where(mask, dy.reshape(-1, cout), torch.zeros_like(dy.reshape(-1, cout))))
+    _close(sums, sums_ref, 5e-5)
+    dz = torch.empty_like(z)
+    _lib.check(LIB.im2im_bn_relu_bwd_apply_bf16(gm.data_ptr(), z.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
+                                                rstd.data_ptr(), sums.data_ptr(), n_pix, cout, 1, dz.data_ptr(), _st()))
+    _close(dz.float(), dz_ref.float(), 1e-2)

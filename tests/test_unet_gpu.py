@@ -147,8 +147,8 @@ def test_conv_igemm_tf32_vs_torch_fp32(c1, c2, cout, taps, shape):
     nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
     got = conv_igemm_tf32(nhwc(x1), pack_conv_weight_tf32(wt), bias, relu=True, x2=nhwc(x2) if x2 is not None else None)
     got = got.permute(0, 3, 1, 2)
-    # outputs are rounded onto the TF32 grid (2^-11 relative) on store
-    assert ((got - ref).abs() <= 6e-4 * ref.abs() + 2e-5).all(), float((got - ref).abs().max())
+    # outputs are rounded onto the TF32 grid on store (half an ulp = 2^-11 = 4.9e-4 relative); the rest is fp32 accumulation order
+    assert ((got - ref).abs() <= 5.2e-4 * ref.abs() + 1e-4).all(), float((got - ref).abs().max())
 
 
 def test_tf32_forward_matches_reference_output():
