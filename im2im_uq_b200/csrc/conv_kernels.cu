@@ -498,9 +498,8 @@ struct HaloParams {
     // [B, n_real, H, W] (the reference's (B, planes, C, H, W) head tensor), planes >= act_from get act_kind (1 relu, 2 abs)
     float* out_planar;
     int n_real, act_kind, act_from;
-    // bf16 output: the tile is staged through shared memory (per epilogue warp: 32 pixels x 32 channels) and written with
-    // 16-byte stores whose lanes cover whole 64-byte runs, instead of 16 bytes per lane at a 128/256-byte stride.
-    // Per-channel statistics can be accumulated on the way out (training), from the bf16 values that are stored:
+    // Per-channel statistics can be accumulated on the way out (training), from the bf16 values that are stored; each
+    // epilogue thread keeps the partial sums of its pixel row for all 64 channels in registers until the end of the kernel:
     //   stat_mode 1  sums[c] += z, sums[C+c] += z*z                         BatchNorm batch statistics of this conv's output
     //   stat_mode 2  this conv is a data gradient producing dy for a BatchNorm+ReLU layer whose pre-normalisation output is
     //                bn_z: g = dy * (bn_z*scale + shift > 0) is stored INSTEAD of dy, and
@@ -511,8 +510,7 @@ struct HaloParams {
     const float* bn_gamma; const float* bn_beta; const float* bn_mean; const float* bn_rstd;
 };
 
-constexpr int kHaloStageCols = 32;                                   // channels per staging pass
-constexpr int kHaloStagingBytes = 128 * kHaloStageCols * 2;          // 4 epilogue warps x 32 pixels x 64 B = 8 KB
+constexpr int kHaloStatBn = 64;      // fused statistics need the per-thread accumulators in registers: N tile of 64
 
 constexpr int kHaloW = 16, kHaloH = 18, kHaloTileW = 8, kHaloTileH = 16;
 constexpr int kHaloBytes = kHaloW * kHaloH * kKStep * 2;  // 36864
@@ -548,9 +546,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     uint64_t* tmem_full = w_bar + 1;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    // [staging 8 KB, 16-byte aligned][scale bn f32][shift bn f32] after the barrier block (64 B reserved for 2*stages+5 words)
-    unsigned char* staging = reinterpret_cast<unsigned char*>(full_bar) + 128;
-    float* s_scale = reinterpret_cast<float*>(staging + kHaloStagingBytes);
+    // behind the barrier block (128 B reserved): [scale bn f32][shift bn f32] for stat_mode 2
+    float* s_scale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(full_bar) + 128);
     float* s_shift = s_scale + p.bn;
 
     const int warp = threadIdx.x >> 5;
@@ -654,15 +651,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         const int iw = row % kHaloTileW, ih = row / kHaloTileW;
         unsigned full_phase = 0u;
         int buf = 0;
-        constexpr int kMaxGroups = 4;                      // bn <= 128: up to four 32-channel staging passes per tile
-        const bool staged = p.out_bf16 != nullptr && p.out_f32 == nullptr && p.out_planar == nullptr;
-        const int n_groups = p.bn / 32;
-        // per-thread partial statistics of its fixed 8 channels (chunk lane&3) of every column group, over all tiles
-        float acc0[kMaxGroups][8], acc1[kMaxGroups][8];
+        // fused statistics (bn == 64 only): this thread's partial sums over its pixel row of every tile, all 64 channels
+        float acc0[kHaloStatBn], acc1[kHaloStatBn];
 #pragma unroll
-        for (int gi = 0; gi < kMaxGroups; ++gi)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc0[gi][j] = acc1[gi][j] = 0.f;
+        for (int j = 0; j < kHaloStatBn; ++j) acc0[j] = acc1[j] = 0.f;
         for (int tile = blockIdx.x; tile < n_tiles_m; tile += gridDim.x) {
             int t = tile;
             const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -701,92 +693,62 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 buf ^= 1;
                 continue;
             }
-            if (staged) {
-                // ---- staged bf16 epilogue (+ fused per-channel statistics)
-                const int tile_w0 = tw * kHaloTileW, tile_h0 = th * kHaloTileH;
-                unsigned char* my_stage = staging + quad * (32 * kHaloStageCols * 2);
-                // stat_mode 2: this thread's bn_z chunks of the whole tile are requested now, in the shadow of the MMAs
-                uint4 zreg[kMaxGroups][4];
-                if (p.stat_mode == 2) {
+            if (p.stat_mode != 0) {
+                // ---- bf16 output + fused per-channel statistics, registers only (bn == 64): this kernel is bound by shared-
+                // memory bandwidth (operand reads of N = 64 MMAs + the TMA fill), so the epilogue must not touch shared memory
+                // - measured: staging the tile for coalesced / TMA stores made it slower, not faster
+                uint4 zreg[kHaloStatBn / 8];
+                if (p.stat_mode == 2) {   // this thread's bn_z row (its pixel, 64 channels), requested in the shadow of the MMAs
+                    const uint4* zsrc = reinterpret_cast<const uint4*>(p.bn_z + pix * p.c_out + n0);
 #pragma unroll
-                    for (int gi = 0; gi < kMaxGroups; ++gi)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (gi < n_groups) {
-                                const int pr = 8 * i + (lane >> 2);
-                                const int rr = quad * 32 + pr;
-                                const size_t px_ = (static_cast<size_t>(b) * p.H + tile_h0 + rr / kHaloTileW) * p.W + tile_w0 + rr % kHaloTileW;
-                                zreg[gi][i] = __ldg(reinterpret_cast<const uint4*>(p.bn_z + px_ * p.c_out + n0 + gi * 32 + (lane & 3) * 8));
-                            }
+                    for (int q = 0; q < kHaloStatBn / 8; ++q) zreg[q] = __ldg(zsrc + q);
                 }
 #pragma unroll
-                for (int gi = 0; gi < kMaxGroups; ++gi) {
-                    if (gi >= n_groups) break;
-                    const int c = gi * 32;
+                for (int hh = 0; hh < kHaloStatBn / 32; ++hh) {
+                    const int c = hh * 32;
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(tmem_acc + static_cast<uint32_t>(c), v);
                     tmem_ld_wait();
-                    if (gi == n_groups - 1) {   // last read of this accumulator: hand it back to the MMA warp
+                    if (hh == kHaloStatBn / 32 - 1) {   // last read of this accumulator: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                     }
-                    // registers -> bf16 -> staging row `lane` (64 B); 16-byte slot = chunk ^ ((row >> 1) & 3): conflict-free
+                    uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.c_out + n0 + c);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float f[8];
+                        __nv_bfloat162 h2[4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float x = __uint_as_float(v[8 * q + j]);
-                            if (p.bias) x += __ldg(p.bias + n0 + c + 8 * q + j);
-                            if (p.relu) x = fmaxf(x, 0.f);
-                            f[j] = x;
-                        }
-                        uint4 pk;
-                        __nv_bfloat162 h0_ = __floats2bfloat162_rn(f[0], f[1]), h1_ = __floats2bfloat162_rn(f[2], f[3]);
-                        __nv_bfloat162 h2_ = __floats2bfloat162_rn(f[4], f[5]), h3_ = __floats2bfloat162_rn(f[6], f[7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0_); pk.y = *reinterpret_cast<uint32_t*>(&h1_);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2_); pk.w = *reinterpret_cast<uint32_t*>(&h3_);
-                        *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = pk;
-                    }
-                    __syncwarp();
-                    // read phase: store instruction i covers pixels 8i .. 8i+7 of this warp's 32, 4 lanes x 16 B = 64 B each
-                    const int ch = lane & 3;
+                        for (int j = 0; j < 4; ++j)
+                            h2[j] = __floats2bfloat162_rn(__uint_as_float(v[8 * q + 2 * j]), __uint_as_float(v[8 * q + 2 * j + 1]));
+                        if (p.stat_mode == 1) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int pr = 8 * i + (lane >> 2);
-                        uint4 val = *reinterpret_cast<const uint4*>(my_stage + pr * 64 + ((ch ^ ((pr >> 1) & 3)) << 4));
-                        const int rr = quad * 32 + pr;
-                        const size_t px_ = (static_cast<size_t>(b) * p.H + tile_h0 + rr / kHaloTileW) * p.W + tile_w0 + rr % kHaloTileW;
-                        if (p.stat_mode != 0) {
-                            const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&val);
-                            float f[8];
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 r = __bfloat1622float2(h2[j]);      // the values as stored
+                                const int cc = c + 8 * q + 2 * j;
+                                acc0[cc] += r.x; acc1[cc] = fmaf(r.x, r.x, acc1[cc]);
+                                acc0[cc + 1] += r.y; acc1[cc + 1] = fmaf(r.y, r.y, acc1[cc + 1]);
+                            }
+                        } else {
+                            const __nv_bfloat162* hz = reinterpret_cast<const __nv_bfloat162*>(&zreg[hh * 4 + q]);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) { const float2 t2 = __bfloat1622float2(hv[j]); f[2 * j] = t2.x; f[2 * j + 1] = t2.y; }
-                            if (p.stat_mode == 1) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) { acc0[gi][j] += f[j]; acc1[gi][j] = fmaf(f[j], f[j], acc1[gi][j]); }
-                            } else {
-                                const __nv_bfloat162* hz = reinterpret_cast<const __nv_bfloat162*>(&zreg[gi][i]);
-                                float z[8], gm[8];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) { const float2 t2 = __bfloat1622float2(hz[j]); z[2 * j] = t2.x; z[2 * j + 1] = t2.y; }
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const int cc = c + ch * 8 + j;
-                                    gm[j] = fmaf(z[j], s_scale[cc], s_shift[cc]) > 0.f ? f[j] : 0.f;   // ReLU mask as the forward saw it
-                                    acc0[gi][j] += gm[j];
-                                    acc1[gi][j] = fmaf(gm[j], z[j], acc1[gi][j]);
-                                }
-                                __nv_bfloat162 g0 = __floats2bfloat162_rn(gm[0], gm[1]), g1 = __floats2bfloat162_rn(gm[2], gm[3]);
-                                __nv_bfloat162 g2 = __floats2bfloat162_rn(gm[4], gm[5]), g3 = __floats2bfloat162_rn(gm[6], gm[7]);
-                                val.x = *reinterpret_cast<uint32_t*>(&g0); val.y = *reinterpret_cast<uint32_t*>(&g1);
-                                val.z = *reinterpret_cast<uint32_t*>(&g2); val.w = *reinterpret_cast<uint32_t*>(&g3);
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 r = __bfloat1622float2(h2[j]);
+                                const float2 z2 = __bfloat1622float2(hz[j]);
+                                const int cc = c + 8 * q + 2 * j;
+                                // ReLU mask exactly as the forward saw it; g replaces dy in the stored tensor
+                                const float g0 = fmaf(z2.x, s_scale[cc], s_shift[cc]) > 0.f ? r.x : 0.f;
+                                const float g1 = fmaf(z2.y, s_scale[cc + 1], s_shift[cc + 1]) > 0.f ? r.y : 0.f;
+                                acc0[cc] += g0; acc1[cc] = fmaf(g0, z2.x, acc1[cc]);
+                                acc0[cc + 1] += g1; acc1[cc + 1] = fmaf(g1, z2.y, acc1[cc + 1]);
+                                h2[j] = __floats2bfloat162_rn(g0, g1);
                             }
                         }
-                        *reinterpret_cast<uint4*>(p.out_bf16 + px_ * p.c_out + n0 + c + ch * 8) = val;
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<uint32_t*>(&h2[0]); pk.y = *reinterpret_cast<uint32_t*>(&h2[1]);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2[2]); pk.w = *reinterpret_cast<uint32_t*>(&h2[3]);
+                        if (in_range) dst[q] = pk;
                     }
-                    __syncwarp();   // the staging rows are rewritten by the next column group
                 }
                 buf ^= 1;
                 continue;
@@ -832,22 +794,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             }
             buf ^= 1;
         }
-        if (staged && p.stat_mode != 0) {
-            // lanes with equal (lane & 3) hold partial sums of the same 8 channels: butterfly over lane bits 2..4, then one
-            // global atomicAdd per channel and warp
+        {
+            if (p.stat_mode != 0) {
+                // column sums over the 32 pixel rows of this warp (butterfly), then one global atomicAdd per channel and warp
 #pragma unroll
-            for (int gi = 0; gi < kMaxGroups; ++gi) {
-                if (gi >= n_groups) break;
+                for (int j = 0; j < kHaloStatBn; ++j) {
+                    float a0 = acc0[j], a1 = acc1[j];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float a0 = acc0[gi][j], a1 = acc1[gi][j];
-#pragma unroll
-                    for (int o = 4; o < 32; o <<= 1) {
+                    for (int o = 16; o > 0; o >>= 1) {
                         a0 += __shfl_xor_sync(0xffffffffu, a0, o);
                         a1 += __shfl_xor_sync(0xffffffffu, a1, o);
                     }
-                    if (lane < 4) {
-                        const int ch_g = n0 + gi * 32 + lane * 8 + j;
+                    if (lane == (j & 31)) {
+                        const int ch_g = n0 + j;
                         if (p.stat_mode == 2) a1 = p.bn_rstd[ch_g] * (a1 - p.bn_mean[ch_g] * a0);
                         atomicAdd(p.stat_sums + ch_g, a0);
                         atomicAdd(p.stat_sums + p.c_out + ch_g, a1);
@@ -1289,23 +1248,23 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
     static const bool no_halo = (getenv("IM2IM_CONV_NO_HALO") != nullptr);
     if (!no_halo && taps == 9 && W % kHaloTileW == 0 && H % kHaloTileH == 0) {
         const int c_in = c_in1 + c_in2;
+        const bool staged = d_out_bf16 != nullptr && d_out_f32 == nullptr;
+        const bool want_stats = staged && fs.mode != 0;
         int hbn = 0;
         for (int cand : {128, 64})
-            if (hbn == 0 && c_out % cand == 0 && 9ll * c_in * cand * 2 <= 147456) hbn = cand;
+            if (hbn == 0 && c_out % cand == 0 && 9ll * c_in * cand * 2 <= 147456 && !(want_stats && cand != kHaloStatBn)) hbn = cand;
         if (hbn != 0) {
             HaloParams h{};
             h.c_in1 = c_in1; h.c_in2 = c_in2; h.c_out = c_out; h.B = B; h.H = H; h.W = W;
             h.tiles_w = W / kHaloTileW; h.tiles_h = H / kHaloTileH; h.bn = hbn; h.relu = relu; h.bias = d_bias;
             h.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16); h.out_f32 = d_out_f32;
             h.out_planar = nullptr; h.n_real = 0; h.act_kind = 0; h.act_from = 0;
-            const bool staged = d_out_bf16 != nullptr && d_out_f32 == nullptr;
-            if (staged && fs.mode != 0) {
+            if (want_stats) {
                 h.stat_mode = fs.mode; h.stat_sums = fs.sums; h.bn_z = static_cast<const __nv_bfloat16*>(fs.bn_z);
                 h.bn_gamma = fs.gamma; h.bn_beta = fs.beta; h.bn_mean = fs.mean; h.bn_rstd = fs.rstd;
             }
             const int w_bytes = 9 * c_in * hbn * 2;
-            // barriers (128 B) + staging (8 KB) + scale/shift (2 x bn floats) sit behind the ring
-            const int tail_bytes = 128 + kHaloStagingBytes + 2 * hbn * 4;
+            const int tail_bytes = 128 + 2 * hbn * 4;      // barriers + scale/shift behind the A ring
             h.a_stages = (232448 - 1024 - w_bytes - tail_bytes) / kHaloBytes;
             if (h.a_stages > 4) h.a_stages = 4;
             if (h.a_stages >= 2) {
@@ -1451,8 +1410,7 @@ extern "C" int im2im_head_conv3x3_tc_f32(const void* d_x, const void* d_weight, 
     if (rc) return rc;
     rc = make_weight_map(&hw, d_weight, 64, 9 * 64, h.bn);
     if (rc) return rc;
-    const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * kHaloBytes + 128 +
-                         kHaloStagingBytes + 2 * h.bn * 4 + 1024;
+    const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * kHaloBytes + 128 + 2 * h.bn * 4 + 1024;
     IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
     const long long m_tiles = static_cast<long long>(h.tiles_w) * h.tiles_h * B;
     long long gx = sm_count();

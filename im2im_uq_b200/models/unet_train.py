@@ -324,7 +324,10 @@ class UNetTrainEngine:
             C = la.c_out
             bn = la.bn
             sums = self._zero.take(2 * C)
-            if getattr(self, "fuse_stats", True):
+            # Measured on B200 (tools/halo_modes_bench.py, batch 78): the backward fusion costs the halo kernel more (the
+            # epilogue's bn_z reads: +0.38 ms on 64->64 @320^2) than the separate reduction pass it replaces, so it is off by
+            # default; the forward fusion (stat_mode 1) is +6 % on the convolution and replaces a full pass over z.
+            if getattr(self, "fuse_bwd_stats", False):
                 g, fused = conv_igemm_stats(dz, layer.w_bwd, 2, sums,
                                             bn=(sa["z"], bn.weight.detach(), bn.bias.detach(), sa["mean"], sa["rstd"]))
             else:

@@ -69,6 +69,33 @@ def test_native_step_is_as_close_to_fp32_as_bf16_autocast():
             assert float(gr.abs().max()) == 0.0 and float(g_ref[n].abs().max()) < 1e-5
 
 
+def test_backward_stat_fusion_matches_separate_reduction():
+    """The optional BatchNorm-backward fusion into the data-gradient epilogues (engine.fuse_bwd_stats) and the forward
+    statistics fusion (engine.fuse_stats) change where sums are computed, not what is computed."""
+    g = torch.Generator(device="cuda:0").manual_seed(4)
+    x = torch.randn(2, 1, 64, 64, device="cuda:0", generator=g)
+    y = x + 0.3 * torch.randn(2, 1, 64, 64, device="cuda:0", generator=g)
+    results = []
+    for fwd, bwd in ((True, False), (True, True), (False, False)):
+        model = _build()
+        model(x)                                          # builds the engine
+        eng = model.__dict__["_native_train_engine"]
+        eng.fuse_stats, eng.fuse_bwd_stats = fwd, bwd
+        model = _build()
+        model.__dict__["_native_train_engine"] = None
+        from im2im_uq_b200.models.unet_train import UNetTrainEngine
+        eng = UNetTrainEngine(model)
+        eng.fuse_stats, eng.fuse_bwd_stats = fwd, bwd
+        model.__dict__["_native_train_engine"] = eng
+        results.append(_grads(model, x, y, native=True))
+    (p0, l0, g0), (p1, l1, g1), (p2, l2, g2) = results
+    assert abs(l0 - l1) <= 1e-5 * abs(l0) and abs(l0 - l2) <= 1e-5 * abs(l0)
+    for n in g0:
+        if g0[n].norm() > 1e-6:
+            # fp32 atomics in a different order + sums taken in a different pass: agreement to rounding, not bit for bit
+            assert _rel(g1[n], g0[n]) <= 2e-2 and _rel(g2[n], g0[n]) <= 2e-2, (n, _rel(g1[n], g0[n]), _rel(g2[n], g0[n]))
+
+
 def test_loss_trajectory_tracks_torch_adam():
     from im2im_uq_b200.models.unet_train import FusedAdam
     g = torch.Generator(device="cuda:0").manual_seed(2)
