@@ -76,14 +76,9 @@ def test_backward_stat_fusion_matches_separate_reduction():
     x = torch.randn(2, 1, 64, 64, device="cuda:0", generator=g)
     y = x + 0.3 * torch.randn(2, 1, 64, 64, device="cuda:0", generator=g)
     results = []
+    from im2im_uq_b200.models.unet_train import UNetTrainEngine
     for fwd, bwd in ((True, False), (True, True), (False, False)):
         model = _build()
-        model(x)                                          # builds the engine
-        eng = model.__dict__["_native_train_engine"]
-        eng.fuse_stats, eng.fuse_bwd_stats = fwd, bwd
-        model = _build()
-        model.__dict__["_native_train_engine"] = None
-        from im2im_uq_b200.models.unet_train import UNetTrainEngine
         eng = UNetTrainEngine(model)
         eng.fuse_stats, eng.fuse_bwd_stats = fwd, bwd
         model.__dict__["_native_train_engine"] = eng
