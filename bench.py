@@ -652,7 +652,7 @@ def main():
         plan = cm.RcpsGraph(out, lab, cfg, group=group, n_total=args.images)
 
         def step(i=None):  # noqa: F811 - replaces the kernel-by-kernel step above
-            lhat_t, stop, decided = plan.run()
+            lhat_t, stop, decided = plan.run(after_replay=k_end[i].record if i is not None else None)
             replayed = 0
             if not decided:
                 stats = {}
@@ -696,8 +696,6 @@ def main():
         if plan is not None:
             k_start[i].record()     # graph path: the events bracket the replay = the step's kernel(s), inside the timed region
         step(i)
-        if plan is not None:
-            k_end[i].record()
     t_end.record()
     sync_all()
     launches = _lib.launch_count() - launches0
@@ -707,6 +705,12 @@ def main():
     if clocks is not None:
         clocks["window"] = "the timed region (%d steps, %.1f ms)" % (args.steps, t_start.elapsed_time(t_end))
     ms_total = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+    tail_stamps = plan.tail_stamps_us() if plan is not None else None
+    if tail_stamps is not None and world > 1:
+        # every rank's view of the last step's tail (when its last block finished streaming, when the peers had arrived ...)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, tail_stamps)
+        tail_stamps = {"per_rank": gathered}
     plan_fused = plan is not None and plan.fused
     plan_peer = plan is not None and plan.peer is not None
     plan_launches = plan.kernels_per_replay if plan is not None else None
@@ -812,7 +816,7 @@ def main():
                 "config": {"workload": workload_name(args), "images_per_gpu": n_local,
                            "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % (n_local * px * 16 / 1e9),
                            "cuda_graph": plan is not None,
-                           "launches_per_step": plan_launches,
+                           "launches_per_step": plan_launches, "fused_tail_us": tail_stamps,
                            "totals_allreduce": (("inside the one fused launch, over NVLink peer memory (im2im_rcps_calibrate_fused)"
                                                  if plan_fused else
                                                  "fused with the decision over NVLink peer memory (im2im_rcps_decide_p2p)")

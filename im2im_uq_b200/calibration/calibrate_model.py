@@ -444,8 +444,12 @@ class RcpsGraph:
             self._decide(self.totals, self.n_total, read=False)
         rcps.loss_table(self.counts, self.px, out=self.table, first_visited_dev=self.result[3:])
 
-    def run(self):
+    def run(self, after_replay=None):
+        """One calibration: replay the graph, wait for the 16-byte result.  ``after_replay`` (optional callable) runs right
+        after the replay was enqueued - benchmarks record a CUDA event there, so that the event brackets the device work only."""
         self.graph.replay()
+        if after_replay is not None:
+            after_replay()
         if self.fused:
             # the kernel stores the result into mapped pinned memory and tags it with its launch epoch: spin on the tag
             self._launches += 1
@@ -467,6 +471,16 @@ class RcpsGraph:
         stop, decided = int(res[0]), bool(res[1])
         lhat = self.lambdas[stop] if stop >= 0 else self.default_lhat
         return lhat, stop, decided
+
+    def tail_stamps_us(self):
+        """Profiling aid (fused path): microseconds, relative to the first block's start, at which the LAST launch's last block
+        took its ticket, had read the totals, had pushed them to every peer, saw all peers arrive, and published the decision."""
+        if not self.fused:
+            return None
+        torch.cuda.current_stream(self.result.device).synchronize()
+        st = self.workspace[64:128].view(torch.int64).cpu().tolist()
+        names = ("ticket", "totals_read", "pushed", "peers_arrived", "published")
+        return {n: (st[i + 1] - st[0]) / 1e3 for i, n in enumerate(names) if st[i + 1] != 0}
 
     def close(self):
         """Destroy the captured graph (it may hold NCCL kernels and peer mappings) - call before

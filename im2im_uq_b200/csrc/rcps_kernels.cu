@@ -55,6 +55,8 @@ struct FusedParams {
     unsigned* ticket;                   // workspace: CTAs finished so far
     unsigned* go;                       // workspace u32[2]: {epoch of the published decision, first visited column}
     unsigned* err;                      // workspace u32: set when an intra-GPU wait gave up (a bug or a lost block, never a peer)
+    unsigned long long* stamps;         // workspace u64[8]: globaltimer (ns) at {first CTA start, last CTA's ticket, totals read,
+                                        //   pushed + fenced, all peers arrived, decision published, -, -} of the last launch
     unsigned* head_flag;                // workspace u32[grid]: epoch at which CTA b published its head-partial row
     int* head_partial;                  // workspace i32[grid][L]: miss counts of the image a CTA starts in the middle of
     unsigned* epoch;                    // device-side launch counter (incremented by the kernel: graph replays need no new args)
@@ -277,6 +279,11 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -320,6 +327,7 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
     unsigned* rise = (HEAD == IM2IM_HEAD_RESIDUAL) ? reinterpret_cast<unsigned*>(cursor) : nullptr;
     __shared__ int s_tail[4];   // fused tail: {is last CTA, first visited column, stop verdict, timeout}
     const unsigned epoch = FUSED ? (*fz.epoch + 1u) : 0u;   // read before anything can bump it (only the last CTA does, at the end)
+    if (FUSED && blockIdx.x == 0 && threadIdx.x == 0) fz.stamps[0] = global_timer_ns();
 
     const int tid = threadIdx.x;
     for (int j = tid; j < L; j += kThreads) {
@@ -505,13 +513,14 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
         int first_visited = 0;
         if (s_tail[0]) {
             // ---- last CTA: totals are complete.  Read + clean the workspace, (multi-GPU) exchange, decide, publish.
+            if (ctid == 0) fz.stamps[1] = global_timer_ns();
             __threadfence();
             unsigned long long* sum = tot;   // reuse the per-CTA totals array as the reduced totals
             for (int j = ctid; j < L; j += kConsumerThreads) {
                 sum[j] = __ldcg(fz.totals_acc + j);
                 fz.totals_acc[j] = 0ull;
             }
-            if (ctid == 0) *fz.ticket = 0u;
+            if (ctid == 0) { *fz.ticket = 0u; fz.stamps[2] = global_timer_ns(); }
             named_bar_sync(kFlushBarrier, kConsumerThreads);
             if (fz.world > 1) {
                 // one-shot push all-reduce over peer memory (protocol of rcps_decide_p2p_kernel)
@@ -522,6 +531,7 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
                 }
                 __threadfence_system();
                 named_bar_sync(kFlushBarrier, kConsumerThreads);
+                if (ctid == 0) fz.stamps[3] = global_timer_ns();
                 if (ctid < fz.world) {
                     st_release_sys_u32(fz.peer_flags[ctid] + fz.rank, epoch);
                     const unsigned* f = fz.peer_flags[fz.rank] + ctid;
@@ -531,6 +541,7 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
                     }
                 }
                 named_bar_sync(kFlushBarrier, kConsumerThreads);
+                if (ctid == 0) fz.stamps[4] = global_timer_ns();
                 if (!s_tail[3]) {
                     const unsigned long long* mine = fz.peer_mailbox[fz.rank] + static_cast<size_t>(epoch & 1u) * fz.world * L;
                     for (int j = ctid; j < L; j += kConsumerThreads) {
@@ -561,15 +572,18 @@ __global__ void __launch_bounds__(kThreads, STAGED ? 1 : 2) rcps_hist_kernel(con
             else { r0_ = -1; r1_ = 0; r2_ = first; r3_ = 0; }                  // unsure: the host replays from `first`
             first_visited = r3_;
             if (ctid == 0) {
+                // release the other blocks first (they only need the first visited column), then publish to the host: the
+                // system-scope fence of the host write (a PCIe flush, ~3 us) is off the other blocks' critical path
+                fz.go[1] = static_cast<unsigned>(r3_);
+                __threadfence();
+                st_release_gpu_u32(fz.go, epoch);
                 fz.result[0] = r0_; fz.result[1] = r1_; fz.result[2] = r2_; fz.result[3] = r3_;
                 if (fz.result_host != nullptr) {
                     fz.result_host[0] = r0_; fz.result_host[1] = r1_; fz.result_host[2] = r2_; fz.result_host[3] = r3_;
                     __threadfence_system();
                     fz.result_host[4] = static_cast<int>(epoch);               // tag last: the host polls this word
                 }
-                fz.go[1] = static_cast<unsigned>(r3_);
-                __threadfence();
-                st_release_gpu_u32(fz.go, epoch);
+                fz.stamps[5] = global_timer_ns();
                 *fz.epoch = epoch;   // a peer timeout (result -2) leaves the ranks out of step: the caller must rebuild
             }
         } else if (fz.table != nullptr) {
@@ -838,9 +852,29 @@ __global__ void __launch_bounds__(256) fraction_missed_kernel(const float* __res
 
 // Softmax head: logits -> (lower quantile, argmax prediction, upper quantile), the lambda-independent part of
 // softmax_nested_sets_from_output (softmax_layer.py:34-48); the lambda-dependent part (:50-51) is the SOFTMAX_SETS head
-// kind of the sweep / nested-set kernels.  One thread per pixel, classes strided by `sk` elements (coalesced across
-// pixels); K <= kMaxSoftmax values are held in registers so the logits are read from HBM once.
+// kind of the sweep / nested-set kernels.  Operation order of the reference: p_k = e_k / sum with one IEEE division per
+// class (:34), cumulative sum accumulated in double and rounded to fp32 at every step (torch.cumsum on the CPU, :38),
+// compared with fp32 0.05 / 0.95 (:40-41), first maximal p_k as the prediction (:42).  exp is portable_expf - the same fixed
+// sequence of IEEE operations as oracle/rcps_oracle.c, so kernel and oracle agree bit for bit.
+// One thread per pixel, classes strided by `sk` elements (coalesced across pixels); the K <= kMaxSoftmax exponentials are
+// kept in registers between the two passes, so the logits are read from HBM once.
 constexpr int kMaxSoftmax = 64;
+
+__device__ __forceinline__ float portable_expf(float x) {   // x <= 0; see oracle/rcps_oracle.c::portable_expf
+    const float q = rintf(__fmul_rn(x, 1.4426950408889634f));
+    float s = __fmaf_rn(q, -0.693145751953125f, x);
+    s = __fmaf_rn(q, -1.428606765330187045e-06f, s);
+    float u = 0.000198527617612853646278381f;
+    u = __fmaf_rn(u, s, 0.00139304355252534151077271f);
+    u = __fmaf_rn(u, s, 0.00833336077630519866943359f);
+    u = __fmaf_rn(u, s, 0.0416664853692054748535156f);
+    u = __fmaf_rn(u, s, 0.166666671633720397949219f);
+    u = __fmaf_rn(u, s, 0.5f);
+    u = __fadd_rn(__fmaf_rn(__fmul_rn(s, s), u, s), 1.0f);
+    const int qi = static_cast<int>(q), q1 = qi >> 1, q2 = qi - q1;   // 2^q as two exact factors in the normal range
+    u = __fmul_rn(__fmul_rn(u, __int_as_float((q1 + 127) << 23)), __int_as_float((q2 + 127) << 23));
+    return x < -104.0f ? 0.0f : u;
+}
 
 template <int KMAX>
 __global__ void __launch_bounds__(256) softmax_sets_kernel(const float* __restrict__ logits, long long n_images, int K,
@@ -868,24 +902,22 @@ __global__ void __launch_bounds__(256) softmax_sets_kernel(const float* __restri
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             if (k < K) {
-                v[k] = expf(__fsub_rn(v[k], m));
+                v[k] = portable_expf(__fsub_rn(v[k], m));
                 ssum = __fadd_rn(ssum, v[k]);
             }
         }
-        // The reference compares cumsum(e_k / s) with 0.05 / 0.95; here the running sum of the UN-normalised e_k is compared
-        // with 0.05*s / 0.95*s - no division per class (50 IEEE divisions were a third of the kernel).  The two differ
-        // only by fp32 rounding, i.e. only where a cumulative probability lies within rounding distance of a threshold,
-        // which is the tolerance this half of the head has anyway (0 mismatches on the reference fixtures).
-        const float t_lo = __fmul_rn(0.05f, ssum), t_hi = __fmul_rn(0.95f, ssum);
-        float cum = 0.f, best = -INFINITY;
+        double cum = 0.0;
+        float best = -INFINITY;
         int n_lo = 0, n_hi = 0, arg = 0;
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             if (k < K) {
-                cum = __fadd_rn(cum, v[k]);
-                n_lo += (cum <= t_lo) ? 1 : 0;
-                n_hi += (cum <= t_hi) ? 1 : 0;
-                if (v[k] > best) { best = v[k]; arg = k; }  // first maximal element, like torch.argmax
+                const float pk = __fdiv_rn(v[k], ssum);
+                cum += static_cast<double>(pk);
+                const float cf = static_cast<float>(cum);
+                n_lo += (cf <= 0.05f) ? 1 : 0;
+                n_hi += (cf <= 0.95f) ? 1 : 0;
+                if (pk > best) { best = pk; arg = k; }  // first maximal element, like torch.argmax
             }
         }
         float lq, pr, uq;
@@ -1017,8 +1049,9 @@ extern "C" int im2im_rcps_miss_counts(const float* d_lower, const float* d_pred,
 namespace im2im { namespace {
 constexpr int kFusedMaxGrid = 256;
 struct FusedWorkspace {      // byte offsets inside the caller's workspace
-    static size_t head_flag() { return 32; }
-    static size_t totals_acc() { return 32 + sizeof(unsigned) * kFusedMaxGrid; }
+    static size_t stamps() { return 64; }       // u64[8] %globaltimer stamps of the last launch (profiling aid)
+    static size_t head_flag() { return 128; }
+    static size_t totals_acc() { return 128 + sizeof(unsigned) * kFusedMaxGrid; }
     static size_t head_partial(int L) { return totals_acc() + sizeof(unsigned long long) * L; }
     static size_t bytes(int L) { return head_partial(L) + sizeof(int) * static_cast<size_t>(kFusedMaxGrid) * L; }
 };
@@ -1103,6 +1136,7 @@ extern "C" int im2im_rcps_calibrate_fused(const float* d_lower, const float* d_p
     fz.ticket = reinterpret_cast<unsigned*>(ws) + 1;
     fz.go = reinterpret_cast<unsigned*>(ws) + 2;
     fz.err = reinterpret_cast<unsigned*>(ws) + 4;
+    fz.stamps = reinterpret_cast<unsigned long long*>(ws + FusedWorkspace::stamps());
     fz.head_flag = reinterpret_cast<unsigned*>(ws + FusedWorkspace::head_flag());
     fz.totals_acc = reinterpret_cast<unsigned long long*>(ws + FusedWorkspace::totals_acc());
     fz.head_partial = reinterpret_cast<int*>(ws + FusedWorkspace::head_partial(n_lambdas));

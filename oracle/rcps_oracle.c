@@ -193,9 +193,39 @@ void oracle_head_miss_map(int32_t kind, const float* a, const float* p, const fl
                                        label[i * stride_label + k], lam);
 }
 
-/* softmax_layer.py:34-48: logits (n, K, inner) -> sets (n, 3, inner) = (lower quantile, prediction, upper quantile).
- * expf / summation order are libm's and sequential; torch's differ by an ulp, so this half of the oracle is pinned to
- * the reference only up to threshold ties (see tests). */
+/* Portable exp for x <= 0 with a fixed operation sequence (IEEE fp32 multiply, fused multiply-add, round-to-nearest-even
+ * integer rounding, exact power-of-two scaling): Cody-Waite reduction + degree-6 polynomial (the scheme and constants of
+ * SLEEF's expf, Boost licence), about 1 ulp.  The CUDA kernel (rcps_kernels.cu::portable_expf) executes the identical
+ * sequence, so both produce the same bits on every input - libm's / torch's / CUDA's own exp functions each round
+ * differently in the last place, which is what made this head "equal up to threshold ties" between any two of them. */
+static inline float portable_expf(float x) {
+    volatile float t = x * 1.4426950408889634f;
+    const float q = rintf(t);
+    float s = fmaf(q, -0.693145751953125f, x);
+    s = fmaf(q, -1.428606765330187045e-06f, s);
+    float u = 0.000198527617612853646278381f;
+    u = fmaf(u, s, 0.00139304355252534151077271f);
+    u = fmaf(u, s, 0.00833336077630519866943359f);
+    u = fmaf(u, s, 0.0416664853692054748535156f);
+    u = fmaf(u, s, 0.166666671633720397949219f);
+    u = fmaf(u, s, 0.5f);
+    volatile float s2 = s * s;
+    u = f_add(fmaf(s2, u, s), 1.0f);
+    const int qi = (int)q, q1 = qi >> 1, q2 = qi - q1;      /* 2^q in two exact factors: stays in the normal range */
+    union { uint32_t i; float f; } a, b2;
+    a.i = (uint32_t)(q1 + 127) << 23;
+    b2.i = (uint32_t)(q2 + 127) << 23;
+    u = f_mul(f_mul(u, a.f), b2.f);
+    if (x < -104.0f) u = 0.0f;
+    return u;
+}
+
+/* softmax_layer.py:34-48: logits (n, K, inner) -> sets (n, 3, inner) = (lower quantile, prediction, upper quantile), in the
+ * reference's operation order: p_k = e_k / sum (one IEEE division per class, :34), cumulative sum accumulated in DOUBLE and
+ * rounded to fp32 at every step (what torch.cumsum does on the CPU: probed, acc_type<float> = double; :38), compared with
+ * fp32 0.05 / 0.95 (:40-41), argmax of p (:42).  exp is portable_expf and the denominator a sequential fp32 sum; torch's own
+ * exp / summation order differ from that in the last place, so against the reference fixtures this half is pinned up to
+ * cumulative-probability threshold ties (tests assert the fixture's recorded margins); the CUDA kernel is bit-identical. */
 void oracle_softmax_sets(const float* logits, int64_t n_images, int64_t K, int64_t inner, float* sets) {
     const float step = (float)(1.0 / (double)K);
     for (int64_t i = 0; i < n_images; ++i) {
@@ -213,14 +243,16 @@ void oracle_softmax_sets(const float* logits, int64_t n_images, int64_t K, int64
                 lq = 0.0f; uq = 0.0f; pr = 0.0f; /* softmax makes the whole row NaN: counts 0, argmax = first NaN = 0 */
             } else {
                 float ssum = 0.0f;
-                for (int64_t k = 0; k < K; ++k) ssum = f_add(ssum, expf(f_sub(x[k * inner], m)));
-                float cum = 0.0f, best = -INFINITY;
+                for (int64_t k = 0; k < K; ++k) ssum = f_add(ssum, portable_expf(f_sub(x[k * inner], m)));
+                double cum = 0.0;
+                float best = -INFINITY;
                 int n_lo = 0, n_hi = 0, arg = 0;
                 for (int64_t k = 0; k < K; ++k) {
-                    volatile float pk = expf(f_sub(x[k * inner], m)) / ssum;
-                    cum = f_add(cum, pk);
-                    n_lo += cum <= 0.05f;
-                    n_hi += cum <= 0.95f;
+                    volatile float pk = portable_expf(f_sub(x[k * inner], m)) / ssum;
+                    cum += (double)pk;
+                    volatile float cf = (float)cum;
+                    n_lo += cf <= 0.05f;
+                    n_hi += cf <= 0.95f;
                     if (pk > best) { best = pk; arg = (int)k; }
                 }
                 lq = (float)n_lo / (float)K; uq = (float)n_hi / (float)K; pr = (float)arg / (float)K;
