@@ -906,17 +906,31 @@ __global__ void __launch_bounds__(256) softmax_sets_kernel(const float* __restri
                 ssum = __fadd_rn(ssum, v[k]);
             }
         }
+        // p_k = RN(e_k / s): the denominator is common to the row, so the correctly rounded quotient comes from ONE IEEE
+        // reciprocal and Markstein's sequence q = RN(e*r), rem = e - q*s (exact, fma), q' = RN(q + rem*r) == RN(e/s) whenever
+        // r = RN(1/s), nothing underflows and s is not all-ones in the mantissa; everything else takes the IEEE division.
+        // (float)cum <= 0.05f  <=>  cum <= T_LO with T_LO the largest double that rounds to a float <= 0.05f (rounding is
+        // monotone): no double->float conversion per class.
+        constexpr double T_LO = 0x1.99999afffffffp-5, T_HI = 0x1.e66666fffffffp-1;
+        const float rcp_s = __frcp_rn(ssum);
+        const bool fast_div = (ssum >= 1.0f) && (ssum <= 128.0f) && ((__float_as_uint(ssum) & 0x7FFFFFu) != 0x7FFFFFu);
         double cum = 0.0;
         float best = -INFINITY;
         int n_lo = 0, n_hi = 0, arg = 0;
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             if (k < K) {
-                const float pk = __fdiv_rn(v[k], ssum);
+                float pk;
+                if (fast_div && v[k] >= 0x1p-60f) {
+                    const float q = __fmul_rn(v[k], rcp_s);
+                    const float rem = __fmaf_rn(-q, ssum, v[k]);
+                    pk = __fmaf_rn(rem, rcp_s, q);
+                } else {
+                    pk = __fdiv_rn(v[k], ssum);
+                }
                 cum += static_cast<double>(pk);
-                const float cf = static_cast<float>(cum);
-                n_lo += (cf <= 0.05f) ? 1 : 0;
-                n_hi += (cf <= 0.95f) ? 1 : 0;
+                n_lo += (cum <= T_LO) ? 1 : 0;
+                n_hi += (cum <= T_HI) ? 1 : 0;
                 if (pk > best) { best = pk; arg = k; }  // first maximal element, like torch.argmax
             }
         }

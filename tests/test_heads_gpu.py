@@ -95,7 +95,8 @@ def test_softmax_sets_kernel_vs_reference(head_golden):
     assert np.allclose(sets * k, np.round(sets * k), atol=1e-4) and sets.min() >= 0 and sets.max() <= 1
 
 
-@pytest.mark.parametrize("K,shape", [(50, (3, 40, 36)), (64, (2, 17, 9)), (7, (5, 8, 8)), (1, (2, 4, 4))])
+@pytest.mark.parametrize("K,shape", [(50, (3, 40, 36)), (64, (2, 17, 9)), (7, (5, 8, 8)), (1, (2, 4, 4)),
+                                     (50, (16, 128, 128))])   # 13 M divisions through the one-reciprocal (Markstein) path
 def test_softmax_sets_kernel_equals_oracle_on_random_logits(K, shape):
     """Integer result, no tolerance: planes identical to the oracle's for wide-range logits, NaN / inf rows included."""
     n, h, w = shape
