@@ -803,10 +803,11 @@ def main():
         achieved = alg_bytes / (float(kernel_ms) * 1e-3) / 1e9
         traffic, traffic_src = None, None
         try:   # DRAM bytes per launch are an ncu counter: read from the committed capture of this very shape, if there is one
-            prof = json.load(open(os.path.join(ROOT, "profiles", "rcps_hist_ncu_summary.json")))
+            name = "r2_rcps_fused_ncu_summary.json" if plan_fused else "rcps_hist_ncu_summary.json"
+            prof = json.load(open(os.path.join(ROOT, "profiles", name)))
             if prof.get("images") == n_local and prof.get("side") == args.side:
                 traffic = prof.get("dram_bytes_per_launch")
-                traffic_src = "from profile: profiles/rcps_hist_ncu_summary.json (ncu --set full, dram__bytes_read.sum + " \
+                traffic_src = f"from profile: profiles/{name} (ncu --set full, dram__bytes_read.sum + " \
                               "dram__bytes_write.sum of one launch at this shape; not measured in this run)"
         except Exception:
             pass

