@@ -638,12 +638,30 @@ def rank_shard(dataset, group):
     return torch.utils.data.Subset(dataset, range(lo, hi))
 
 
-def calibrate_model(model, dataset, config, group=None):
+def gather_loss_table(table: torch.Tensor, group, device) -> torch.Tensor:
+    """All ranks' rows of the loss table, concatenated in rank order (= image order of the unsharded set), on every rank.
+    Off the hot path: the reference's table has one row per calibration image, and a caller that saves it (router.py:138)
+    needs all of them."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rows = torch.tensor([table.shape[0]], dtype=torch.int64, device=device)
+    all_rows = [torch.zeros_like(rows) for _ in range(world)]
+    dist.all_gather(all_rows, rows, group=group)
+    counts = [int(r) for r in all_rows]
+    pad = torch.zeros((max(counts), table.shape[1]), dtype=table.dtype, device=device)
+    pad[:table.shape[0]] = table.to(device)
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0).to(table.device)
+
+
+def calibrate_model(model, dataset, config, group=None, gather_table: bool = False):
     """Drop-in for the reference's ``calibrate_model``: returns ``(model, calib_loss_table)`` with ``model.lhat`` set.
 
     ``group`` (optional, a torch.distributed process group, one process per GPU) shards the calibration set: every rank
     runs the model over its contiguous block of a map-style ``dataset`` and keeps its rows of the table; the only
-    collective on the data path is the all-reduce of the per-lambda miss totals (int64[L]); all ranks get the same lhat."""
+    collective on the data path is the all-reduce of the per-lambda miss totals (int64[L]); all ranks get the same lhat.
+    ``gather_table=True`` returns the FULL (N, L) table on every rank, like the reference's, at the cost of one all-gather."""
     with torch.no_grad():
         print(f"Calibrating...")
         model.eval()
@@ -654,5 +672,7 @@ def calibrate_model(model, dataset, config, group=None):
             dataset = rank_shard(dataset, group)
         outputs, labels = collect_outputs(model, dataset, config, device)
         model, calib_loss_table = calibrate_from_outputs(model, outputs, labels, config, group=group)
+        if group is not None and gather_table:
+            calib_loss_table = gather_loss_table(calib_loss_table, group, device)
         print(f"Model's lhat set to {model.lhat}")
         return model, calib_loss_table

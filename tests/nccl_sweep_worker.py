@@ -47,6 +47,8 @@ def main():
         lo, hi = n * rank // world, n * (rank + 1) // world
         assert np.float32(model.lhat.numpy()) == g["lhat"], (case, rank)
         assert np.array_equal(table.numpy(), g["calib_loss_table"][lo:hi]), (case, rank)
+        model, full = cm.calibrate_model(model, ds, cfg, group=dist.group.WORLD, gather_table=True)
+        assert np.array_equal(full.numpy(), g["calib_loss_table"]), (case, rank)     # the reference's whole table, on every rank
     # the captured plan: all-reduce fused with the decision over peer memory when symmetric memory works here, NCCL otherwise;
     # both must reproduce the reference's lhat / table rows, replay after replay
     for p2p, fused in ((True, True), (True, False), (False, False)):

@@ -102,3 +102,33 @@ def test_rank_shard_partitions_the_calibration_set_in_row_order(n):
     assert results[0][1] + results[1][1] == list(range(n))
     for rank, idx, xs, ys in results:
         assert xs == [float(i) for i in idx] and ys == [i + 0.5 for i in idx]
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from im2im_uq_b200.calibration.calibrate_model import gather_loss_table
+        rows = [3, 5][rank]                                   # uneven shards
+        table = torch.arange(rows * 4, dtype=torch.float32).reshape(rows, 4) + 100 * rank
+        full = gather_loss_table(table, dist.group.WORLD, torch.device("cpu"))
+        q.put((rank, full.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_loss_table_rank_order_uneven_shards():
+    """calibrate_model(..., group=, gather_table=True): rows of all ranks in rank order, uneven shard sizes (host logic, gloo)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.concatenate([np.arange(12, dtype=np.float32).reshape(3, 4), np.arange(20, dtype=np.float32).reshape(5, 4) + 100])
+    assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
