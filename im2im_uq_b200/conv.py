@@ -165,13 +165,22 @@ def head_conv_tc(x: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[to
     return out
 
 
-def planar_to_nhwc64(src: torch.Tensor) -> torch.Tensor:
-    """fp32 planes [B, n, H, W] -> bf16 NHWC [B, H, W, 64], channels >= n zero."""
+def planar_to_nhwc64(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 planes [B, n, H, W] -> bf16 NHWC [B, H, W, 64], channels >= n zero.
+
+    ``out``: a persistent [B, H, W, 64] bf16 buffer whose channels 8..63 are zero and stay zero (n <= 8): only channels
+    0..7 are rewritten - an eighth of the bytes."""
     lib = _lib.load()
     assert src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 4 and src.shape[1] <= 64
     B, n, H, W = src.shape
-    dst = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=src.device)
     with torch.cuda.device(src.device):
+        if out is not None and n <= 8:
+            assert out.dtype == torch.bfloat16 and out.is_contiguous() and tuple(out.shape) == (B, H, W, 64)
+            rc = lib.im2im_planar_to_nhwc64_first8_bf16(src.data_ptr(), n, B, H, W, out.data_ptr(),
+                                                        torch.cuda.current_stream(src.device).cuda_stream)
+            _lib.check(rc, "im2im_planar_to_nhwc64_first8_bf16")
+            return out
+        dst = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=src.device)
         rc = lib.im2im_planar_to_nhwc64_bf16(src.data_ptr(), n, B, H, W, dst.data_ptr(),
                                              torch.cuda.current_stream(src.device).cuda_stream)
     _lib.check(rc, "im2im_planar_to_nhwc64_bf16")

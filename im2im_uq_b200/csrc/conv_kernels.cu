@@ -1375,6 +1375,40 @@ __global__ void __launch_bounds__(256) planar_to_nhwc64_kernel(const float* __re
 }
 } }
 
+namespace im2im { namespace {
+// n <= 8 planes: only the first 16 bytes (channels 0..7) of every 128-byte pixel row are written; the caller keeps the
+// other 56 channels zero across calls (a persistent buffer), which cuts the bytes written 8x
+__global__ void __launch_bounds__(256) planar_to_nhwc64_first8_kernel(const float* __restrict__ src, int n, long long hw,
+                                                                      long long total_pix, __nv_bfloat16* __restrict__ dst) {
+    for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < total_pix;
+         pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = pix / hw, k = pix - b * hw;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = j < n ? __ldg(src + (b * n + j) * hw + k) : 0.f;
+        uint4 pk;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst + pix * 64) = pk;
+    }
+}
+} }
+
+extern "C" int im2im_planar_to_nhwc64_first8_bf16(const float* d_src, int32_t n_planes, int32_t B, int32_t H, int32_t W,
+                                                  void* d_dst, void* stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || n_planes < 1 || n_planes > 8) return fail(IM2IM_EINVAL, "planar_to_nhwc64_first8: bad shape");
+    if (!d_src || !d_dst) return fail(IM2IM_EINVAL, "planar_to_nhwc64_first8: null tensor");
+    const long long hw = static_cast<long long>(H) * W, pix = hw * B;
+    long long blocks = (pix + 255) / 256;
+    const long long cap = 16ll * sm_count();
+    if (blocks > cap) blocks = cap;
+    planar_to_nhwc64_first8_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_src, n_planes, hw, pix, static_cast<__nv_bfloat16*>(d_dst));
+    return check_launch("planar_to_nhwc64_first8_kernel");
+}
+
 extern "C" int im2im_planar_to_nhwc64_bf16(const float* d_src, int32_t n_planes, int32_t B, int32_t H, int32_t W,
                                            void* d_dst, void* stream) {
     if (B <= 0 || H <= 0 || W <= 0 || n_planes < 1 || n_planes > 64) return fail(IM2IM_EINVAL, "planar_to_nhwc64: bad shape");

@@ -326,29 +326,29 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16
             wx[a] = upsample_axis_weight(2 * ix - 2 + a, uw, w, sx, ix);
         }
         const __nv_bfloat16* base = du + ((static_cast<long long>(b) * Ho + (2 * iy - 2 + pad_top)) * Wo + (2 * ix - 2 + pad_left)) * C + g * 8;
-        Bf16x8 t[5][5];
-#pragma unroll
-        for (int a = 0; a < 5; ++a)
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                t[a][c].u = make_uint4(0u, 0u, 0u, 0u);
-                if (wy[a] != 0.f && wx[c] != 0.f)
-                    t[a][c].u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(a) * Wo + c) * C);
-            }
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        // same accumulation order as the forward-difference formulation: rows outer, columns inner, fp32 FMAs
+        // rows outer (wy is uniform over the block: blockIdx.y = iy, so skipping a zero-weight row does not diverge), the
+        // five column taps of a row are loaded together; fp32 FMAs in the order rows outer / columns inner
 #pragma unroll
-        for (int a = 0; a < 5; ++a)
+        for (int a = 0; a < 5; ++a) {
+            if (wy[a] == 0.f) continue;
+            Bf16x8 t[5];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                t[c].u = make_uint4(0u, 0u, 0u, 0u);
+                if (wx[c] != 0.f) t[c].u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(a) * Wo + c) * C);
+            }
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
                 const float wgt = wy[a] * wx[c];
                 float f[8];
-                unpack8(t[a][c], f);
+                unpack8(t[c], f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, f[j], acc[j]);
             }
+        }
         *reinterpret_cast<uint4*>(dx + pix * C + g * 8) = pack8(acc);
     }
 }

@@ -365,7 +365,11 @@ class UNetTrainEngine:
             if ctx.get("head_tc"):
                 # head gradients on tensor cores: dOut as a 64-channel NHWC bf16 operand, weight gradient through the halo
                 # wgrad kernel, data gradient = the halo conv with the flipped / transposed head weights
-                dout_nhwc = planar_to_nhwc64(dout)
+                buf = self.__dict__.get("_dout_nhwc")      # channels >= n_out stay zero for the engine's lifetime
+                if buf is None or tuple(buf.shape) != (B, H, W, 64) or buf.device != dev:
+                    buf = torch.zeros((B, H, W, 64), dtype=torch.bfloat16, device=dev)
+                    self._dout_nhwc = buf
+                dout_nhwc = planar_to_nhwc64(dout, out=buf if self.n_out <= 8 else None)
                 dw64 = conv_wgrad(m, dout_nhwc, 9, out=self._zero.take(64, 9, 64))          # [plane, tap, feature]
                 dwh = dw64[:self.n_out, :, :self.c_mid].permute(0, 2, 1).reshape(self.n_out, self.c_mid, 3, 3)
                 dbh = dout.sum(dim=(0, 2, 3))

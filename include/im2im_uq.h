@@ -349,6 +349,10 @@ int im2im_head_conv3x3_tc_f32(const void* d_x, const void* d_weight, const float
  * operand of im2im_conv_wgrad_bf16 / im2im_conv_igemm_bf16 (head weight / data gradient on tensor cores). */
 int im2im_planar_to_nhwc64_bf16(const float* d_src, int32_t n_planes, int32_t B, int32_t H, int32_t W, void* d_dst,
                                 void* stream);
+/* The same for n_planes <= 8 into a buffer whose channels 8..63 the caller keeps zero across calls: only the first 16 bytes
+ * of each 128-byte pixel row are written (8x fewer bytes per training step). */
+int im2im_planar_to_nhwc64_first8_bf16(const float* d_src, int32_t n_planes, int32_t B, int32_t H, int32_t W, void* d_dst,
+                                       void* stream);
 
 /*
  * Training-side passes of the UNet path (autograd of core/scripts/train.py:152-162 through the modules of
