@@ -304,8 +304,32 @@ class UNetTrainEngine:
         x1, x2 = saved["x_in"], saved.get("x_in2")
         main = torch.cuda.current_stream(dz.device)
         side = self._side_stream(dz.device)
-        side.wait_stream(main)                      # dz (and everything before it) is ready
         c_out = dz.shape[3]
+        # 1. the data gradient first, on the main stream: it is the critical path of the backward pass
+        dx1 = dx2 = None
+        fused = False
+        if need_dx:
+            if x2 is None and bn_next is not None:
+                la, sa = bn_next
+                sums = self._zero.take(2 * la.c_out)
+                # Measured on B200 (tools/halo_modes_bench.py, batch 78): the backward fusion costs the halo kernel more
+                # (the epilogue's bn_z reads: +0.38 ms on 64->64 @320^2) than the separate reduction pass it replaces, so it
+                # is off by default; the forward fusion (stat_mode 1) is +6 % on the convolution and replaces a pass over z.
+                if getattr(self, "fuse_bwd_stats", False):
+                    bn = la.bn
+                    dx1, fused = conv_igemm_stats(dz, layer.w_bwd, 2, sums,
+                                                  bn=(sa["z"], bn.weight.detach(), bn.bias.detach(), sa["mean"], sa["rstd"]))
+                else:
+                    dx1 = conv_igemm(dz, layer.w_bwd)
+            elif x2 is None:
+                dx1 = conv_igemm(dz, layer.w_bwd)
+            else:
+                c1 = x1.shape[3]
+                dx1, dx2 = conv_igemm(dz, layer.w_bwd[:c1]), conv_igemm(dz, layer.w_bwd[c1:])
+        # 2. the weight gradient on the side stream, ordered AFTER the data gradient (both are tensor-bound kernels that fill
+        #    the GPU, so they cannot share it anyway): it then runs next to the bandwidth-bound BatchNorm / pool / upsample
+        #    backward kernels that follow on the main stream, instead of delaying the data gradient they are waiting for
+        side.wait_stream(main)
         with torch.cuda.stream(side):
             dw1 = conv_wgrad(x1, dz, 9, out=self._zero.take(c_out, 9, x1.shape[3]))
             if x2 is None:
@@ -319,35 +343,22 @@ class UNetTrainEngine:
                 t.record_stream(side)
         if not need_dx:
             return None, None
+        # 3. BatchNorm + ReLU backward of the layer that produced this conv's input
         if x2 is None and bn_next is not None:
             la, sa = bn_next
-            C = la.c_out
-            bn = la.bn
-            sums = self._zero.take(2 * C)
-            # Measured on B200 (tools/halo_modes_bench.py, batch 78): the backward fusion costs the halo kernel more (the
-            # epilogue's bn_z reads: +0.38 ms on 64->64 @320^2) than the separate reduction pass it replaces, so it is off by
-            # default; the forward fusion (stat_mode 1) is +6 % on the convolution and replaces a full pass over z.
-            if getattr(self, "fuse_bwd_stats", False):
-                g, fused = conv_igemm_stats(dz, layer.w_bwd, 2, sums,
-                                            bn=(sa["z"], bn.weight.detach(), bn.bias.detach(), sa["mean"], sa["rstd"]))
-            else:
-                g, fused = conv_igemm(dz, layer.w_bwd), False
             if not fused:
-                return self._bn_relu_bwd(g, la, sa, grads), None
-            z = sa["z"]
+                return self._bn_relu_bwd(dx1, la, sa, grads), None
+            bn, C, z = la.bn, la.c_out, sa["z"]
             dza = torch.empty_like(z)
             n_pix = z.shape[0] * z.shape[1] * z.shape[2]
-            _lib.check(self.lib.im2im_bn_relu_bwd_apply_bf16(g.data_ptr(), z.data_ptr(), bn.weight.data_ptr(),
+            _lib.check(self.lib.im2im_bn_relu_bwd_apply_bf16(dx1.data_ptr(), z.data_ptr(), bn.weight.data_ptr(),
                                                              bn.bias.data_ptr(), sa["mean"].data_ptr(), sa["rstd"].data_ptr(),
                                                              sums.data_ptr(), n_pix, C, 1, dza.data_ptr(), _st(dz.device)),
                        "bn_relu_bwd_apply")
             grads[bn.bias] = sums[:C]
             grads[bn.weight] = sums[C:]
             return dza, None
-        if x2 is None:
-            return conv_igemm(dz, layer.w_bwd), None
-        c1 = x1.shape[3]
-        return conv_igemm(dz, layer.w_bwd[:c1]), conv_igemm(dz, layer.w_bwd[c1:])
+        return dx1, dx2
 
     def backward(self, ctx: dict, dout: torch.Tensor) -> Dict[torch.Tensor, torch.Tensor]:
         lib, dev = self.lib, dout.device
@@ -370,10 +381,13 @@ class UNetTrainEngine:
                     buf = torch.zeros((B, H, W, 64), dtype=torch.bfloat16, device=dev)
                     self._dout_nhwc = buf
                 dout_nhwc = planar_to_nhwc64(dout, out=buf if self.n_out <= 8 else None)
-                dw64 = conv_wgrad(m, dout_nhwc, 9, out=self._zero.take(64, 9, 64))          # [plane, tap, feature]
+                dm = conv_igemm(dout_nhwc, self._head_bufs[2])                               # channels >= c_mid come out zero
+                side = self._side_stream(dev)                # weight gradients after the data gradient, off the critical path
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    dw64 = conv_wgrad(m, dout_nhwc, 9, out=self._zero.take(64, 9, 64))      # [plane, tap, feature]
                 dwh = dw64[:self.n_out, :, :self.c_mid].permute(0, 2, 1).reshape(self.n_out, self.c_mid, 3, 3)
                 dbh = dout.sum(dim=(0, 2, 3))
-                dm = conv_igemm(dout_nhwc, self._head_bufs[2])                               # channels >= c_mid come out zero
             else:
                 dm = torch.empty_like(m)
                 dwh = self._zero.take(self.n_out, self.c_mid, 3, 3)
@@ -385,14 +399,18 @@ class UNetTrainEngine:
             for i, conv in enumerate(self.head_convs):
                 grads[conv.weight] = dwh[i * co:(i + 1) * co]
                 grads[conv.bias] = dbh[i * co:(i + 1) * co]
-            # 1x1 out conv: wgrad, bias grad (channel sums of dm), dgrad
-            dw_out = conv_wgrad(y_last, dm, 1, out=self._zero.take(64, 1, 64))   # [64 (32 real), 1, 64]
+            # 1x1 out conv: dgrad, then (side stream) wgrad; bias grad = channel sums of dm
+            w_out_bwd = ctx["w_out_pad"].permute(2, 1, 0).contiguous()  # [64 ci, 1, 64 co]
+            dy = conv_igemm(dm, w_out_bwd)
+            side = self._side_stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                dw_out = conv_wgrad(y_last, dm, 1, out=self._zero.take(64, 1, 64))   # [64 (32 real), 1, 64]
+            dm.record_stream(side)
             grads[self.out_conv.weight] = dw_out[:self.c_mid].view(self.c_mid, -1, 1, 1)
             sums = self._zero.take(128)
             _lib.check(lib.im2im_channel_stats_bf16(dm.data_ptr(), B * H * W, 64, sums.data_ptr(), _st(dev)), "dbias")
             grads[self.out_conv.bias] = sums[:self.c_mid]
-            w_out_bwd = ctx["w_out_pad"].permute(2, 1, 0).contiguous()  # [64 ci, 1, 64 co]
-            dy = conv_igemm(dm, w_out_bwd)
             # up path, reversed
             skip_grads: List[Optional[torch.Tensor]] = [None] * 4      # for x1..x4
             for k in range(3, -1, -1):
