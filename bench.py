@@ -456,6 +456,9 @@ def run_unet_bench(args, world, rank, dev, group):
     model.eval()
     with torch.no_grad():
         fwd_ms = timed(lambda: model(x), args.unet_steps)
+        model.native_precision = "tf32"          # the reference's precision: fp32 activations, tcgen05 kind::tf32
+        fwd_tf32_ms = timed(lambda: model(x), args.unet_steps)
+        model.native_precision = "bf16"
     model.train()
     opt = FusedAdam(model.parameters(), lr=1e-4)
     last = {}
@@ -531,7 +534,12 @@ def run_unet_bench(args, world, rank, dev, group):
     train_tf = B * train_flop * scale / (train_ms * 1e-3) / 1e12
     return {"model": "UNet(1,1)+quantile head, 17.27M params", "image": f"1x{side}x{side}", "batch_per_gpu": B,
             "scaling": "weak", "dtype": "bf16 operands, fp32 accumulate/params",
+            "precision": {"headline": "bf16 (forward_*, train_*): bf16 operands/activations, tcgen05 kind::f16, fp32 accumulation, "
+                          "fp32 master weights / statistics / optimizer", "reference_precision_mode": "tf32 (forward_tf32_*): fp32 "
+                          "activations, tcgen05 kind::tf32 - what torch does with the reference's fp32 modules on a GPU; "
+                          "inference only"},
             "forward_images_per_s": world * B / (fwd_ms * 1e-3), "forward_ms": fwd_ms,
+            "forward_tf32_images_per_s": world * B / (fwd_tf32_ms * 1e-3), "forward_tf32_ms": fwd_tf32_ms,
             "train_images_per_s": world * B / (train_ms * 1e-3), "train_ms_per_step": train_ms,
             "train_step": "one CUDA graph per step: H2D of the batch from pinned memory + forward + fused pinball/MSE "
                           "loss + backward + " + ("NCCL all-reduce of 69 MB fp32 grads + " if world > 1 else "") +
@@ -542,6 +550,8 @@ def run_unet_bench(args, world, rank, dev, group):
                          "forward_achieved": fwd_tf, "forward_frac": fwd_tf / peak,
                          "train_achieved": train_tf, "train_frac": train_tf / peak,
                          "train_frac_of_sustained": train_tf / peak_sus, "forward_frac_of_sustained": fwd_tf / peak_sus,
+                         "forward_tf32_achieved": B * fwd_flop * scale / (fwd_tf32_ms * 1e-3) / 1e12,
+                         "forward_tf32_frac_of_half_rate_peak": B * fwd_flop * scale / (fwd_tf32_ms * 1e-3) / 1e12 / (peak / 2),
                          "flops": "conv 2*MACs only: 125.29 GFLOP fwd, 375.87 GFLOP train per 320x320 image"}}
 
 
