@@ -61,12 +61,13 @@ struct Vec8<float> {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// x: fp32 NCHW [B, c_in, H, W] (c_in <= 8) -> y: bf16 NHWC [B, H, W, c_out], 3x3 pad 1, + bias, ReLU.
-// One thread = TWO horizontally adjacent pixels x 16 output channels: the 3x4 input window is loaded once (12 loads for
-// 2 pixels) and every 128-bit weight load from shared memory feeds 8 FMAs, so the kernel is FMA- rather than
-// load/address-bound.  Weights fp32 [c_out, c_in, 3, 3] are staged transposed in shared memory.
+// x: fp32 NCHW [B, c_in, H, W] (c_in <= 8) -> y: NHWC [B, H, W, c_out] (bf16, or fp32 in tf32 mode), 3x3 pad 1, + bias, ReLU.
+// One thread = FOUR horizontally adjacent pixels x 16 output channels: the 3x6 input window is loaded once (18 loads for
+// 4 pixels) and every 128-bit weight load from shared memory feeds 16 FMAs (ncu on the 2-pixel version: 42 % of the stall
+// samples were short_scoreboard = waiting for those shared-memory loads, issue slots 53 % busy).  Weights fp32
+// [c_out, c_in, 3, 3] are staged transposed in shared memory.
 template <typename T>
-__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, int B, int c_in, int H,
                                                          int W, int c_out, int relu, T* __restrict__ y) {
     extern __shared__ __align__(16) float s_w[];  // [c_in*9][c_out] (a thread's 16 channels are contiguous), bias [c_out]
@@ -75,54 +76,59 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
     float* s_b = s_w + c_out * kk;
     for (int i = threadIdx.x; i < c_out; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
     __syncthreads();
+    constexpr int kPx = 4;
     const int groups = c_out / 16;
-    const int wp = (W + 1) / 2;  // pixel pairs per row
-    const long long total = static_cast<long long>(B) * H * wp * groups;
+    const int wq = (W + kPx - 1) / kPx;  // pixel quads per row
+    const long long total = static_cast<long long>(B) * H * wq * groups;
     for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
          e += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int g = static_cast<int>(e % groups);
         long long pp = e / groups;
-        const int xw = 2 * static_cast<int>(pp % wp);
-        const int yh = static_cast<int>((pp / wp) % H);
-        const int b = static_cast<int>(pp / (static_cast<long long>(wp) * H));
-        float acc0[16], acc1[16];
+        const int xw = kPx * static_cast<int>(pp % wq);
+        const int yh = static_cast<int>((pp / wq) % H);
+        const int b = static_cast<int>(pp / (static_cast<long long>(wq) * H));
+        float acc[kPx][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc0[j] = acc1[j] = s_b[g * 16 + j];
+        for (int px = 0; px < kPx; ++px)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[px][j] = s_b[g * 16 + j];
         for (int ci = 0; ci < c_in; ++ci) {
             const float* xp = x + (static_cast<long long>(b) * c_in + ci) * H * W;
-            float v[3][4];
+            float v[3][kPx + 2];
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < kPx + 2; ++c) {
                     const int yy = yh + r - 1, xx = xw + c - 1;
                     v[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + static_cast<long long>(yy) * W + xx) : 0.f;
                 }
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-                const float a0 = v[t / 3][t % 3], a1 = v[t / 3][t % 3 + 1];
                 const float* wt = s_w + (ci * 9 + t) * c_out + g * 16;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 wq = *reinterpret_cast<const float4*>(wt + 4 * q);
-                    acc0[4 * q + 0] = fmaf(a0, wq.x, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(a1, wq.x, acc1[4 * q + 0]);
-                    acc0[4 * q + 1] = fmaf(a0, wq.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(a1, wq.y, acc1[4 * q + 1]);
-                    acc0[4 * q + 2] = fmaf(a0, wq.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(a1, wq.z, acc1[4 * q + 2]);
-                    acc0[4 * q + 3] = fmaf(a0, wq.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(a1, wq.w, acc1[4 * q + 3]);
+                    const float4 wv = *reinterpret_cast<const float4*>(wt + 4 * q);
+#pragma unroll
+                    for (int px = 0; px < kPx; ++px) {
+                        const float a = v[t / 3][t % 3 + px];
+                        acc[px][4 * q + 0] = fmaf(a, wv.x, acc[px][4 * q + 0]);
+                        acc[px][4 * q + 1] = fmaf(a, wv.y, acc[px][4 * q + 1]);
+                        acc[px][4 * q + 2] = fmaf(a, wv.z, acc[px][4 * q + 2]);
+                        acc[px][4 * q + 3] = fmaf(a, wv.w, acc[px][4 * q + 3]);
+                    }
                 }
             }
         }
         const long long pix = (static_cast<long long>(b) * H + yh) * W + xw;
 #pragma unroll
-        for (int px2 = 0; px2 < 2; ++px2) {
-            if (xw + px2 >= W) break;
-            const float* acc = px2 ? acc1 : acc0;
+        for (int px = 0; px < kPx; ++px) {
+            if (xw + px >= W) break;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = relu ? fmaxf(acc[8 * half + j], 0.f) : acc[8 * half + j];
-                Vec8<T>::store(y + (pix + px2) * c_out + g * 16 + 8 * half, o);
+                for (int j = 0; j < 8; ++j) o[j] = relu ? fmaxf(acc[px][8 * half + j], 0.f) : acc[px][8 * half + j];
+                Vec8<T>::store(y + (pix + px) * c_out + g * 16 + 8 * half, o);
             }
         }
     }
@@ -187,8 +193,17 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ x
             Vec8<T>::load(base + (static_cast<long long>(y0) * w + x1) * C, v01);
             Vec8<T>::load(base + (static_cast<long long>(y1) * w + x0) * C, v10);
             Vec8<T>::load(base + (static_cast<long long>(y1) * w + x1) * C, v11);
+            if (sizeof(T) == 2) {
+                // bf16 storage: four pre-multiplied weights (4 FMAs per value instead of 7 flops; this kernel is issue-bound,
+                // ncu: issue slots 82 % busy); the result differs from ATen's factored form by an fp32 ulp, far below the
+                // bf16 rounding of the store.  The fp32 (tf32-mode) instantiation keeps ATen's exact expression.
+                const float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
+                for (int j = 0; j < 8; ++j) o[j] = fmaf(w00, v00[j], fmaf(w01, v01[j], fmaf(w10, v10[j], w11 * v11[j])));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
+            }
         }
         Vec8<T>::store(y + pix * C + g * 8, o);
     }
@@ -309,7 +324,7 @@ int conv_first_launch(const float* d_x, const float* d_weight, const float* d_bi
     if (!d_x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "null tensor");
     const size_t smem = sizeof(float) * (static_cast<size_t>(c_out) * c_in * 9 + c_out);
     if (smem > 48 * 1024) return fail(IM2IM_ERANGE, "conv_first: weights do not fit shared memory");
-    const long long items = static_cast<long long>(B) * H * ((W + 1) / 2) * (c_out / 16);
+    const long long items = static_cast<long long>(B) * H * ((W + 3) / 4) * (c_out / 16);
     conv_first_kernel<T><<<grid_for(items, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         d_x, d_weight, d_bias, B, c_in, H, W, c_out, relu, d_out);
     return check_launch("conv_first_kernel");
