@@ -8,6 +8,8 @@
 //   Adam                    core/scripts/train.py:120,162 (torch.optim.Adam defaults: betas .9/.999, eps 1e-8, no decay)
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace im2im {
@@ -65,7 +67,12 @@ __global__ void __launch_bounds__(256, 3) channel_reduce_kernel(const __nv_bfloa
                                                              const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, long long n_pix, int C,
                                                              float* __restrict__ sums) {
-    __shared__ float s_part[2][256][8 + 1];
+    // Block-level combination through 2*C shared-memory accumulators (<= 8 KB): the 18 KB partial-sum array this replaced
+    // kept the kernel from sharing an SM with the tensor-core kernels (which leave ~13 KB of shared memory free), so it
+    // could not overlap the side-stream weight gradients it is meant to run next to.
+    extern __shared__ float s_acc[];   // [2][C]
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) s_acc[c] = 0.f;
+    __syncthreads();
     const int groups = C / 8;
     const int g = threadIdx.x % groups;
     const int lane_p = threadIdx.x / groups;
@@ -119,13 +126,11 @@ __global__ void __launch_bounds__(256, 3) channel_reduce_kernel(const __nv_bfloa
         }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s_part[0][threadIdx.x][j] = acc0[j]; s_part[1][threadIdx.x][j] = acc1[j]; }
+    for (int j = 0; j < 8; ++j) { atomicAdd(&s_acc[g * 8 + j], acc0[j]); atomicAdd(&s_acc[C + g * 8 + j], acc1[j]); }
     __syncthreads();
     // thread c < C finalises channel c
     for (int c = threadIdx.x; c < C; c += 256) {
-        const int gg = c / 8, j = c % 8;
-        float s0 = 0.f, s1 = 0.f;
-        for (int l = 0; l < lanes; ++l) { s0 += s_part[0][l * groups + gg][j]; s1 += s_part[1][l * groups + gg][j]; }
+        float s0 = s_acc[c], s1 = s_acc[C + c];
         if (MODE == 1) s1 = rstd[c] * (s1 - mean[c] * s0);
         atomicAdd(&sums[c], s0);
         atomicAdd(&sums[C + c], s1);
@@ -732,11 +737,19 @@ static int check_channels(int C, const char* what) {
     return IM2IM_OK;
 }
 
+// dynamic shared memory of channel_reduce_kernel: 2*C floats are used; IM2IM_REDUCE_EXCLUSIVE=1 pads the request to 18 KB, which
+// keeps the kernel from sharing an SM with the tensor-core kernels (A/B switch for the co-residency experiment)
+static size_t reduce_smem_bytes(int C) {
+    static const bool exclusive = (getenv("IM2IM_REDUCE_EXCLUSIVE") != nullptr);
+    const size_t need = sizeof(float) * 2 * C;
+    return (exclusive && need < 18432) ? 18432 : need;
+}
+
 extern "C" int im2im_channel_stats_bf16(const void* d_z, int64_t n_pix, int32_t C, float* d_sums, void* stream) {
     if (int rc = check_channels(C, "channel_stats")) return rc;
     if (n_pix <= 0 || !d_z || !d_sums) return fail(IM2IM_EINVAL, "channel_stats: bad arguments");
     const int lanes = 256 / (C / 8);
-    channel_reduce_kernel<0><<<grid_for((n_pix + 3) / 4, lanes, 3), 256, 0, ST(stream)>>>(BF(d_z), nullptr, nullptr, nullptr, nullptr,
+    channel_reduce_kernel<0><<<grid_for((n_pix + 3) / 4, lanes, 3), 256, reduce_smem_bytes(C), ST(stream)>>>(BF(d_z), nullptr, nullptr, nullptr, nullptr,
                                                                                nullptr, n_pix, C, d_sums);
     return check_launch("channel_reduce_kernel<stats>");
 }
@@ -770,7 +783,7 @@ extern "C" int im2im_bn_relu_bwd_bf16(const void* d_dy, const void* d_z, const f
         return fail(IM2IM_EINVAL, "bn_relu_bwd: bad arguments");
     IM2IM_CUDA_TRY(cudaMemsetAsync(d_sums, 0, sizeof(float) * 2 * C, ST(stream)));
     const int lanes = 256 / (C / 8);
-    channel_reduce_kernel<1><<<grid_for((n_pix + 3) / 4, lanes, 3), 256, 0, ST(stream)>>>(BF(d_dy), BF(d_z), d_gamma, d_beta, d_mean,
+    channel_reduce_kernel<1><<<grid_for((n_pix + 3) / 4, lanes, 3), 256, reduce_smem_bytes(C), ST(stream)>>>(BF(d_dy), BF(d_z), d_gamma, d_beta, d_mean,
                                                                                d_rstd, n_pix, C, d_sums);
     if (int rc = check_launch("channel_reduce_kernel<bn_bwd>")) return rc;
     bn_relu_bwd_apply_kernel<<<grid_for(n_pix * (C / 8), 256, 12), 256, 0, ST(stream)>>>(
