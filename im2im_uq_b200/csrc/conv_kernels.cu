@@ -504,6 +504,7 @@ struct HaloParams {
     //   stat_mode 2  this conv is a data gradient producing dy for a BatchNorm+ReLU layer whose pre-normalisation output is
     //                bn_z: g = dy * (bn_z*scale + shift > 0) is stored INSTEAD of dy, and
     //                sums[c] += g, sums[C+c] += rstd*(sum(g*z) - mean*sum(g))   (what channel_reduce_kernel<1> computes)
+    int debug_skip_store;          // IM2IM_HALO_SKIP_STORE=1: compute, do not store (upper bound of an ideal epilogue; dev only)
     int stat_mode;
     float* stat_sums;              // fp32 [2 * c_out], accumulated into
     const __nv_bfloat16* bn_z;     // stat_mode 2: NHWC [B,H,W,c_out]
@@ -660,7 +661,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             const int tw = t % p.tiles_w; t /= p.tiles_w;
             const int th = t % p.tiles_h; t /= p.tiles_h;
             const int w = tw * kHaloTileW + iw, h = th * kHaloTileH + ih, b = t;
-            const bool in_range = (w < p.W) && (h < p.H);
+            const bool in_range = (w < p.W) && (h < p.H) && !p.debug_skip_store;
             const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
             mbar_wait(&tmem_full[buf], (full_phase >> buf) & 1u);
             full_phase ^= 1u << buf;
@@ -1257,6 +1258,8 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
             HaloParams h{};
             h.c_in1 = c_in1; h.c_in2 = c_in2; h.c_out = c_out; h.B = B; h.H = H; h.W = W;
             h.tiles_w = W / kHaloTileW; h.tiles_h = H / kHaloTileH; h.bn = hbn; h.relu = relu; h.bias = d_bias;
+            static const bool skip_store = (getenv("IM2IM_HALO_SKIP_STORE") != nullptr);
+            h.debug_skip_store = skip_store ? 1 : 0;
             h.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16); h.out_f32 = d_out_f32;
             h.out_planar = nullptr; h.n_real = 0; h.act_kind = 0; h.act_from = 0;
             if (want_stats) {
