@@ -855,12 +855,12 @@ __global__ void __launch_bounds__(256) fraction_missed_kernel(const float* __res
 // kind of the sweep / nested-set kernels.  Operation order of the reference: p_k = e_k / sum with one IEEE division per
 // class (:34), cumulative sum accumulated in double and rounded to fp32 at every step (torch.cumsum on the CPU, :38),
 // compared with fp32 0.05 / 0.95 (:40-41), first maximal p_k as the prediction (:42).  exp is portable_expf - the same fixed
-// sequence of IEEE operations as oracle/rcps_oracle.c, so kernel and oracle agree bit for bit.
+// sequence of IEEE operations as the CPU checker's C restatement (tests), so the two agree bit for bit.
 // One thread per pixel, classes strided by `sk` elements (coalesced across pixels); the K <= kMaxSoftmax exponentials are
 // kept in registers between the two passes, so the logits are read from HBM once.
 constexpr int kMaxSoftmax = 64;
 
-__device__ __forceinline__ float portable_expf(float x) {   // x <= 0; see oracle/rcps_oracle.c::portable_expf
+__device__ __forceinline__ float portable_expf(float x) {   // x <= 0; the test suite's C checker carries the same sequence
     const float q = rintf(__fmul_rn(x, 1.4426950408889634f));
     float s = __fmaf_rn(q, -0.693145751953125f, x);
     s = __fmaf_rn(q, -1.428606765330187045e-06f, s);
