@@ -283,11 +283,12 @@ def device_decide_fn(px: int, config: dict, result: Optional[torch.Tensor] = Non
 
 
 def _peer_timeout_s() -> float:
-    """Bound on the in-kernel wait for the peers' flags (seconds; 0 = wait for ever).  Generous by default: normal rank
-    skew (a slow data loader, a first-call JIT, a debugger) must not fail a healthy job; a dead peer is the host
-    watchdog's business.  Override with IM2IM_P2P_TIMEOUT_S."""
+    """Bound on the in-kernel wait for the peers' flags (seconds; 0 = wait for ever).  Two minutes by default - the ranks
+    call ``RcpsGraph.run()`` in lockstep, so this only has to absorb host-side skew (a slow loader, a first-call JIT), and
+    a spinning kernel must not outlive a crashed peer for long; raise it (or set 0) with IM2IM_P2P_TIMEOUT_S when a
+    debugger or a very uneven pipeline sits between the ranks."""
     import os
-    return float(os.environ.get("IM2IM_P2P_TIMEOUT_S", "600"))
+    return float(os.environ.get("IM2IM_P2P_TIMEOUT_S", "120"))
 
 
 def peer_memory_available(group) -> bool:
@@ -395,8 +396,18 @@ class RcpsGraph:
         if self.fused:
             ws_bytes = int(lib.im2im_rcps_fused_workspace_bytes(L))
             self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)   # zero-filled ONCE
-        self._enqueue()                      # warm-up outside capture (lazy module loads, NCCL channel setup)
-        torch.cuda.synchronize(dev)
+        try:
+            self._enqueue()                  # warm-up outside capture (lazy module loads, NCCL channel setup)
+            torch.cuda.synchronize(dev)
+        except _lib.Im2ImError:
+            if not (self.fused and world == 1):
+                raise
+            # e.g. the cooperative launch was refused (not every block can be resident: MPS / a shared GPU): the separate
+            # kernels need no co-residency
+            self.fused = False
+            self._launches = 0
+            self._enqueue()
+            torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
         with torch.cuda.graph(self.graph):

@@ -1465,10 +1465,11 @@ extern "C" int im2im_conv_wgrad_bf16(const void* d_x, const void* d_dz, int32_t 
     if (!d_x || !d_dz || !d_dw) return fail(IM2IM_EINVAL, "null tensor");
     // wide layers: halo kernel (one X box per channel block serves all nine taps; transposed GEMM, no wasted MMA rows)
     static const bool no_halo = (getenv("IM2IM_WGRAD_NO_HALO") != nullptr);
-    if (!no_halo && taps == 9 && W % kHaloTileW == 0 && H % kHaloTileH == 0) {
+    static const bool halo_any = (getenv("IM2IM_WGRAD_HALO_ANY") != nullptr);   // experiment: partial tiles (TMA zero fill)
+    if (!no_halo && taps == 9 && ((W % kHaloTileW == 0 && H % kHaloTileH == 0) || halo_any)) {
         WgradHaloParams h;
         h.c_in = c_in; h.c_out = c_out; h.B = B; h.H = H; h.W = W;
-        h.tiles_w = W / kHaloTileW; h.tiles_h = (H + kHaloTileH - 1) / kHaloTileH;
+        h.tiles_w = (W + kHaloTileW - 1) / kHaloTileW; h.tiles_h = (H + kHaloTileH - 1) / kHaloTileH;
         h.cblocks = c_in / kKStep;
         const int n_blocks = c_out / 64;
         const long long items = static_cast<long long>(h.cblocks) * n_blocks;

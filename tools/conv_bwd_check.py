@@ -55,5 +55,7 @@ def bench(B, H, W, cin, cout, iters=10):
     print(f"wgrad B{B} {H}x{W} {cin}->{cout}: {ms:.3f} ms {fl / ms * 1e-9:.0f} TFLOP/s", flush=True)
 
 if ok:
-    bench(16, 320, 320, 64, 64); bench(16, 320, 320, 128, 64); bench(16, 160, 160, 128, 128); bench(16, 80, 80, 256, 256)
-    bench(16, 40, 40, 512, 512); bench(16, 40, 40, 1024, 512); bench(16, 20, 20, 512, 512)
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    bench(B, 320, 320, 64, 64); bench(B, 320, 320, 128, 64); bench(B, 160, 160, 128, 128); bench(B, 80, 80, 256, 256)
+    bench(B, 40, 40, 256, 512); bench(B, 40, 40, 512, 512); bench(B, 40, 40, 1024, 512); bench(B, 40, 40, 512, 256)
+    bench(B, 20, 20, 512, 512)
