@@ -162,6 +162,8 @@ def _declare_train(lib):
         "im2im_bn_apply_relu_bf16": [vp, vp, vp, i64, i32, vp, vp],
         "im2im_bn_relu_bwd_bf16": [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp],
         "im2im_bn_relu_bwd_apply_bf16": [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp, vp],
+        "im2im_bn_apply_relu_pool_bf16": [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
+        "im2im_bn_relu_pool_bwd_bf16": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
         "im2im_maxpool2x2_bwd_bf16": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
         "im2im_upsample2x_bilinear_bwd_bf16": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
         "im2im_quantile_loss_f32": [vp, vp, i64, i64, f32, f32, f32, f32, f32, vp, vp, vp],
@@ -191,7 +193,7 @@ EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im
            "im2im_host_wait_flag", "im2im_rcps_calibrate_fused_check", "im2im_conv_igemm_tf32",
            "im2im_conv_first_nhwc_f32", "im2im_maxpool2x2_nhwc_f32", "im2im_upsample2x_bilinear_nhwc_f32",
            "im2im_head_conv3x3_act_nhwc_f32", "im2im_conv_igemm_bf16_stats", "im2im_bn_relu_bwd_apply_bf16",
-           "im2im_planar_to_nhwc64_first8_bf16"]
+           "im2im_planar_to_nhwc64_first8_bf16", "im2im_bn_apply_relu_pool_bf16", "im2im_bn_relu_pool_bwd_bf16"]
 
 
 def load():

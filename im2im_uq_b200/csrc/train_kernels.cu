@@ -251,6 +251,159 @@ __global__ void __launch_bounds__(256, 3) bn_relu_bwd_apply_kernel(const __nv_bf
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Skip layers (x1..x4 of the UNet: the block output feeds the skip connection AND the next block's 2x2 max-pool,
+// unet.py:35-39, unet_parts.py:34): BatchNorm+ReLU and the pool in ONE pass forward, and backward the pool's gradient
+// folded into the BatchNorm backward, instead of a separate scatter pass that reads y and read-modify-writes the skip
+// gradient.  One thread = one 2x2 window x 8 channels; H and W even.
+//   forward   y = relu(z*scale + shift) (4 pixels), p = max of the four y (as stored, bf16)
+//   backward  y is recomputed from the saved z (same two ops as the forward, so the same bf16 values), the window's
+//             gradient d_p goes to its FIRST maximal element (ATen's order, like maxpool2x2_bwd_kernel), is added to the
+//             gradient from the up path and rounded to bf16 exactly as the two-kernel sequence stores it; then
+//             g = dy * relu_mask,  PASS 0: sums[c] += g, sums[C+c] += rstd*(sum(g*z) - mean*sum(g));
+//                                  PASS 1: dz = sc*g + c0 - z*k1   (bn_relu_bwd_apply_kernel's formula)
+__global__ void __launch_bounds__(256) bn_apply_relu_pool_kernel(const __nv_bfloat16* __restrict__ z,
+                                                                 const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift, int B, int H, int W,
+                                                                 int C, __nv_bfloat16* __restrict__ y,
+                                                                 __nv_bfloat16* __restrict__ p) {
+    const int Ho = H / 2, Wo = W / 2, groups = C / 8;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Wo * groups) return;
+    const int g = idx % groups, ox = idx / groups;
+    const int oy = blockIdx.y, b = blockIdx.z;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + g * 8 + j); sh[j] = __ldg(shift + g * 8 + j); }
+    const long long base = ((static_cast<long long>(b) * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+    const long long offs[4] = {0, C, static_cast<long long>(W) * C, static_cast<long long>(W) * C + C};
+    Bf16x8 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q].u = ld_stream_u4(z + base + offs[q]);
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float f[8];
+        unpack8(v[q], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+        Bf16x8 o;
+        o.u = pack8(f);
+        *reinterpret_cast<uint4*>(y + base + offs[q]) = o.u;
+        float r[8];
+        unpack8(o, r);                       // the values as stored: max commutes with the (monotone) rounding
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = q == 0 ? r[j] : fmaxf(m[j], r[j]);
+    }
+    const long long pix = (static_cast<long long>(b) * Ho + oy) * Wo + ox;
+    *reinterpret_cast<uint4*>(p + pix * C + g * 8) = pack8(m);
+}
+
+// g[q][j] of one window (see above); z, d_skip: the four pixels, d_p: the pooled gradient
+__device__ __forceinline__ void pool_window_grad(const Bf16x8* vz, const Bf16x8* vd, const Bf16x8& vp, const float* sc,
+                                                 const float* sh, float z[4][8], float g[4][8]) {
+    float dsk[4][8], dp[8], yv[4][8];
+    bool pos[4][8];
+    unpack8(vp, dp);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unpack8(vz[q], z[q]);
+        unpack8(vd[q], dsk[q]);
+        float pre[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { pre[j] = fmaf(z[q][j], sc[j], sh[j]); pos[q][j] = pre[j] > 0.f; pre[j] = fmaxf(pre[j], 0.f); }
+        Bf16x8 o;
+        o.u = pack8(pre);
+        unpack8(o, yv[q]);                   // y exactly as the forward stored it
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int arg = 0;
+        float m = yv[0][j];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) if (yv[q][j] > m) { m = yv[q][j]; arg = q; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            // what maxpool2x2_bwd_kernel(accumulate = 1) leaves in the skip gradient: bf16(prev + routed), prev untouched elsewhere
+            float dy = dsk[q][j];
+            if (q == arg) dy = __bfloat162float(__float2bfloat16_rn(dy + dp[j]));
+            g[q][j] = pos[q][j] ? dy : 0.f;
+        }
+    }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256, 2) bn_pool_bwd_kernel(const __nv_bfloat16* __restrict__ d_skip,
+                                                             const __nv_bfloat16* __restrict__ d_p,
+                                                             const __nv_bfloat16* __restrict__ zt,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             float* __restrict__ sums, float inv_count, int B, int H, int W,
+                                                             int C, __nv_bfloat16* __restrict__ dz) {
+    extern __shared__ float s_acc[];   // PASS 0: [2][C]
+    const int Ho = H / 2, Wo = W / 2, groups = C / 8;
+    const int g = threadIdx.x % groups;
+    const int lane_p = threadIdx.x / groups;
+    const int lanes = 256 / groups;
+    if (PASS == 0) {
+        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) s_acc[c] = 0.f;
+        __syncthreads();
+    }
+    float sc[8], sh[8], c0[8], k1[8], acc0[8], acc1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        const float rs = __ldg(rstd + c), mu = __ldg(mean + c);
+        sc[j] = __ldg(gamma + c) * rs;
+        sh[j] = __ldg(beta + c) - mu * sc[j];
+        acc0[j] = acc1[j] = 0.f;
+        if (PASS == 1) {
+            k1[j] = sc[j] * (rs * (__ldg(sums + C + c) * inv_count));
+            c0[j] = mu * k1[j] - sc[j] * (__ldg(sums + c) * inv_count);
+        }
+    }
+    const long long n_win = static_cast<long long>(B) * Ho * Wo;
+    const long long stride = static_cast<long long>(gridDim.x) * lanes;
+    const long long offs[4] = {0, C, static_cast<long long>(W) * C, static_cast<long long>(W) * C + C};
+    for (long long wi = static_cast<long long>(blockIdx.x) * lanes + lane_p; wi < n_win; wi += stride) {
+        const long long b = wi / (static_cast<long long>(Ho) * Wo);
+        const int r = static_cast<int>(wi - b * Ho * Wo);
+        const int oy = r / Wo, ox = r - oy * Wo;
+        const long long base = ((b * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+        Bf16x8 vz[4], vd[4], vp;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { vz[q].u = ld_stream_u4(zt + base + offs[q]); vd[q].u = ld_stream_u4(d_skip + base + offs[q]); }
+        vp.u = ld_stream_u4(d_p + wi * C + g * 8);
+        float z[4][8], gg[4][8];
+        pool_window_grad(vz, vd, vp, sc, sh, z, gg);
+        if (PASS == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { acc0[j] += gg[q][j]; acc1[j] = fmaf(gg[q][j], z[q][j], acc1[j]); }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = fmaf(-z[q][j], k1[j], fmaf(sc[j], gg[q][j], c0[j]));
+                *reinterpret_cast<uint4*>(dz + base + offs[q]) = pack8(o);
+            }
+        }
+    }
+    if (PASS == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&s_acc[g * 8 + j], acc0[j]); atomicAdd(&s_acc[C + g * 8 + j], acc1[j]); }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += 256) {
+            const float s0 = s_acc[c];
+            const float s1 = rstd[c] * (s_acc[C + c] - mean[c] * s0);
+            atomicAdd(&sums[c], s0);
+            atomicAdd(&sums[C + c], s1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Max-pool backward: the gradient of each 2x2 window goes to its first maximal element (ATen's argmax order);
 // accumulate != 0 adds into dx (skip tensors receive a second gradient from the up path).
 __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x,
@@ -801,6 +954,38 @@ extern "C" int im2im_bn_relu_bwd_apply_bf16(const void* d_g, const void* d_z, co
         BF(d_g), BF(d_z), d_gamma, d_beta, d_mean, d_rstd, d_sums, 1.f / static_cast<float>(n_pix), n_pix, C,
         premasked ? 1 : 0, BFW(d_dz));
     return check_launch("bn_relu_bwd_apply_kernel");
+}
+
+extern "C" int im2im_bn_apply_relu_pool_bf16(const void* d_z, const float* d_scale, const float* d_shift, int32_t B, int32_t H,
+                                            int32_t W, int32_t C, void* d_y, void* d_pooled, void* stream) {
+    if (int rc = check_channels(C, "bn_apply_pool")) return rc;
+    if (B <= 0 || H < 2 || W < 2 || (H % 2) || (W % 2)) return fail(IM2IM_ENOTSUP, "bn_apply_pool: needs even H and W (got %dx%d)", H, W);
+    if (!d_z || !d_scale || !d_shift || !d_y || !d_pooled) return fail(IM2IM_EINVAL, "bn_apply_pool: bad arguments");
+    if (B > 65535 || H / 2 > 65535) return fail(IM2IM_ERANGE, "bn_apply_pool: B and H/2 must be <= 65535");
+    const dim3 grid(static_cast<unsigned>(((W / 2) * (C / 8) + 255) / 256), static_cast<unsigned>(H / 2), static_cast<unsigned>(B));
+    bn_apply_relu_pool_kernel<<<grid, 256, 0, ST(stream)>>>(BF(d_z), d_scale, d_shift, B, H, W, C, BFW(d_y), BFW(d_pooled));
+    return check_launch("bn_apply_relu_pool_kernel");
+}
+
+extern "C" int im2im_bn_relu_pool_bwd_bf16(const void* d_dskip, const void* d_dpooled, const void* d_z, const float* d_gamma,
+                                           const float* d_beta, const float* d_mean, const float* d_rstd, int32_t B,
+                                           int32_t H, int32_t W, int32_t C, float* d_sums, void* d_dz, void* stream) {
+    if (int rc = check_channels(C, "bn_relu_pool_bwd")) return rc;
+    if (B <= 0 || H < 2 || W < 2 || (H % 2) || (W % 2)) return fail(IM2IM_ENOTSUP, "bn_relu_pool_bwd: needs even H and W");
+    if (!d_dskip || !d_dpooled || !d_z || !d_gamma || !d_beta || !d_mean || !d_rstd || !d_sums || !d_dz)
+        return fail(IM2IM_EINVAL, "bn_relu_pool_bwd: bad arguments");
+    IM2IM_CUDA_TRY(cudaMemsetAsync(d_sums, 0, sizeof(float) * 2 * C, ST(stream)));
+    const long long n_win = static_cast<long long>(B) * (H / 2) * (W / 2);
+    const long long n_pix = static_cast<long long>(B) * H * W;
+    const int lanes = 256 / (C / 8);
+    const unsigned grid = grid_for(n_win, lanes, 2);
+    bn_pool_bwd_kernel<0><<<grid, 256, sizeof(float) * 2 * C, ST(stream)>>>(BF(d_dskip), BF(d_dpooled), BF(d_z), d_gamma, d_beta,
+                                                                            d_mean, d_rstd, d_sums, 0.f, B, H, W, C, nullptr);
+    if (int rc = check_launch("bn_pool_bwd_kernel<reduce>")) return rc;
+    bn_pool_bwd_kernel<1><<<grid_for(n_win, lanes, 8), 256, 0, ST(stream)>>>(BF(d_dskip), BF(d_dpooled), BF(d_z), d_gamma, d_beta,
+                                                                             d_mean, d_rstd, d_sums, 1.f / static_cast<float>(n_pix),
+                                                                             B, H, W, C, BFW(d_dz));
+    return check_launch("bn_pool_bwd_kernel<apply>");
 }
 
 extern "C" int im2im_maxpool2x2_bwd_bf16(const void* d_x, const void* d_dy, int32_t B, int32_t H, int32_t W, int32_t C,

@@ -83,6 +83,8 @@ class UNetTrainEngine:
         self.model = model
         t, self.head = model.baseModel, model.last_layer
         self.lib = _lib.load()
+        import os
+        self.fuse_pool = os.environ.get("IM2IM_NO_POOL_FUSION") is None    # A/B switch (tools/train_profile.py)
 
         def dc(d):
             s = d.double_conv
@@ -108,27 +110,30 @@ class UNetTrainEngine:
                                  + pad(layers[0].c_out * 8 * 9))
 
     # ------------------------------------------------------------------------------------------- primitive launches
-    def _conv_bn_relu(self, x: torch.Tensor, layer: _ConvBN, saved: dict, x2: Optional[torch.Tensor] = None):
+    def _conv_bn_relu(self, x: torch.Tensor, layer: _ConvBN, saved: dict, x2: Optional[torch.Tensor] = None,
+                      pool: bool = False):
         """conv3x3 on tensor cores -> BatchNorm (batch statistics) -> ReLU.  Where the layer runs on the halo kernel the
         statistics come out of the convolution's epilogue (im2im_conv_igemm_bf16_stats): no separate pass over z."""
-        pool = self.__dict__.get("_zero")
+        zero_pool = self.__dict__.get("_zero")
         C = layer.c_out
-        sums = pool.take(2 * C) if pool is not None else torch.zeros(2 * C, dtype=torch.float32, device=x.device)
+        sums = zero_pool.take(2 * C) if zero_pool is not None else torch.zeros(2 * C, dtype=torch.float32, device=x.device)
         if getattr(self, "fuse_stats", True):
             z, fused = conv_igemm_stats(x, layer.w_fwd, 1, sums, x2=x2)
         else:
             z, fused = conv_igemm(x, layer.w_fwd, x2=x2), False
-        return self._bn_relu(z, layer, saved, sums=sums, have_stats=fused)
+        return self._bn_relu(z, layer, saved, sums=sums, have_stats=fused, pool=pool)
 
     def _bn_relu(self, z: torch.Tensor, layer: _ConvBN, saved: dict, sums: Optional[torch.Tensor] = None,
-                 have_stats: bool = False):
+                 have_stats: bool = False, pool: bool = False):
+        """BatchNorm (batch statistics) + ReLU of the bias-free convolution output z.  ``pool=True`` (skip layers): also
+        returns maxpool2x2(y), computed in the same pass when H and W are even."""
         lib, dev = self.lib, z.device
         B, H, W, C = z.shape
         n_pix = B * H * W
         bn = layer.bn
-        pool = self.__dict__.get("_zero")     # set by forward(); a direct call (unit tests) allocates its own
+        zero_pool = self.__dict__.get("_zero")     # set by forward(); a direct call (unit tests) allocates its own
         if sums is None:
-            sums = pool.take(2 * C) if pool is not None else torch.zeros(2 * C, dtype=torch.float32, device=dev)
+            sums = zero_pool.take(2 * C) if zero_pool is not None else torch.zeros(2 * C, dtype=torch.float32, device=dev)
         scale = torch.empty(C, dtype=torch.float32, device=dev)
         shift = torch.empty_like(scale)
         rstd = torch.empty_like(scale)
@@ -148,10 +153,15 @@ class UNetTrainEngine:
             else:
                 bn.num_batches_tracked.add_(1)
         y = torch.empty_like(z)
+        saved["z"], saved["mean"], saved["rstd"] = z, mean, rstd  # backward needs xhat everywhere: keep z, not y
+        if pool and H % 2 == 0 and W % 2 == 0 and getattr(self, "fuse_pool", True):
+            p = torch.empty((B, H // 2, W // 2, C), dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.im2im_bn_apply_relu_pool_bf16(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), B, H, W, C,
+                                                         y.data_ptr(), p.data_ptr(), _st(dev)), "bn_apply_relu_pool")
+            return y, p
         _lib.check(lib.im2im_bn_apply_relu_bf16(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), n_pix, C,
                                                 y.data_ptr(), _st(dev)), "bn_apply_relu")
-        saved["z"], saved["mean"], saved["rstd"] = z, mean, rstd  # backward needs xhat everywhere: keep z, not y
-        return y
+        return (y, self._pool(y)) if pool else y
 
     def _bn_relu_bwd(self, dy: torch.Tensor, layer: _ConvBN, saved: dict, grads: Dict):
         lib, dev = self.lib, dy.device
@@ -167,6 +177,26 @@ class UNetTrainEngine:
         grads[layer.bn.weight] = sums[C:]
         # layer.conv.bias gets no entry: its gradient is exactly zero (cancelled by the batch mean, see module doc), and
         # returning None to autograd leaves the zeroed .grad untouched instead of launching a fill and an add per layer
+        return dz
+
+    def _bn_relu_pool_bwd(self, d_skip: torch.Tensor, d_p: torch.Tensor, layer: _ConvBN, saved: dict, grads: Dict):
+        """BatchNorm+ReLU backward of a skip layer whose output also fed a 2x2 max-pool: d_skip (gradient through the skip
+        connection) and d_p (gradient of the pooled tensor) in, dz out - the pool's scatter pass is folded in."""
+        z = saved["z"]
+        B, H, W, C = z.shape
+        dev = z.device
+        if not (H % 2 == 0 and W % 2 == 0 and getattr(self, "fuse_pool", True)):
+            _lib.check(self.lib.im2im_maxpool2x2_bwd_bf16(saved["y_out"].data_ptr(), d_p.data_ptr(), B, H, W, C, 1,
+                                                          d_skip.data_ptr(), _st(dev)), "maxpool_bwd")
+            return self._bn_relu_bwd(d_skip, layer, saved, grads)
+        sums = torch.empty(2 * C, dtype=torch.float32, device=dev)
+        dz = torch.empty_like(z)
+        _lib.check(self.lib.im2im_bn_relu_pool_bwd_bf16(d_skip.data_ptr(), d_p.data_ptr(), z.data_ptr(),
+                                                        layer.bn.weight.data_ptr(), layer.bn.bias.data_ptr(),
+                                                        saved["mean"].data_ptr(), saved["rstd"].data_ptr(), B, H, W, C,
+                                                        sums.data_ptr(), dz.data_ptr(), _st(dev)), "bn_relu_pool_bwd")
+        grads[layer.bn.bias] = sums[:C]
+        grads[layer.bn.weight] = sums[C:]
         return dz
 
     def _side_stream(self, dev):
@@ -218,16 +248,21 @@ class UNetTrainEngine:
             s0 = {}
             y0 = self._bn_relu(z, first, s0)
             s1 = {"x_in": y0}
-            x1 = self._conv_bn_relu(y0, self.inc[1], s1)
+            x1, p = self._conv_bn_relu(y0, self.inc[1], s1, pool=True)    # x1 feeds the skip connection and down1's pool
+            s1["y_out"] = x1
             ctx["inc"] = (s0, s1)
             skips = [x1]
             ctx["down"] = []
-            for (a, b) in self.down:
-                p = self._pool(skips[-1])
+            for k, (a, b) in enumerate(self.down):
                 sa = {"x_in": p}
                 ya = self._conv_bn_relu(p, a, sa)
                 sb = {"x_in": ya}
-                skips.append(self._conv_bn_relu(ya, b, sb))
+                if k < len(self.down) - 1:
+                    xk, p = self._conv_bn_relu(ya, b, sb, pool=True)
+                    sb["y_out"] = xk
+                else:
+                    xk = self._conv_bn_relu(ya, b, sb)                  # x5: bottom of the U, not pooled
+                skips.append(xk)
                 ctx["down"].append((sa, sb))
             ctx["skips"] = list(skips)
             y = skips.pop()
@@ -425,19 +460,18 @@ class UNetTrainEngine:
                                                                   d_u.shape[2], dy.data_ptr(), _st(dev)), "upsample_bwd")
             # dy is now the gradient of x5; down path, reversed
             skips = ctx["skips"]                                        # [x1, x2, x3, x4, x5]
+            d_p = None                                                  # gradient of the pooled tensor below a skip layer
             for k in range(3, -1, -1):
                 (a, b), (sa, sb) = self.down[k], ctx["down"][k]
-                dz = self._bn_relu_bwd(dy, b, sb, grads)
+                if d_p is None:
+                    dz = self._bn_relu_bwd(dy, b, sb, grads)            # x5: no pool below it
+                else:                                                   # x2..x4: skip gradient + the pool's, one pass
+                    dz = self._bn_relu_pool_bwd(skip_grads[k + 1], d_p, b, sb, grads)
                 dz, _ = self._conv_bwd(b, sb, dz, grads, bn_next=(a, sa))     # dz of layer a
-                d_p, _ = self._conv_bwd(a, sa, dz, grads)
-                src = skips[k]                                          # input of this block's max-pool
-                dy = skip_grads[k]                                      # gradient from the up path, accumulated into
-                sb_, sh, sw, sc = src.shape
-                _lib.check(lib.im2im_maxpool2x2_bwd_bf16(src.data_ptr(), d_p.data_ptr(), sb_, sh, sw, sc, 1,
-                                                         dy.data_ptr(), _st(dev)), "maxpool_bwd")
-            # inc block
+                d_p, _ = self._conv_bwd(a, sa, dz, grads)               # gradient of this block's max-pool output
+            # inc block: x1 = skip gradient from up4 + the gradient through down1's pool
             s0, s1 = ctx["inc"]
-            dz = self._bn_relu_bwd(dy, self.inc[1], s1, grads)
+            dz = self._bn_relu_pool_bwd(skip_grads[0], d_p, self.inc[1], s1, grads)
             dz0, _ = self._conv_bwd(self.inc[1], s1, dz, grads, bn_next=(self.inc[0], s0))
             first = self.inc[0]
             dw0 = self._zero.take(first.c_out, c_in, 3, 3)

@@ -389,6 +389,17 @@ int im2im_bn_relu_bwd_bf16(const void* d_dy, const void* d_z, const float* d_gam
 int im2im_bn_relu_bwd_apply_bf16(const void* d_g, const void* d_z, const float* d_gamma, const float* d_beta,
                                  const float* d_mean, const float* d_rstd, const float* d_sums, int64_t n_pix, int32_t C,
                                  int32_t premasked, void* d_dz, void* stream);
+/* Skip layers (the block output feeds the skip connection AND the next block's MaxPool2d(2), core/models/trunks/unet.py:35-39,
+ * unet_parts.py:34): BatchNorm+ReLU and the pool in one pass - y = relu(z*scale + shift), pooled = maxpool2x2(y) - and,
+ * backward, the pool's gradient folded into the BatchNorm backward: dy = d_skip + (pooled gradient routed to the first
+ * maximal element of each window, rounded to bf16 as the two-kernel sequence stores it), then exactly
+ * im2im_bn_relu_bwd_bf16 on dy.  Replaces im2im_maxpool2x2_bf16 / im2im_maxpool2x2_bwd_bf16(accumulate) + the BatchNorm
+ * kernels for those layers (5.5 bytes per activation value less traffic per step).  H and W even (IM2IM_ENOTSUP otherwise). */
+int im2im_bn_apply_relu_pool_bf16(const void* d_z, const float* d_scale, const float* d_shift, int32_t B, int32_t H, int32_t W,
+                                  int32_t C, void* d_y, void* d_pooled, void* stream);
+int im2im_bn_relu_pool_bwd_bf16(const void* d_dskip, const void* d_dpooled, const void* d_z, const float* d_gamma,
+                                const float* d_beta, const float* d_mean, const float* d_rstd, int32_t B, int32_t H,
+                                int32_t W, int32_t C, float* d_sums, void* d_dz, void* stream);
 int im2im_maxpool2x2_bwd_bf16(const void* d_x, const void* d_dy, int32_t B, int32_t H, int32_t W, int32_t C,
                               int32_t accumulate, void* d_dx, void* stream);
 int im2im_upsample2x_bilinear_bwd_bf16(const void* d_du, int32_t B, int32_t h, int32_t w, int32_t C, int32_t H_out,

@@ -243,3 +243,59 @@ def test_dgrad_epilogue_batchnorm_backward_sums(cin, cout, shape):
     _lib.check(LIB.im2im_bn_relu_bwd_apply_bf16(gm.data_ptr(), z.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
                                                 rstd.data_ptr(), sums.data_ptr(), n_pix, cout, 1, dz.data_ptr(), _st()))
     _close(dz.float(), dz_ref.float(), 1e-2)
+
+
+# ------------------------------------------------------------------------------------------- pool fused into BatchNorm (skip layers)
+@pytest.mark.parametrize("shape", [(3, 64, 20, 12), (2, 128, 16, 16), (1, 512, 8, 4), (2, 256, 6, 10)])
+def test_bn_relu_pool_forward_and_backward_equal_the_separate_kernels(shape):
+    """im2im_bn_apply_relu_pool_bf16 / im2im_bn_relu_pool_bwd_bf16 against the sequences they replace:
+    bn_apply_relu -> maxpool2x2 forward, maxpool2x2_bwd(accumulate) -> bn_relu_bwd backward.  Same arithmetic per element,
+    so y / pooled / dz are bit-identical; the per-channel sums differ only in summation order."""
+    B, C, H, W = shape
+    g = torch.Generator(device=DEV).manual_seed(8)
+    z = _nhwc(torch.randn(B, C, H, W, device=DEV, generator=g) * 1.5 + 0.3)
+    flat = z.view(-1)
+    n5 = flat.numel() // 5 * 5
+    flat[0:n5:5] = flat[1:n5:5].clone()                                    # ties inside pooling windows
+    scale = torch.rand(C, device=DEV, generator=g) + 0.5
+    shift = torch.rand(C, device=DEV, generator=g) - 0.7
+    n_pix = B * H * W
+    y_ref = torch.empty_like(z)
+    _lib.check(LIB.im2im_bn_apply_relu_bf16(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), n_pix, C, y_ref.data_ptr(), _st()))
+    p_ref = torch.empty((B, H // 2, W // 2, C), dtype=torch.bfloat16, device=DEV)
+    _lib.check(LIB.im2im_maxpool2x2_bf16(y_ref.data_ptr(), B, H, W, C, p_ref.data_ptr(), _st()))
+    y, p = torch.empty_like(z), torch.empty_like(p_ref)
+    _lib.check(LIB.im2im_bn_apply_relu_pool_bf16(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), B, H, W, C, y.data_ptr(),
+                                                 p.data_ptr(), _st()))
+    assert torch.equal(y, y_ref) and torch.equal(p, p_ref)
+    # backward: scale/shift expressed through (gamma, beta, mean, rstd) exactly as the kernels recompute them
+    rstd = torch.rand(C, device=DEV, generator=g) + 0.5
+    gamma = scale / rstd
+    mean = torch.randn(C, device=DEV, generator=g) * 0.1
+    beta = shift + mean * (gamma * rstd)
+    y2 = torch.empty_like(z)
+    sc2 = (gamma * rstd).contiguous()
+    sh2 = (beta - mean * sc2).contiguous()
+    _lib.check(LIB.im2im_bn_apply_relu_bf16(z.data_ptr(), sc2.data_ptr(), sh2.data_ptr(), n_pix, C, y2.data_ptr(), _st()))
+    d_skip = _nhwc(torch.randn(B, C, H, W, device=DEV, generator=g))
+    d_p = torch.randn(B, H // 2, W // 2, C, device=DEV, generator=g).to(torch.bfloat16)
+    dy = d_skip.clone()
+    _lib.check(LIB.im2im_maxpool2x2_bwd_bf16(y2.data_ptr(), d_p.data_ptr(), B, H, W, C, 1, dy.data_ptr(), _st()))
+    sums_ref = torch.empty(2 * C, device=DEV)
+    dz_ref = torch.empty_like(z)
+    _lib.check(LIB.im2im_bn_relu_bwd_bf16(dy.data_ptr(), z.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
+                                          rstd.data_ptr(), n_pix, C, sums_ref.data_ptr(), dz_ref.data_ptr(), _st()))
+    sums = torch.empty(2 * C, device=DEV)
+    dz = torch.empty_like(z)
+    _lib.check(LIB.im2im_bn_relu_pool_bwd_bf16(d_skip.data_ptr(), d_p.data_ptr(), z.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                               mean.data_ptr(), rstd.data_ptr(), B, H, W, C, sums.data_ptr(), dz.data_ptr(), _st()))
+    _close(sums, sums_ref, 2e-5)
+    _close(dz.float(), dz_ref.float(), 4e-3)          # one bf16 ulp where the sums' last bits move a rounding
+    assert (dz != dz_ref).float().mean().item() < 0.02
+
+
+def test_bn_relu_pool_rejects_odd_sizes():
+    z = torch.zeros(1, 5, 4, 64, dtype=torch.bfloat16, device=DEV)
+    s = torch.zeros(64, device=DEV)
+    rc = LIB.im2im_bn_apply_relu_pool_bf16(z.data_ptr(), s.data_ptr(), s.data_ptr(), 1, 5, 4, 64, z.data_ptr(), z.data_ptr(), _st())
+    assert rc == -95          # IM2IM_ENOTSUP: the engine then runs the separate kernels
