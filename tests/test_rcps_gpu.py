@@ -365,6 +365,32 @@ def test_fused_single_launch_equals_multi_launch(shape, L, head):
     plan.close(); ref.close()
 
 
+@pytest.mark.parametrize("n,side,lam_min,lam_max,L,noise", [(1000, 320, 0.0, 6.0, 1000, 1.0), (250, 640, 0.0, 6.0, 1000, 1.0),
+                                                            (400, 512, 7.0, 10.0, 100, 4.6)])
+def test_fused_single_launch_at_baseline_image_sizes(n, side, lam_min, lam_max, L, noise):
+    """BASELINE configs C2 / C5 / C4 image sizes and grids (per-GPU slices of them): the one-launch calibration against the
+    separate kernels - counts, totals, table, decision - and the size-independent properties of the counts."""
+    out, lab = synth_scores(11, n, 1, side, side, device=DEV, noise=noise)
+    cfg = dict(uncertainty_type="quantiles", minimum_lambda=lam_min, maximum_lambda=lam_max, num_lambdas=L, alpha=0.1,
+               delta=0.1, device="cuda:0", dataset="synthetic", rcps_loss="fraction_missed")
+    ref = cm.RcpsGraph(out, lab, cfg, fused=False)
+    plan = cm.RcpsGraph(out, lab, cfg, fused=True)
+    assert plan.fused and plan.kernels_per_replay == 1
+    want, got = ref.run(), plan.run()
+    torch.cuda.synchronize()
+    assert (got[1], got[2]) == (want[1], want[2])
+    assert torch.equal(plan.counts, ref.counts) and torch.equal(plan.totals, ref.totals) and torch.equal(plan.table, ref.table)
+    c = plan.counts
+    assert bool((c[:, 1:] <= c[:, :-1]).all())                       # misses are non-increasing in lambda
+    assert int(c.max()) <= side * side and int(c.min()) >= 0
+    assert torch.equal(plan.totals, c.sum(0, dtype=torch.int64))     # checksum of checksums
+    if got[2]:
+        first = got[1] if got[1] >= 0 else 0
+        assert float(plan.table[:, :first].abs().max()) == 0.0 if first > 0 else True
+        assert torch.equal(plan.table[:, first:], c[:, first:].float() / float(side * side))
+    plan.close(); ref.close()
+
+
 def test_fused_rejects_what_it_cannot_take():
     lib = _lib.load()
     out, lab = synth_scores(1, 4, 1, 9, 7, device=DEV)          # 63 values per image: not a multiple of 4
