@@ -387,7 +387,9 @@ def test_fused_single_launch_at_baseline_image_sizes(n, side, lam_min, lam_max, 
     if got[2]:
         first = got[1] if got[1] >= 0 else 0
         assert float(plan.table[:, :first].abs().max()) == 0.0 if first > 0 else True
-        assert torch.equal(plan.table[:, first:], c[:, first:].float() / float(side * side))
+        # IEEE division on the CPU (torch's CUDA `tensor / scalar` multiplies by a rounded reciprocal: 1 ulp apart for a
+        # pixel count that is not a power of two; the reference's CPU table - and ours - is count / px correctly rounded)
+        assert torch.equal(plan.table[:, first:].cpu(), c[:, first:].cpu().float() / float(side * side))
     plan.close(); ref.close()
 
 
