@@ -465,10 +465,11 @@ __device__ __forceinline__ float upsample_axis_weight(int u, int n_out, int n_in
     return w;
 }
 
+template <int CPT>   // 8-channel chunks per thread: 2 when C % 16 == 0 (the ten axis weights are shared by both chunks)
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ du, int B, int h, int w,
                                                              int C, int Ho, int Wo, int pad_top, int pad_left,
                                                              __nv_bfloat16* __restrict__ dx) {
-    const int uh = 2 * h, uw = 2 * w, groups = C / 8;
+    const int uh = 2 * h, uw = 2 * w, groups = C / (8 * CPT);
     const float sy = uh > 1 ? static_cast<float>(h - 1) / static_cast<float>(uh - 1) : 0.f;
     const float sx = uw > 1 ? static_cast<float>(w - 1) / static_cast<float>(uw - 1) : 0.f;
     // grid = (ceil(w*groups / 256), h, B): row and image from the block index
@@ -483,31 +484,41 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16
             wy[a] = upsample_axis_weight(2 * iy - 2 + a, uh, h, sy, iy);
             wx[a] = upsample_axis_weight(2 * ix - 2 + a, uw, w, sx, ix);
         }
-        const __nv_bfloat16* base = du + ((static_cast<long long>(b) * Ho + (2 * iy - 2 + pad_top)) * Wo + (2 * ix - 2 + pad_left)) * C + g * 8;
-        float acc[8];
+        const __nv_bfloat16* base = du + ((static_cast<long long>(b) * Ho + (2 * iy - 2 + pad_top)) * Wo + (2 * ix - 2 + pad_left)) * C +
+                                    g * (8 * CPT);
+        float acc[CPT][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int c = 0; c < CPT; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
         // rows outer (wy is uniform over the block: blockIdx.y = iy, so skipping a zero-weight row does not diverge), the
         // five column taps of a row are loaded together; fp32 FMAs in the order rows outer / columns inner
 #pragma unroll
         for (int a = 0; a < 5; ++a) {
             if (wy[a] == 0.f) continue;
-            Bf16x8 t[5];
+            Bf16x8 t[CPT][5];
 #pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                t[c].u = make_uint4(0u, 0u, 0u, 0u);
-                if (wx[c] != 0.f) t[c].u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(a) * Wo + c) * C);
-            }
+            for (int c5 = 0; c5 < 5; ++c5)
 #pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                const float wgt = wy[a] * wx[c];
-                float f[8];
-                unpack8(t[c], f);
+                for (int c = 0; c < CPT; ++c) {
+                    t[c][c5].u = make_uint4(0u, 0u, 0u, 0u);
+                    if (wx[c5] != 0.f)
+                        t[c][c5].u = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(a) * Wo + c5) * C + 8 * c);
+                }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, f[j], acc[j]);
+            for (int c5 = 0; c5 < 5; ++c5) {
+                const float wgt = wy[a] * wx[c5];
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    float f[8];
+                    unpack8(t[c][c5], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[c][j] = fmaf(wgt, f[j], acc[c][j]);
+                }
             }
         }
-        *reinterpret_cast<uint4*>(dx + pix * C + g * 8) = pack8(acc);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) *reinterpret_cast<uint4*>(dx + pix * C + g * (8 * CPT) + 8 * c) = pack8(acc[c]);
     }
 }
 
@@ -1006,9 +1017,13 @@ extern "C" int im2im_upsample2x_bilinear_bwd_bf16(const void* d_du, int32_t B, i
         return fail(IM2IM_EINVAL, "upsample_bwd: bad arguments");
     const int pad_top = (H_out - 2 * h) / 2, pad_left = (W_out - 2 * w) / 2;
     if (B > 65535 || h > 65535) return fail(IM2IM_ERANGE, "upsample_bwd: B and h must be <= 65535");
-    const dim3 ugrid(static_cast<unsigned>((w * (C / 8) + 255) / 256), static_cast<unsigned>(h), static_cast<unsigned>(B));
-    upsample2x_bwd_kernel<<<ugrid, 256, 0, ST(stream)>>>(BF(d_du), B, h, w, C, H_out, W_out, pad_top,
-                                                                           pad_left, BFW(d_dx));
+    if (C % 16 == 0) {
+        const dim3 ugrid(static_cast<unsigned>((w * (C / 16) + 255) / 256), static_cast<unsigned>(h), static_cast<unsigned>(B));
+        upsample2x_bwd_kernel<2><<<ugrid, 256, 0, ST(stream)>>>(BF(d_du), B, h, w, C, H_out, W_out, pad_top, pad_left, BFW(d_dx));
+    } else {
+        const dim3 ugrid(static_cast<unsigned>((w * (C / 8) + 255) / 256), static_cast<unsigned>(h), static_cast<unsigned>(B));
+        upsample2x_bwd_kernel<1><<<ugrid, 256, 0, ST(stream)>>>(BF(d_du), B, h, w, C, H_out, W_out, pad_top, pad_left, BFW(d_dx));
+    }
     return check_launch("upsample2x_bwd_kernel");
 }
 

@@ -163,49 +163,59 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const T* __restrict__ x
 // Bilinear x2 upsample with align_corners=True of x [B,h,w,C], written into y [B,Ho,Wo,C] at offset (pad_top, pad_left)
 // with zeros elsewhere (F.pad to the skip connection's size).  Source index and weights follow ATen's
 // upsample_bilinear2d: src = dst * (in-1)/(out-1) in fp32, i0 = (int)src, frac = src - i0.
-template <typename T>
+template <typename T, int CPT>   // CPT = 8-channel chunks per thread (2 when C % 16 == 0: the index / weight math is shared)
 __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ x, int B, int h, int w,
                                                          int C, int Ho, int Wo, int pad_top, int pad_left,
                                                          T* __restrict__ y) {
-    const int uh = 2 * h, uw = 2 * w, groups = C / 8;
+    const int uh = 2 * h, uw = 2 * w, groups = C / (8 * CPT);
     const float sy = uh > 1 ? static_cast<float>(h - 1) / static_cast<float>(uh - 1) : 0.f;
     const float sx = uw > 1 ? static_cast<float>(w - 1) / static_cast<float>(uw - 1) : 0.f;
-    // grid = (ceil(Wo*groups / 256), Ho, B): see maxpool2x2_kernel (ncu: this kernel was instruction-bound, issue 76 %)
+    // grid = (ceil(Wo*groups / 256), Ho, B): see maxpool2x2_kernel (ncu: this kernel is instruction-bound, issue 82 %)
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < Wo * groups) {
         const int g = idx % groups, ox = idx / groups;
         const int oy = blockIdx.y, b = blockIdx.z;
         const long long pix = (static_cast<long long>(b) * Ho + oy) * Wo + ox;
         const int uy = oy - pad_top, ux = ox - pad_left;
-        float o[8];
+        T* dst = y + pix * C + g * (8 * CPT);
         if (uy < 0 || uy >= uh || ux < 0 || ux >= uw) {
+            float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = 0.f;
-        } else {
-            const float fy = sy * uy, fx = sx * ux;
-            const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-            const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-            const float ly = fy - y0, lx = fx - x0;
-            const float hy = 1.f - ly, hx = 1.f - lx;
-            const T* base = x + static_cast<long long>(b) * h * w * C + g * 8;
-            float v00[8], v01[8], v10[8], v11[8];
-            Vec8<T>::load(base + (static_cast<long long>(y0) * w + x0) * C, v00);
-            Vec8<T>::load(base + (static_cast<long long>(y0) * w + x1) * C, v01);
-            Vec8<T>::load(base + (static_cast<long long>(y1) * w + x0) * C, v10);
-            Vec8<T>::load(base + (static_cast<long long>(y1) * w + x1) * C, v11);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) Vec8<T>::store(dst + 8 * c, o);
+            return;
+        }
+        const float fy = sy * uy, fx = sx * ux;
+        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float ly = fy - y0, lx = fx - x0;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const T* base = x + static_cast<long long>(b) * h * w * C + g * (8 * CPT);
+        const T* p00 = base + (static_cast<long long>(y0) * w + x0) * C;
+        const T* p01 = base + (static_cast<long long>(y0) * w + x1) * C;
+        const T* p10 = base + (static_cast<long long>(y1) * w + x0) * C;
+        const T* p11 = base + (static_cast<long long>(y1) * w + x1) * C;
+        // bf16 storage: four pre-multiplied weights (4 FMAs per value instead of 7 flops); the result differs from ATen's
+        // factored form by an fp32 ulp, far below the bf16 rounding of the store.  The fp32 (tf32-mode) instantiation keeps
+        // ATen's exact expression.
+        const float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            float v00[8], v01[8], v10[8], v11[8], o[8];
+            Vec8<T>::load(p00 + 8 * c, v00);
+            Vec8<T>::load(p01 + 8 * c, v01);
+            Vec8<T>::load(p10 + 8 * c, v10);
+            Vec8<T>::load(p11 + 8 * c, v11);
             if (sizeof(T) == 2) {
-                // bf16 storage: four pre-multiplied weights (4 FMAs per value instead of 7 flops; this kernel is issue-bound,
-                // ncu: issue slots 82 % busy); the result differs from ATen's factored form by an fp32 ulp, far below the
-                // bf16 rounding of the store.  The fp32 (tf32-mode) instantiation keeps ATen's exact expression.
-                const float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = fmaf(w00, v00[j], fmaf(w01, v01[j], fmaf(w10, v10[j], w11 * v11[j])));
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
             }
+            Vec8<T>::store(dst + 8 * c, o);
         }
-        Vec8<T>::store(y + pix * C + g * 8, o);
     }
 }
 
@@ -347,9 +357,15 @@ int upsample_launch(const T* d_x, int B, int h, int w, int C, int H_out, int W_o
     if (!d_x || !d_out) return fail(IM2IM_EINVAL, "null tensor");
     const int pad_top = (H_out - 2 * h) / 2, pad_left = (W_out - 2 * w) / 2;  // F.pad split of unet_parts.py:63-64
     if (B > 65535 || H_out > 65535) return fail(IM2IM_ERANGE, "upsample: B and H_out must be <= 65535");
-    const dim3 ugrid(static_cast<unsigned>((W_out * (C / 8) + 255) / 256), static_cast<unsigned>(H_out), static_cast<unsigned>(B));
-    upsample2x_kernel<T><<<ugrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, B, h, w, C, H_out, W_out, pad_top, pad_left,
-                                                                              d_out);
+    if (C % 16 == 0) {
+        const dim3 ugrid(static_cast<unsigned>((W_out * (C / 16) + 255) / 256), static_cast<unsigned>(H_out), static_cast<unsigned>(B));
+        upsample2x_kernel<T, 2><<<ugrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, B, h, w, C, H_out, W_out, pad_top,
+                                                                                     pad_left, d_out);
+    } else {
+        const dim3 ugrid(static_cast<unsigned>((W_out * (C / 8) + 255) / 256), static_cast<unsigned>(H_out), static_cast<unsigned>(B));
+        upsample2x_kernel<T, 1><<<ugrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, B, h, w, C, H_out, W_out, pad_top,
+                                                                                     pad_left, d_out);
+    }
     return check_launch("upsample2x_kernel");
 }
 
