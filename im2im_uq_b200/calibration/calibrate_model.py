@@ -530,25 +530,37 @@ def rcps_sweep(outputs: torch.Tensor, labels: torch.Tensor, config: dict, device
     all-reduced (one int64 vector of length L over NCCL) and every rank reaches the same decision.
     """
     device = _cuda_device(device if device is not None else config['device'])
+    lam_dev, order, ascending = _sorted_grid(config, device)
+    n_local = outputs.shape[0]
+    px = labels[0].numel() if n_local else 0
+    counts, totals = _miss_counts_any_device(outputs, labels, lam_dev, device, head=head)
+    return _sweep_counts(counts, totals, order, ascending, px, config, group=group, verbose=verbose, stats=stats,
+                         n_total=n_total)
+
+
+def _sorted_grid(config: dict, device):
+    """(ascending lambda grid on the device, permutation or None, was it ascending already) - the kernels rank on a sorted
+    grid; a descending one (minimum_lambda > maximum_lambda) is un-permuted afterwards."""
     lambdas, dlambda, lam_prime, default_lhat = sweep.lambda_grid(config)
-    L = lambdas.shape[0]
     if not bool(torch.isfinite(lam_prime).all()):
         raise ValueError("lambda grid must be finite")
     ascending = bool((lam_prime[1:] >= lam_prime[:-1]).all())
     if ascending:
-        order = None
-        lam_sorted = lam_prime
-    else:  # e.g. minimum_lambda > maximum_lambda: rank on the sorted grid, un-permute the columns afterwards
-        lam_sorted, order = torch.sort(lam_prime)
-    n_local = outputs.shape[0]
-    px = labels[0].numel() if n_local else 0
-    lam_dev = lam_sorted.to(device)
-    counts, totals = _miss_counts_any_device(outputs, labels, lam_dev, device, head=head)
+        return lam_prime.to(device), None, True
+    lam_sorted, order = torch.sort(lam_prime)
+    return lam_sorted.to(device), order, False
+
+
+def _sweep_counts(counts, totals, order, ascending, px, config, group=None, verbose=False, stats=None, n_total=None):
+    """The stopping rule on per-image miss counts (N_local, L) + their column totals; returns as ``rcps_sweep``."""
+    device = counts.device
+    L = counts.shape[1]
     if order is not None:
         inv = torch.empty_like(order)
         inv[order] = torch.arange(L)
         counts = counts[:, inv.to(device)].contiguous()
         totals = totals[inv.to(device)].contiguous()
+
     def column_to_losses(col: torch.Tensor) -> torch.Tensor:
         return rcps.loss_table(col.reshape(-1, 1).contiguous(), px)[:, 0]
 
@@ -571,18 +583,22 @@ def calibrate_from_outputs(model, outputs: torch.Tensor, labels: torch.Tensor, c
         lhat, stop, counts, visited = rcps_sweep(scores, labels, config, device=device, group=group, stats=stats,
                                                  head=kind)
         model.set_lhat(lhat)
-        px = labels[0].numel()
-        L = counts.shape[1]
-        first = int(torch.nonzero(visited)[0]) if bool(visited.any()) else L
-        contiguous_suffix = bool(visited[first:].all())
-        table = rcps.loss_table(counts, px, first_visited_col=first if contiguous_suffix else 0)
-        if not contiguous_suffix:  # duplicate lambdas: a non-suffix set of columns was written
-            table = table * visited.to(device=table.device, dtype=table.dtype)[None, :]
-        if table_device == "cpu":
-            host = torch.empty(table.shape, dtype=torch.float32, pin_memory=True)
-            host.copy_(table, non_blocking=False)
-            table = host
-        return model, table
+        return model, _table_from_counts(counts, visited, labels[0].numel(), table_device)
+
+
+def _table_from_counts(counts, visited, px, table_device: str = "cpu"):
+    """(N, L) fp32 loss table with never-visited columns zero (calibrate_model.py:133-136), pinned host memory by default."""
+    L = counts.shape[1]
+    first = int(torch.nonzero(visited)[0]) if bool(visited.any()) else L
+    contiguous_suffix = bool(visited[first:].all())
+    table = rcps.loss_table(counts, px, first_visited_col=first if contiguous_suffix else 0)
+    if not contiguous_suffix:  # duplicate lambdas: a non-suffix set of columns was written
+        table = table * visited.to(device=table.device, dtype=table.dtype)[None, :]
+    if table_device == "cpu":
+        host = torch.empty(table.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(table, non_blocking=False)
+        table = host
+    return table
 
 
 def _tensor_pair(dataset):
@@ -638,6 +654,84 @@ def collect_outputs(model, dataset, config, device):
     return outputs, labels
 
 
+_HIST_MAX_LAMBDAS = 4096   # the head-fused histogram keeps 16 bytes per lambda in shared memory next to the convolution
+
+
+def streaming_applicable(model, dataset, config) -> bool:
+    """Streaming calibration covers the built-in heads whose scores ARE the head outputs (every head but softmax), on
+    map-style datasets; config['streaming_calibration'] = False keeps the two-stage path (outputs materialised)."""
+    if not config.get('streaming_calibration', True) or config.get('dataset') == 'temca':
+        return False
+    fused = _fused_head(model)
+    return fused is not None and fused[1] is None
+
+
+def calibrate_streaming(model, dataset, config, device, group=None, stats: Optional[dict] = None,
+                        table_device: str = "cpu"):
+    """Stages 1+2 of ``calibrate_model`` (reference :106-136) batch by batch, without the (N, 3, C, H, W) output tensor:
+    each batch goes model -> per-image miss counts at once and only the (N, L) int32 counts stay in HBM.
+
+    With the native bf16 engine and a one-channel quantile head the ranks are booked by the head convolution's own
+    epilogue (``UNetInferenceEngine.forward_hist``: the head tensor is never written at all); otherwise the batch's
+    outputs live for one ``miss_counts`` pass and are dropped.  Counts, lhat and the loss table are bit-identical to the
+    two-stage path (same per-pixel rank code, integer sums)."""
+    from ..models.unet_engine import UNetInferenceEngine, native_forward_applicable
+    kind, _ = _fused_head(model)
+    lam_dev, order, ascending = _sorted_grid(config, device)
+    L = lam_dev.numel()
+    n = len(dataset)
+    if n == 0:
+        raise IndexError("empty calibration set")             # the reference fails on dataset[0]
+    bs = int(config['batch_size'])
+    pair = _tensor_pair(dataset)
+    if pair is not None:
+        batches = ((pair[0][lo:lo + bs], pair[1][lo:lo + bs]) for lo in range(0, n, bs))
+    else:
+        batches = ((b[0], b[1]) for b in DataLoader(dataset, num_workers=0, batch_size=bs, pin_memory=True))
+    counts = torch.empty((n, L), dtype=torch.int32, device=device)
+    totals = torch.zeros((L,), dtype=torch.int64, device=device)
+    hist = None
+    px = None
+    lo = 0
+    fused_batches = 0
+    for xb, yb in batches:
+        xb = xb.to(device, non_blocking=True)
+        yb = yb.to(device, non_blocking=True).to(torch.get_default_dtype()).contiguous()
+        b = xb.shape[0]
+        px = yb[0].numel()
+        eng = None
+        if (kind == _lib.IM2IM_HEAD_QUANTILES and L <= _HIST_MAX_LAMBDAS and yb.dim() == 4 and yb.shape[1] == 1
+                and yb.dtype == torch.float32 and native_forward_applicable(model, xb)):
+            eng = model.__dict__.get("_native_engine")
+            if eng is None:
+                eng = model.__dict__["_native_engine"] = UNetInferenceEngine(model)
+            if not eng.hist_applicable(xb):
+                eng = None
+        if eng is not None:
+            if hist is None or hist.shape[0] < b:
+                hist = torch.zeros((b, L + 1), dtype=torch.int32, device=device)
+            eng.forward_hist(xb, yb, lam_dev, hist[:b])
+            rcps.counts_from_hist(hist[:b], counts[lo:lo + b], totals)
+            fused_batches += 1
+        else:
+            out = model(xb)
+            _count_batch(out, yb, lam_dev, counts[lo:lo + b], totals, kind)
+            del out
+        lo += b
+    if stats is not None:
+        stats["streaming"] = True
+        stats["head_fused_batches"] = fused_batches
+    lhat, stop, counts, visited = _sweep_counts(counts, totals, order, ascending, px, config, group=group, stats=stats)
+    model.set_lhat(lhat)
+    return model, _table_from_counts(counts, visited, px, table_device)
+
+
+def _count_batch(out, labels, lam_dev, counts_rows, totals, kind):
+    """miss counts of one batch into its rows of the counts table; the running totals keep accumulating."""
+    counts_rows.zero_()
+    rcps.miss_counts(out, labels, lam_dev, counts=counts_rows, totals=totals, zero=False, head=kind)
+
+
 def rank_shard(dataset, group):
     """This rank's contiguous block of a map-style calibration set (rank order = row order of the loss table)."""
     import torch.distributed as dist
@@ -681,8 +775,11 @@ def calibrate_model(model, dataset, config, group=None, gather_table: bool = Fal
         model = model.to(device)
         if group is not None:
             dataset = rank_shard(dataset, group)
-        outputs, labels = collect_outputs(model, dataset, config, device)
-        model, calib_loss_table = calibrate_from_outputs(model, outputs, labels, config, group=group)
+        if streaming_applicable(model, dataset, config):
+            model, calib_loss_table = calibrate_streaming(model, dataset, config, device, group=group)
+        else:
+            outputs, labels = collect_outputs(model, dataset, config, device)
+            model, calib_loss_table = calibrate_from_outputs(model, outputs, labels, config, group=group)
         if group is not None and gather_table:
             calib_loss_table = gather_loss_table(calib_loss_table, group, device)
         print(f"Model's lhat set to {model.lhat}")

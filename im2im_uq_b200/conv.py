@@ -165,6 +165,32 @@ def head_conv_tc(x: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[to
     return out
 
 
+def head_conv_tc_hist(x: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[torch.Tensor], labels: torch.Tensor,
+                      lambdas_sorted: torch.Tensor, hist: torch.Tensor, act_kind: int = 0, act_from: int = 0,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One-channel quantile head on tensor cores whose epilogue books every pixel's rank on the ascending lambda grid into
+    ``hist`` (int32 [B, L+1], accumulated into) instead of writing the (B, 3, 1, H, W) head tensor
+    (im2im_head_conv3x3_tc_hist).  ``labels`` fp32 [B, 1, H, W]; ``out`` (fp32 [B, 3, H, W]) also receives the planes."""
+    lib = _lib.load()
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[3] == 64
+    assert weight_packed.dtype == torch.bfloat16 and weight_packed.is_contiguous() and tuple(weight_packed.shape) == (64, 9, 64)
+    B, H, W, _ = x.shape
+    L = lambdas_sorted.numel()
+    assert labels.is_cuda and labels.dtype == torch.float32 and labels.is_contiguous() and labels.numel() == B * H * W
+    assert lambdas_sorted.is_cuda and lambdas_sorted.dtype == torch.float32 and lambdas_sorted.is_contiguous()
+    assert hist.is_cuda and hist.is_contiguous() and hist.element_size() == 4 and tuple(hist.shape) == (B, L + 1)
+    if out is not None:
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, 3, H, W)
+    with torch.cuda.device(x.device):
+        rc = lib.im2im_head_conv3x3_tc_hist(x.data_ptr(), weight_packed.data_ptr(),
+                                            bias.data_ptr() if bias is not None else None, B, H, W, 3, act_kind, act_from,
+                                            out.data_ptr() if out is not None else None, labels.data_ptr(),
+                                            lambdas_sorted.data_ptr(), L, hist.data_ptr(),
+                                            torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "im2im_head_conv3x3_tc_hist")
+    return hist
+
+
 def planar_to_nhwc64(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 planes [B, n, H, W] -> bf16 NHWC [B, H, W, 64], channels >= n zero.
 

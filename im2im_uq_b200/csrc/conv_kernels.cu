@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "rcps_rank.cuh"
 
 namespace im2im {
 namespace {
@@ -498,6 +499,15 @@ struct HaloParams {
     // [B, n_real, H, W] (the reference's (B, planes, C, H, W) head tensor), planes >= act_from get act_kind (1 relu, 2 abs)
     float* out_planar;
     int n_real, act_kind, act_from;
+    // head mode + calibration histogram (quantile head, one output channel: planes = lower, prediction, upper): every pixel
+    // is ranked against the sorted lambda grid exactly as rcps_hist_kernel ranks it (rcps_rank.cuh) from the fp32 values
+    // that out_planar would hold, and booked into hist_global[b][k] (u32 [B][hist_L + 1], accumulated into) - the
+    // (B, 3, 1, H, W) head tensor need not exist (out_planar may be null).  Tiles are then dealt to the CTAs in contiguous
+    // runs so that a CTA flushes its shared-memory histogram once per image it touches.
+    unsigned* hist_global;
+    const float* hist_labels;      // fp32 [B, 1, H, W]
+    const float* hist_lambdas;     // device, ascending, hist_L entries
+    int hist_L;
     // Per-channel statistics can be accumulated on the way out (training), from the bf16 values that are stored; each
     // epilogue thread keeps the partial sums of its pixel row for all 64 channels in registers until the end of the kernel:
     //   stat_mode 1  sums[c] += z, sums[C+c] += z*z                         BatchNorm batch statistics of this conv's output
@@ -550,6 +560,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     // behind the barrier block (128 B reserved): [scale bn f32][shift bn f32] for stat_mode 2
     float* s_scale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(full_bar) + 128);
     float* s_shift = s_scale + p.bn;
+    // histogram mode: [lambda pairs f32x2 x (L+1)][lambda f32 x L][hist u32 x (L+1)] behind them
+    float2* s_pair = reinterpret_cast<float2*>(s_shift + p.bn);
+    float* s_lam = reinterpret_cast<float*>(s_pair + (p.hist_L + 1));
+    unsigned* s_hist = reinterpret_cast<unsigned*>(s_lam + p.hist_L);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -562,6 +576,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             const float sc = p.bn_gamma[ch] * p.bn_rstd[ch];
             s_scale[c] = sc;
             s_shift[c] = p.bn_beta[ch] - p.bn_mean[ch] * sc;
+        }
+    }
+    if (p.hist_global != nullptr) {
+        const int L = p.hist_L;
+        for (int j = threadIdx.x; j <= L; j += blockDim.x) {
+            s_hist[j] = 0u;
+            s_pair[j] = make_float2(j > 0 ? p.hist_lambdas[j - 1] : -INFINITY, j < L ? p.hist_lambdas[j] : INFINITY);
+            if (j < L) s_lam[j] = p.hist_lambdas[j];
         }
     }
     if (threadIdx.x == 0) {
@@ -585,6 +607,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     // the N blocks first (blockIdx.y), then stride over the pixel tiles
     const int tn = blockIdx.y;
     const int n0 = tn * p.bn;
+    // tile order: strided over the CTAs, or (histogram mode) one contiguous run per CTA
+    int tile_first = blockIdx.x, tile_last = n_tiles_m, tile_step = gridDim.x;
+    if (p.hist_global != nullptr) {
+        tile_first = static_cast<int>(static_cast<long long>(n_tiles_m) * blockIdx.x / gridDim.x);
+        tile_last = static_cast<int>(static_cast<long long>(n_tiles_m) * (blockIdx.x + 1) / gridDim.x);
+        tile_step = 1;
+    }
 
     if (warp == 0) {
         if (lane == 0) {
@@ -596,7 +625,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                                 tap * c_in + cb * kKStep, n0);
             int stage = 0;
             unsigned phase = 1;
-            for (int tile = blockIdx.x; tile < n_tiles_m; tile += gridDim.x) {
+            for (int tile = tile_first; tile < tile_last; tile += tile_step) {
                 int t = tile;
                 const int tw = t % p.tiles_w; t /= p.tiles_w;
                 const int th = t % p.tiles_h; t /= p.tiles_h;
@@ -620,7 +649,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             unsigned phase = 0;
             unsigned acc_phase = 3u;
             int buf = 0;
-            for (int tile = blockIdx.x; tile < n_tiles_m; tile += gridDim.x) {
+            for (int tile = tile_first; tile < tile_last; tile += tile_step) {
                 mbar_wait(&tmem_empty[buf], (acc_phase >> buf) & 1u);
                 acc_phase ^= 1u << buf;
                 tc_fence_after();
@@ -656,7 +685,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         float acc0[kHaloStatBn], acc1[kHaloStatBn];
 #pragma unroll
         for (int j = 0; j < kHaloStatBn; ++j) acc0[j] = acc1[j] = 0.f;
-        for (int tile = blockIdx.x; tile < n_tiles_m; tile += gridDim.x) {
+        for (int tile = tile_first; tile < tile_last; tile += tile_step) {
             int t = tile;
             const int tw = t % p.tiles_w; t /= p.tiles_w;
             const int th = t % p.tiles_h; t /= p.tiles_h;
@@ -667,7 +696,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             full_phase ^= 1u << buf;
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(buf) * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
-            if (p.out_planar != nullptr) {
+            if (p.out_planar != nullptr || p.hist_global != nullptr) {
                 // head mode: the real outputs live in the first 32 accumulator columns; one TMEM load, then the buffer is free
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tmem_acc, v);
@@ -675,7 +704,43 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-                if (in_range) {
+                if (p.hist_global != nullptr) {
+                    // planes 0..2 = lower, prediction, upper of this thread's pixel, as fp32 exactly as they would be stored
+                    const int L = p.hist_L;
+                    if (in_range) {
+                        float o[3];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            float x = __uint_as_float(v[j]);
+                            if (p.bias) x += __ldg(p.bias + j);
+                            if (j >= p.act_from) {
+                                if (p.act_kind == 1) x = (x != x) ? x : fmaxf(x, 0.f);
+                                else if (p.act_kind == 2) x = fabsf(x);
+                            }
+                            o[j] = x;
+                        }
+                        const float y = __ldg(p.hist_labels + pix);
+                        const float lam0 = s_lam[0], span = s_lam[L - 1] - lam0;
+                        const float guess_scale = (L > 1 && span > 0.f) ? static_cast<float>(L - 1) / span : 0.f;
+                        const PixelQuery q = make_query<IM2IM_HEAD_QUANTILES>(o[0], o[1], o[2], y);
+                        bool ok;
+                        int k = rank_guess<IM2IM_HEAD_QUANTILES>(q, s_pair, L, guess_scale, -lam0 * guess_scale, ok);
+                        if (!ok) k = rank_bisect(q.d, q.P, q.Y, s_lam, L);
+                        if (k > 0) atomicAdd(&s_hist[k], 1u);
+                    }
+                    // last tile of this image in this CTA's run: move the shared histogram into the image's global row
+                    const int per_image = p.tiles_w * p.tiles_h;
+                    if (tile + 1 == tile_last || (tile + 1) / per_image != b) {
+                        named_bar_sync(2, 128);
+                        unsigned* grow = p.hist_global + static_cast<size_t>(b) * (L + 1);
+                        for (int k = row; k <= L; k += 128) {
+                            const unsigned c = s_hist[k];
+                            if (c != 0u) { atomicAdd(grow + k, c); s_hist[k] = 0u; }
+                        }
+                        named_bar_sync(2, 128);
+                    }
+                }
+                if (in_range && p.out_planar != nullptr) {
                     const size_t hw = static_cast<size_t>(p.H) * p.W;
                     float* dst = p.out_planar + static_cast<size_t>(b) * p.n_real * hw + static_cast<size_t>(h) * p.W + w;
 #pragma unroll
@@ -1425,15 +1490,17 @@ extern "C" int im2im_planar_to_nhwc64_bf16(const float* d_src, int32_t n_planes,
     return check_launch("planar_to_nhwc64_kernel");
 }
 
-extern "C" int im2im_head_conv3x3_tc_f32(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H,
-                                         int32_t W, int32_t n_real, int32_t act_kind, int32_t act_from_plane,
-                                         float* d_out, void* stream) {
+namespace im2im {
+namespace {
+int head_tc_impl(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t n_real,
+                 int32_t act_kind, int32_t act_from_plane, float* d_out, const float* d_labels, const float* d_lambdas,
+                 int32_t n_lambdas, uint32_t* d_hist, void* stream) {
     if (B <= 0 || H <= 0 || W <= 0) return fail(IM2IM_EINVAL, "head_tc: bad activation shape");
     if (n_real < 1 || n_real > 32) return fail(IM2IM_ERANGE, "head_tc: n_real=%d outside [1, 32]", n_real);
     if (act_kind < 0 || act_kind > 2) return fail(IM2IM_EINVAL, "head_tc: act_kind=%d", act_kind);
     if (W % kHaloTileW || H % kHaloTileH)
         return fail(IM2IM_ENOTSUP, "head_tc: needs W %% 8 == 0 and H %% 16 == 0 (got %dx%d); use im2im_head_conv3x3_act_f32", H, W);
-    if (!d_x || !d_weight || !d_out) return fail(IM2IM_EINVAL, "head_tc: null tensor");
+    if (!d_x || !d_weight || (!d_out && !d_hist)) return fail(IM2IM_EINVAL, "head_tc: null tensor");
     HaloParams h{};
     h.c_in1 = 64; h.c_in2 = 0; h.c_out = 64; h.B = B; h.H = H; h.W = W;
     // N = 32: only the first n_real <= 32 weight rows are real, so half of the 64 packed rows are never loaded or multiplied
@@ -1442,18 +1509,48 @@ extern "C" int im2im_head_conv3x3_tc_f32(const void* d_x, const void* d_weight, 
     h.out_planar = d_out; h.n_real = n_real; h.act_kind = act_kind; h.act_from = act_kind ? act_from_plane : n_real;
     const int w_bytes = 9 * 64 * h.bn * 2;
     h.a_stages = 4;
+    size_t hist_bytes = 0;
+    if (d_hist != nullptr) {
+        if (n_real != 3) return fail(IM2IM_ENOTSUP, "head_tc_hist: the histogram epilogue ranks (lower, prediction, upper) planes of a one-channel quantile head (n_real=%d)", n_real);
+        if (!d_labels || !d_lambdas || n_lambdas < 1) return fail(IM2IM_EINVAL, "head_tc_hist: labels / lambda grid missing");
+        h.hist_global = d_hist; h.hist_labels = d_labels; h.hist_lambdas = d_lambdas; h.hist_L = n_lambdas;
+        hist_bytes = static_cast<size_t>(n_lambdas + 1) * 12 + static_cast<size_t>(n_lambdas) * 4 + 16;
+        while (h.a_stages > 2 && w_bytes + static_cast<size_t>(h.a_stages) * kHaloBytes + 128 + 2 * h.bn * 4 + 1024 + hist_bytes > 232448)
+            --h.a_stages;
+        if (w_bytes + static_cast<size_t>(h.a_stages) * kHaloBytes + 128 + 2 * h.bn * 4 + 1024 + hist_bytes > 232448)
+            return fail(IM2IM_ERANGE, "head_tc_hist: %d lambdas do not fit in shared memory next to the convolution", n_lambdas);
+    }
     CUtensorMap h1, hw;
     int rc = make_act_map(&h1, d_x, B, H, W, 64, kHaloW, kHaloH, 1);
     if (rc) return rc;
     rc = make_weight_map(&hw, d_weight, 64, 9 * 64, h.bn);
     if (rc) return rc;
-    const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * kHaloBytes + 128 + 2 * h.bn * 4 + 1024;
+    const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * kHaloBytes + 128 + 2 * h.bn * 4 + 1024 + hist_bytes;
     IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
     const long long m_tiles = static_cast<long long>(h.tiles_w) * h.tiles_h * B;
     long long gx = sm_count();
     if (gx > m_tiles) gx = m_tiles;
     conv_halo_kernel<<<dim3(static_cast<unsigned>(gx), 1), kConvThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h1, hw, h);
-    return check_launch("conv_halo_kernel<head>");
+    return check_launch(d_hist ? "conv_halo_kernel<head+hist>" : "conv_halo_kernel<head>");
+}
+}  // namespace
+}  // namespace im2im
+
+extern "C" int im2im_head_conv3x3_tc_f32(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H,
+                                         int32_t W, int32_t n_real, int32_t act_kind, int32_t act_from_plane,
+                                         float* d_out, void* stream) {
+    if (!d_out) return fail(IM2IM_EINVAL, "head_tc: null tensor");
+    return head_tc_impl(d_x, d_weight, d_bias, B, H, W, n_real, act_kind, act_from_plane, d_out, nullptr, nullptr, 0, nullptr,
+                        stream);
+}
+
+extern "C" int im2im_head_conv3x3_tc_hist(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H,
+                                          int32_t W, int32_t n_real, int32_t act_kind, int32_t act_from_plane,
+                                          float* d_out_or_null, const float* d_labels, const float* d_lambdas_sorted,
+                                          int32_t n_lambdas, uint32_t* d_hist, void* stream) {
+    if (!d_hist) return fail(IM2IM_EINVAL, "head_tc_hist: null histogram");
+    return head_tc_impl(d_x, d_weight, d_bias, B, H, W, n_real, act_kind, act_from_plane, d_out_or_null, d_labels,
+                        d_lambdas_sorted, n_lambdas, d_hist, stream);
 }
 
 extern "C" int im2im_conv_wgrad_bf16(const void* d_x, const void* d_dz, int32_t B, int32_t H, int32_t W, int32_t c_in,

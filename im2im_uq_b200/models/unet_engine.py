@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..conv import (conv_igemm, conv_igemm_tf32, head_conv_tc, head_tc_applicable, pack_conv_weight,
+from ..conv import (conv_igemm, conv_igemm_tf32, head_conv_tc, head_conv_tc_hist, head_tc_applicable, pack_conv_weight,
                     pack_conv_weight_tf32, pad_head_weight)
 
 
@@ -153,6 +153,45 @@ class UNetInferenceEngine:
                    "im2im_head_conv3x3_act_f32")
         return y.view(B, self.n_planes, self.c_out, H, W)
 
+    def _trunk(self, x: torch.Tensor) -> torch.Tensor:
+        """UNet body up to the last 64-channel feature map (NHWC bf16), the input of OutConv (unet.py:33-45)."""
+        a = self._conv_first(x, *self.first)
+        skips: List[torch.Tensor] = [conv_igemm(a, self.inc2[0], self.inc2[1], relu=True)]
+        for (c1, c2) in self.down:
+            p = self._pool(skips[-1])
+            p = conv_igemm(p, c1[0], c1[1], relu=True)
+            skips.append(conv_igemm(p, c2[0], c2[1], relu=True))
+        y = skips.pop()
+        for (c1, c2) in self.up:
+            skip = skips.pop()
+            u = self._upsample_to(y, skip.shape[1], skip.shape[2])
+            y = conv_igemm(skip, c1[0], c1[1], relu=True, x2=u)   # torch.cat([skip, up]) without the copy
+            y = conv_igemm(y, c2[0], c2[1], relu=True)
+        return y
+
+    def hist_applicable(self, x: torch.Tensor) -> bool:
+        """Can ``forward_hist`` take this batch?  (bf16 mode, one-channel QuantileRegressionLayer, 8x16-pixel tiles.)"""
+        from .quantile_layer import QuantileRegressionLayer
+        if self._stamp != self._param_stamp():
+            self.refresh()
+        return (self.precision == "bf16" and type(self.model.last_layer) is QuantileRegressionLayer
+                and self.head is not None and self.head_tc is not None and self.n_planes == 3 and self.c_out == 1
+                and self.head_act[0] == 0 and x.is_cuda and x.dim() == 4
+                and head_tc_applicable(x.shape[2], x.shape[3], 3, self.c_mid))
+
+    def forward_hist(self, x: torch.Tensor, labels: torch.Tensor, lambdas_sorted: torch.Tensor, hist: torch.Tensor,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The forward of ``forward`` with the head's epilogue booking every pixel's RCPS rank into ``hist`` (int32
+        [B, L+1]) instead of writing the (B, 3, 1, H, W) tensor: calibrate_model.py:121-123 + :134-136 of the reference
+        without the 12 bytes per pixel in between.  ``out`` (fp32 [B, 3, H, W]) additionally receives the planes."""
+        if not self.hist_applicable(x):
+            raise _lib.Im2ImError("forward_hist: needs the bf16 engine, a one-channel quantile head and H % 16 == W % 8 == 0")
+        x = x.contiguous().float()
+        with torch.cuda.device(x.device):
+            y = self._trunk(x)
+            m = conv_igemm(y, self.out64[0], self.out64[1], relu=False)
+            return head_conv_tc_hist(m, self.head_tc[0], self.head_tc[1], labels, lambdas_sorted, hist, out=out)
+
     # ---- the forward
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self._stamp != self._param_stamp():
@@ -163,18 +202,7 @@ class UNetInferenceEngine:
         if self.precision == "tf32":
             return self._forward_tf32(x)
         with torch.cuda.device(x.device):
-            a = self._conv_first(x, *self.first)
-            skips: List[torch.Tensor] = [conv_igemm(a, self.inc2[0], self.inc2[1], relu=True)]
-            for (c1, c2) in self.down:
-                p = self._pool(skips[-1])
-                p = conv_igemm(p, c1[0], c1[1], relu=True)
-                skips.append(conv_igemm(p, c2[0], c2[1], relu=True))
-            y = skips.pop()
-            for (c1, c2) in self.up:
-                skip = skips.pop()
-                u = self._upsample_to(y, skip.shape[1], skip.shape[2])
-                y = conv_igemm(skip, c1[0], c1[1], relu=True, x2=u)   # torch.cat([skip, up]) without the copy
-                y = conv_igemm(y, c2[0], c2[1], relu=True)
+            y = self._trunk(x)
             if (self.head is not None and self.head_tc is not None
                     and head_tc_applicable(y.shape[1], y.shape[2], self.head[0].shape[0], self.c_mid)):
                 m = conv_igemm(y, self.out64[0], self.out64[1], relu=False)   # 1x1 OutConv, 64 -> 32 (+32 zero channels)

@@ -88,6 +88,25 @@ def miss_counts(outputs: torch.Tensor, labels: torch.Tensor, lambdas_sorted: tor
     return counts, totals
 
 
+def counts_from_hist(hist: torch.Tensor, counts: torch.Tensor, totals: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-image rank histograms (uint32/int32 [n, L+1], written by the head-fused convolution epilogue,
+    conv.head_conv_tc_hist) -> counts int32 [n, L] as ``miss_counts`` writes them; ``totals`` (int64 [L]) += column sums.
+    The histogram is zero again afterwards (im2im_rcps_counts_from_hist)."""
+    lib = _lib.load()
+    if not hist.is_cuda:
+        raise _lib.Im2ImError(f"hist must be a CUDA tensor: im2im_uq_b200 has no CPU path (got device {hist.device})")
+    n, l1 = hist.shape
+    assert hist.is_contiguous() and hist.dtype in (torch.int32, torch.uint32)
+    assert counts.is_cuda and counts.is_contiguous() and counts.dtype == torch.int32 and tuple(counts.shape) == (n, l1 - 1)
+    if totals is not None:
+        assert totals.is_cuda and totals.is_contiguous() and totals.dtype == torch.int64 and totals.numel() == l1 - 1
+    with torch.cuda.device(hist.device):
+        rc = lib.im2im_rcps_counts_from_hist(hist.data_ptr(), n, l1 - 1, counts.data_ptr(),
+                                             totals.data_ptr() if totals is not None else None, _stream_ptr(hist.device))
+    _lib.check(rc, "im2im_rcps_counts_from_hist")
+    return counts
+
+
 def loss_table(counts: torch.Tensor, px: int, first_visited_col: int = 0, out: Optional[torch.Tensor] = None,
                first_visited_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 table[i,j] = float(counts[i,j])/float(px); columns below first_visited_col are zero.

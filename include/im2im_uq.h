@@ -345,6 +345,21 @@ int im2im_head_conv3x3_act_nhwc_f32(const float* d_x, const float* d_weight, con
  * CUDA-core entry points above).  The head's weights enter as bf16 here (fp32 above); accumulation is fp32. */
 int im2im_head_conv3x3_tc_f32(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W,
                               int32_t n_real, int32_t act_kind, int32_t act_from_plane, float* d_out, void* stream);
+/* Head -> calibration histogram without the head tensor (streaming calibrate_model: replaces writing outputs[counter:...]
+ * at calibrate_model.py:121-123 and re-reading them at :134-136 for a one-channel quantile head, quantile_layer.py:19-21).
+ * The same convolution as above with n_real == 3 (lower, prediction, upper); in its epilogue every pixel is ranked against
+ * the ascending lambda grid from the fp32 values im2im_head_conv3x3_tc_f32 would store - bit for bit the rank
+ * im2im_rcps_miss_counts gives that pixel - and booked into d_hist[b][k], k = 1..n_lambdas (u32 [B][n_lambdas + 1],
+ * ACCUMULATED into: zero it once; im2im_rcps_counts_from_hist leaves it zero again).  d_labels fp32 [B, 1, H, W].
+ * d_out_or_null: also write the planes (tests), or NULL.  IM2IM_ENOTSUP for other plane counts. */
+int im2im_head_conv3x3_tc_hist(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W,
+                               int32_t n_real, int32_t act_kind, int32_t act_from_plane, float* d_out_or_null,
+                               const float* d_labels, const float* d_lambdas_sorted, int32_t n_lambdas, uint32_t* d_hist,
+                               void* stream);
+/* d_hist (above) -> d_counts int32 [n_images, n_lambdas] exactly as im2im_rcps_miss_counts writes them (counts[i][j] =
+ * #pixels of image i missed at lambda_j), d_totals_or_null u64 [n_lambdas] += column sums; zeroes d_hist. */
+int im2im_rcps_counts_from_hist(uint32_t* d_hist, int64_t n_images, int32_t n_lambdas, int32_t* d_counts,
+                                unsigned long long* d_totals_or_null, void* stream);
 /* fp32 planes [B, n_planes, H, W] -> bf16 NHWC [B, H, W, 64] (channels >= n_planes zero): the head's output gradient as an
  * operand of im2im_conv_wgrad_bf16 / im2im_conv_igemm_bf16 (head weight / data gradient on tensor cores). */
 int im2im_planar_to_nhwc64_bf16(const float* d_src, int32_t n_planes, int32_t B, int32_t H, int32_t W, void* d_dst,

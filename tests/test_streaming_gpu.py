@@ -1,0 +1,140 @@
+"""GPU (-m gpu): streaming calibration - the quantile head's convolution books every pixel's RCPS rank in its own
+epilogue (im2im_head_conv3x3_tc_hist) so that calibrate_model never writes the (N, 3, C, H, W) head tensor
+(reference: calibrate_model.py:106-136 parks it on the CPU and re-reads it once per lambda).
+
+Bar: integer results - the per-image miss counts, their totals, lhat's index and the fp32 loss table are BIT-IDENTICAL
+to the two-stage path (head tensor materialised -> im2im_rcps_miss_counts), which the other GPU tests pin to the
+reference's fixtures and to the oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _head_inputs(B, H, W, seed, c_mid=32):
+    from im2im_uq_b200.conv import pack_conv_weight, pad_head_weight
+    g = torch.Generator().manual_seed(seed)
+    m = torch.zeros(B, H, W, 64)
+    m[..., :c_mid] = torch.randn(B, H, W, c_mid, generator=g)
+    hw = torch.randn(3, c_mid, 3, 3, generator=g) * 0.08
+    hb = torch.tensor([-0.4, 0.0, 0.4]) + 0.05 * torch.randn(3, generator=g)
+    packed = pack_conv_weight(pad_head_weight(hw.to(DEV)))
+    return m.to(DEV).to(torch.bfloat16).contiguous(), packed, hb.to(DEV), g
+
+
+@pytest.mark.parametrize("B,H,W,L,lam_hi", [(3, 32, 48, 1000, 6.0), (5, 64, 64, 257, 3.0), (400, 16, 8, 100, 2.0),
+                                            (2, 320, 320, 1000, 6.0), (7, 48, 40, 4000, 1.5), (1, 16, 8, 1, 1.0)])
+def test_head_histogram_equals_miss_counts_of_the_materialised_head(B, H, W, L, lam_hi):
+    from im2im_uq_b200 import rcps
+    from im2im_uq_b200.conv import head_conv_tc, head_conv_tc_hist
+    m, packed, hb, g = _head_inputs(B, H, W, seed=B * 1000 + H)
+    planes = head_conv_tc(m, packed, hb, 3)                                 # fp32 [B, 3, H, W]
+    labels = (planes[:, 1:2] + 0.6 * torch.randn(B, 1, H, W, generator=g).to(DEV)).contiguous()
+    labels[0, 0, 0, :4] = float("nan")                                      # NaN labels never miss
+    labels[-1, 0, -1, -3:] = planes[-1, 1, -1, -3:]                         # label == prediction: inside every set
+    lam = torch.linspace(0.0, lam_hi, L, device=DEV)
+    want_counts, want_totals = rcps.miss_counts(planes.view(B, 3, 1, H, W), labels, lam)
+
+    hist = torch.zeros((B, L + 1), dtype=torch.int32, device=DEV)
+    planes2 = torch.full_like(planes, float("nan"))
+    head_conv_tc_hist(m, packed, hb, labels, lam, hist, out=planes2)
+    assert torch.equal(planes2, planes)                                     # the planes it ranked are the planes it stores
+    assert int(hist[:, 0].abs().sum()) == 0 and int(hist.sum()) <= B * H * W
+    counts = torch.full((B, L), -1, dtype=torch.int32, device=DEV)
+    totals = torch.zeros(L, dtype=torch.int64, device=DEV)
+    rcps.counts_from_hist(hist, counts, totals)
+    assert torch.equal(counts, want_counts) and torch.equal(totals, want_totals)
+    assert int(hist.abs().sum()) == 0                                       # self-cleaning: ready for the next batch
+
+    # without the planes at all, twice into the same histogram buffer; the totals keep accumulating
+    for rep in (2, 3):
+        head_conv_tc_hist(m, packed, hb, labels, lam, hist)
+        rcps.counts_from_hist(hist, counts, totals)
+        assert torch.equal(counts, want_counts) and torch.equal(totals, rep * want_totals)
+
+
+def test_head_histogram_refuses_what_it_cannot_rank():
+    from im2im_uq_b200 import _lib
+    from im2im_uq_b200.conv import head_conv_tc_hist
+    m, packed, hb, g = _head_inputs(1, 16, 8, seed=3)
+    labels = torch.zeros(1, 1, 16, 8, device=DEV)
+    lam = torch.linspace(0, 1, 20000, device=DEV)                           # does not fit in shared memory
+    hist = torch.zeros((1, 20001), dtype=torch.int32, device=DEV)
+    with pytest.raises(_lib.Im2ImError):
+        head_conv_tc_hist(m, packed, hb, labels, lam, hist)
+    lib = _lib.load()
+    lam = torch.linspace(0, 1, 10, device=DEV)
+    hist = torch.zeros((1, 11), dtype=torch.int32, device=DEV)
+    rc = lib.im2im_head_conv3x3_tc_hist(m.data_ptr(), packed.data_ptr(), hb.data_ptr(), 1, 16, 8, 2, 0, 0, None,
+                                        labels.data_ptr(), lam.data_ptr(), 10, hist.data_ptr(), None)
+    assert rc == -95                                         # IM2IM_ENOTSUP: two-plane heads are not ranked here
+
+
+PARAMS = dict(uncertainty_type="quantiles", q_lo=0.05, q_hi=0.95, q_lo_weight=1.0, q_hi_weight=1.0, mse_weight=1.0)
+
+
+def _model(seed=0):
+    from core.models.add_uncertainty import add_uncertainty
+    from core.models.trunks.unet import UNet
+    torch.manual_seed(seed)
+    model = add_uncertainty(UNet(1, 1), PARAMS)
+    gen = torch.Generator().manual_seed(seed + 1)
+    model.train()
+    with torch.no_grad():
+        for _ in range(3):
+            model(torch.randn(4, 1, 32, 32, generator=gen))
+    return model.eval().to(DEV), gen
+
+
+@pytest.mark.parametrize("shape,fused", [((32, 32), True), ((64, 48), True), ((40, 36), False)])
+def test_streaming_calibration_equals_two_stage(shape, fused):
+    """calibrate_model batch by batch without the head tensor == collect_outputs + calibrate_from_outputs, bit for bit;
+    shapes the tensor-core head cannot tile fall back to per-batch outputs (still no (N, 3, C, H, W) tensor)."""
+    from im2im_uq_b200.calibration import calibrate_model as cm
+    model, gen = _model()
+    n = 29                                                                  # ragged last batch
+    x = torch.randn(n, 1, *shape, generator=gen)
+    with torch.no_grad():                      # labels scattered around the prediction at ~40 interval half-widths
+        o = torch.cat([model(x[i:i + 8].to(DEV)) for i in range(0, n, 8)]).cpu()
+    s = 40.0 * torch.randn(n, 1, *shape, generator=gen)   # (an untrained head has upper < prediction on many pixels: zero width)
+    y = o[:, 1] + torch.relu(s) * torch.relu(o[:, 2] - o[:, 1]) - torch.relu(-s) * torch.relu(o[:, 1] - o[:, 0])
+    ds = torch.utils.data.TensorDataset(x, y)
+    cfg = dict(PARAMS, alpha=0.4, delta=0.1, device=DEV, minimum_lambda=0.0, maximum_lambda=60.0, num_lambdas=300,
+               rcps_loss="fraction_missed", dataset="synthetic", batch_size=8)
+    stats = {}
+    with torch.no_grad():
+        model, table_s = cm.calibrate_streaming(model, ds, cfg, torch.device(DEV), stats=stats)
+        lhat_s = model.lhat.clone()
+        assert stats["streaming"] and (stats["head_fused_batches"] == 4) == fused, stats
+        model.set_lhat(None)
+        model, table_2 = cm.calibrate_model(model, ds, dict(cfg, streaming_calibration=False))
+    assert torch.equal(lhat_s, model.lhat) and torch.equal(table_s, table_2)
+    assert float(table_s.max()) > 0 and 0 < float(lhat_s) < 60.0             # a non-trivial sweep
+    model, table_d = cm.calibrate_model(model, ds, cfg)                      # the default route is the streaming one
+    assert torch.equal(table_d, table_2)
+
+
+def test_streaming_calibration_descending_grid_and_dataloader_dataset():
+    from im2im_uq_b200.calibration import calibrate_model as cm
+    model, gen = _model(3)
+    n = 12
+    x = torch.randn(n, 1, 32, 32, generator=gen)
+    y = x + 0.3 * torch.randn(n, 1, 32, 32, generator=gen)
+
+    class Pairs(torch.utils.data.Dataset):                                   # map-style, not a TensorDataset
+        def __len__(self):
+            return n
+
+        def __getitem__(self, i):
+            return x[i], y[i]
+
+    cfg = dict(PARAMS, alpha=0.4, delta=0.1, device=DEV, minimum_lambda=60.0, maximum_lambda=0.0, num_lambdas=120,
+               rcps_loss="fraction_missed", dataset="synthetic", batch_size=5)
+    with torch.no_grad():
+        model, t1 = cm.calibrate_model(model, Pairs(), cfg)
+        l1 = model.lhat.clone()
+        model, t2 = cm.calibrate_model(model, Pairs(), dict(cfg, streaming_calibration=False))
+    assert torch.equal(l1, model.lhat) and torch.equal(t1, t2)
