@@ -502,19 +502,31 @@ def run_unet_bench(args, world, rank, dev, group):
         cfg.update(minimum_lambda=0.0, maximum_lambda=60.0, batch_size=50)
         model.eval()
         import contextlib, io
-        with contextlib.redirect_stdout(io.StringIO()):
-            calibrate_model(model, ds, cfg)          # warm-up (engine build, allocator)
+        def timed_calibration(c):
+            calibrate_model(model, ds, c)            # warm-up (engine build, allocator)
             torch.cuda.synchronize()
+            torch.cuda.reset_peak_memory_stats(dev)
+            base = torch.cuda.memory_allocated(dev)
             runs = []
             for _ in range(3):                       # wall clock around a 0.2 s host-driven call: report the median
                 t0 = time.perf_counter()
-                calibrate_model(model, ds, cfg)
+                _, tab = calibrate_model(model, ds, c)
                 torch.cuda.synchronize()
                 runs.append(time.perf_counter() - t0)
-            dt = sorted(runs)[1]
-        cal = {"images": n_cal, "seconds": dt, "images_per_s": n_cal / dt, "runs_s": runs, "lhat": float(model.lhat),
+            return sorted(runs)[1], runs, (torch.cuda.max_memory_allocated(dev) - base) / 2**20, float(model.lhat), tab
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            dt, runs, peak_mib, lhat_s, tab_s = timed_calibration(cfg)                    # streaming: no (N,3,C,H,W) tensor
+            dt2, runs2, peak2_mib, lhat_2, tab_2 = timed_calibration(dict(cfg, streaming_calibration=False))
+        assert lhat_s == lhat_2 and torch.equal(tab_s, tab_2), "streaming and two-stage calibration disagree"
+        cal = {"images": n_cal, "seconds": dt, "images_per_s": n_cal / dt, "runs_s": runs, "lhat": lhat_s,
+               "peak_extra_hbm_mib": peak_mib,
+               "two_stage": {"seconds": dt2, "images_per_s": n_cal / dt2, "runs_s": runs2, "peak_extra_hbm_mib": peak2_mib,
+                             "note": "config['streaming_calibration'] = False: head outputs of the whole set kept in HBM, "
+                                     "then one RCPS pass; same lhat and table bit for bit (asserted)"},
                "api": "core.calibration.calibrate_model.calibrate_model(model, dataset, config)",
-               "note": "host TensorDataset -> H2D -> native UNet forward -> RCPS sweep -> table D2H; random-init weights"}
+               "note": "host TensorDataset -> H2D -> native UNet forward whose head epilogue books the RCPS ranks (no head "
+                       "tensor) -> sweep on the (N, L) counts -> table D2H; random-init weights"}
         model.train()
     reference = None
     if rank == 0 and not args.no_unet_reference:
