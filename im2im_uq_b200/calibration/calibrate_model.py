@@ -666,18 +666,16 @@ def streaming_applicable(model, dataset, config) -> bool:
     return fused is not None and fused[1] is None
 
 
-def calibrate_streaming(model, dataset, config, device, group=None, stats: Optional[dict] = None,
-                        table_device: str = "cpu"):
-    """Stages 1+2 of ``calibrate_model`` (reference :106-136) batch by batch, without the (N, 3, C, H, W) output tensor:
-    each batch goes model -> per-image miss counts at once and only the (N, L) int32 counts stay in HBM.
+def stream_miss_counts(model, dataset, config, device, lam_dev: torch.Tensor, stats: Optional[dict] = None):
+    """Run the model over a map-style dataset batch by batch and keep only the per-image miss counts on the ascending grid
+    ``lam_dev``: (counts int32 (N, L) on the device, totals int64 (L,), pixels per image).  The (N, 3, C, H, W) output
+    tensor of the reference's stage 1 (calibrate_model.py:106-123, eval.py:100-112) is never built.
 
     With the native bf16 engine and a one-channel quantile head the ranks are booked by the head convolution's own
     epilogue (``UNetInferenceEngine.forward_hist``: the head tensor is never written at all); otherwise the batch's
-    outputs live for one ``miss_counts`` pass and are dropped.  Counts, lhat and the loss table are bit-identical to the
-    two-stage path (same per-pixel rank code, integer sums)."""
+    outputs live for one ``miss_counts`` pass and are dropped."""
     from ..models.unet_engine import UNetInferenceEngine, native_forward_applicable
     kind, _ = _fused_head(model)
-    lam_dev, order, ascending = _sorted_grid(config, device)
     L = lam_dev.numel()
     n = len(dataset)
     if n == 0:
@@ -721,6 +719,16 @@ def calibrate_streaming(model, dataset, config, device, group=None, stats: Optio
     if stats is not None:
         stats["streaming"] = True
         stats["head_fused_batches"] = fused_batches
+    return counts, totals, px
+
+
+def calibrate_streaming(model, dataset, config, device, group=None, stats: Optional[dict] = None,
+                        table_device: str = "cpu"):
+    """Stages 1+2 of ``calibrate_model`` (reference :106-136) without the (N, 3, C, H, W) output tensor: each batch goes
+    model -> per-image miss counts at once (``stream_miss_counts``) and only the (N, L) int32 counts stay in HBM.  Counts,
+    lhat and the loss table are bit-identical to the two-stage path (same per-pixel rank code, integer sums)."""
+    lam_dev, order, ascending = _sorted_grid(config, device)
+    counts, totals, px = stream_miss_counts(model, dataset, config, device, lam_dev, stats=stats)
     lhat, stop, counts, visited = _sweep_counts(counts, totals, order, ascending, px, config, group=group, stats=stats)
     model.set_lhat(lhat)
     return model, _table_from_counts(counts, visited, px, table_device)

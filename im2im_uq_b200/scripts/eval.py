@@ -35,17 +35,24 @@ def get_loss_table(model, dataset, config):
         device = cm._cuda_device(config['device'])
         cm.get_rcps_loss_fn(config)
         model = model.to(device)
-        outputs, labels = cm.collect_outputs(model, dataset, config, device)
-        kind, scores = cm._head_scores(model, outputs, device)
-        print("GET LOSS TABLE FROM OUTPUTS")
         ascending = bool((lambdas[1:] >= lambdas[:-1]).all()) if lambdas.numel() > 1 else True
         lam_sorted, order = (lambdas, None) if ascending else torch.sort(lambdas)
-        counts, _ = rcps.miss_counts(scores, labels, lam_sorted.to(device), head=kind)
+        if cm.streaming_applicable(model, dataset, config) and len(dataset) > 0:
+            # batch by batch, the (N, 3, C, H, W) tensor of eval.py:100-112 is never built (quantile head: the head
+            # convolution's epilogue books the ranks itself)
+            print("GET LOSS TABLE FROM OUTPUTS")
+            counts, _, px = cm.stream_miss_counts(model, dataset, config, device, lam_sorted.to(device))
+        else:
+            outputs, labels = cm.collect_outputs(model, dataset, config, device)
+            kind, scores = cm._head_scores(model, outputs, device)
+            print("GET LOSS TABLE FROM OUTPUTS")
+            counts, _ = rcps.miss_counts(scores, labels, lam_sorted.to(device), head=kind)
+            px = max(labels[0].numel(), 1) if labels.shape[0] else 1
         if order is not None:
             inv = torch.empty_like(order)
             inv[order] = torch.arange(order.numel())
             counts = counts[:, inv.to(device)].contiguous()
-        table = rcps.loss_table(counts, max(labels[0].numel(), 1) if labels.shape[0] else 1)
+        table = rcps.loss_table(counts, px)
         print("DONE!")
         return table.cpu()
 

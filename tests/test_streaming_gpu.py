@@ -115,6 +115,11 @@ def test_streaming_calibration_equals_two_stage(shape, fused):
     assert float(table_s.max()) > 0 and 0 < float(lhat_s) < 60.0             # a non-trivial sweep
     model, table_d = cm.calibrate_model(model, ds, cfg)                      # the default route is the streaming one
     assert torch.equal(table_d, table_2)
+    # eval.py:84-126 (dense table at lambdas[j], no early stop) takes the same streaming route
+    from core.scripts.eval import get_loss_table
+    dense_s = get_loss_table(model, ds, cfg)
+    dense_2 = get_loss_table(model, ds, dict(cfg, streaming_calibration=False))
+    assert torch.equal(dense_s, dense_2) and float(dense_s[:, 0].min()) > 0
 
 
 def test_streaming_calibration_descending_grid_and_dataloader_dataset():
