@@ -692,9 +692,28 @@ def stream_miss_counts(model, dataset, config, device, lam_dev: torch.Tensor, st
     px = None
     lo = 0
     fused_batches = 0
-    for xb, yb in batches:
-        xb = xb.to(device, non_blocking=True)
-        yb = yb.to(device, non_blocking=True).to(torch.get_default_dtype()).contiguous()
+    # the next batch's host->device copy runs on its own stream under the current batch's kernels (pinned sources)
+    copy_stream = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream(device)
+
+    def upload(pair_):
+        with torch.cuda.stream(copy_stream):
+            x_ = pair_[0].to(device, non_blocking=True)
+            y_ = pair_[1].to(device, non_blocking=True).to(torch.get_default_dtype()).contiguous()
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        return x_, y_, ready
+
+    it = iter(batches)
+    nxt = next(it, None)
+    pending = upload(nxt) if nxt is not None else None
+    while pending is not None:
+        xb, yb, ready = pending
+        nxt = next(it, None)
+        pending = upload(nxt) if nxt is not None else None
+        main.wait_event(ready)
+        xb.record_stream(main)
+        yb.record_stream(main)
         b = xb.shape[0]
         px = yb[0].numel()
         eng = None
