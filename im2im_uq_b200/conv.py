@@ -149,25 +149,55 @@ def pad_head_weight(weight: torch.Tensor, out: Optional[torch.Tensor] = None) ->
 
 
 def head_conv_tc(x: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[torch.Tensor], n_out: int,
-                 act_kind: int = 0, act_from: int = 0) -> torch.Tensor:
+                 act_kind: int = 0, act_from: int = 0, tap_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Head on tensor cores: x NHWC bf16 [B,H,W,64], weight bf16 [64,9,64] (pad_head_weight + pack_conv_weight) ->
-    fp32 planes [B, n_out, H, W] with the head's activation fused."""
+    fp32 planes [B, n_out, H, W] with the head's activation fused.  ``tap_bias`` (fp32 [9, n_out]): the head has a 1x1
+    convolution folded into it (fold_outconv_into_head): border pixels drop the bias of the taps in the padding."""
     lib = _lib.load()
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[3] == 64
     assert weight_packed.dtype == torch.bfloat16 and weight_packed.is_contiguous() and tuple(weight_packed.shape) == (64, 9, 64)
     B, H, W, _ = x.shape
     out = torch.empty((B, n_out, H, W), dtype=torch.float32, device=x.device)
+    st = torch.cuda.current_stream(x.device).cuda_stream
     with torch.cuda.device(x.device):
-        rc = lib.im2im_head_conv3x3_tc_f32(x.data_ptr(), weight_packed.data_ptr(),
-                                           bias.data_ptr() if bias is not None else None, B, H, W, n_out, act_kind,
-                                           act_from, out.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+        if tap_bias is not None:
+            assert tap_bias.is_cuda and tap_bias.dtype == torch.float32 and tap_bias.is_contiguous() and tuple(tap_bias.shape) == (9, n_out)
+            rc = lib.im2im_head_conv3x3_tc_folded_f32(x.data_ptr(), weight_packed.data_ptr(), bias.data_ptr(),
+                                                      tap_bias.data_ptr(), B, H, W, n_out, act_kind, act_from,
+                                                      out.data_ptr(), st)
+        else:
+            rc = lib.im2im_head_conv3x3_tc_f32(x.data_ptr(), weight_packed.data_ptr(),
+                                               bias.data_ptr() if bias is not None else None, B, H, W, n_out, act_kind,
+                                               act_from, out.data_ptr(), st)
     _lib.check(rc, "im2im_head_conv3x3_tc_f32")
     return out
 
 
+def fold_outconv_into_head(head_w: torch.Tensor, head_b: torch.Tensor, out_w: torch.Tensor, out_b: torch.Tensor):
+    """head(OutConv(x)) as ONE 3x3 convolution of x: (weight fp32 [n_out, c_in, 3, 3], bias fp32 [n_out], tap_bias fp32
+    [9 border classes, n_out]).  head_w [n_out, c_mid, 3, 3], out_w [c_mid, c_in, 1, 1] (unet_parts.py:87-93 followed by
+    quantile_layer.py:15-20).  OutConv's bias reaches an output pixel once per in-range tap (its output is zero-PADDED, not
+    bias-padded, at the image border): bias = head_b + sum over taps of tap_bias, and the kernel takes the out-of-range
+    taps' share back on border pixels."""
+    hw64, ow64 = head_w.double(), out_w.double()[:, :, 0, 0]
+    w = torch.einsum('omyx,mc->ocyx', hw64, ow64).float().contiguous()
+    tap = torch.einsum('omyx,m->oyx', hw64, out_b.double())                      # [n_out, 3, 3]
+    bias = (head_b.double() + tap.sum((1, 2))).float().contiguous()
+    # border class = 3 * (0 inside | 1 first row | 2 last row) + (0 inside | 1 first column | 2 last column)
+    rows = (slice(0, 0), slice(0, 1), slice(2, 3))                               # kernel rows in the padding per row class
+    border = torch.zeros(9, head_w.shape[0], dtype=torch.float64, device=head_w.device)
+    for rc in range(3):
+        for cc in range(3):
+            oob = torch.zeros(3, 3, dtype=torch.bool, device=head_w.device)
+            oob[rows[rc], :] = True
+            oob[:, rows[cc]] = True
+            border[3 * rc + cc] = (tap * oob).sum((1, 2))
+    return w, bias, border.float().contiguous()
+
+
 def head_conv_tc_hist(x: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[torch.Tensor], labels: torch.Tensor,
                       lambdas_sorted: torch.Tensor, hist: torch.Tensor, act_kind: int = 0, act_from: int = 0,
-                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      out: Optional[torch.Tensor] = None, tap_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One-channel quantile head on tensor cores whose epilogue books every pixel's rank on the ascending lambda grid into
     ``hist`` (int32 [B, L+1], accumulated into) instead of writing the (B, 3, 1, H, W) head tensor
     (im2im_head_conv3x3_tc_hist).  ``labels`` fp32 [B, 1, H, W]; ``out`` (fp32 [B, 3, H, W]) also receives the planes."""
@@ -183,7 +213,8 @@ def head_conv_tc_hist(x: torch.Tensor, weight_packed: torch.Tensor, bias: Option
         assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, 3, H, W)
     with torch.cuda.device(x.device):
         rc = lib.im2im_head_conv3x3_tc_hist(x.data_ptr(), weight_packed.data_ptr(),
-                                            bias.data_ptr() if bias is not None else None, B, H, W, 3, act_kind, act_from,
+                                            bias.data_ptr() if bias is not None else None,
+                                            tap_bias.data_ptr() if tap_bias is not None else None, B, H, W, 3, act_kind, act_from,
                                             out.data_ptr() if out is not None else None, labels.data_ptr(),
                                             lambdas_sorted.data_ptr(), L, hist.data_ptr(),
                                             torch.cuda.current_stream(x.device).cuda_stream)

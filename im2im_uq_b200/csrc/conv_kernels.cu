@@ -504,6 +504,11 @@ struct HaloParams {
     // that out_planar would hold, and booked into hist_global[b][k] (u32 [B][hist_L + 1], accumulated into) - the
     // (B, 3, 1, H, W) head tensor need not exist (out_planar may be null).  Tiles are then dealt to the CTAs in contiguous
     // runs so that a CTA flushes its shared-memory histogram once per image it touches.
+    // head mode, optional (a 1x1 convolution with a bias folded into this head's weights): tap_bias[cls * n_real + j] = the
+    // part of bias[j] that came through the taps of the 3x3 window that lie in the zero padding for a pixel of border class
+    // cls = 3 * (0 inside | 1 top row | 2 bottom row) + (0 inside | 1 left column | 2 right column) - where the folded-in
+    // convolution's output, bias included, does not exist; such pixels subtract it.
+    const float* tap_bias;
     unsigned* hist_global;
     const float* hist_labels;      // fp32 [B, 1, H, W]
     const float* hist_lambdas;     // device, ascending, hist_L entries
@@ -521,6 +526,7 @@ struct HaloParams {
     const float* bn_gamma; const float* bn_beta; const float* bn_mean; const float* bn_rstd;
 };
 
+constexpr int kMaxFoldedPlanes = 7;    // head mode with tap_bias: 9 border classes x planes fit the 64-float scale/shift area
 constexpr int kHaloStatBn = 64;      // fused statistics need the per-thread accumulators in registers: N tile of 64
 
 constexpr int kHaloW = 16, kHaloH = 18, kHaloTileW = 8, kHaloTileH = 16;
@@ -578,6 +584,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             s_shift[c] = p.bn_beta[ch] - p.bn_mean[ch] * sc;
         }
     }
+    if (p.tap_bias != nullptr)   // 9 border classes x n_real <= 2 * bn floats (checked by the launcher)
+        for (int j = threadIdx.x; j < 9 * p.n_real; j += blockDim.x) s_scale[j] = p.tap_bias[j];
     if (p.hist_global != nullptr) {
         const int L = p.hist_L;
         for (int j = threadIdx.x; j <= L; j += blockDim.x) {
@@ -704,6 +712,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                if (p.tap_bias != nullptr && (tw == 0 || th == 0 || tw == p.tiles_w - 1 || th == p.tiles_h - 1)) {
+                    // head with a 1x1 convolution folded in, tile on the image border (warp-uniform test): a border pixel takes
+                    // back the share of the bias that belongs to the taps lying in the zero padding; the table (staged in shared
+                    // memory, where the statistics modes keep their scale/shift) is indexed by the pixel's border class
+                    const int cls = (h == 0 ? 3 : (h == p.H - 1 ? 6 : 0)) + (w == 0 ? 1 : (w == p.W - 1 ? 2 : 0));
+                    if (cls != 0) {
+                        const float* corr = s_scale + cls * p.n_real;
+#pragma unroll
+                        for (int j = 0; j < kMaxFoldedPlanes; ++j)
+                            if (j < p.n_real) v[j] = __float_as_uint(__uint_as_float(v[j]) - corr[j]);
+                    }
+                }
                 if (p.hist_global != nullptr) {
                     // planes 0..2 = lower, prediction, upper of this thread's pixel, as fp32 exactly as they would be stored
                     const int L = p.hist_L;
@@ -1492,9 +1512,9 @@ extern "C" int im2im_planar_to_nhwc64_bf16(const float* d_src, int32_t n_planes,
 
 namespace im2im {
 namespace {
-int head_tc_impl(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t n_real,
-                 int32_t act_kind, int32_t act_from_plane, float* d_out, const float* d_labels, const float* d_lambdas,
-                 int32_t n_lambdas, uint32_t* d_hist, void* stream) {
+int head_tc_impl(const void* d_x, const void* d_weight, const float* d_bias, const float* d_tap_bias, int32_t B, int32_t H,
+                 int32_t W, int32_t n_real, int32_t act_kind, int32_t act_from_plane, float* d_out, const float* d_labels,
+                 const float* d_lambdas, int32_t n_lambdas, uint32_t* d_hist, void* stream) {
     if (B <= 0 || H <= 0 || W <= 0) return fail(IM2IM_EINVAL, "head_tc: bad activation shape");
     if (n_real < 1 || n_real > 32) return fail(IM2IM_ERANGE, "head_tc: n_real=%d outside [1, 32]", n_real);
     if (act_kind < 0 || act_kind > 2) return fail(IM2IM_EINVAL, "head_tc: act_kind=%d", act_kind);
@@ -1507,6 +1527,10 @@ int head_tc_impl(const void* d_x, const void* d_weight, const float* d_bias, int
     h.tiles_w = W / kHaloTileW; h.tiles_h = H / kHaloTileH; h.bn = 32; h.relu = 0; h.bias = d_bias;
     h.out_bf16 = nullptr; h.out_f32 = nullptr;
     h.out_planar = d_out; h.n_real = n_real; h.act_kind = act_kind; h.act_from = act_kind ? act_from_plane : n_real;
+    h.tap_bias = d_tap_bias;
+    if (d_tap_bias && !d_bias) return fail(IM2IM_EINVAL, "head_tc: tap_bias without bias");
+    if (d_tap_bias && n_real > kMaxFoldedPlanes)
+        return fail(IM2IM_ENOTSUP, "head_tc: a folded 1x1 convolution is supported for up to %d planes (got %d)", kMaxFoldedPlanes, n_real);
     const int w_bytes = 9 * 64 * h.bn * 2;
     h.a_stages = 4;
     size_t hist_bytes = 0;
@@ -1540,17 +1564,26 @@ extern "C" int im2im_head_conv3x3_tc_f32(const void* d_x, const void* d_weight, 
                                          int32_t W, int32_t n_real, int32_t act_kind, int32_t act_from_plane,
                                          float* d_out, void* stream) {
     if (!d_out) return fail(IM2IM_EINVAL, "head_tc: null tensor");
-    return head_tc_impl(d_x, d_weight, d_bias, B, H, W, n_real, act_kind, act_from_plane, d_out, nullptr, nullptr, 0, nullptr,
-                        stream);
+    return head_tc_impl(d_x, d_weight, d_bias, nullptr, B, H, W, n_real, act_kind, act_from_plane, d_out, nullptr, nullptr, 0,
+                        nullptr, stream);
 }
 
-extern "C" int im2im_head_conv3x3_tc_hist(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H,
-                                          int32_t W, int32_t n_real, int32_t act_kind, int32_t act_from_plane,
-                                          float* d_out_or_null, const float* d_labels, const float* d_lambdas_sorted,
-                                          int32_t n_lambdas, uint32_t* d_hist, void* stream) {
+extern "C" int im2im_head_conv3x3_tc_folded_f32(const void* d_x, const void* d_weight, const float* d_bias,
+                                                const float* d_tap_bias, int32_t B, int32_t H, int32_t W, int32_t n_real,
+                                                int32_t act_kind, int32_t act_from_plane, float* d_out, void* stream) {
+    if (!d_out) return fail(IM2IM_EINVAL, "head_tc: null tensor");
+    return head_tc_impl(d_x, d_weight, d_bias, d_tap_bias, B, H, W, n_real, act_kind, act_from_plane, d_out, nullptr, nullptr,
+                        0, nullptr, stream);
+}
+
+extern "C" int im2im_head_conv3x3_tc_hist(const void* d_x, const void* d_weight, const float* d_bias,
+                                          const float* d_tap_bias_or_null, int32_t B, int32_t H, int32_t W, int32_t n_real,
+                                          int32_t act_kind, int32_t act_from_plane, float* d_out_or_null,
+                                          const float* d_labels, const float* d_lambdas_sorted, int32_t n_lambdas,
+                                          uint32_t* d_hist, void* stream) {
     if (!d_hist) return fail(IM2IM_EINVAL, "head_tc_hist: null histogram");
-    return head_tc_impl(d_x, d_weight, d_bias, B, H, W, n_real, act_kind, act_from_plane, d_out_or_null, d_labels,
-                        d_lambdas_sorted, n_lambdas, d_hist, stream);
+    return head_tc_impl(d_x, d_weight, d_bias, d_tap_bias_or_null, B, H, W, n_real, act_kind, act_from_plane, d_out_or_null,
+                        d_labels, d_lambdas_sorted, n_lambdas, d_hist, stream);
 }
 
 extern "C" int im2im_conv_wgrad_bf16(const void* d_x, const void* d_dz, int32_t B, int32_t H, int32_t W, int32_t c_in,

@@ -20,7 +20,8 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..conv import (conv_igemm, conv_igemm_tf32, head_conv_tc, head_conv_tc_hist, head_tc_applicable, pack_conv_weight,
+from ..conv import (conv_igemm, conv_igemm_tf32, fold_outconv_into_head, head_conv_tc, head_conv_tc_hist,
+                    head_tc_applicable, pack_conv_weight,
                     pack_conv_weight_tf32, pad_head_weight)
 
 
@@ -109,8 +110,15 @@ class UNetInferenceEngine:
             ob64[:c_mid] = ob
             self.out64 = (pack_conv_weight(ow64), ob64)
             self.head_tc = (pack_conv_weight(pad_head_weight(hw)), hb)
+            # OutConv (1x1) folded into the head's 3x3 weights: one convolution of the 64-channel feature map, the
+            # (B, H, W, 32) tensor in between is never written (IM2IM_NO_HEAD_FOLD=1 keeps the two convolutions)
+            self.head_fold = None
+            if (ow.shape[1] == 64 and tuple(ow.shape[2:]) == (1, 1) and hw.shape[0] <= 7
+                    and not os.environ.get("IM2IM_NO_HEAD_FOLD")):
+                wf, bf, tb = fold_outconv_into_head(hw, hb, ow, ob)
+                self.head_fold = (pack_conv_weight(pad_head_weight(wf)), bf, tb)
         else:
-            self.out64 = self.head_tc = None
+            self.out64 = self.head_tc = self.head_fold = None
         self._stamp = self._param_stamp()
 
     # ---- single launches
@@ -189,6 +197,9 @@ class UNetInferenceEngine:
         x = x.contiguous().float()
         with torch.cuda.device(x.device):
             y = self._trunk(x)
+            if self.head_fold is not None:
+                return head_conv_tc_hist(y, self.head_fold[0], self.head_fold[1], labels, lambdas_sorted, hist, out=out,
+                                         tap_bias=self.head_fold[2])
             m = conv_igemm(y, self.out64[0], self.out64[1], relu=False)
             return head_conv_tc_hist(m, self.head_tc[0], self.head_tc[1], labels, lambdas_sorted, hist, out=out)
 
@@ -205,9 +216,13 @@ class UNetInferenceEngine:
             y = self._trunk(x)
             if (self.head is not None and self.head_tc is not None
                     and head_tc_applicable(y.shape[1], y.shape[2], self.head[0].shape[0], self.c_mid)):
-                m = conv_igemm(y, self.out64[0], self.out64[1], relu=False)   # 1x1 OutConv, 64 -> 32 (+32 zero channels)
                 n_out = self.head[0].shape[0]
-                out = head_conv_tc(m, self.head_tc[0], self.head_tc[1], n_out, self.head_act[0], self.head_act[1])
+                if self.head_fold is not None:   # OutConv folded into the head: one 3x3 convolution of y
+                    out = head_conv_tc(y, self.head_fold[0], self.head_fold[1], n_out, self.head_act[0], self.head_act[1],
+                                       tap_bias=self.head_fold[2])
+                else:
+                    m = conv_igemm(y, self.out64[0], self.out64[1], relu=False)   # 1x1 OutConv, 64 -> 32 (+32 zero channels)
+                    out = head_conv_tc(m, self.head_tc[0], self.head_tc[1], n_out, self.head_act[0], self.head_act[1])
                 return out.view(x.shape[0], self.n_planes, self.c_out, y.shape[1], y.shape[2])
             m = conv_igemm(y, self.out[0], self.out[1], relu=False)  # 1x1 OutConv, 64 -> 32 (tensor cores)
             if self.head is None:  # heads without a native kernel (softmax: 50 planes) run their own module on the features

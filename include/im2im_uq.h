@@ -345,17 +345,29 @@ int im2im_head_conv3x3_act_nhwc_f32(const float* d_x, const float* d_weight, con
  * CUDA-core entry points above).  The head's weights enter as bf16 here (fp32 above); accumulation is fp32. */
 int im2im_head_conv3x3_tc_f32(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W,
                               int32_t n_real, int32_t act_kind, int32_t act_from_plane, float* d_out, void* stream);
+/* im2im_head_conv3x3_tc_f32 with the trunk's 1x1 OutConv (unet.py:45, unet_parts.py:87-93) FOLDED into the head's weights, so
+ * that the head reads the 64-channel feature map directly and the (B, H, W, 32) OutConv output is never written or read:
+ * d_weight[o][tap][c] = sum_m head[o][m][tap] * out[m][c] (bf16, packed as above), d_bias[o] = head bias + sum over the nine
+ * taps of t[o][tap], t[o][tap] = sum_m head[o][m][tap] * out_bias[m].  A border pixel subtracts the tap terms that fall into the
+ * zero padding (where the reference's OutConv output, bias included, is padding, not bias): d_tap_bias is fp32 [9][n_real],
+ * d_tap_bias[cls][o] = sum of t[o][tap] over the out-of-range taps of border class cls = 3 * (0 inside | 1 first row | 2 last
+ * row) + (0 inside | 1 first column | 2 last column); n_real <= 7.  The result equals head(OutConv(x)) up to fp32 summation
+ * order and one bf16 rounding less. */
+int im2im_head_conv3x3_tc_folded_f32(const void* d_x, const void* d_weight, const float* d_bias, const float* d_tap_bias,
+                                     int32_t B, int32_t H, int32_t W, int32_t n_real, int32_t act_kind, int32_t act_from_plane,
+                                     float* d_out, void* stream);
 /* Head -> calibration histogram without the head tensor (streaming calibrate_model: replaces writing outputs[counter:...]
  * at calibrate_model.py:121-123 and re-reading them at :134-136 for a one-channel quantile head, quantile_layer.py:19-21).
  * The same convolution as above with n_real == 3 (lower, prediction, upper); in its epilogue every pixel is ranked against
  * the ascending lambda grid from the fp32 values im2im_head_conv3x3_tc_f32 would store - bit for bit the rank
  * im2im_rcps_miss_counts gives that pixel - and booked into d_hist[b][k], k = 1..n_lambdas (u32 [B][n_lambdas + 1],
  * ACCUMULATED into: zero it once; im2im_rcps_counts_from_hist leaves it zero again).  d_labels fp32 [B, 1, H, W].
- * d_out_or_null: also write the planes (tests), or NULL.  IM2IM_ENOTSUP for other plane counts. */
-int im2im_head_conv3x3_tc_hist(const void* d_x, const void* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W,
-                               int32_t n_real, int32_t act_kind, int32_t act_from_plane, float* d_out_or_null,
-                               const float* d_labels, const float* d_lambdas_sorted, int32_t n_lambdas, uint32_t* d_hist,
-                               void* stream);
+ * d_out_or_null: also write the planes (tests), or NULL.  d_tap_bias_or_null: as im2im_head_conv3x3_tc_folded_f32.
+ * IM2IM_ENOTSUP for other plane counts. */
+int im2im_head_conv3x3_tc_hist(const void* d_x, const void* d_weight, const float* d_bias, const float* d_tap_bias_or_null,
+                               int32_t B, int32_t H, int32_t W, int32_t n_real, int32_t act_kind, int32_t act_from_plane,
+                               float* d_out_or_null, const float* d_labels, const float* d_lambdas_sorted, int32_t n_lambdas,
+                               uint32_t* d_hist, void* stream);
 /* d_hist (above) -> d_counts int32 [n_images, n_lambdas] exactly as im2im_rcps_miss_counts writes them (counts[i][j] =
  * #pixels of image i missed at lambda_j), d_totals_or_null u64 [n_lambdas] += column sums; zeroes d_hist. */
 int im2im_rcps_counts_from_hist(uint32_t* d_hist, int64_t n_images, int32_t n_lambdas, int32_t* d_counts,

@@ -68,7 +68,7 @@ def test_head_histogram_refuses_what_it_cannot_rank():
     lib = _lib.load()
     lam = torch.linspace(0, 1, 10, device=DEV)
     hist = torch.zeros((1, 11), dtype=torch.int32, device=DEV)
-    rc = lib.im2im_head_conv3x3_tc_hist(m.data_ptr(), packed.data_ptr(), hb.data_ptr(), 1, 16, 8, 2, 0, 0, None,
+    rc = lib.im2im_head_conv3x3_tc_hist(m.data_ptr(), packed.data_ptr(), hb.data_ptr(), None, 1, 16, 8, 2, 0, 0, None,
                                         labels.data_ptr(), lam.data_ptr(), 10, hist.data_ptr(), None)
     assert rc == -95                                         # IM2IM_ENOTSUP: two-plane heads are not ranked here
 
@@ -143,3 +143,29 @@ def test_streaming_calibration_descending_grid_and_dataloader_dataset():
         l1 = model.lhat.clone()
         model, t2 = cm.calibrate_model(model, Pairs(), dict(cfg, streaming_calibration=False))
     assert torch.equal(l1, model.lhat) and torch.equal(t1, t2)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 24), (1, 16, 8), (3, 48, 64)])
+def test_outconv_folded_into_the_head_equals_the_two_convolutions(B, H, W):
+    """head(OutConv(x)) as one tensor-core convolution (im2im_head_conv3x3_tc_folded_f32): equal to the fp32 composition of
+    the reference's two modules (unet_parts.py:87-93 -> quantile_layer.py:19-21) up to the bf16 rounding of the operands,
+    on the image border as well as inside (OutConv's bias must not leak into the zero padding)."""
+    import torch.nn.functional as F
+    from im2im_uq_b200.conv import fold_outconv_into_head, head_conv_tc, pack_conv_weight, pad_head_weight
+    g = torch.Generator().manual_seed(B * 100 + W)
+    y = torch.randn(B, H, W, 64, generator=g).to(torch.bfloat16)
+    ow, ob = torch.randn(32, 64, 1, 1, generator=g) * 0.1, torch.randn(32, generator=g) * 3.0   # a LARGE OutConv bias
+    hw, hb = torch.randn(3, 32, 3, 3, generator=g) * 0.1, torch.randn(3, generator=g)
+    ref = F.conv2d(F.conv2d(y.float().permute(0, 3, 1, 2), ow, ob), hw, hb, padding=1)
+    wf, bf, tb = fold_outconv_into_head(hw.to(DEV), hb.to(DEV), ow.to(DEV), ob.to(DEV))
+    packed = pack_conv_weight(pad_head_weight(wf))
+    got = head_conv_tc(y.to(DEV), packed, bf, 3, tap_bias=tb).cpu()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs()
+    border = torch.ones(H, W, dtype=torch.bool)
+    border[1:-1, 1:-1] = False
+    assert err.max().item() <= 1e-2 * scale, (err.max().item(), scale)
+    assert err[..., border].max().item() <= 1e-2 * scale
+    naive = head_conv_tc(y.to(DEV), packed, bf, 3).cpu()                      # without the border correction: visibly wrong
+    assert (naive - ref).abs()[..., border].max().item() > 0.1 * scale
+    assert torch.equal(naive[..., ~border], got[..., ~border])              # interior pixels: the very same arithmetic

@@ -50,6 +50,12 @@ for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
         name = ev.name.replace("void ", "").replace("im2im::(anonymous namespace)::", "")[:90]
         a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+if os.environ.get("IM2IM_PROFILE_LIST"):      # every launch of the last profiled step, in launch order
+    evs = sorted((ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+    per = len(evs) // N
+    for ev in evs[-per:]:
+        d = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+        print(f"  {d:9.1f} us  {ev.name.replace('void ', '').replace('im2im::(anonymous namespace)::', '')[:60]}")
 tot = sum(v[1] for v in agg.values())
 print(f"sum of kernel time {tot / N / 1e3:.3f} ms/step over {sum(v[0] for v in agg.values()) // N} launches/step")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
