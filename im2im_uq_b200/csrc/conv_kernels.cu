@@ -104,6 +104,24 @@ __device__ __forceinline__ float round_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// One lane of a converged warp.  The MMA-issuing warps run their loops with ALL 32 lanes (warp-uniform control flow, the
+// warp index taken through a shuffle so that the compiler knows it is uniform) and predicate only the tcgen05.mma /
+// tcgen05.commit instructions with this: the shared-memory descriptors then live in uniform registers.  Issued from inside
+// an `if (lane == 0)` region instead, every UTCHMMA was wrapped in an ELECT + 5x R2UR.BROADCAST + branch loop (the compiler
+// must move per-thread registers into uniform ones one lane at a time) - ~75 cycles per instruction, which capped the
+// N = 64 (32-cycle) and N = 32 MMAs of the halo kernel at 40 % / 20 % of the tensor pipe.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_index() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
 // mbarrier arrives when all previously issued tcgen05 ops of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -163,7 +181,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_const
     uint64_t* accum_bar = empty_bar + p.stages;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = uniform_warp_index();
     const int lane = threadIdx.x & 31;
     const uint32_t tmem_cols = p.bn < 32 ? 32u : static_cast<uint32_t>(p.bn);  // power of two >= 32 (bn in {32,64,128,256})
 
@@ -197,7 +215,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_const
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        {   // all lanes walk the loop (uniform control flow: TMA operands stay in uniform registers), one lane issues
+            const bool leader = elect_one_sync();
             int stage = 0;
             unsigned phase = 1;  // fresh barriers: waiting on parity 1 passes immediately
             for (int it = 0; it < n_k; ++it) {
@@ -208,39 +227,45 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_const
                 mbar_wait(&empty_bar[stage], phase);
                 unsigned char* a_dst = tiles + static_cast<size_t>(stage) * stage_bytes;
                 unsigned char* b_dst = a_dst + kATileBytes;
-                mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(stage_bytes));
                 const int c0 = cblk * p.kstep;
-                if (c0 < p.c_in1) tma_load_4d(a_dst, &map_x1, &full_bar[stage], c0, w0 + dx, h0 + dy, b0);
-                else tma_load_4d(a_dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0 + dx, h0 + dy, b0);
-                tma_load_2d(b_dst, &map_w, &full_bar[stage], tap * c_in + c0, n0);
+                if (leader) {
+                    mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(stage_bytes));
+                    if (c0 < p.c_in1) tma_load_4d(a_dst, &map_x1, &full_bar[stage], c0, w0 + dx, h0 + dy, b0);
+                    else tma_load_4d(a_dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0 + dx, h0 + dy, b0);
+                    tma_load_2d(b_dst, &map_w, &full_bar[stage], tap * c_in + c0, n0);
+                }
+                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = p.tf32 ? make_idesc_tf32(p.bn) : make_idesc_bf16(p.bn);
-            int stage = 0;
-            unsigned phase = 0;
-            for (int it = 0; it < n_k; ++it) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const unsigned char* a_src = tiles + static_cast<size_t>(stage) * stage_bytes;
-                const uint64_t desc_a = make_sw128_desc(a_src);
-                const uint64_t desc_b = make_sw128_desc(a_src + kATileBytes);
+        // ------------------------------------------------------------------ MMA issuer (all lanes walk, one issues)
+        const bool leader = elect_one_sync();
+        const uint32_t idesc = p.tf32 ? make_idesc_tf32(p.bn) : make_idesc_bf16(p.bn);
+        int stage = 0;
+        unsigned phase = 0;
+        for (int it = 0; it < n_k; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const unsigned char* a_src = tiles + static_cast<size_t>(stage) * stage_bytes;
+            const uint64_t desc_a = make_sw128_desc(a_src);
+            const uint64_t desc_b = make_sw128_desc(a_src + kATileBytes);
 #pragma unroll
-                for (int k = 0; k < kKStep / kUmmaK; ++k) {
-                    // advance 32 bytes (16 bf16 / 8 tf32 elements) along K inside the 128-byte swizzle row: +2 in 16-byte units
+            for (int k = 0; k < kKStep / kUmmaK; ++k) {
+                // advance 32 bytes (16 bf16 / 8 tf32 elements) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                if (leader) {
                     if (p.tf32) umma_tf32(tmem_base, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
                                           idesc, (it > 0 || k > 0) ? 1u : 0u);
                     else umma_bf16(tmem_base, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
                                    idesc, (it > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(accum_bar);  // accumulator complete
+            if (leader) umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        if (leader) umma_commit(accum_bar);  // accumulator complete
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue warps (2..5)
         const int quad = warp & 3;               // TMEM lane quadrant this warp may access
@@ -313,7 +338,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
     uint64_t* tmem_empty = tmem_full + 2;         // [2] accumulator drained, MMA may overwrite
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = uniform_warp_index();
     const int lane = threadIdx.x & 31;
     const uint32_t acc_cols = p.bn < 32 ? 32u : static_cast<uint32_t>(p.bn);
     const uint32_t tmem_cols = 2 * acc_cols;  // power of two: 64..512
@@ -346,7 +371,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
     const int n_k = p.taps * kblocks_per_tap;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // all lanes walk the loops (uniform control flow: TMA operands stay in uniform registers), one lane issues
+            const bool leader = elect_one_sync();
             int stage = 0;
             unsigned phase = 1;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -362,50 +388,57 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
                     const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
                     mbar_wait(&empty_bar[stage], phase);
                     unsigned char* a_dst = tiles + static_cast<size_t>(stage) * stage_bytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(stage_bytes));
                     const int c0 = cblk * p.kstep;
-                    if (c0 < p.c_in1) tma_load_4d(a_dst, &map_x1, &full_bar[stage], c0, w0 + dx, h0 + dy, b0);
-                    else tma_load_4d(a_dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0 + dx, h0 + dy, b0);
-                    tma_load_2d(a_dst + kATileBytes, &map_w, &full_bar[stage], tap * c_in + c0, n0);
+                    if (leader) {
+                        mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(stage_bytes));
+                        if (c0 < p.c_in1) tma_load_4d(a_dst, &map_x1, &full_bar[stage], c0, w0 + dx, h0 + dy, b0);
+                        else tma_load_4d(a_dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0 + dx, h0 + dy, b0);
+                        tma_load_2d(a_dst + kATileBytes, &map_w, &full_bar[stage], tap * c_in + c0, n0);
+                    }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = p.tf32 ? make_idesc_tf32(p.bn) : make_idesc_bf16(p.bn);
-            int stage = 0;
-            unsigned phase = 0;
-            unsigned acc_phase = 3u;  // bit b = parity to wait for on tmem_empty[b]; fresh barriers: parity 1 passes
-            int buf = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[buf], (acc_phase >> buf) & 1u);
-                acc_phase ^= 1u << buf;
+        // all 32 lanes walk the loops (uniform control flow); the elected lane issues - see elect_one_sync()
+        const bool leader = elect_one_sync();
+        const uint32_t idesc = p.tf32 ? make_idesc_tf32(p.bn) : make_idesc_bf16(p.bn);
+        int stage = 0;
+        unsigned phase = 0;
+        unsigned acc_phase = 3u;  // bit b = parity to wait for on tmem_empty[b]; fresh barriers: parity 1 passes
+        int buf = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(&tmem_empty[buf], (acc_phase >> buf) & 1u);
+            acc_phase ^= 1u << buf;
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf) * acc_cols;
+            for (int it = 0; it < n_k; ++it) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf) * acc_cols;
-                for (int it = 0; it < n_k; ++it) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const unsigned char* a_src = tiles + static_cast<size_t>(stage) * stage_bytes;
-                    const uint64_t desc_a = make_sw128_desc(a_src);
-                    const uint64_t desc_b = make_sw128_desc(a_src + kATileBytes);
-                    if (p.tf32) {
+                const unsigned char* a_src = tiles + static_cast<size_t>(stage) * stage_bytes;
+                const uint64_t desc_a = make_sw128_desc(a_src);
+                const uint64_t desc_b = make_sw128_desc(a_src + kATileBytes);
+                if (p.tf32) {
 #pragma unroll
-                        for (int k = 0; k < kKStep / kUmmaK; ++k)
+                    for (int k = 0; k < kKStep / kUmmaK; ++k)
+                        if (leader)
                             umma_tf32(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
                                       idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    } else {
+                } else {
 #pragma unroll
-                        for (int k = 0; k < kKStep / kUmmaK; ++k)
+                    for (int k = 0; k < kKStep / kUmmaK; ++k)
+                        if (leader)
                             umma_bf16(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
                                       idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    }
-                    umma_commit(&empty_bar[stage]);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tmem_full[buf]);
-                buf ^= 1;
+                if (leader) umma_commit(&empty_bar[stage]);
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
+            if (leader) umma_commit(&tmem_full[buf]);
+            __syncwarp();
+            buf ^= 1;
         }
     } else {
         const int quad = warp & 3;
@@ -571,7 +604,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     float* s_lam = reinterpret_cast<float*>(s_pair + (p.hist_L + 1));
     unsigned* s_hist = reinterpret_cast<unsigned*>(s_lam + p.hist_L);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = uniform_warp_index();
     const int lane = threadIdx.x & 31;
     const uint32_t acc_cols = p.bn < 32 ? 32u : static_cast<uint32_t>(p.bn);
     const uint32_t tmem_cols = 2 * acc_cols;
@@ -624,13 +657,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     }
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // all lanes walk the loops (uniform control flow: TMA operands stay in uniform registers), one lane issues
+            const bool leader = elect_one_sync();
             // resident weights, once
-            mbar_arrive_expect_tx(w_bar, static_cast<unsigned>(w_bytes));
+            if (leader) mbar_arrive_expect_tx(w_bar, static_cast<unsigned>(w_bytes));
             for (int tap = 0; tap < 9; ++tap)
                 for (int cb = 0; cb < cblocks; ++cb)
-                    tma_load_2d(w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes, &map_w, w_bar,
-                                tap * c_in + cb * kKStep, n0);
+                    if (leader)
+                        tma_load_2d(w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes, &map_w, w_bar,
+                                    tap * c_in + cb * kKStep, n0);
+            __syncwarp();
             int stage = 0;
             unsigned phase = 1;
             for (int tile = tile_first; tile < tile_last; tile += tile_step) {
@@ -641,47 +677,53 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 for (int cb = 0; cb < cblocks; ++cb) {
                     mbar_wait(&empty_bar[stage], phase);
                     unsigned char* dst = a_ring + static_cast<size_t>(stage) * kHaloBytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(kHaloBytes));
                     const int c0 = cb * kKStep;
-                    if (c0 < p.c_in1) tma_load_4d(dst, &map_x1, &full_bar[stage], c0, w0, h0, b0);
-                    else tma_load_4d(dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0, h0, b0);
+                    if (leader) {
+                        mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(kHaloBytes));
+                        if (c0 < p.c_in1) tma_load_4d(dst, &map_x1, &full_bar[stage], c0, w0, h0, b0);
+                        else tma_load_4d(dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0, h0, b0);
+                    }
+                    __syncwarp();
                     if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(p.bn);
-            mbar_wait(w_bar, 0);
-            int stage = 0;
-            unsigned phase = 0;
-            unsigned acc_phase = 3u;
-            int buf = 0;
-            for (int tile = tile_first; tile < tile_last; tile += tile_step) {
-                mbar_wait(&tmem_empty[buf], (acc_phase >> buf) & 1u);
-                acc_phase ^= 1u << buf;
+        // all 32 lanes walk the loops (uniform control flow); the elected lane issues - see elect_one_sync()
+        const bool leader = elect_one_sync();
+        const uint32_t idesc = make_idesc_bf16(p.bn);
+        mbar_wait(w_bar, 0);
+        int stage = 0;
+        unsigned phase = 0;
+        unsigned acc_phase = 3u;
+        int buf = 0;
+        for (int tile = tile_first; tile < tile_last; tile += tile_step) {
+            mbar_wait(&tmem_empty[buf], (acc_phase >> buf) & 1u);
+            acc_phase ^= 1u << buf;
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf) * acc_cols;
+            for (int cb = 0; cb < cblocks; ++cb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf) * acc_cols;
-                for (int cb = 0; cb < cblocks; ++cb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const unsigned char* a_src = a_ring + static_cast<size_t>(stage) * kHaloBytes;
+                const unsigned char* a_src = a_ring + static_cast<size_t>(stage) * kHaloBytes;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int dy = tap / 3, dx = tap % 3;  // already offset by +1 (halo origin is (w0-1, h0-1))
-                        const uint64_t desc_a = make_sw128_desc_halo(a_src + (dy * kHaloW + dx) * 128);
-                        const uint64_t desc_b = make_sw128_desc(w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes);
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int dy = tap / 3, dx = tap % 3;  // already offset by +1 (halo origin is (w0-1, h0-1))
+                    const uint64_t desc_a = make_sw128_desc_halo(a_src + (dy * kHaloW + dx) * 128);
+                    const uint64_t desc_b = make_sw128_desc(w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes);
 #pragma unroll
-                        for (int k = 0; k < kKStep / kUmmaK; ++k)
+                    for (int k = 0; k < kKStep / kUmmaK; ++k)
+                        if (leader)
                             umma_bf16(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
                                       idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                    }
-                    umma_commit(&empty_bar[stage]);
-                    if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tmem_full[buf]);
-                buf ^= 1;
+                if (leader) umma_commit(&empty_bar[stage]);
+                __syncwarp();
+                if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
             }
+            if (leader) umma_commit(&tmem_full[buf]);
+            __syncwarp();
+            buf ^= 1;
         }
     } else {
         const int quad = warp & 3;
@@ -951,7 +993,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_const
     uint64_t* accum_bar = empty_bar + p.stages;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = uniform_warp_index();
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_dz);
@@ -979,7 +1021,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_const
     const int bn = n_slab * 64;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // all lanes walk the loop (uniform control flow: TMA operands stay in uniform registers), one lane issues
+            const bool leader = elect_one_sync();
             int stage = 0;
             unsigned phase = 1;
             for (int kt = k_begin; kt < k_end; ++kt) {
@@ -989,21 +1032,26 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_const
                 const int w0 = tw * p.bw, h0 = th * p.bh, b0 = t * p.bb;
                 mbar_wait(&empty_bar[stage], phase);
                 unsigned char* dst = tiles + static_cast<size_t>(stage) * kStageBytes;
-                mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>((2 + n_slab) * kSlabBytes));
-                tma_load_4d(dst, &map_dz, &full_bar[stage], m0, w0, h0, b0);
-                tma_load_4d(dst + kSlabBytes, &map_dz, &full_bar[stage], m0 + 64, w0, h0, b0);  // zero fill if >= c_out
+                if (leader) {
+                    mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>((2 + n_slab) * kSlabBytes));
+                    tma_load_4d(dst, &map_dz, &full_bar[stage], m0, w0, h0, b0);
+                    tma_load_4d(dst + kSlabBytes, &map_dz, &full_bar[stage], m0 + 64, w0, h0, b0);  // zero fill if >= c_out
+                }
                 for (int sl = 0; sl < n_slab; ++sl) {
                     const int slab = slab0 + sl;
                     const int tap = slab / cblocks, cb = slab - tap * cblocks;
                     const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
                     const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
-                    tma_load_4d(dst + (2 + sl) * kSlabBytes, &map_x, &full_bar[stage], cb * kKStep, w0 + dx, h0 + dy, b0);
+                    if (leader)
+                        tma_load_4d(dst + (2 + sl) * kSlabBytes, &map_x, &full_bar[stage], cb * kKStep, w0 + dx, h0 + dy, b0);
                 }
+                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && k_end > k_begin) {
+        if (k_end > k_begin) {   // all lanes walk the loop, the elected lane issues (see elect_one_sync)
+            const bool leader = elect_one_sync();
             // D = F32, A = B = BF16, both MN-major (bits 15, 16), M = 128, N = bn
             const uint32_t idesc = make_idesc_bf16(bn) | (1u << 15) | (1u << 16);
             int stage = 0;
@@ -1016,12 +1064,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_const
                 for (int k = 0; k < kTileM / kUmmaK; ++k) {  // 8 MMAs, 16 pixel rows (2 KB) each
                     const uint64_t desc_a = make_sw128_mn_desc(src + k * 2048, kSlabBytes);
                     const uint64_t desc_b = make_sw128_mn_desc(src + 2 * kSlabBytes + k * 2048, kSlabBytes);
-                    umma_bf16(tmem_base, desc_a, desc_b, idesc, (kt > k_begin || k > 0) ? 1u : 0u);
+                    if (leader) umma_bf16(tmem_base, desc_a, desc_b, idesc, (kt > k_begin || k > 0) ? 1u : 0u);
                 }
-                umma_commit(&empty_bar[stage]);
+                if (leader) umma_commit(&empty_bar[stage]);
+                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(accum_bar);
+            if (leader) umma_commit(accum_bar);
+            __syncwarp();
         }
     } else if (k_end > k_begin) {
         const int quad = warp & 3;
@@ -1092,7 +1142,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_
     uint64_t* accum_bar = empty_bar + p.stages;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = uniform_warp_index();
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_dz);
@@ -1116,7 +1166,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_
     const int k_end = static_cast<int>(static_cast<long long>(n_pix_tiles) * (split + 1) / p.splits);
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // all lanes walk the loop (uniform control flow: TMA operands stay in uniform registers), one lane issues
+            const bool leader = elect_one_sync();
             int stage = 0;
             unsigned phase = 1;
             for (int kt = k_begin; kt < k_end; ++kt) {
@@ -1126,14 +1177,18 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_
                 const int w0 = tw * kHaloTileW, h0 = th * kHaloTileH, b0 = t;
                 mbar_wait(&empty_bar[stage], phase);
                 unsigned char* dst = tiles + static_cast<size_t>(stage) * kWgHaloStageBytes;
-                mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(kWgHaloStageBytes));
-                tma_load_4d(dst, &map_x, &full_bar[stage], cb * kKStep, w0 - 1, h0 - 1, b0);
-                tma_load_4d(dst + kHaloBytes, &map_dz, &full_bar[stage], n0, w0, h0, b0);
+                if (leader) {
+                    mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(kWgHaloStageBytes));
+                    tma_load_4d(dst, &map_x, &full_bar[stage], cb * kKStep, w0 - 1, h0 - 1, b0);
+                    tma_load_4d(dst + kHaloBytes, &map_dz, &full_bar[stage], n0, w0, h0, b0);
+                }
+                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && k_end > k_begin) {
+        if (k_end > k_begin) {   // all lanes walk the loop, the elected lane issues (see elect_one_sync)
+            const bool leader = elect_one_sync();
             // D = F32, A = B = BF16, both MN-major (bits 15, 16), M = 128, N = 64
             const uint32_t idesc = make_idesc_bf16(64) | (1u << 15) | (1u << 16);
             int stage = 0;
@@ -1153,14 +1208,17 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_
                         const int off1 = ((t1 / 3) * kHaloW + (t1 % 3)) * 128;
                         const uint32_t lbo = (pr < 4) ? static_cast<uint32_t>(off1 - off0) : 128u;
                         const uint64_t desc_a = make_sw128_mn_desc_halo(halo + off0 + (2 * k) * kHaloW * 128, lbo);
-                        umma_bf16(tmem_base + static_cast<uint32_t>(pr * 64), desc_a, desc_b, idesc,
-                                  (kt > k_begin || k > 0) ? 1u : 0u);
+                        if (leader)
+                            umma_bf16(tmem_base + static_cast<uint32_t>(pr * 64), desc_a, desc_b, idesc,
+                                      (kt > k_begin || k > 0) ? 1u : 0u);
                     }
                 }
-                umma_commit(&empty_bar[stage]);
+                if (leader) umma_commit(&empty_bar[stage]);
+                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(accum_bar);
+            if (leader) umma_commit(accum_bar);
+            __syncwarp();
         }
     } else if (k_end > k_begin) {
         const int quad = warp & 3;
