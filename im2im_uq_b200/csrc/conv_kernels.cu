@@ -140,6 +140,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) 
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32-byte global store (STG.256, sm_100): an epilogue thread owns a pixel's channel run, and the lanes of a warp are 128+
+// bytes apart, so every store instruction touches 32 separate sectors - with 16-byte stores each 32-byte sector was written
+// half at a time by two instructions; p must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float* f) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+    return pk;
+}
 
 // Shared-memory matrix descriptor for a K-major, SWIZZLE_128B tile whose rows are 128 bytes (64 bf16):
 // start address (>>4), LBO = 1 (ignored for swizzled K-major), SBO = 1024 B between 8-row groups, version 1 (sm_100),
@@ -481,23 +497,15 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
                         f[j] = x;
                     }
                     if (p.out_bf16) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.c_out + n0 + c);
+                        __nv_bfloat16* dst = p.out_bf16 + pix * p.c_out + n0 + c;   // 64-byte aligned (c_out, n0, c: x32)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 pk;
-                            __nv_bfloat162 h0_ = __floats2bfloat162_rn(f[8 * q + 0], f[8 * q + 1]);
-                            __nv_bfloat162 h1_ = __floats2bfloat162_rn(f[8 * q + 2], f[8 * q + 3]);
-                            __nv_bfloat162 h2_ = __floats2bfloat162_rn(f[8 * q + 4], f[8 * q + 5]);
-                            __nv_bfloat162 h3_ = __floats2bfloat162_rn(f[8 * q + 6], f[8 * q + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0_); pk.y = *reinterpret_cast<uint32_t*>(&h1_);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2_); pk.w = *reinterpret_cast<uint32_t*>(&h3_);
-                            dst[q] = pk;
-                        }
+                        for (int q = 0; q < 2; ++q) st_global_256(dst + 16 * q, pack8_bf16(f + 16 * q), pack8_bf16(f + 16 * q + 8));
                     }
                     if (p.out_f32) {
-                        float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.c_out + n0 + c);
+                        float* dst = p.out_f32 + pix * p.c_out + n0 + c;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                        for (int q = 0; q < 4; ++q)
+                            st_global_256(dst + 8 * q, *reinterpret_cast<const uint4*>(f + 8 * q), *reinterpret_cast<const uint4*>(f + 8 * q + 4));
                     }
                 }
             }
@@ -843,6 +851,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                     }
                     uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.c_out + n0 + c);
+                    uint4 pk_even = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         __nv_bfloat162 h2[4];
@@ -875,7 +884,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                         uint4 pk;
                         pk.x = *reinterpret_cast<uint32_t*>(&h2[0]); pk.y = *reinterpret_cast<uint32_t*>(&h2[1]);
                         pk.z = *reinterpret_cast<uint32_t*>(&h2[2]); pk.w = *reinterpret_cast<uint32_t*>(&h2[3]);
-                        if (in_range) dst[q] = pk;
+                        if (q & 1) {
+                            if (in_range) st_global_256(dst + (q - 1), pk_even, pk);   // 32-byte stores: whole sectors
+                        } else {
+                            pk_even = pk;
+                        }
                     }
                 }
                 buf ^= 1;
@@ -900,23 +913,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                         f[j] = x;
                     }
                     if (p.out_bf16) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.c_out + n0 + c);
+                        __nv_bfloat16* dst = p.out_bf16 + pix * p.c_out + n0 + c;   // 64-byte aligned (c_out, n0, c: x32)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 pk;
-                            __nv_bfloat162 h0_ = __floats2bfloat162_rn(f[8 * q + 0], f[8 * q + 1]);
-                            __nv_bfloat162 h1_ = __floats2bfloat162_rn(f[8 * q + 2], f[8 * q + 3]);
-                            __nv_bfloat162 h2_ = __floats2bfloat162_rn(f[8 * q + 4], f[8 * q + 5]);
-                            __nv_bfloat162 h3_ = __floats2bfloat162_rn(f[8 * q + 6], f[8 * q + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0_); pk.y = *reinterpret_cast<uint32_t*>(&h1_);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2_); pk.w = *reinterpret_cast<uint32_t*>(&h3_);
-                            dst[q] = pk;
-                        }
+                        for (int q = 0; q < 2; ++q) st_global_256(dst + 16 * q, pack8_bf16(f + 16 * q), pack8_bf16(f + 16 * q + 8));
                     }
                     if (p.out_f32) {
-                        float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.c_out + n0 + c);
+                        float* dst = p.out_f32 + pix * p.c_out + n0 + c;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                        for (int q = 0; q < 4; ++q)
+                            st_global_256(dst + 8 * q, *reinterpret_cast<const uint4*>(f + 8 * q), *reinterpret_cast<const uint4*>(f + 8 * q + 4));
                     }
                 }
             }
@@ -1371,6 +1376,8 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
     if (c_out < 32 || c_out % 32) return fail(IM2IM_ERANGE, "c_out must be a multiple of 32 (got %d)", c_out);
     if (!d_x1 || !d_weight || (!d_out_bf16 && !d_out_f32) || (c_in2 > 0 && !d_x2))
         return fail(IM2IM_EINVAL, "null tensor");
+    if ((reinterpret_cast<uintptr_t>(d_out_bf16) | reinterpret_cast<uintptr_t>(d_out_f32)) & 31u)
+        return fail(IM2IM_EINVAL, "conv_igemm: the output tensor must be 32-byte aligned (the epilogue stores 32 bytes at a time)");
     ConvParams p;
     p.taps = taps; p.c_in1 = c_in1; p.c_in2 = c_in2; p.c_out = c_out; p.B = B; p.H = H; p.W = W;
     pick_box(B, H, W, p.bw, p.bh, p.bb);
@@ -1466,6 +1473,8 @@ extern "C" int im2im_conv_igemm_tf32(const float* d_x1, int32_t c_in1, const flo
         return fail(IM2IM_ERANGE, "tf32: input channels must be multiples of %d (got %d + %d)", ks, c_in1, c_in2);
     if (c_out < 32 || c_out % 32) return fail(IM2IM_ERANGE, "c_out must be a multiple of 32 (got %d)", c_out);
     if (!d_x1 || !d_weight || !d_out || (c_in2 > 0 && !d_x2)) return fail(IM2IM_EINVAL, "null tensor");
+    if (reinterpret_cast<uintptr_t>(d_out) & 31u)
+        return fail(IM2IM_EINVAL, "conv_igemm_tf32: the output tensor must be 32-byte aligned (the epilogue stores 32 bytes at a time)");
     ConvParams p;
     p.taps = taps; p.c_in1 = c_in1; p.c_in2 = c_in2; p.c_out = c_out; p.B = B; p.H = H; p.W = W;
     pick_box(B, H, W, p.bw, p.bh, p.bb);
