@@ -24,6 +24,7 @@ namespace im2im {
 namespace {
 
 constexpr int kConvThreads = 192;     // 6 warps
+constexpr int kHaloThreads = 320;     // conv_halo_kernel: + 4 more epilogue warps
 constexpr int kTileM = 128;           // output pixels per CTA
 constexpr int kKStep = 64;            // bf16 channels per K step = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;            // K of one tcgen05.mma for 16-bit inputs
@@ -587,7 +588,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc_halo(const void* smem_ptr) {
     return desc;
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
                  const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -616,6 +617,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     const int lane = threadIdx.x & 31;
     const uint32_t acc_cols = p.bn < 32 ? 32u : static_cast<uint32_t>(p.bn);
     const uint32_t tmem_cols = 2 * acc_cols;
+    // Eight epilogue warps: warps 2-5 drain the first half of the accumulator columns, warps 6-9 the second half (a warp can
+    // only read the TMEM lanes of its quadrant, so two warps share each quadrant).  With one 36 KB halo box per tile the
+    // epilogue (TMEM -> registers -> bf16 -> global), not the 36 MMAs, set the pace of the 64-channel layers.  Head mode and
+    // N = 32 tiles have too few columns to split: warps 6-9 idle there.
+    const bool head_mode = (p.out_planar != nullptr || p.hist_global != nullptr);
+    const bool split_epilogue = !head_mode && p.bn >= 64;
 
     if (p.stat_mode == 2) {   // the forward's per-channel affine, recomputed with the same ops (bn_relu_bwd kernels do the same)
         for (int c = threadIdx.x; c < p.bn; c += blockDim.x) {
@@ -641,7 +648,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         prefetch_tmap(&map_w);
         for (int s = 0; s < p.a_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(w_bar, 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], split_epilogue ? 8 : 4); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr_smem, tmem_cols);
@@ -733,16 +740,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             __syncwarp();
             buf ^= 1;
         }
-    } else {
+    } else if (warp < 6 || split_epilogue) {
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;                    // 0: warps 2-5, 1: warps 6-9
         const int row = quad * 32 + lane;
         const int iw = row % kHaloTileW, ih = row / kHaloTileW;
+        const int c_lo = split_epilogue ? half * (p.bn / 2) : 0;        // this warp's accumulator columns [c_lo, c_hi)
+        const int c_hi = split_epilogue ? c_lo + p.bn / 2 : p.bn;
         unsigned full_phase = 0u;
         int buf = 0;
-        // fused statistics (bn == 64 only): this thread's partial sums over its pixel row of every tile, all 64 channels
-        float acc0[kHaloStatBn], acc1[kHaloStatBn];
+        // fused statistics (bn == 64 only): this thread's partial sums over its pixel row of every tile, for the 32 channels
+        // [c_lo, c_lo + 32) of its warp
+        float acc0[kHaloStatBn / 2], acc1[kHaloStatBn / 2];
 #pragma unroll
-        for (int j = 0; j < kHaloStatBn; ++j) acc0[j] = acc1[j] = 0.f;
+        for (int j = 0; j < kHaloStatBn / 2; ++j) acc0[j] = acc1[j] = 0.f;
         for (int tile = tile_first; tile < tile_last; tile += tile_step) {
             int t = tile;
             const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -830,75 +841,70 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 continue;
             }
             if (p.stat_mode != 0) {
-                // ---- bf16 output + fused per-channel statistics, registers only (bn == 64): this kernel is bound by shared-
-                // memory bandwidth (operand reads of N = 64 MMAs + the TMA fill), so the epilogue must not touch shared memory
-                // - measured: staging the tile for coalesced / TMA stores made it slower, not faster
-                uint4 zreg[kHaloStatBn / 8];
-                if (p.stat_mode == 2) {   // this thread's bn_z row (its pixel, 64 channels), requested in the shadow of the MMAs
-                    const uint4* zsrc = reinterpret_cast<const uint4*>(p.bn_z + pix * p.c_out + n0);
+                // ---- bf16 output + fused per-channel statistics, registers only (bn == 64, 32 channels per warp): this
+                // kernel is bound by shared-memory bandwidth (operand reads of N = 64 MMAs + the TMA fill), so the epilogue
+                // must not touch shared memory - measured: staging the tile for coalesced / TMA stores made it slower
+                const int c = c_lo;
+                uint4 zreg[4];
+                if (p.stat_mode == 2) {   // this thread's bn_z values (its pixel, 32 channels), requested in the shadow of the MMAs
+                    const uint4* zsrc = reinterpret_cast<const uint4*>(p.bn_z + pix * p.c_out + n0 + c);
 #pragma unroll
-                    for (int q = 0; q < kHaloStatBn / 8; ++q) zreg[q] = __ldg(zsrc + q);
+                    for (int q = 0; q < 4; ++q) zreg[q] = __ldg(zsrc + q);
                 }
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_acc + static_cast<uint32_t>(c), v);
+                tmem_ld_wait();
+                tc_fence_before();          // only read of this accumulator by this warp: hand it back to the MMA warp
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.c_out + n0 + c);
+                uint4 pk_even = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                for (int hh = 0; hh < kHaloStatBn / 32; ++hh) {
-                    const int c = hh * 32;
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tmem_acc + static_cast<uint32_t>(c), v);
-                    tmem_ld_wait();
-                    if (hh == kHaloStatBn / 32 - 1) {   // last read of this accumulator: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                for (int q = 0; q < 4; ++q) {
+                    __nv_bfloat162 h2[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        h2[j] = __floats2bfloat162_rn(__uint_as_float(v[8 * q + 2 * j]), __uint_as_float(v[8 * q + 2 * j + 1]));
+                    if (p.stat_mode == 1) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 r = __bfloat1622float2(h2[j]);      // the values as stored
+                            const int cc = 8 * q + 2 * j;
+                            acc0[cc] += r.x; acc1[cc] = fmaf(r.x, r.x, acc1[cc]);
+                            acc0[cc + 1] += r.y; acc1[cc + 1] = fmaf(r.y, r.y, acc1[cc + 1]);
+                        }
+                    } else {
+                        const __nv_bfloat162* hz = reinterpret_cast<const __nv_bfloat162*>(&zreg[q]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 r = __bfloat1622float2(h2[j]);
+                            const float2 z2 = __bfloat1622float2(hz[j]);
+                            const int cc = 8 * q + 2 * j;
+                            // ReLU mask exactly as the forward saw it; g replaces dy in the stored tensor
+                            const float g0 = fmaf(z2.x, s_scale[c + cc], s_shift[c + cc]) > 0.f ? r.x : 0.f;
+                            const float g1 = fmaf(z2.y, s_scale[c + cc + 1], s_shift[c + cc + 1]) > 0.f ? r.y : 0.f;
+                            acc0[cc] += g0; acc1[cc] = fmaf(g0, z2.x, acc1[cc]);
+                            acc0[cc + 1] += g1; acc1[cc + 1] = fmaf(g1, z2.y, acc1[cc + 1]);
+                            h2[j] = __floats2bfloat162_rn(g0, g1);
+                        }
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.c_out + n0 + c);
-                    uint4 pk_even = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        __nv_bfloat162 h2[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            h2[j] = __floats2bfloat162_rn(__uint_as_float(v[8 * q + 2 * j]), __uint_as_float(v[8 * q + 2 * j + 1]));
-                        if (p.stat_mode == 1) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 r = __bfloat1622float2(h2[j]);      // the values as stored
-                                const int cc = c + 8 * q + 2 * j;
-                                acc0[cc] += r.x; acc1[cc] = fmaf(r.x, r.x, acc1[cc]);
-                                acc0[cc + 1] += r.y; acc1[cc + 1] = fmaf(r.y, r.y, acc1[cc + 1]);
-                            }
-                        } else {
-                            const __nv_bfloat162* hz = reinterpret_cast<const __nv_bfloat162*>(&zreg[hh * 4 + q]);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 r = __bfloat1622float2(h2[j]);
-                                const float2 z2 = __bfloat1622float2(hz[j]);
-                                const int cc = c + 8 * q + 2 * j;
-                                // ReLU mask exactly as the forward saw it; g replaces dy in the stored tensor
-                                const float g0 = fmaf(z2.x, s_scale[cc], s_shift[cc]) > 0.f ? r.x : 0.f;
-                                const float g1 = fmaf(z2.y, s_scale[cc + 1], s_shift[cc + 1]) > 0.f ? r.y : 0.f;
-                                acc0[cc] += g0; acc1[cc] = fmaf(g0, z2.x, acc1[cc]);
-                                acc0[cc + 1] += g1; acc1[cc + 1] = fmaf(g1, z2.y, acc1[cc + 1]);
-                                h2[j] = __floats2bfloat162_rn(g0, g1);
-                            }
-                        }
-                        uint4 pk;
-                        pk.x = *reinterpret_cast<uint32_t*>(&h2[0]); pk.y = *reinterpret_cast<uint32_t*>(&h2[1]);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2[2]); pk.w = *reinterpret_cast<uint32_t*>(&h2[3]);
-                        if (q & 1) {
-                            if (in_range) st_global_256(dst + (q - 1), pk_even, pk);   // 32-byte stores: whole sectors
-                        } else {
-                            pk_even = pk;
-                        }
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&h2[0]); pk.y = *reinterpret_cast<uint32_t*>(&h2[1]);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2[2]); pk.w = *reinterpret_cast<uint32_t*>(&h2[3]);
+                    if (q & 1) {
+                        if (in_range) st_global_256(dst + (q - 1), pk_even, pk);   // 32-byte stores: whole sectors
+                    } else {
+                        pk_even = pk;
                     }
                 }
                 buf ^= 1;
                 continue;
             }
-            for (int c = 0; c < p.bn; c += 32) {
+            for (int c = c_lo; c < c_hi; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tmem_acc + static_cast<uint32_t>(c), v);
                 tmem_ld_wait();
-                if (c + 32 >= p.bn) {
+                if (c + 32 >= c_hi) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -931,15 +937,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             if (p.stat_mode != 0) {
                 // column sums over the 32 pixel rows of this warp (butterfly), then one global atomicAdd per channel and warp
 #pragma unroll
-                for (int j = 0; j < kHaloStatBn; ++j) {
+                for (int j = 0; j < kHaloStatBn / 2; ++j) {
                     float a0 = acc0[j], a1 = acc1[j];
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         a0 += __shfl_xor_sync(0xffffffffu, a0, o);
                         a1 += __shfl_xor_sync(0xffffffffu, a1, o);
                     }
-                    if (lane == (j & 31)) {
-                        const int ch_g = n0 + j;
+                    if (lane == j) {
+                        const int ch_g = n0 + c_lo + j;
                         if (p.stat_mode == 2) a1 = p.bn_rstd[ch_g] * (a1 - p.bn_mean[ch_g] * a0);
                         atomicAdd(p.stat_sums + ch_g, a0);
                         atomicAdd(p.stat_sums + p.c_out + ch_g, a1);
@@ -1437,7 +1443,7 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
                 if (gx < 1) gx = 1;
                 if (gx > m_tiles) gx = m_tiles;
                 dim3 hgrid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks_n));
-                conv_halo_kernel<<<hgrid, kConvThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h2, hw, h);
+                conv_halo_kernel<<<hgrid, kHaloThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h2, hw, h);
                 return check_launch("conv_halo_kernel");
             }
         }
@@ -1621,7 +1627,7 @@ int head_tc_impl(const void* d_x, const void* d_weight, const float* d_bias, con
     const long long m_tiles = static_cast<long long>(h.tiles_w) * h.tiles_h * B;
     long long gx = sm_count();
     if (gx > m_tiles) gx = m_tiles;
-    conv_halo_kernel<<<dim3(static_cast<unsigned>(gx), 1), kConvThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h1, hw, h);
+    conv_halo_kernel<<<dim3(static_cast<unsigned>(gx), 1), kHaloThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h1, hw, h);
     return check_launch(d_hist ? "conv_halo_kernel<head+hist>" : "conv_halo_kernel<head>");
 }
 }  // namespace
