@@ -16,6 +16,7 @@ Precision: activations and GEMM operands bf16, accumulation / statistics / param
 Known deviation: convolution biases that feed a BatchNorm receive an exactly-zero gradient (their true gradient is
 zero up to rounding noise, because the batch mean cancels them); torch produces ~1e-9 noise there instead.
 """
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -350,7 +351,7 @@ class UNetTrainEngine:
                 # Measured on B200 (tools/halo_modes_bench.py, batch 78): the backward fusion costs the halo kernel more
                 # (the epilogue's bn_z reads: +0.38 ms on 64->64 @320^2) than the separate reduction pass it replaces, so it
                 # is off by default; the forward fusion (stat_mode 1) is +6 % on the convolution and replaces a pass over z.
-                if getattr(self, "fuse_bwd_stats", False):
+                if getattr(self, "fuse_bwd_stats", os.environ.get("IM2IM_FUSE_BWD_STATS") == "1"):
                     bn = la.bn
                     dx1, fused = conv_igemm_stats(dz, layer.w_bwd, 2, sums,
                                                   bn=(sa["z"], bn.weight.detach(), bn.bias.detach(), sa["mean"], sa["rstd"]))
