@@ -129,7 +129,7 @@ def _miss_counts_any_device(outputs, labels, lam_sorted_dev, device, counts=None
         rcps.miss_counts(outputs, labels, lam_sorted_dev, counts=counts, totals=totals, zero=False, head=head)
         return counts, totals
     per_image = (outputs[0].numel() + labels[0].numel()) * 4 if n else 1
-    copy_stream = torch.cuda.Stream(device=device)
+    copy_stream = _copy_stream(device)
     main = torch.cuda.current_stream(device)
     prev = None
     for lo, hi in _chunks(n, per_image):
@@ -666,6 +666,19 @@ def streaming_applicable(model, dataset, config) -> bool:
     return fused is not None and fused[1] is None
 
 
+_COPY_STREAMS: dict = {}
+
+
+def _copy_stream(device) -> "torch.cuda.Stream":
+    """One upload stream per device for the life of the process: the caching allocator keeps a pool per stream, so a fresh
+    stream per call meant fresh cudaMallocs per call (seen as a 0.2 s outlier on every second calibration)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _COPY_STREAMS.get(key)
+    if st is None:
+        st = _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 def stream_miss_counts(model, dataset, config, device, lam_dev: torch.Tensor, stats: Optional[dict] = None):
     """Run the model over a map-style dataset batch by batch and keep only the per-image miss counts on the ascending grid
     ``lam_dev``: (counts int32 (N, L) on the device, totals int64 (L,), pixels per image).  The (N, 3, C, H, W) output
@@ -693,7 +706,7 @@ def stream_miss_counts(model, dataset, config, device, lam_dev: torch.Tensor, st
     lo = 0
     fused_batches = 0
     # the next batch's host->device copy runs on its own stream under the current batch's kernels (pinned sources)
-    copy_stream = torch.cuda.Stream(device=device)
+    copy_stream = _copy_stream(device)
     main = torch.cuda.current_stream(device)
 
     def upload(pair_):
