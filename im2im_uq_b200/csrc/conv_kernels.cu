@@ -45,6 +45,9 @@ struct ConvParams {
     const float* bias;       // [c_out] or null
     __nv_bfloat16* out_bf16; // NHWC [B,H,W,c_out] or null
     float* out_f32;          // NHWC fp32 or null
+    // persistent kernel, training forward: per-channel sum / sum of squares of the bf16 values that are stored, accumulated
+    // into stat_sums[c] / stat_sums[c_out + c] (fp32 atomics) - BatchNorm's batch statistics without a pass over the output
+    float* stat_sums;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -508,6 +511,35 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const _
                         for (int q = 0; q < 4; ++q)
                             st_global_256(dst + 8 * q, *reinterpret_cast<const uint4*>(f + 8 * q), *reinterpret_cast<const uint4*>(f + 8 * q + 4));
                     }
+                }
+                if (p.stat_sums != nullptr) {
+                    // Column sums over the 32 pixel rows of this warp by recursive halving: at distance o a lane keeps the
+                    // half of its columns selected by bit o of its lane index and adds the partner's copy of that half -
+                    // 16+8+4+2+1 = 31 shuffles per statistic instead of 5 per column; lane j ends with column c + j.
+                    // Values as stored (bf16-rounded); rows outside the image contribute zero.
+                    float s0[32], s1[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(v[j]);
+                        if (p.bias) x += __ldg(p.bias + n0 + c + j);
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        x = in_range ? __bfloat162float(__float2bfloat16_rn(x)) : 0.f;
+                        s0[j] = x;
+                        s1[j] = x * x;
+                    }
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        const bool upper = (lane & o) != 0;
+#pragma unroll
+                        for (int i = 0; i < o; ++i) {
+                            const float send0 = upper ? s0[i] : s0[i + o], keep0 = upper ? s0[i + o] : s0[i];
+                            const float send1 = upper ? s1[i] : s1[i + o], keep1 = upper ? s1[i + o] : s1[i];
+                            s0[i] = keep0 + __shfl_xor_sync(0xffffffffu, send0, o);
+                            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, o);
+                        }
+                    }
+                    atomicAdd(p.stat_sums + n0 + c + lane, s0[0]);
+                    atomicAdd(p.stat_sums + p.c_out + n0 + c + lane, s1[0]);
                 }
             }
             buf ^= 1;
@@ -1393,7 +1425,7 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
     p.stages = (200 * 1024) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     p.relu = relu; p.bias = d_bias; p.tf32 = 0; p.kstep = kKStep;
-    p.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16); p.out_f32 = d_out_f32;
+    p.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16); p.out_f32 = d_out_f32; p.stat_sums = nullptr;
     CUtensorMap m1, m2, mw;
     int rc = make_act_map(&m1, d_x1, B, H, W, c_in1, p.bw, p.bh, p.bb);
     if (rc) return rc;
@@ -1458,6 +1490,13 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
     }
     IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
+    // forward statistics in the persistent kernel's epilogue when the K loop is long enough to hide the extra shuffles
+    // (>= 256 input channels: >= 9 k cycles of MMAs per tile); shallower layers keep the separate reduction pass
+    static const bool no_pstats = (getenv("IM2IM_NO_PERSISTENT_STATS") != nullptr);
+    if (fs.mode == 1 && !no_pstats && c_in1 + c_in2 >= 256 && d_out_bf16 != nullptr && d_out_f32 == nullptr) {
+        p.stat_sums = fs.sums;
+        if (fused) *fused = 1;
+    }
     const long long n_tiles = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_b * (c_out / p.bn);
     const int sms = sm_count();
     const unsigned grid = static_cast<unsigned>(n_tiles < sms ? n_tiles : sms);
@@ -1490,7 +1529,7 @@ extern "C" int im2im_conv_igemm_tf32(const float* d_x1, int32_t c_in1, const flo
     p.stages = (200 * 1024) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     p.relu = relu; p.bias = d_bias; p.tf32 = 1; p.kstep = ks;
-    p.out_bf16 = nullptr; p.out_f32 = d_out;
+    p.out_bf16 = nullptr; p.out_f32 = d_out; p.stat_sums = nullptr;
     CUtensorMap m1, m2, mw;
     int rc = make_act_map(&m1, d_x1, B, H, W, c_in1, p.bw, p.bh, p.bb, true);
     if (rc) return rc;

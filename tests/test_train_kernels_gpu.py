@@ -199,12 +199,35 @@ def test_conv_epilogue_batch_statistics(c1, c2, cout, shape):
     _close(sums[:cout], 2 * zf.sum(0), 2e-5)
 
 
-def test_conv_epilogue_statistics_fall_back_off_the_halo_kernel():
+@pytest.mark.parametrize("c1,c2,cout,shape", [(512, 0, 512, (2, 20, 20)), (256, 0, 512, (3, 40, 40)), (512, 512, 512, (1, 40, 40)),
+                                              (256, 0, 128, (2, 20, 12)), (256, 256, 256, (1, 10, 10)), (512, 0, 256, (5, 5, 7))])
+def test_persistent_conv_epilogue_batch_statistics(c1, c2, cout, shape):
+    """The deep layers (not 8x16-tile shapes / weights too large for the halo kernel) run on the persistent kernel; with
+    >= 256 input channels its epilogue accumulates the same statistics (recursive-halving column sums + fp32 atomics),
+    ragged tiles included (rows outside the image contribute nothing)."""
+    from im2im_uq_b200.conv import conv_igemm, conv_igemm_stats, pack_conv_weight
+    B, H, W = shape
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x1 = _nhwc(torch.randn(B, c1, H, W, device=DEV, generator=g))
+    x2 = _nhwc(torch.randn(B, c2, H, W, device=DEV, generator=g)) if c2 else None
+    w = pack_conv_weight(torch.randn(cout, c1 + c2, 3, 3, device=DEV, generator=g) / (9 * (c1 + c2)) ** 0.5)
+    sums = torch.zeros(2 * cout, device=DEV)
+    z, fused = conv_igemm_stats(x1, w, 1, sums, x2=x2)
+    assert fused
+    assert torch.equal(z, conv_igemm(x1, w, x2=x2))
+    zf = z.float().reshape(-1, cout)
+    _close(sums[:cout], zf.sum(0), 2e-5)
+    _close(sums[cout:], (zf * zf).sum(0), 2e-5)
+    conv_igemm_stats(x1, w, 1, sums, x2=x2)                                # accumulates
+    _close(sums[:cout], 2 * zf.sum(0), 2e-5)
+
+
+def test_conv_epilogue_statistics_fall_back_for_shallow_layers_off_the_halo_kernel():
     from im2im_uq_b200.conv import conv_igemm, conv_igemm_stats, pack_conv_weight
     g = torch.Generator(device=DEV).manual_seed(5)
-    x = _nhwc(torch.randn(2, 512, 20, 20, device=DEV, generator=g))     # 20x20: not an 8x16-tile shape
-    w = pack_conv_weight(torch.randn(512, 512, 3, 3, device=DEV, generator=g) / 70)
-    sums = torch.zeros(1024, device=DEV)
+    x = _nhwc(torch.randn(2, 128, 20, 20, device=DEV, generator=g))     # 20x20: not an 8x16-tile shape, K loop too short
+    w = pack_conv_weight(torch.randn(256, 128, 3, 3, device=DEV, generator=g) / 34)
+    sums = torch.zeros(512, device=DEV)
     z, fused = conv_igemm_stats(x, w, 1, sums)
     assert not fused and float(sums.abs().max()) == 0.0 and torch.equal(z, conv_igemm(x, w))
 
