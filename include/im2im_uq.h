@@ -263,7 +263,7 @@ int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void* d_x2, int
  *                           d_stat_sums[c] += g, d_stat_sums[c_out + c] += rstd*(sum(g*bn_z) - mean*sum(g))
  *                           (the reduction half of im2im_bn_relu_bwd_bf16; finish with im2im_bn_relu_bwd_apply_bf16).
  * d_stat_sums is ACCUMULATED into (zero it first).  *h_fused (HOST int) = 1 when the statistics were produced (the layer
- * ran on the halo kernel); 0 means only the convolution ran - stored values are then plain dy / z and the caller runs the
+ * ran on the halo kernel, or - stat_mode 1 only - on the persistent kernel with >= 256 input channels); 0 means only the convolution ran - stored values are then plain dy / z and the caller runs the
  * separate reduction.
  */
 int im2im_conv_igemm_bf16_stats(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2, const void* d_weight,
