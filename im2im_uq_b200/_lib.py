@@ -145,6 +145,8 @@ def _declare_more(lib):
     lib.im2im_head_conv3x3_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.im2im_head_conv3x3_tc_f32.restype = c.c_int
     lib.im2im_head_conv3x3_tc_f32.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.im2im_conv_igemm_bf16_pool.restype = c.c_int
+    lib.im2im_conv_igemm_bf16_pool.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.im2im_head_conv3x3_tc_hist.restype = c.c_int
     lib.im2im_head_conv3x3_tc_hist.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]
     lib.im2im_head_conv3x3_tc_folded_f32.restype = c.c_int
@@ -194,7 +196,7 @@ EXPORTS = ["im2im_abi_version", "im2im_last_error", "im2im_launch_count", "im2im
            "im2im_maxpool2x2_bwd_bf16", "im2im_upsample2x_bilinear_bwd_bf16", "im2im_quantile_loss_f32",
            "im2im_adam_step_f32", "im2im_head_bwd", "im2im_conv_first_wgrad", "im2im_nested_sets",
            "im2im_softmax_sets", "im2im_head_conv3x3_act_f32", "im2im_head_loss_f32",
-           "im2im_adam_step_dev_f32", "im2im_head_conv3x3_tc_f32", "im2im_head_conv3x3_tc_hist", "im2im_head_conv3x3_tc_folded_f32", "im2im_rcps_counts_from_hist", "im2im_planar_to_nhwc64_bf16",
+           "im2im_adam_step_dev_f32", "im2im_head_conv3x3_tc_f32", "im2im_head_conv3x3_tc_hist", "im2im_conv_igemm_bf16_pool", "im2im_head_conv3x3_tc_folded_f32", "im2im_rcps_counts_from_hist", "im2im_planar_to_nhwc64_bf16",
            "im2im_rcps_decide_p2p", "im2im_rcps_fused_workspace_bytes", "im2im_rcps_calibrate_fused",
            "im2im_host_wait_flag", "im2im_rcps_calibrate_fused_check", "im2im_conv_igemm_tf32",
            "im2im_conv_first_nhwc_f32", "im2im_maxpool2x2_nhwc_f32", "im2im_upsample2x_bilinear_nhwc_f32",

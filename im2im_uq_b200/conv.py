@@ -74,6 +74,31 @@ def conv_igemm_stats(x1: torch.Tensor, weight_packed: torch.Tensor, stat_mode: i
     return out, bool(fused.value)
 
 
+def conv_igemm_pool(x1: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+                    x2: Optional[torch.Tensor] = None):
+    """conv_igemm (bf16 out) that also returns maxpool2x2 of its output when the layer runs on the halo kernel
+    (im2im_conv_igemm_bf16_pool): (out, pooled or None).  ``pooled`` is bit-identical to maxpool2x2 of ``out``."""
+    import ctypes
+    lib = _lib.load()
+    assert x1.is_cuda and x1.dtype == torch.bfloat16 and x1.is_contiguous() and x1.dim() == 4
+    B, H, W, c1 = x1.shape
+    c2 = x2.shape[3] if x2 is not None else 0
+    c_out, taps, c_in = weight_packed.shape
+    assert weight_packed.dtype == torch.bfloat16 and weight_packed.is_contiguous() and c_in == c1 + c2
+    if H % 2 or W % 2:
+        return conv_igemm(x1, weight_packed, bias, relu, x2), None
+    out = torch.empty((B, H, W, c_out), dtype=torch.bfloat16, device=x1.device)
+    pooled = torch.empty((B, H // 2, W // 2, c_out), dtype=torch.bfloat16, device=x1.device)
+    done = ctypes.c_int32(0)
+    with torch.cuda.device(x1.device):
+        rc = lib.im2im_conv_igemm_bf16_pool(x1.data_ptr(), c1, x2.data_ptr() if x2 is not None else None, c2,
+                                            weight_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                            B, H, W, c_out, taps, 1 if relu else 0, out.data_ptr(), pooled.data_ptr(),
+                                            ctypes.byref(done), torch.cuda.current_stream(x1.device).cuda_stream)
+    _lib.check(rc, "im2im_conv_igemm_bf16_pool")
+    return out, (pooled if done.value else None)
+
+
 def round_to_tf32(t: torch.Tensor) -> torch.Tensor:
     """fp32 tensor rounded to nearest (ties away from zero, like cvt.rna.tf32.f32) onto the TF32 grid (10-bit mantissa)."""
     bits = t.detach().float().contiguous().view(torch.int32)

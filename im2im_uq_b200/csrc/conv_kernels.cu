@@ -583,6 +583,9 @@ struct HaloParams {
     // cls = 3 * (0 inside | 1 top row | 2 bottom row) + (0 inside | 1 left column | 2 right column) - where the folded-in
     // convolution's output, bias included, does not exist; such pixels subtract it.
     const float* tap_bias;
+    // plain bf16 epilogue, optional: also write maxpool2x2 of the (bias + ReLU'd, bf16-rounded) output, NHWC
+    // [B, H/2, W/2, c_out] - the 2x2 window of a pixel lives in lanes l, l^1, l^8 of its epilogue warp (tile rows are 8 wide)
+    __nv_bfloat16* pool_out;
     unsigned* hist_global;
     const float* hist_labels;      // fp32 [B, 1, H, W]
     const float* hist_lambdas;     // device, ascending, hist_L entries
@@ -941,15 +944,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                 }
-                if (in_range) {
-                    float f[32];
+                float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = __uint_as_float(v[j]);
-                        if (p.bias) x += __ldg(p.bias + n0 + c + j);
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        f[j] = x;
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    if (p.bias) x += __ldg(p.bias + n0 + c + j);
+                    if (p.relu) x = fmaxf(x, 0.f);
+                    f[j] = x;
+                }
+                if (in_range) {
                     if (p.out_bf16) {
                         __nv_bfloat16* dst = p.out_bf16 + pix * p.c_out + n0 + c;   // 64-byte aligned (c_out, n0, c: x32)
 #pragma unroll
@@ -960,6 +963,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             st_global_256(dst + 8 * q, *reinterpret_cast<const uint4*>(f + 8 * q), *reinterpret_cast<const uint4*>(f + 8 * q + 4));
+                    }
+                }
+                if (p.pool_out != nullptr) {
+                    // 2x2 max-pool of the values as stored: max over lanes {l, l^1} (neighbour in the row) and {l, l^8} (the
+                    // row below); rounding to bf16 is monotone, so this equals pooling the stored tensor (maxpool2x2_kernel)
+                    uint4 pk[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pk[q] = pack8_bf16(f + 8 * q);
+                    uint32_t* r = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        uint32_t o = __shfl_xor_sync(0xffffffffu, r[i], 1);
+                        __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&r[i]), *reinterpret_cast<__nv_bfloat162*>(&o));
+                        uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
+                        o = __shfl_xor_sync(0xffffffffu, mu, 8);
+                        m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o));
+                        r[i] = *reinterpret_cast<uint32_t*>(&m);
+                    }
+                    if ((lane & 9) == 0 && in_range) {
+                        const size_t ppix = (static_cast<size_t>(b) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+                        __nv_bfloat16* dst = p.pool_out + ppix * p.c_out + n0 + c;
+                        st_global_256(dst, pk[0], pk[1]);
+                        st_global_256(dst + 16, pk[2], pk[3]);
                     }
                 }
             }
@@ -1373,7 +1399,8 @@ struct FusedStats {          // optional per-channel statistics fused into the h
 };
 int conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2, const void* d_weight,
                     const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps, int32_t relu,
-                    void* d_out_bf16, float* d_out_f32, const FusedStats& fs, int* fused, void* stream);
+                    void* d_out_bf16, float* d_out_f32, const FusedStats& fs, int* fused, void* stream,
+                    void* d_pool_out = nullptr, int* pooled = nullptr);
 }
 
 extern "C" int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2,
@@ -1382,6 +1409,19 @@ extern "C" int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void
                                      void* stream) {
     return conv_igemm_impl(d_x1, c_in1, d_x2, c_in2, d_weight, d_bias, B, H, W, c_out, taps, relu, d_out_bf16, d_out_f32,
                            FusedStats{}, nullptr, stream);
+}
+
+extern "C" int im2im_conv_igemm_bf16_pool(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2,
+                                          const void* d_weight, const float* d_bias, int32_t B, int32_t H, int32_t W,
+                                          int32_t c_out, int32_t taps, int32_t relu, void* d_out_bf16, void* d_pool_out,
+                                          int32_t* h_pooled, void* stream) {
+    if (!d_out_bf16 || !d_pool_out || !h_pooled) return fail(IM2IM_EINVAL, "conv_igemm_pool: null pointer");
+    if (reinterpret_cast<uintptr_t>(d_pool_out) & 31u) return fail(IM2IM_EINVAL, "conv_igemm_pool: the pooled tensor must be 32-byte aligned");
+    int pooled = 0;
+    const int rc = conv_igemm_impl(d_x1, c_in1, d_x2, c_in2, d_weight, d_bias, B, H, W, c_out, taps, relu, d_out_bf16, nullptr,
+                                   FusedStats{}, nullptr, stream, d_pool_out, &pooled);
+    *h_pooled = pooled;
+    return rc;
 }
 
 extern "C" int im2im_conv_igemm_bf16_stats(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2,
@@ -1406,7 +1446,8 @@ extern "C" int im2im_conv_igemm_bf16_stats(const void* d_x1, int32_t c_in1, cons
 
 int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2, const void* d_weight,
                            const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps, int32_t relu,
-                           void* d_out_bf16, float* d_out_f32, const FusedStats& fs, int* fused, void* stream) {
+                           void* d_out_bf16, float* d_out_f32, const FusedStats& fs, int* fused, void* stream,
+                           void* d_pool_out, int* pooled) {
     if (taps != 9 && taps != 1) return fail(IM2IM_EINVAL, "taps must be 9 (3x3) or 1 (1x1), got %d", taps);
     if (B <= 0 || H <= 0 || W <= 0) return fail(IM2IM_EINVAL, "bad activation shape %dx%dx%d", B, H, W);
     if (c_in1 <= 0 || c_in1 % kKStep || c_in2 < 0 || c_in2 % kKStep)
@@ -1469,6 +1510,10 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
                 const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * kHaloBytes + tail_bytes + 1024;
                 IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
                 if (fused) *fused = h.stat_mode != 0 ? 1 : 0;
+                if (d_pool_out != nullptr && h.stat_mode == 0 && d_out_bf16 != nullptr && d_out_f32 == nullptr && H % 2 == 0 && W % 2 == 0) {
+                    h.pool_out = static_cast<__nv_bfloat16*>(d_pool_out);
+                    if (pooled) *pooled = 1;
+                }
                 const int n_blocks_n = c_out / hbn;
                 const long long m_tiles = static_cast<long long>(h.tiles_w) * h.tiles_h * B;
                 long long gx = sm_count() / n_blocks_n;

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..conv import (conv_igemm, conv_igemm_tf32, fold_outconv_into_head, head_conv_tc, head_conv_tc_hist,
+from ..conv import (conv_igemm, conv_igemm_pool, conv_igemm_tf32, fold_outconv_into_head, head_conv_tc, head_conv_tc_hist,
                     head_tc_applicable, pack_conv_weight,
                     pack_conv_weight_tf32, pad_head_weight)
 
@@ -164,11 +164,18 @@ class UNetInferenceEngine:
     def _trunk(self, x: torch.Tensor) -> torch.Tensor:
         """UNet body up to the last 64-channel feature map (NHWC bf16), the input of OutConv (unet.py:33-45)."""
         a = self._conv_first(x, *self.first)
-        skips: List[torch.Tensor] = [conv_igemm(a, self.inc2[0], self.inc2[1], relu=True)]
-        for (c1, c2) in self.down:
-            p = self._pool(skips[-1])
+        # a skip layer's convolution also writes its own 2x2 max-pool where it runs on the halo kernel (the pooling pass over
+        # the full-resolution skip tensor disappears); deeper layers pool separately
+        s, pooled = conv_igemm_pool(a, self.inc2[0], self.inc2[1], relu=True)
+        skips: List[torch.Tensor] = [s]
+        for k, (c1, c2) in enumerate(self.down):
+            p = pooled if pooled is not None else self._pool(skips[-1])
             p = conv_igemm(p, c1[0], c1[1], relu=True)
-            skips.append(conv_igemm(p, c2[0], c2[1], relu=True))
+            if k + 1 < len(self.down):
+                s, pooled = conv_igemm_pool(p, c2[0], c2[1], relu=True)
+            else:
+                s, pooled = conv_igemm(p, c2[0], c2[1], relu=True), None
+            skips.append(s)
         y = skips.pop()
         for (c1, c2) in self.up:
             skip = skips.pop()

@@ -252,6 +252,13 @@ int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void* d_x2, int
                           const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps,
                           int32_t relu, void* d_out_bf16, float* d_out_f32, void* stream);
 
+/* im2im_conv_igemm_bf16 that ALSO writes maxpool2x2 of its (bias + ReLU'd) output - Down = MaxPool2d(2) -> DoubleConv
+ * (unet_parts.py:27-36) without the separate pooling pass over the skip tensor: d_pool_out bf16 NHWC [B, H/2, W/2, c_out].
+ * *h_pooled (HOST int) = 1 when the pooled tensor was written (layer on the halo kernel, H and W even); 0: only the
+ * convolution ran and the caller pools (im2im_maxpool2x2_bf16).  Bit-identical to the two-kernel sequence. */
+int im2im_conv_igemm_bf16_pool(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2, const void* d_weight,
+                               const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps,
+                               int32_t relu, void* d_out_bf16, void* d_pool_out, int32_t* h_pooled, void* stream);
 /*
  * im2im_conv_igemm_bf16 (no bias, no ReLU, bf16 output) with per-channel statistics accumulated in the convolution's
  * epilogue, from the bf16 values it stores - one pass over the activations less per BatchNorm layer of the training step

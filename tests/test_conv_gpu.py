@@ -68,3 +68,26 @@ def test_conv_argument_validation():
     w = torch.zeros(24, 9, 64, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(_lib.Im2ImError, match="c_out"):
         conv.conv_igemm(x, w)
+
+
+@pytest.mark.parametrize("B,H,W,c1,c2,cout,halo", [(2, 32, 48, 64, 0, 64, True), (1, 48, 40, 128, 0, 128, True),
+                                                   (3, 16, 16, 64, 64, 64, True), (2, 64, 24, 64, 0, 128, True),
+                                                   (2, 20, 20, 256, 0, 256, False)])
+def test_conv_with_fused_maxpool_equals_conv_then_pool(B, H, W, c1, c2, cout, halo):
+    """im2im_conv_igemm_bf16_pool: the convolution's epilogue also writes maxpool2x2 of its output (Down = MaxPool2d(2) ->
+    DoubleConv, unet_parts.py:27-36); full-resolution output and pooled tensor bit-identical to conv -> maxpool kernel."""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x1 = conv.to_nhwc_bf16(torch.randn(B, c1, H, W, device=DEV, generator=g))
+    x2 = conv.to_nhwc_bf16(torch.randn(B, c2, H, W, device=DEV, generator=g)) if c2 else None
+    w = conv.pack_conv_weight(torch.randn(cout, c1 + c2, 3, 3, device=DEV, generator=g) / (9 * (c1 + c2)) ** 0.5)
+    b = torch.randn(cout, device=DEV, generator=g)
+    want = conv.conv_igemm(x1, w, b, True, x2)
+    got, pooled = conv.conv_igemm_pool(x1, w, b, True, x2)
+    assert torch.equal(got, want)
+    assert (pooled is not None) == halo
+    if halo:
+        ref = torch.empty((B, H // 2, W // 2, cout), dtype=torch.bfloat16, device=DEV)
+        _lib.check(_lib.load().im2im_maxpool2x2_bf16(want.data_ptr(), B, H, W, cout, ref.data_ptr(),
+                                                     torch.cuda.current_stream(DEV).cuda_stream), "maxpool")
+        assert torch.equal(pooled, ref)
+        assert float(pooled.float().abs().max()) > 0
