@@ -131,6 +131,69 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// ---- CTA pair (cluster of two CTAs on one TPC, tcgen05 cta_group::2): M = 256 MMAs whose A rows and accumulator lanes are
+// split between the two CTAs (128 each) and whose B rows are split too (N/2 per CTA), so a CTA reads 4 KB of A + half the
+// B bytes per K = 16 step - 160 B/cycle instead of 192 for N = 64.  The leader (cluster rank 0) issues every MMA; both CTAs
+// issue their own TMA loads, whose bytes are counted on the LEADER's mbarrier.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Arrive on a barrier of the cluster.  Relaxed on purpose: what the arrival hands over is a TMEM accumulator, ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync; `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. every
+// tile's hand-over waited for the previous tile's global stores to drain (measured: 64->64 @320^2 0.55 -> 0.86 ms).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1,
+                                                 int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {   // one warp of EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once all earlier MMAs of this thread are complete) on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -623,13 +686,21 @@ __device__ __forceinline__ uint64_t make_sw128_desc_halo(const void* smem_ptr) {
     return desc;
 }
 
+// kPair: the kernel runs as clusters of two CTAs (a TPC's two SMs) that work on two neighbouring pixel tiles with M = 256
+// cta_group::2 MMAs: each CTA keeps only HALF of the weight rows resident (rows [rank * bn/2, +bn/2) of the N block) and
+// reads its own halo box, the leader issues the MMAs for both, every CTA drains its own 128 TMEM lanes.  Per K = 16 step a
+// CTA's shared memory serves 4 KB of A + bn/2 rows of B instead of bn rows - the operand traffic that capped the N = 64
+// layers at 67 % of the tensor pipe.
+template <bool kPair>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
                  const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int c_in = p.c_in1 + p.c_in2;
     const int cblocks = c_in / kKStep;
-    const int b_tile_bytes = p.bn * kKStep * 2;
+    const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+    const int bn_local = kPair ? p.bn / 2 : p.bn;              // weight rows resident in THIS CTA
+    const int b_tile_bytes = bn_local * kKStep * 2;
     const int w_bytes = 9 * cblocks * b_tile_bytes;           // resident weights: [tap][cblock][bn rows x 128 B]
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* w_smem = base;
@@ -683,10 +754,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         prefetch_tmap(&map_w);
         for (int s = 0; s < p.a_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(w_bar, 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], split_epilogue ? 8 : 4); }
+        // pair: the leader's tmem_empty collects the epilogue warps of both CTAs (the other CTA's copy is not used)
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], (kPair ? 2 : 1) * (split_epilogue ? 8 : 4)); }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr_smem, tmem_cols);
+    if (kPair) { __syncthreads(); cluster_sync_all(); }   // the peer's barriers exist before anything is sent to them; both CTAs allocate together
+    if (warp == 1) { if (kPair) tmem_alloc_pair(tmem_ptr_smem, tmem_cols); else tmem_alloc(tmem_ptr_smem, tmem_cols); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -699,7 +772,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     const int tn = blockIdx.y;
     const int n0 = tn * p.bn;
     // tile order: strided over the CTAs, or (histogram mode) one contiguous run per CTA
+    // (pair: the loop variable counts tile PAIRS, the CTA's own tile is 2 * pair + rank; with an odd tile count the last
+    // pair's second tile lies behind the batch: TMA zero-fills it, the epilogue skips it)
     int tile_first = blockIdx.x, tile_last = n_tiles_m, tile_step = gridDim.x;
+    if (kPair) { tile_first = blockIdx.x >> 1; tile_last = (n_tiles_m + 1) >> 1; tile_step = gridDim.x >> 1; }
     if (p.hist_global != nullptr) {
         tile_first = static_cast<int>(static_cast<long long>(n_tiles_m) * blockIdx.x / gridDim.x);
         tile_last = static_cast<int>(static_cast<long long>(n_tiles_m) * (blockIdx.x + 1) / gridDim.x);
@@ -709,17 +785,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     if (warp == 0) {
         {   // all lanes walk the loops (uniform control flow: TMA operands stay in uniform registers), one lane issues
             const bool leader = elect_one_sync();
-            // resident weights, once
-            if (leader) mbar_arrive_expect_tx(w_bar, static_cast<unsigned>(w_bytes));
+            // resident weights, once (pair: this CTA's half of the rows; all bytes are counted on the leader's barrier)
+            const uint32_t w_bar_lead = kPair ? mapa_u32(smem_u32(w_bar), 0u) : 0u;
+            if (leader && cta_rank == 0) mbar_arrive_expect_tx(w_bar, static_cast<unsigned>(w_bytes) * (kPair ? 2u : 1u));
             for (int tap = 0; tap < 9; ++tap)
                 for (int cb = 0; cb < cblocks; ++cb)
-                    if (leader)
-                        tma_load_2d(w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes, &map_w, w_bar,
-                                    tap * c_in + cb * kKStep, n0);
+                    if (leader) {
+                        unsigned char* wdst = w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes;
+                        if (kPair) tma_load_2d_pair(wdst, &map_w, w_bar_lead, tap * c_in + cb * kKStep, n0 + static_cast<int>(cta_rank) * bn_local);
+                        else tma_load_2d(wdst, &map_w, w_bar, tap * c_in + cb * kKStep, n0);
+                    }
             __syncwarp();
             int stage = 0;
             unsigned phase = 1;
-            for (int tile = tile_first; tile < tile_last; tile += tile_step) {
+            for (int it = tile_first; it < tile_last; it += tile_step) {
+                const int tile = kPair ? 2 * it + static_cast<int>(cta_rank) : it;
                 int t = tile;
                 const int tw = t % p.tiles_w; t /= p.tiles_w;
                 const int th = t % p.tiles_h; t /= p.tiles_h;
@@ -729,9 +809,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                     unsigned char* dst = a_ring + static_cast<size_t>(stage) * kHaloBytes;
                     const int c0 = cb * kKStep;
                     if (leader) {
-                        mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(kHaloBytes));
-                        if (c0 < p.c_in1) tma_load_4d(dst, &map_x1, &full_bar[stage], c0, w0, h0, b0);
-                        else tma_load_4d(dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0, h0, b0);
+                        if (kPair) {
+                            // both boxes of the pair complete on the leader's barrier, which expects their sum
+                            const uint32_t full_lead = mapa_u32(smem_u32(&full_bar[stage]), 0u);
+                            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<unsigned>(kHaloBytes));
+                            if (c0 < p.c_in1) tma_load_4d_pair(dst, &map_x1, full_lead, c0, w0, h0, b0);
+                            else tma_load_4d_pair(dst, &map_x2, full_lead, c0 - p.c_in1, w0, h0, b0);
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(kHaloBytes));
+                            if (c0 < p.c_in1) tma_load_4d(dst, &map_x1, &full_bar[stage], c0, w0, h0, b0);
+                            else tma_load_4d(dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0, h0, b0);
+                        }
                     }
                     __syncwarp();
                     if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
@@ -739,9 +827,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             }
         }
     } else if (warp == 1) {
+      if (!kPair || cta_rank == 0) {     // pair: the leader CTA issues the MMAs of both
         // all 32 lanes walk the loops (uniform control flow); the elected lane issues - see elect_one_sync()
         const bool leader = elect_one_sync();
-        const uint32_t idesc = make_idesc_bf16(p.bn);
+        // pair: M = 256 (bits 24-28 hold M >> 4)
+        const uint32_t idesc = make_idesc_bf16(p.bn) + (kPair ? (static_cast<uint32_t>(kTileM >> 4) << 24) : 0u);
         mbar_wait(w_bar, 0);
         int stage = 0;
         unsigned phase = 0;
@@ -763,18 +853,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                     const uint64_t desc_b = make_sw128_desc(w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes);
 #pragma unroll
                     for (int k = 0; k < kKStep / kUmmaK; ++k)
-                        if (leader)
-                            umma_bf16(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
-                                      idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        if (leader) {
+                            if (kPair)
+                                umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
+                                               idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                            else
+                                umma_bf16(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
+                                          idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        }
                 }
-                if (leader) umma_commit(&empty_bar[stage]);
+                if (leader) { if (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]); }
                 __syncwarp();
                 if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
             }
-            if (leader) umma_commit(&tmem_full[buf]);
+            if (leader) { if (kPair) umma_commit_pair(&tmem_full[buf]); else umma_commit(&tmem_full[buf]); }
             __syncwarp();
             buf ^= 1;
         }
+      }
     } else if (warp < 6 || split_epilogue) {
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;                    // 0: warps 2-5, 1: warps 6-9
@@ -789,7 +885,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         float acc0[kHaloStatBn / 2], acc1[kHaloStatBn / 2];
 #pragma unroll
         for (int j = 0; j < kHaloStatBn / 2; ++j) acc0[j] = acc1[j] = 0.f;
-        for (int tile = tile_first; tile < tile_last; tile += tile_step) {
+        // where this warp hands an accumulator back: the MMA warp's barrier (pair: the leader CTA's, through the cluster window)
+        const uint32_t tmem_empty_lead0 = kPair ? mapa_u32(smem_u32(&tmem_empty[0]), 0u) : 0u;
+        auto release_acc = [&](int which) {
+            if (kPair) mbar_arrive_cluster(tmem_empty_lead0 + 8u * static_cast<uint32_t>(which));
+            else mbar_arrive(&tmem_empty[which]);
+        };
+        for (int it = tile_first; it < tile_last; it += tile_step) {
+            const int tile = kPair ? 2 * it + static_cast<int>(cta_rank) : it;
             int t = tile;
             const int tw = t % p.tiles_w; t /= p.tiles_w;
             const int th = t % p.tiles_h; t /= p.tiles_h;
@@ -799,6 +902,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             mbar_wait(&tmem_full[buf], (full_phase >> buf) & 1u);
             full_phase ^= 1u << buf;
             tc_fence_after();
+            if (kPair && tile >= n_tiles_m) {   // the odd tile out of the last pair: nothing to store, hand the accumulator back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) release_acc(buf);
+                buf ^= 1;
+                continue;
+            }
             const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(buf) * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
             if (p.out_planar != nullptr || p.hist_global != nullptr) {
                 // head mode: the real outputs live in the first 32 accumulator columns; one TMEM load, then the buffer is free
@@ -807,7 +917,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                if (lane == 0) release_acc(buf);
                 if (p.tap_bias != nullptr && (tw == 0 || th == 0 || tw == p.tiles_w - 1 || th == p.tiles_h - 1)) {
                     // head with a 1x1 convolution folded in, tile on the image border (warp-uniform test): a border pixel takes
                     // back the share of the bias that belongs to the taps lying in the zero padding; the table (staged in shared
@@ -891,7 +1001,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 tmem_ld_wait();
                 tc_fence_before();          // only read of this accumulator by this warp: hand it back to the MMA warp
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                if (lane == 0) release_acc(buf);
                 uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.c_out + n0 + c);
                 uint4 pk_even = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
@@ -942,7 +1052,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 if (c + 32 >= c_hi) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                    if (lane == 0) release_acc(buf);
                 }
                 float f[32];
 #pragma unroll
@@ -1014,7 +1124,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+    if (kPair) cluster_sync_all();   // the leader's MMAs read the peer's shared memory and write its TMEM: leave together
+    if (warp == 1) { if (kPair) tmem_dealloc_pair(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
@@ -1495,7 +1606,10 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
                 h.stat_mode = fs.mode; h.stat_sums = fs.sums; h.bn_z = static_cast<const __nv_bfloat16*>(fs.bn_z);
                 h.bn_gamma = fs.gamma; h.bn_beta = fs.beta; h.bn_mean = fs.mean; h.bn_rstd = fs.rstd;
             }
-            const int w_bytes = 9 * c_in * hbn * 2;
+            // CTA pairs (cta_group::2, each CTA keeps half of the weight rows): IM2IM_HALO_PAIR=1 (bring-up switch)
+            static const bool pair_env = [] { const char* e = getenv("IM2IM_HALO_PAIR"); return e != nullptr && e[0] == '1'; }();
+            const bool pair = pair_env && sm_count() >= 2;
+            const int w_bytes = 9 * c_in * hbn * 2 / (pair ? 2 : 1);
             const int tail_bytes = 128 + 2 * hbn * 4;      // barriers + scale/shift behind the A ring
             h.a_stages = (232448 - 1024 - w_bytes - tail_bytes) / kHaloBytes;
             if (h.a_stages > 4) h.a_stages = 4;
@@ -1505,10 +1619,11 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
                 if (rc) return rc;
                 if (c_in2 > 0) { rc = make_act_map(&h2, d_x2, B, H, W, c_in2, kHaloW, kHaloH, 1); if (rc) return rc; }
                 else h2 = h1;
-                rc = make_weight_map(&hw, d_weight, c_out, taps * c_in, hbn);
+                rc = make_weight_map(&hw, d_weight, c_out, taps * c_in, pair ? hbn / 2 : hbn);
                 if (rc) return rc;
                 const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * kHaloBytes + tail_bytes + 1024;
-                IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+                IM2IM_CUDA_TRY(cudaFuncSetAttribute(pair ? conv_halo_kernel<true> : conv_halo_kernel<false>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
                 if (fused) *fused = h.stat_mode != 0 ? 1 : 0;
                 if (d_pool_out != nullptr && h.stat_mode == 0 && d_out_bf16 != nullptr && d_out_f32 == nullptr && H % 2 == 0 && W % 2 == 0) {
                     h.pool_out = static_cast<__nv_bfloat16*>(d_pool_out);
@@ -1519,8 +1634,26 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
                 long long gx = sm_count() / n_blocks_n;
                 if (gx < 1) gx = 1;
                 if (gx > m_tiles) gx = m_tiles;
+                if (pair) {
+                    // clusters of two CTAs along x; a pair takes two neighbouring tiles per step
+                    const long long pairs = (m_tiles + 1) / 2;
+                    long long gp = sm_count() / 2 / n_blocks_n;
+                    if (gp < 1) gp = 1;
+                    if (gp > pairs) gp = pairs;
+                    cudaLaunchConfig_t cfg{};
+                    cfg.gridDim = dim3(static_cast<unsigned>(2 * gp), static_cast<unsigned>(n_blocks_n));
+                    cfg.blockDim = dim3(kHaloThreads);
+                    cfg.dynamicSmemBytes = hsmem;
+                    cfg.stream = static_cast<cudaStream_t>(stream);
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeClusterDimension;
+                    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                    cfg.attrs = attr; cfg.numAttrs = 1;
+                    IM2IM_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true>, h1, h2, hw, h));
+                    return check_launch("conv_halo_kernel<pair>");
+                }
                 dim3 hgrid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks_n));
-                conv_halo_kernel<<<hgrid, kHaloThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h2, hw, h);
+                conv_halo_kernel<false><<<hgrid, kHaloThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h2, hw, h);
                 return check_launch("conv_halo_kernel");
             }
         }
@@ -1707,11 +1840,11 @@ int head_tc_impl(const void* d_x, const void* d_weight, const float* d_bias, con
     rc = make_weight_map(&hw, d_weight, 64, 9 * 64, h.bn);
     if (rc) return rc;
     const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * kHaloBytes + 128 + 2 * h.bn * 4 + 1024 + hist_bytes;
-    IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+    IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
     const long long m_tiles = static_cast<long long>(h.tiles_w) * h.tiles_h * B;
     long long gx = sm_count();
     if (gx > m_tiles) gx = m_tiles;
-    conv_halo_kernel<<<dim3(static_cast<unsigned>(gx), 1), kHaloThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h1, hw, h);
+    conv_halo_kernel<false><<<dim3(static_cast<unsigned>(gx), 1), kHaloThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h1, hw, h);
     return check_launch(d_hist ? "conv_halo_kernel<head+hist>" : "conv_halo_kernel<head>");
 }
 }  // namespace
