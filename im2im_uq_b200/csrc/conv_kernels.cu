@@ -1591,9 +1591,20 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
         const int c_in = c_in1 + c_in2;
         const bool staged = d_out_bf16 != nullptr && d_out_f32 == nullptr;
         const bool want_stats = staged && fs.mode != 0;
+        // CTA pairs (cta_group::2): each CTA keeps half of the weight rows resident.  IM2IM_HALO_PAIR=0 restores single CTAs
+        // (read per call so that a test can compare the two in one process).  A pair also takes N blocks whose weights only
+        // fit when halved - 128 -> 128 and 128 -> 256 run as N = 128 tiles (1.6 PFLOP/s at batch 78) instead of N = 64 -
+        // unless IM2IM_HALO_PAIR_WIDE=0
+        const char* pair_e = getenv("IM2IM_HALO_PAIR");
+        const bool pair = !(pair_e != nullptr && pair_e[0] == '0') && sm_count() >= 2;
+        const char* wide_e = getenv("IM2IM_HALO_PAIR_WIDE");
+        const long long w_budget = (pair && !(wide_e != nullptr && wide_e[0] == '0')) ? 2 * 147456 : 147456;
         int hbn = 0;
         for (int cand : {128, 64})
-            if (hbn == 0 && c_out % cand == 0 && 9ll * c_in * cand * 2 <= 147456 && !(want_stats && cand != kHaloStatBn)) hbn = cand;
+            // (the doubled budget is for N = 128 only: a layer whose N = 64 block needs it - 256 input channels - is better
+            // off on the persistent kernel's N = 256 tiles; measured 256 -> 256 @80^2: 0.42 ms there, 0.47 ms here)
+            if (hbn == 0 && c_out % cand == 0 && 9ll * c_in * cand * 2 <= (cand == 128 ? w_budget : 147456) &&
+                !(want_stats && cand != kHaloStatBn)) hbn = cand;
         if (hbn != 0) {
             HaloParams h{};
             h.c_in1 = c_in1; h.c_in2 = c_in2; h.c_out = c_out; h.B = B; h.H = H; h.W = W;
@@ -1606,9 +1617,6 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
                 h.stat_mode = fs.mode; h.stat_sums = fs.sums; h.bn_z = static_cast<const __nv_bfloat16*>(fs.bn_z);
                 h.bn_gamma = fs.gamma; h.bn_beta = fs.beta; h.bn_mean = fs.mean; h.bn_rstd = fs.rstd;
             }
-            // CTA pairs (cta_group::2, each CTA keeps half of the weight rows): IM2IM_HALO_PAIR=1 (bring-up switch)
-            static const bool pair_env = [] { const char* e = getenv("IM2IM_HALO_PAIR"); return e != nullptr && e[0] == '1'; }();
-            const bool pair = pair_env && sm_count() >= 2;
             const int w_bytes = 9 * c_in * hbn * 2 / (pair ? 2 : 1);
             const int tail_bytes = 128 + 2 * hbn * 4;      // barriers + scale/shift behind the A ring
             h.a_stages = (232448 - 1024 - w_bytes - tail_bytes) / kHaloBytes;

@@ -91,3 +91,55 @@ def test_conv_with_fused_maxpool_equals_conv_then_pool(B, H, W, c1, c2, cout, ha
                                                      torch.cuda.current_stream(DEV).cuda_stream), "maxpool")
         assert torch.equal(pooled, ref)
         assert float(pooled.float().abs().max()) > 0
+
+
+@pytest.mark.parametrize("B,H,W,c1,c2,cout", [
+    (1, 16, 8, 64, 0, 64),       # one tile: the pair's second tile lies behind the batch (TMA zero fill, epilogue skips it)
+    (3, 16, 8, 64, 0, 64),       # odd number of tiles
+    (2, 32, 32, 64, 64, 64),     # concatenated inputs: two tensor maps, two channel blocks per tile
+    (1, 48, 40, 64, 0, 128),     # N = 128: 64 weight rows per CTA
+    (2, 32, 32, 128, 0, 128),    # weights of an N = 128 block fit only when halved (two ring stages)
+    (3, 48, 40, 128, 0, 256),    # ... with two such N blocks
+    (4, 160, 160, 64, 0, 64),    # more tile pairs than clusters: persistent loop, both TMEM buffers, ring wrap-around
+])
+def test_halo_conv_cta_pair_equals_single_cta(B, H, W, c1, c2, cout, monkeypatch):
+    """The halo convolution runs as clusters of two CTAs (tcgen05 cta_group::2, M = 256; each CTA keeps half of the weight
+    rows resident, the leader issues the MMAs for both).  Every output element is accumulated over the same K order as in
+    the single-CTA kernel (IM2IM_HALO_PAIR=0), so outputs - fp32, bf16 + ReLU, with the fused max-pool - are bit-identical;
+    the fused BatchNorm statistics are fp32 atomics issued in another order (relative 1e-5)."""
+    g = torch.Generator(device=DEV).manual_seed(7)
+    x1 = conv.to_nhwc_bf16(torch.randn(B, c1, H, W, device=DEV, generator=g))
+    x2 = conv.to_nhwc_bf16(torch.randn(B, c2, H, W, device=DEV, generator=g)) if c2 else None
+    w = conv.pack_conv_weight(torch.randn(cout, c1 + c2, 3, 3, device=DEV, generator=g) / (9 * (c1 + c2)) ** 0.5)
+    b = torch.randn(cout, device=DEV, generator=g)
+
+    def run():
+        out = [conv.conv_igemm(x1, w, b, False, x2, torch.float32), conv.conv_igemm(x1, w, b, True, x2)]
+        out += list(conv.conv_igemm_pool(x1, w, b, True, x2))
+        sums = torch.zeros(2 * cout, device=DEV)
+        z, fused = conv.conv_igemm_stats(x1, w, 1, sums, x2=x2)
+        torch.cuda.synchronize()
+        return out + [z], sums, fused
+
+    monkeypatch.setenv("IM2IM_HALO_PAIR", "0")
+    single, sums_single, fused_single = run()
+    monkeypatch.setenv("IM2IM_HALO_PAIR", "1")
+    before = _lib.launch_count()
+    pair, sums_pair, fused_pair = run()
+    assert _lib.launch_count() - before == 4
+    for a, p in zip(single, pair):
+        assert (a is None) == (p is None)
+        if a is not None:
+            assert torch.equal(a, p)
+    assert fused_single == fused_pair
+    if fused_pair:
+        assert torch.allclose(sums_single, sums_pair, rtol=1e-5, atol=1e-5 * float(sums_single.abs().max()))
+    # and against the fp32 reference of the op (the parity yardstick of this file)
+    xin = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], dim=3)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(xin.permute(0, 3, 1, 2), w.float().view(cout, 3, 3, c1 + c2).permute(0, 3, 1, 2), b, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert (pair[0].permute(0, 3, 1, 2) - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()

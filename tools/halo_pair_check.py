@@ -16,6 +16,8 @@ CASES = [  # B, H, W, c1, c2, cout
     (1, 48, 40, 64, 0, 128),      # N = 128: 64 weight rows per CTA
     (5, 64, 64, 128, 0, 64),
     (4, 160, 160, 64, 0, 64),     # more tiles than pairs: persistent loop, both TMEM buffers, ring wrap-around
+    (2, 32, 32, 128, 0, 128),     # IM2IM_HALO_PAIR_WIDE: N = 128 blocks whose weights fit only when halved (two ring stages)
+    (3, 48, 40, 128, 0, 256),
 ]
 
 
@@ -79,7 +81,7 @@ def worker(tag, bench_b):
 def main():
     bench_b = sys.argv[1] if len(sys.argv) > 1 else "78"
     for tag, val in (("single", "0"), ("pair", "1")):
-        env = dict(os.environ, IM2IM_HALO_PAIR=val)
+        env = dict(os.environ, IM2IM_HALO_PAIR=val, IM2IM_HALO_PAIR_WIDE=val)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", tag, bench_b], env=env, timeout=150)
         if r.returncode != 0:
             print(f"{tag}: worker failed rc={r.returncode}")
