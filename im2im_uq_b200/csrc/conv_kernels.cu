@@ -738,6 +738,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             s_shift[c] = p.bn_beta[ch] - p.bn_mean[ch] * sc;
         }
     }
+    // plain epilogue: the N block's bias staged once (read back as float4 broadcasts).  32 scalar __ldg per thread and tile
+    // cost the layers whose epilogue sets the pace (ncu, 64 -> 128 @160^2: LSU wavefronts 67 %, tensor pipe 64 %)
+    const bool bias_staged = p.bias != nullptr && !head_mode && p.stat_mode == 0;
+    if (bias_staged)
+        for (int c = threadIdx.x; c < p.bn; c += blockDim.x) s_scale[c] = p.bias[blockIdx.y * p.bn + c];
     if (p.tap_bias != nullptr)   // 9 border classes x n_real <= 2 * bn floats (checked by the launcher)
         for (int j = threadIdx.x; j < 9 * p.n_real; j += blockDim.x) s_scale[j] = p.tap_bias[j];
     if (p.hist_global != nullptr) {
@@ -1056,11 +1061,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 }
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    if (p.bias) x += __ldg(p.bias + n0 + c + j);
-                    if (p.relu) x = fmaxf(x, 0.f);
-                    f[j] = x;
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias_staged) bv = *reinterpret_cast<const float4*>(s_scale + c + 4 * j4);
+                    const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        float x = __uint_as_float(v[4 * j4 + jj]);
+                        if (bias_staged) x += bb[jj];
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        f[4 * j4 + jj] = x;
+                    }
                 }
                 if (in_range) {
                     if (p.out_bf16) {
