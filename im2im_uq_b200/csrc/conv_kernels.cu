@@ -628,6 +628,9 @@ struct HaloParams {
     int tiles_w, tiles_h;   // 8-wide, 16-tall tiles
     int bn;
     int a_stages;
+    // 0: the layer's weights (this CTA's rows of the N block, all taps and channel blocks) stay resident in shared memory;
+    // 1: they do not fit - every ring stage carries the nine tap slabs of its channel block behind the halo box
+    int w_stream;
     int relu;
     const float* bias;
     __nv_bfloat16* out_bf16;
@@ -701,11 +704,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
     const int bn_local = kPair ? p.bn / 2 : p.bn;              // weight rows resident in THIS CTA
     const int b_tile_bytes = bn_local * kKStep * 2;
-    const int w_bytes = 9 * cblocks * b_tile_bytes;           // resident weights: [tap][cblock][bn rows x 128 B]
+    const bool w_stream = p.w_stream != 0;
+    const int w_bytes = w_stream ? 0 : 9 * cblocks * b_tile_bytes;   // resident weights: [tap][cblock][bn rows x 128 B]
+    // ring stage: one 36 KB halo box (+ streamed weights: the nine tap slabs of the stage's channel block)
+    const int stage_bytes = kHaloBytes + (w_stream ? 9 * b_tile_bytes : 0);
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* w_smem = base;
-    unsigned char* a_ring = base + w_bytes;                    // a_stages x 36 KB halo boxes
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_ring + static_cast<size_t>(p.a_stages) * kHaloBytes);
+    unsigned char* a_ring = base + w_bytes;                    // a_stages stages
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_ring + static_cast<size_t>(p.a_stages) * stage_bytes);
     uint64_t* empty_bar = full_bar + p.a_stages;
     uint64_t* w_bar = empty_bar + p.a_stages;
     uint64_t* tmem_full = w_bar + 1;
@@ -792,8 +798,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             const bool leader = elect_one_sync();
             // resident weights, once (pair: this CTA's half of the rows; all bytes are counted on the leader's barrier)
             const uint32_t w_bar_lead = kPair ? mapa_u32(smem_u32(w_bar), 0u) : 0u;
-            if (leader && cta_rank == 0) mbar_arrive_expect_tx(w_bar, static_cast<unsigned>(w_bytes) * (kPair ? 2u : 1u));
-            for (int tap = 0; tap < 9; ++tap)
+            if (leader && cta_rank == 0 && !w_stream) mbar_arrive_expect_tx(w_bar, static_cast<unsigned>(w_bytes) * (kPair ? 2u : 1u));
+            for (int tap = 0; tap < 9 && !w_stream; ++tap)
                 for (int cb = 0; cb < cblocks; ++cb)
                     if (leader) {
                         unsigned char* wdst = w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes;
@@ -811,20 +817,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 const int w0 = tw * kHaloTileW - 1, h0 = th * kHaloTileH - 1, b0 = t;
                 for (int cb = 0; cb < cblocks; ++cb) {
                     mbar_wait(&empty_bar[stage], phase);
-                    unsigned char* dst = a_ring + static_cast<size_t>(stage) * kHaloBytes;
+                    unsigned char* dst = a_ring + static_cast<size_t>(stage) * stage_bytes;
                     const int c0 = cb * kKStep;
                     if (leader) {
                         if (kPair) {
-                            // both boxes of the pair complete on the leader's barrier, which expects their sum
+                            // both CTAs' bytes complete on the leader's barrier, which expects their sum
                             const uint32_t full_lead = mapa_u32(smem_u32(&full_bar[stage]), 0u);
-                            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<unsigned>(kHaloBytes));
+                            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<unsigned>(stage_bytes));
                             if (c0 < p.c_in1) tma_load_4d_pair(dst, &map_x1, full_lead, c0, w0, h0, b0);
                             else tma_load_4d_pair(dst, &map_x2, full_lead, c0 - p.c_in1, w0, h0, b0);
                         } else {
-                            mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(kHaloBytes));
+                            mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(stage_bytes));
                             if (c0 < p.c_in1) tma_load_4d(dst, &map_x1, &full_bar[stage], c0, w0, h0, b0);
                             else tma_load_4d(dst, &map_x2, &full_bar[stage], c0 - p.c_in1, w0, h0, b0);
                         }
+                    }
+                    if (w_stream) {   // this channel block's nine tap slabs ride in the same stage
+                        const uint32_t full_lead = kPair ? mapa_u32(smem_u32(&full_bar[stage]), 0u) : 0u;
+                        for (int tap = 0; tap < 9; ++tap)
+                            if (leader) {
+                                unsigned char* wdst = dst + kHaloBytes + tap * b_tile_bytes;
+                                if (kPair) tma_load_2d_pair(wdst, &map_w, full_lead, tap * c_in + c0, n0 + static_cast<int>(cta_rank) * bn_local);
+                                else tma_load_2d(wdst, &map_w, &full_bar[stage], tap * c_in + c0, n0);
+                            }
                     }
                     __syncwarp();
                     if (++stage == p.a_stages) { stage = 0; phase ^= 1u; }
@@ -837,7 +852,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         const bool leader = elect_one_sync();
         // pair: M = 256 (bits 24-28 hold M >> 4)
         const uint32_t idesc = make_idesc_bf16(p.bn) + (kPair ? (static_cast<uint32_t>(kTileM >> 4) << 24) : 0u);
-        mbar_wait(w_bar, 0);
+        if (!w_stream) mbar_wait(w_bar, 0);
         int stage = 0;
         unsigned phase = 0;
         unsigned acc_phase = 3u;
@@ -850,12 +865,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             for (int cb = 0; cb < cblocks; ++cb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const unsigned char* a_src = a_ring + static_cast<size_t>(stage) * kHaloBytes;
+                const unsigned char* a_src = a_ring + static_cast<size_t>(stage) * stage_bytes;
+                const unsigned char* w_src = w_stream ? a_src + kHaloBytes : w_smem + static_cast<size_t>(cb) * b_tile_bytes;
+                const int w_tap_stride = w_stream ? b_tile_bytes : cblocks * b_tile_bytes;
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int dy = tap / 3, dx = tap % 3;  // already offset by +1 (halo origin is (w0-1, h0-1))
                     const uint64_t desc_a = make_sw128_desc_halo(a_src + (dy * kHaloW + dx) * 128);
-                    const uint64_t desc_b = make_sw128_desc(w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes);
+                    const uint64_t desc_b = make_sw128_desc(w_src + static_cast<size_t>(tap) * w_tap_stride);
 #pragma unroll
                     for (int k = 0; k < kKStep / kUmmaK; ++k)
                         if (leader) {
@@ -890,6 +907,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         float acc0[kHaloStatBn / 2], acc1[kHaloStatBn / 2];
 #pragma unroll
         for (int j = 0; j < kHaloStatBn / 2; ++j) acc0[j] = acc1[j] = 0.f;
+        // forward statistics of an N = 128 tile (64 columns per warp - too many for per-thread accumulators): the column
+        // sums over the warp's 32 pixel rows are formed per tile by recursive halving and lane j keeps the running sums of
+        // columns c_lo + j and c_lo + 32 + j
+        float wide0[2] = {0.f, 0.f}, wide1[2] = {0.f, 0.f};
         // where this warp hands an accumulator back: the MMA warp's barrier (pair: the leader CTA's, through the cluster window)
         const uint32_t tmem_empty_lead0 = kPair ? mapa_u32(smem_u32(&tmem_empty[0]), 0u) : 0u;
         auto release_acc = [&](int which) {
@@ -986,6 +1007,58 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                             dst[static_cast<size_t>(j) * hw] = x;   // lanes = 8 consecutive pixels of a row: 32-byte runs
                         }
                     }
+                }
+                buf ^= 1;
+                continue;
+            }
+            if (p.stat_mode == 1 && p.bn == 128) {
+                // ---- bf16 output + forward statistics of an N = 128 tile (c_in >= 128: >= 4600 tensor cycles per tile pay
+                // for the 2 x 62 shuffles per warp)
+#pragma unroll
+                for (int chunk = 0; chunk < 2; ++chunk) {
+                    const int c = c_lo + 32 * chunk;
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_acc + static_cast<uint32_t>(c), v);
+                    tmem_ld_wait();
+                    if (chunk == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) release_acc(buf);
+                    }
+                    float s0[32], s1[32];
+                    uint4 pk[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        __nv_bfloat162 h2[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            h2[j] = __floats2bfloat162_rn(__uint_as_float(v[8 * q + 2 * j]), __uint_as_float(v[8 * q + 2 * j + 1]));
+                            const float2 r = __bfloat1622float2(h2[j]);      // the values as stored
+                            s0[8 * q + 2 * j] = r.x; s0[8 * q + 2 * j + 1] = r.y;
+                            s1[8 * q + 2 * j] = r.x * r.x; s1[8 * q + 2 * j + 1] = r.y * r.y;
+                        }
+                        pk[q].x = *reinterpret_cast<uint32_t*>(&h2[0]); pk[q].y = *reinterpret_cast<uint32_t*>(&h2[1]);
+                        pk[q].z = *reinterpret_cast<uint32_t*>(&h2[2]); pk[q].w = *reinterpret_cast<uint32_t*>(&h2[3]);
+                    }
+                    if (in_range) {
+                        __nv_bfloat16* dst = p.out_bf16 + pix * p.c_out + n0 + c;
+                        st_global_256(dst, pk[0], pk[1]);
+                        st_global_256(dst + 16, pk[2], pk[3]);
+                    }
+                    // recursive halving over the 32 rows (see conv_igemm_persistent_kernel): lane j ends with column c + j
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        const bool upper = (lane & o) != 0;
+#pragma unroll
+                        for (int i = 0; i < o; ++i) {
+                            const float send0 = upper ? s0[i] : s0[i + o], keep0 = upper ? s0[i + o] : s0[i];
+                            const float send1 = upper ? s1[i] : s1[i + o], keep1 = upper ? s1[i + o] : s1[i];
+                            s0[i] = keep0 + __shfl_xor_sync(0xffffffffu, send0, o);
+                            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, o);
+                        }
+                    }
+                    wide0[chunk] += s0[0];
+                    wide1[chunk] += s1[0];
                 }
                 buf ^= 1;
                 continue;
@@ -1113,7 +1186,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             buf ^= 1;
         }
         {
-            if (p.stat_mode != 0) {
+            if (p.stat_mode == 1 && p.bn == 128) {
+#pragma unroll
+                for (int chunk = 0; chunk < 2; ++chunk) {
+                    atomicAdd(p.stat_sums + n0 + c_lo + 32 * chunk + lane, wide0[chunk]);
+                    atomicAdd(p.stat_sums + p.c_out + n0 + c_lo + 32 * chunk + lane, wide1[chunk]);
+                }
+            } else if (p.stat_mode != 0) {
                 // column sums over the 32 pixel rows of this warp (butterfly), then one global atomicAdd per channel and warp
 #pragma unroll
                 for (int j = 0; j < kHaloStatBn / 2; ++j) {
@@ -1610,12 +1689,25 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
         const bool pair = !(pair_e != nullptr && pair_e[0] == '0') && sm_count() >= 2;
         const char* wide_e = getenv("IM2IM_HALO_PAIR_WIDE");
         const long long w_budget = (pair && !(wide_e != nullptr && wide_e[0] == '0')) ? 2 * 147456 : 147456;
+        // forward statistics on N = 128 tiles (per-tile shuffle reduction) where the K loop is long enough to carry it
+        const char* s128_e = getenv("IM2IM_HALO_STATS128");
+        const bool stats128 = want_stats && fs.mode == 1 && c_in >= 128 && !(s128_e != nullptr && s128_e[0] == '0');
         int hbn = 0;
         for (int cand : {128, 64})
             // (the doubled budget is for N = 128 only: a layer whose N = 64 block needs it - 256 input channels - is better
             // off on the persistent kernel's N = 256 tiles; measured 256 -> 256 @80^2: 0.42 ms there, 0.47 ms here)
             if (hbn == 0 && c_out % cand == 0 && 9ll * c_in * cand * 2 <= (cand == 128 ? w_budget : 147456) &&
-                !(want_stats && cand != kHaloStatBn)) hbn = cand;
+                !(want_stats && cand != kHaloStatBn && !(stats128 && cand == 128))) hbn = cand;
+        // Weights that do not fit at all (256 input channels and more): a pair can still run N = 128 tiles with the weights
+        // STREAMED - each ring stage = halo box + the nine tap slabs of its channel block, 108 KB, two stages.  Per stage
+        // 36 MMAs of 64 cycles: 48 B/cycle of L2->SM traffic per SM, half of what the persistent kernel's 128 x 256 tiles
+        // ask for.  IM2IM_HALO_STREAM_MAX_CIN (default 256, 0 = off) bounds the layers that take this route.
+        int w_stream = 0;
+        if (hbn == 0 && pair && (!want_stats || stats128) && c_out % 128 == 0) {
+            const char* se = getenv("IM2IM_HALO_STREAM_MAX_CIN");
+            const int max_cin = se != nullptr ? atoi(se) : 256;
+            if (c_in <= max_cin) { hbn = 128; w_stream = 1; }
+        }
         if (hbn != 0) {
             HaloParams h{};
             h.c_in1 = c_in1; h.c_in2 = c_in2; h.c_out = c_out; h.B = B; h.H = H; h.W = W;
@@ -1628,9 +1720,11 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
                 h.stat_mode = fs.mode; h.stat_sums = fs.sums; h.bn_z = static_cast<const __nv_bfloat16*>(fs.bn_z);
                 h.bn_gamma = fs.gamma; h.bn_beta = fs.beta; h.bn_mean = fs.mean; h.bn_rstd = fs.rstd;
             }
-            const int w_bytes = 9 * c_in * hbn * 2 / (pair ? 2 : 1);
+            h.w_stream = w_stream;
+            const int w_bytes = w_stream ? 0 : 9 * c_in * hbn * 2 / (pair ? 2 : 1);
+            const int stage_bytes = kHaloBytes + (w_stream ? 9 * (hbn / 2) * kKStep * 2 : 0);
             const int tail_bytes = 128 + 2 * hbn * 4;      // barriers + scale/shift behind the A ring
-            h.a_stages = (232448 - 1024 - w_bytes - tail_bytes) / kHaloBytes;
+            h.a_stages = (232448 - 1024 - w_bytes - tail_bytes) / stage_bytes;
             if (h.a_stages > 4) h.a_stages = 4;
             if (h.a_stages >= 2) {
                 CUtensorMap h1, h2, hw;
@@ -1640,7 +1734,7 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
                 else h2 = h1;
                 rc = make_weight_map(&hw, d_weight, c_out, taps * c_in, pair ? hbn / 2 : hbn);
                 if (rc) return rc;
-                const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * kHaloBytes + tail_bytes + 1024;
+                const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * stage_bytes + tail_bytes + 1024;
                 IM2IM_CUDA_TRY(cudaFuncSetAttribute(pair ? conv_halo_kernel<true> : conv_halo_kernel<false>,
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
                 if (fused) *fused = h.stat_mode != 0 ? 1 : 0;

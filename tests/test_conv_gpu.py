@@ -48,6 +48,9 @@ def _ref_and_got(B, H, W, c1, c2, cout, taps, relu, bias, out_dtype, seed=0):
     (2, 48, 40, 64, 0, 128, 9),      # halo kernel, resident 64x128 weights (bn = 128)
     (1, 32, 16, 128, 0, 128, 9),     # halo kernel, two N blocks of 64 (weights of one block resident per CTA)
     (3, 16, 8, 64, 64, 64, 9),       # halo kernel with concatenated inputs, single tile per image
+    (2, 32, 32, 256, 0, 128, 9),     # halo kernel, CTA pair with STREAMED weights (256 input channels: nothing stays resident)
+    (1, 48, 40, 128, 128, 256, 9),   # ... concatenated inputs, two N blocks of 128
+    (3, 32, 16, 256, 0, 256, 9),     # ... odd number of tiles
 ])
 def test_conv_matches_fp32_reference(shape):
     B, H, W, c1, c2, cout, taps = shape

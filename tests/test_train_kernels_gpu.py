@@ -177,7 +177,10 @@ def test_fused_adam_matches_torch_adam():
 
 # ------------------------------------------------------------------------------------------- statistics fused into conv epilogues
 @pytest.mark.parametrize("c1,c2,cout,shape", [(64, 0, 64, (2, 32, 48)), (64, 64, 64, (3, 16, 16)), (64, 0, 128, (2, 32, 16)),
-                                              (128, 0, 128, (1, 48, 40)), (128, 0, 256, (2, 16, 8))])
+                                              (128, 0, 128, (1, 48, 40)), (128, 0, 256, (2, 16, 8)),
+                                              # N = 128 tiles with the per-tile shuffle reduction; 256 input channels:
+                                              # CTA pair with streamed weights
+                                              (256, 0, 128, (2, 32, 16)), (128, 128, 256, (3, 16, 8)), (256, 0, 256, (1, 48, 40))])
 def test_conv_epilogue_batch_statistics(c1, c2, cout, shape):
     """im2im_conv_igemm_bf16_stats mode 1: output identical to the plain convolution; sums = channel sums / sums of squares
     of the stored bf16 output (what im2im_channel_stats_bf16 would compute in a second pass)."""
