@@ -1387,9 +1387,16 @@ struct WgradHaloParams {
     int splits;
     int stages;
     float* dw;              // fp32 [c_out, 9, c_in], accumulated into
+    // wide != 0 (c_out a multiple of 128): N = 128 - two dZ slabs per stage - so that an MMA's operand reads are 4 KB of A
+    // + 4 KB of B per 64 tensor cycles (128 B/cycle) instead of 4 + 2 KB per 32 (192 B/cycle, which caps N = 64 at 67 % of the
+    // tensor pipe).  Five accumulators of 128 columns do not fit the 512 TMEM columns, so the nine taps are dealt to two
+    // kinds of CTA: tap pairs 0-1 (taps 0..3) and tap pairs 2-4 (taps 4..8); of the `splits` CTAs of a work item the first
+    // `splits0` are of the first kind (2 : 3, the ratio of their MMA counts).
+    int wide;
+    int splits0;
 };
 
-constexpr int kWgHaloStageBytes = kHaloBytes + kSlabBytes;  // 36 KB X halo + 16 KB dZ slab
+constexpr int kWgHaloStageBytes = kHaloBytes + kSlabBytes;  // 36 KB X halo + 16 KB dZ slab (wide: + a second slab)
 
 __device__ __forceinline__ uint64_t make_sw128_mn_desc_halo(const void* smem_ptr, uint32_t lbo_bytes) {
     const uint32_t addr = smem_u32(smem_ptr);
@@ -1407,7 +1414,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_
                        const WgradHaloParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(p.stages) * kWgHaloStageBytes);
+    const int stage_bytes = kWgHaloStageBytes + (p.wide ? kSlabBytes : 0);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(p.stages) * stage_bytes);
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* accum_bar = empty_bar + p.stages;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(accum_bar + 1);
@@ -1427,13 +1435,20 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    // work item: blockIdx.x -> (split, channel block of X), blockIdx.y -> 64-channel block of c_out
+    // work item: blockIdx.x -> (split, channel block of X), blockIdx.y -> 64-channel (wide: 128-channel) block of c_out
     const int cb = blockIdx.x % p.cblocks;
-    const int split = blockIdx.x / p.cblocks;
-    const int n0 = blockIdx.y * 64;
+    int split = blockIdx.x / p.cblocks;
+    int n_splits = p.splits;
+    const int bn = p.wide ? 128 : 64;
+    const int n0 = blockIdx.y * bn;
+    int pr_begin = 0, pr_end = 5;          // tap pairs of this CTA
+    if (p.wide) {
+        if (split < p.splits0) { pr_end = 2; n_splits = p.splits0; }
+        else { pr_begin = 2; split -= p.splits0; n_splits = p.splits - p.splits0; }
+    }
     const int n_pix_tiles = p.tiles_w * p.tiles_h * p.B;
-    const int k_begin = static_cast<int>(static_cast<long long>(n_pix_tiles) * split / p.splits);
-    const int k_end = static_cast<int>(static_cast<long long>(n_pix_tiles) * (split + 1) / p.splits);
+    const int k_begin = static_cast<int>(static_cast<long long>(n_pix_tiles) * split / n_splits);
+    const int k_end = static_cast<int>(static_cast<long long>(n_pix_tiles) * (split + 1) / n_splits);
 
     if (warp == 0) {
         {   // all lanes walk the loop (uniform control flow: TMA operands stay in uniform registers), one lane issues
@@ -1446,11 +1461,12 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_
                 const int th = t % p.tiles_h; t /= p.tiles_h;
                 const int w0 = tw * kHaloTileW, h0 = th * kHaloTileH, b0 = t;
                 mbar_wait(&empty_bar[stage], phase);
-                unsigned char* dst = tiles + static_cast<size_t>(stage) * kWgHaloStageBytes;
+                unsigned char* dst = tiles + static_cast<size_t>(stage) * stage_bytes;
                 if (leader) {
-                    mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(kWgHaloStageBytes));
+                    mbar_arrive_expect_tx(&full_bar[stage], static_cast<unsigned>(stage_bytes));
                     tma_load_4d(dst, &map_x, &full_bar[stage], cb * kKStep, w0 - 1, h0 - 1, b0);
                     tma_load_4d(dst + kHaloBytes, &map_dz, &full_bar[stage], n0, w0, h0, b0);
+                    if (p.wide) tma_load_4d(dst + kHaloBytes + kSlabBytes, &map_dz, &full_bar[stage], n0 + 64, w0, h0, b0);
                 }
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -1459,27 +1475,28 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_
     } else if (warp == 1) {
         if (k_end > k_begin) {   // all lanes walk the loop, the elected lane issues (see elect_one_sync)
             const bool leader = elect_one_sync();
-            // D = F32, A = B = BF16, both MN-major (bits 15, 16), M = 128, N = 64
-            const uint32_t idesc = make_idesc_bf16(64) | (1u << 15) | (1u << 16);
+            // D = F32, A = B = BF16, both MN-major (bits 15, 16), M = 128, N = 64 (wide: 128 = two slabs, LBO apart)
+            const uint32_t idesc = make_idesc_bf16(bn) | (1u << 15) | (1u << 16);
             int stage = 0;
             unsigned phase = 0;
             for (int kt = k_begin; kt < k_end; ++kt) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const unsigned char* halo = tiles + static_cast<size_t>(stage) * kWgHaloStageBytes;
+                const unsigned char* halo = tiles + static_cast<size_t>(stage) * stage_bytes;
                 const unsigned char* dz = halo + kHaloBytes;
 #pragma unroll
                 for (int k = 0; k < kTileM / kUmmaK; ++k) {   // 16 pixels = output rows 2k, 2k+1 of the tile
                     const uint64_t desc_b = make_sw128_mn_desc(dz + k * 2048, kSlabBytes);
 #pragma unroll
                     for (int pr = 0; pr < 5; ++pr) {
+                        if (pr < pr_begin || pr >= pr_end) continue;                  // (warp-uniform) the other kind's pairs
                         const int t0 = 2 * pr, t1 = (pr < 4) ? 2 * pr + 1 : 2 * pr;   // ninth tap: second half unused
                         const int off0 = ((t0 / 3) * kHaloW + (t0 % 3)) * 128;
                         const int off1 = ((t1 / 3) * kHaloW + (t1 % 3)) * 128;
                         const uint32_t lbo = (pr < 4) ? static_cast<uint32_t>(off1 - off0) : 128u;
                         const uint64_t desc_a = make_sw128_mn_desc_halo(halo + off0 + (2 * k) * kHaloW * 128, lbo);
                         if (leader)
-                            umma_bf16(tmem_base + static_cast<uint32_t>(pr * 64), desc_a, desc_b, idesc,
+                            umma_bf16(tmem_base + static_cast<uint32_t>((pr - pr_begin) * bn), desc_a, desc_b, idesc,
                                       (kt > k_begin || k > 0) ? 1u : 0u);
                     }
                 }
@@ -1497,16 +1514,19 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         const size_t K_total = static_cast<size_t>(9) * p.c_in;
+        const int chunks_per_acc = bn / 32;
+        const int n_chunks = (pr_end - pr_begin) * chunks_per_acc;
 #pragma unroll 1
-        for (int it = 0; it < 10; ++it) {
-            // every split adds into the same 576 x 64 block of dW: start each CTA at a different 32-column chunk so that
+        for (int it = 0; it < n_chunks; ++it) {
+            // every split adds into the same block of dW: start each CTA at a different 32-column chunk so that
             // concurrently finishing CTAs do not all hit the same L2 lines at once
-            const int o = (it + split) % 10;
-            const int pr = o >> 1, c = (o & 1) * 32;
+            const int o = (it + split) % n_chunks;
+            const int acc = o / chunks_per_acc, c = (o % chunks_per_acc) * 32;
+            const int pr = pr_begin + acc;
             const int tap = 2 * pr + (row >> 6);
             {
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(pr * 64 + c), v);
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * bn + c), v);
                 tmem_ld_wait();
                 if (tap < 9) {
                     // column j = output channel n0+c+j; the 32 lanes of a warp are 32 consecutive input channels of one tap:
@@ -2004,22 +2024,40 @@ extern "C" int im2im_conv_wgrad_bf16(const void* d_x, const void* d_dz, int32_t 
         h.c_in = c_in; h.c_out = c_out; h.B = B; h.H = H; h.W = W;
         h.tiles_w = (W + kHaloTileW - 1) / kHaloTileW; h.tiles_h = (H + kHaloTileH - 1) / kHaloTileH;
         h.cblocks = c_in / kKStep;
-        const int n_blocks = c_out / 64;
-        const long long items = static_cast<long long>(h.cblocks) * n_blocks;
+        // N = 128 (two dZ slabs per stage, taps dealt to two kinds of CTA) where c_out allows it and a work item gets at least
+        // five CTAs to split 2 : 3; IM2IM_WGRAD_HALO_WIDE=0 keeps N = 64
+        const char* wide_e = getenv("IM2IM_WGRAD_HALO_WIDE");
         const int n_pix_tiles = h.tiles_w * h.tiles_h * B;
-        long long splits = sm_count() / items;   // at most ONE wave of CTAs (rounding up would leave a second, nearly empty
+        // (64 input channels: one channel block per work item, measured 3 % slower than N = 64 at 64 -> 128 @160^2)
+        h.wide = (c_out % 128 == 0 && c_in >= 128 && !(wide_e != nullptr && wide_e[0] == '0')) ? 1 : 0;
+        int n_blocks = 0;
+        long long splits = 0;
+        for (;;) {
+            n_blocks = c_out / (h.wide ? 128 : 64);
+            const long long items = static_cast<long long>(h.cblocks) * n_blocks;
+            splits = sm_count() / items;         // at most ONE wave of CTAs (rounding up would leave a second, nearly empty
                                                  // wave); every split also costs 36.8k fp32 atomics
-        if (splits > n_pix_tiles) splits = n_pix_tiles;
-        if (splits < 1) splits = 1;
+            if (splits > n_pix_tiles) splits = n_pix_tiles;
+            if (splits < 1) splits = 1;
+            if (h.wide && splits < 5) { h.wide = 0; continue; }   // too few CTAs per work item to deal 2 : 3
+            break;
+        }
         h.splits = static_cast<int>(splits);
-        h.stages = 4;
+        h.splits0 = 0;
+        if (h.wide) {
+            h.splits0 = static_cast<int>((2 * splits + 2) / 5);   // 2 : 3 = MMAs per pixel tile of the two kinds
+            if (h.splits0 < 1) h.splits0 = 1;
+            if (h.splits0 > h.splits - 1) h.splits0 = h.splits - 1;
+        }
+        h.stages = h.wide ? 3 : 4;
         h.dw = d_dw;
         CUtensorMap mdz, mx;
         int rc = make_act_map(&mdz, d_dz, B, H, W, c_out, kHaloTileW, kHaloTileH, 1);
         if (rc) return rc;
         rc = make_act_map(&mx, d_x, B, H, W, c_in, kHaloW, kHaloH, 1);
         if (rc) return rc;
-        const size_t smem = static_cast<size_t>(h.stages) * kWgHaloStageBytes + (2 * h.stages + 1) * sizeof(uint64_t) + 16 + 1024;
+        const size_t smem = static_cast<size_t>(h.stages) * (kWgHaloStageBytes + (h.wide ? kSlabBytes : 0)) +
+                            (2 * h.stages + 1) * sizeof(uint64_t) + 16 + 1024;
         IM2IM_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(static_cast<unsigned>(h.cblocks * h.splits), static_cast<unsigned>(n_blocks));
         conv_wgrad_halo_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(mdz, mx, h);

@@ -146,3 +146,39 @@ def test_halo_conv_cta_pair_equals_single_cta(B, H, W, c1, c2, cout, monkeypatch
     finally:
         torch.backends.cudnn.allow_tf32 = old
     assert (pair[0].permute(0, 3, 1, 2) - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [
+    (1, 16, 16, 64, 64),       # halo weight gradient, one pixel tile per image, N = 64
+    (2, 40, 40, 128, 64),      # split-K kernel (40x40 is not an 8x16-tile shape)
+    (3, 20, 20, 256, 512),     # split-K kernel, deep layer
+    (2, 48, 24, 128, 192),     # halo, several channel / c_out blocks, c_out not a multiple of 128
+    (2, 64, 64, 128, 128),     # halo, N = 128: taps dealt to two kinds of CTA
+    (3, 32, 40, 128, 256),     # ... two c_out blocks of 128
+    (1, 48, 40, 256, 128),     # ... four channel blocks
+])
+def test_conv_weight_gradient_matches_autograd(B, H, W, cin, cout, monkeypatch):
+    """im2im_conv_wgrad_bf16 (dW of the 3x3 convolutions of unet_parts.py:16-21) against torch autograd in fp32 on the same
+    bf16-rounded operands; the N = 128 form of the halo kernel against its N = 64 form (fp32 atomics in another order)."""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(B, cin, H, W, device=DEV, generator=g).to(torch.bfloat16)
+    dz = torch.randn(B, cout, H, W, device=DEV, generator=g).to(torch.bfloat16)
+    wf = torch.zeros(cout, cin, 3, 3, device=DEV, requires_grad=True)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        F.conv2d(x.float(), wf, None, padding=1).backward(dz.float())
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    ref = wf.grad.permute(0, 2, 3, 1).reshape(cout, 9, cin)
+    scale = ref.abs().max().item()
+    xn, dzn = conv.to_nhwc_bf16(x), conv.to_nhwc_bf16(dz)
+    got = conv.conv_wgrad(xn, dzn, 9)
+    assert (got - ref).abs().max().item() <= 5e-4 * scale
+    monkeypatch.setenv("IM2IM_WGRAD_HALO_WIDE", "0")
+    narrow = conv.conv_wgrad(xn, dzn, 9)
+    assert (narrow - ref).abs().max().item() <= 5e-4 * scale
+    assert (narrow - got).abs().max().item() <= 1e-4 * scale
+    # accumulates into `out`
+    again = conv.conv_wgrad(xn, dzn, 9, out=got.clone())
+    assert (again - 2 * ref).abs().max().item() <= 1e-3 * scale
