@@ -187,6 +187,17 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a,
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrives (once all earlier MMAs of this thread are complete) on the barrier at this shared-memory offset in BOTH CTAs
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -631,6 +642,8 @@ struct HaloParams {
     // 0: the layer's weights (this CTA's rows of the N block, all taps and channel blocks) stay resident in shared memory;
     // 1: they do not fit - every ring stage carries the nine tap slabs of its channel block behind the halo box
     int w_stream;
+    // 1: fp32 activations / weights, kind::tf32 (a 128-byte K block is 32 channels), fp32 output rounded to TF32; plain epilogue only
+    int tf32;
     int relu;
     const float* bias;
     __nv_bfloat16* out_bf16;
@@ -694,13 +707,17 @@ __device__ __forceinline__ uint64_t make_sw128_desc_halo(const void* smem_ptr) {
 // reads its own halo box, the leader issues the MMAs for both, every CTA drains its own 128 TMEM lanes.  Per K = 16 step a
 // CTA's shared memory serves 4 KB of A + bn/2 rows of B instead of bn rows - the operand traffic that capped the N = 64
 // layers at 67 % of the tensor pipe.
-template <bool kPair>
+// kTf32: fp32 activations / weights through kind::tf32 (HaloParams::tf32).  A template parameter, not a run-time branch: with
+// both instruction kinds in one MMA loop the compiler if-converts them into @UP / @!UP pairs of UTCHMMA and the nullified
+// halves still cost issue time (measured: the bf16 forward's halo launches 4.23 -> 5.56 ms at batch 78).
+template <bool kPair, bool kTf32 = false>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
                  const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int c_in = p.c_in1 + p.c_in2;
-    const int cblocks = c_in / kKStep;
+    constexpr int kch = kTf32 ? kKStep / 2 : kKStep;            // channels per 128-byte K block
+    const int cblocks = c_in / kch;
     const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
     const int bn_local = kPair ? p.bn / 2 : p.bn;              // weight rows resident in THIS CTA
     const int b_tile_bytes = bn_local * kKStep * 2;
@@ -803,8 +820,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 for (int cb = 0; cb < cblocks; ++cb)
                     if (leader) {
                         unsigned char* wdst = w_smem + static_cast<size_t>(tap * cblocks + cb) * b_tile_bytes;
-                        if (kPair) tma_load_2d_pair(wdst, &map_w, w_bar_lead, tap * c_in + cb * kKStep, n0 + static_cast<int>(cta_rank) * bn_local);
-                        else tma_load_2d(wdst, &map_w, w_bar, tap * c_in + cb * kKStep, n0);
+                        if (kPair) tma_load_2d_pair(wdst, &map_w, w_bar_lead, tap * c_in + cb * kch, n0 + static_cast<int>(cta_rank) * bn_local);
+                        else tma_load_2d(wdst, &map_w, w_bar, tap * c_in + cb * kch, n0);
                     }
             __syncwarp();
             int stage = 0;
@@ -818,7 +835,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 for (int cb = 0; cb < cblocks; ++cb) {
                     mbar_wait(&empty_bar[stage], phase);
                     unsigned char* dst = a_ring + static_cast<size_t>(stage) * stage_bytes;
-                    const int c0 = cb * kKStep;
+                    const int c0 = cb * kch;
                     if (leader) {
                         if (kPair) {
                             // both CTAs' bytes complete on the leader's barrier, which expects their sum
@@ -851,7 +868,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         // all 32 lanes walk the loops (uniform control flow); the elected lane issues - see elect_one_sync()
         const bool leader = elect_one_sync();
         // pair: M = 256 (bits 24-28 hold M >> 4)
-        const uint32_t idesc = make_idesc_bf16(p.bn) + (kPair ? (static_cast<uint32_t>(kTileM >> 4) << 24) : 0u);
+        const uint32_t idesc = (kTf32 ? make_idesc_tf32(p.bn) : make_idesc_bf16(p.bn)) + (kPair ? (static_cast<uint32_t>(kTileM >> 4) << 24) : 0u);
         if (!w_stream) mbar_wait(w_bar, 0);
         int stage = 0;
         unsigned phase = 0;
@@ -876,12 +893,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < kKStep / kUmmaK; ++k)
                         if (leader) {
-                            if (kPair)
-                                umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
-                                               idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                            else
-                                umma_bf16(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
-                                          idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                            // (kind::tf32: K = 8 fp32 = the same 32 bytes per instruction, so the descriptor steps are the same)
+                            const uint64_t da = desc_a + static_cast<uint64_t>(2 * k), db = desc_b + static_cast<uint64_t>(2 * k);
+                            const uint32_t acc = (cb > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                            if (kTf32) { if (kPair) umma_tf32_pair(tmem_d, da, db, idesc, acc); else umma_tf32(tmem_d, da, db, idesc, acc); }
+                            else { if (kPair) umma_bf16_pair(tmem_d, da, db, idesc, acc); else umma_bf16(tmem_d, da, db, idesc, acc); }
                         }
                 }
                 if (leader) { if (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]); }
@@ -1143,6 +1159,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                         float x = __uint_as_float(v[4 * j4 + jj]);
                         if (bias_staged) x += bb[jj];
                         if (p.relu) x = fmaxf(x, 0.f);
+                        if (kTf32) x = round_tf32(x);    // stored activations are exactly what the next kind::tf32 MMA reads
                         f[4 * j4 + jj] = x;
                     }
                 }
@@ -1622,6 +1639,9 @@ int conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c
                     const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps, int32_t relu,
                     void* d_out_bf16, float* d_out_f32, const FusedStats& fs, int* fused, void* stream,
                     void* d_pool_out = nullptr, int* pooled = nullptr);
+int halo_dispatch(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2, const void* d_weight, const float* d_bias,
+                  int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps, int32_t relu, void* d_out_bf16, float* d_out_f32,
+                  const FusedStats& fs, int* fused, void* stream, void* d_pool_out, int* pooled, bool tf32, int* launched);
 }
 
 extern "C" int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2,
@@ -1665,6 +1685,122 @@ extern "C" int im2im_conv_igemm_bf16_stats(const void* d_x1, int32_t c_in1, cons
     return rc;
 }
 
+// Wide shallow layers: halo kernel (one activation box per channel block, taps via shifted descriptors, weights resident or
+// streamed).  Shared by the bf16 and the tf32 (fp32 activations / weights, kind::tf32; everything is counted in 128-byte K
+// blocks = 64 bf16 or 32 fp32 channels) entry points.  *launched = 1 when the layer was taken.
+int im2im::halo_dispatch(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2, const void* d_weight,
+                         const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps, int32_t relu,
+                         void* d_out_bf16, float* d_out_f32, const FusedStats& fs, int* fused, void* stream,
+                         void* d_pool_out, int* pooled, bool tf32, int* launched) {
+    int rc = 0;
+    *launched = 0;
+    const int esz = tf32 ? 4 : 2;                 // bytes per activation / weight element
+    const int kch = 128 / esz;                    // channels per 128-byte K block
+    static const bool no_halo = (getenv("IM2IM_CONV_NO_HALO") != nullptr);
+    if (!no_halo && taps == 9 && W % kHaloTileW == 0 && H % kHaloTileH == 0 && c_in1 % kch == 0 && c_in2 % kch == 0) {
+        const int c_in = c_in1 + c_in2;
+        const long long k_bytes = static_cast<long long>(c_in) * esz;   // bytes of one tap of one weight row
+        const bool staged = d_out_bf16 != nullptr && d_out_f32 == nullptr;
+        const bool want_stats = staged && fs.mode != 0;
+        // CTA pairs (cta_group::2): each CTA keeps half of the weight rows resident.  IM2IM_HALO_PAIR=0 restores single CTAs
+        // (read per call so that a test can compare the two in one process).  A pair also takes N blocks whose weights only
+        // fit when halved - 128 -> 128 and 128 -> 256 run as N = 128 tiles (1.6 PFLOP/s at batch 78) instead of N = 64 -
+        // unless IM2IM_HALO_PAIR_WIDE=0
+        const char* pair_e = getenv("IM2IM_HALO_PAIR");
+        const bool pair = !(pair_e != nullptr && pair_e[0] == '0') && sm_count() >= 2;
+        const char* wide_e = getenv("IM2IM_HALO_PAIR_WIDE");
+        const long long w_budget = (pair && !(wide_e != nullptr && wide_e[0] == '0')) ? 2 * 147456 : 147456;
+        // forward statistics on N = 128 tiles (per-tile shuffle reduction) where the K loop is long enough to carry it
+        const char* s128_e = getenv("IM2IM_HALO_STATS128");
+        const bool stats128 = want_stats && fs.mode == 1 && k_bytes >= 256 && !(s128_e != nullptr && s128_e[0] == '0');
+        int hbn = 0;
+        for (int cand : {128, 64})
+            // (the doubled budget is for N = 128 only: a layer whose N = 64 block needs it - 256 input channels - is better
+            // off on the persistent kernel's N = 256 tiles; measured 256 -> 256 @80^2: 0.42 ms there, 0.47 ms here)
+            // (c_out == 64 has no wider alternative, so its N = 64 block may use the doubled budget too)
+            if (hbn == 0 && c_out % cand == 0 && 9ll * k_bytes * cand <= ((cand == 128 || c_out == 64) ? w_budget : 147456) &&
+                !(want_stats && cand != kHaloStatBn && !(stats128 && cand == 128))) hbn = cand;
+        // Weights that do not fit at all (256 input channels and more): a pair can still run N = 128 tiles with the weights
+        // STREAMED - each ring stage = halo box + the nine tap slabs of its channel block, 108 KB, two stages.  Per stage
+        // 36 MMAs of 64 cycles: 48 B/cycle of L2->SM traffic per SM, half of what the persistent kernel's 128 x 256 tiles
+        // ask for.  IM2IM_HALO_STREAM_MAX_CIN (default 256, 0 = off) bounds the layers that take this route.
+        int w_stream = 0;
+        if (hbn == 0 && pair && (!want_stats || stats128) && c_out % 128 == 0) {
+            const char* se = getenv("IM2IM_HALO_STREAM_MAX_CIN");
+            const int max_cin = se != nullptr ? atoi(se) : 256;
+            if (k_bytes <= 2ll * max_cin) { hbn = 128; w_stream = 1; }   // (the bound is stated in bf16 channels)
+        }
+        if (hbn != 0) {
+            HaloParams h{};
+            h.c_in1 = c_in1; h.c_in2 = c_in2; h.c_out = c_out; h.B = B; h.H = H; h.W = W;
+            h.tiles_w = W / kHaloTileW; h.tiles_h = H / kHaloTileH; h.bn = hbn; h.relu = relu; h.bias = d_bias;
+            static const bool skip_store = (getenv("IM2IM_HALO_SKIP_STORE") != nullptr);
+            h.debug_skip_store = skip_store ? 1 : 0;
+            h.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16); h.out_f32 = d_out_f32;
+            h.out_planar = nullptr; h.n_real = 0; h.act_kind = 0; h.act_from = 0;
+            if (want_stats) {
+                h.stat_mode = fs.mode; h.stat_sums = fs.sums; h.bn_z = static_cast<const __nv_bfloat16*>(fs.bn_z);
+                h.bn_gamma = fs.gamma; h.bn_beta = fs.beta; h.bn_mean = fs.mean; h.bn_rstd = fs.rstd;
+            }
+            h.w_stream = w_stream; h.tf32 = tf32 ? 1 : 0;
+            const int w_bytes = w_stream ? 0 : static_cast<int>(9 * k_bytes * hbn / (pair ? 2 : 1));
+            const int stage_bytes = kHaloBytes + (w_stream ? 9 * (hbn / 2) * kKStep * 2 : 0);
+            const int tail_bytes = 128 + 2 * hbn * 4;      // barriers + scale/shift behind the A ring
+            h.a_stages = (232448 - 1024 - w_bytes - tail_bytes) / stage_bytes;
+            if (h.a_stages > 4) h.a_stages = 4;
+            if (h.a_stages >= 2) {
+                CUtensorMap h1, h2, hw;
+                rc = make_act_map(&h1, d_x1, B, H, W, c_in1, kHaloW, kHaloH, 1, tf32);
+                if (rc) return rc;
+                if (c_in2 > 0) { rc = make_act_map(&h2, d_x2, B, H, W, c_in2, kHaloW, kHaloH, 1, tf32); if (rc) return rc; }
+                else h2 = h1;
+                rc = make_weight_map(&hw, d_weight, c_out, taps * c_in, pair ? hbn / 2 : hbn, tf32);
+                if (rc) return rc;
+                const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * stage_bytes + tail_bytes + 1024;
+                void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, HaloParams) =
+                    tf32 ? (pair ? conv_halo_kernel<true, true> : conv_halo_kernel<false, true>)
+                         : (pair ? conv_halo_kernel<true, false> : conv_halo_kernel<false, false>);
+                IM2IM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+                if (fused) *fused = h.stat_mode != 0 ? 1 : 0;
+                if (d_pool_out != nullptr && h.stat_mode == 0 && d_out_bf16 != nullptr && d_out_f32 == nullptr && H % 2 == 0 && W % 2 == 0) {
+                    h.pool_out = static_cast<__nv_bfloat16*>(d_pool_out);
+                    if (pooled) *pooled = 1;
+                }
+                const int n_blocks_n = c_out / hbn;
+                const long long m_tiles = static_cast<long long>(h.tiles_w) * h.tiles_h * B;
+                long long gx = sm_count() / n_blocks_n;
+                if (gx < 1) gx = 1;
+                if (gx > m_tiles) gx = m_tiles;
+                if (pair) {
+                    // clusters of two CTAs along x; a pair takes two neighbouring tiles per step
+                    const long long pairs = (m_tiles + 1) / 2;
+                    long long gp = sm_count() / 2 / n_blocks_n;
+                    if (gp < 1) gp = 1;
+                    if (gp > pairs) gp = pairs;
+                    cudaLaunchConfig_t cfg{};
+                    cfg.gridDim = dim3(static_cast<unsigned>(2 * gp), static_cast<unsigned>(n_blocks_n));
+                    cfg.blockDim = dim3(kHaloThreads);
+                    cfg.dynamicSmemBytes = hsmem;
+                    cfg.stream = static_cast<cudaStream_t>(stream);
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeClusterDimension;
+                    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                    cfg.attrs = attr; cfg.numAttrs = 1;
+                    IM2IM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, h1, h2, hw, h));
+                    *launched = 1;
+                    return check_launch("conv_halo_kernel<pair>");
+                }
+                dim3 hgrid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks_n));
+                kern<<<hgrid, kHaloThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h2, hw, h);
+                *launched = 1;
+                return check_launch("conv_halo_kernel");
+            }
+        }
+    }
+    (void)rc;
+    return IM2IM_OK;
+}
+
 int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2, const void* d_weight,
                            const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps, int32_t relu,
                            void* d_out_bf16, float* d_out_f32, const FusedStats& fs, int* fused, void* stream,
@@ -1695,101 +1831,11 @@ int im2im::conv_igemm_impl(const void* d_x1, int32_t c_in1, const void* d_x2, in
     else m2 = m1;
     rc = make_weight_map(&mw, d_weight, c_out, taps * (c_in1 + c_in2), p.bn);
     if (rc) return rc;
-    // wide shallow layers: halo kernel (one activation box per channel block, taps via shifted descriptors, resident weights)
-    static const bool no_halo = (getenv("IM2IM_CONV_NO_HALO") != nullptr);
-    if (!no_halo && taps == 9 && W % kHaloTileW == 0 && H % kHaloTileH == 0) {
-        const int c_in = c_in1 + c_in2;
-        const bool staged = d_out_bf16 != nullptr && d_out_f32 == nullptr;
-        const bool want_stats = staged && fs.mode != 0;
-        // CTA pairs (cta_group::2): each CTA keeps half of the weight rows resident.  IM2IM_HALO_PAIR=0 restores single CTAs
-        // (read per call so that a test can compare the two in one process).  A pair also takes N blocks whose weights only
-        // fit when halved - 128 -> 128 and 128 -> 256 run as N = 128 tiles (1.6 PFLOP/s at batch 78) instead of N = 64 -
-        // unless IM2IM_HALO_PAIR_WIDE=0
-        const char* pair_e = getenv("IM2IM_HALO_PAIR");
-        const bool pair = !(pair_e != nullptr && pair_e[0] == '0') && sm_count() >= 2;
-        const char* wide_e = getenv("IM2IM_HALO_PAIR_WIDE");
-        const long long w_budget = (pair && !(wide_e != nullptr && wide_e[0] == '0')) ? 2 * 147456 : 147456;
-        // forward statistics on N = 128 tiles (per-tile shuffle reduction) where the K loop is long enough to carry it
-        const char* s128_e = getenv("IM2IM_HALO_STATS128");
-        const bool stats128 = want_stats && fs.mode == 1 && c_in >= 128 && !(s128_e != nullptr && s128_e[0] == '0');
-        int hbn = 0;
-        for (int cand : {128, 64})
-            // (the doubled budget is for N = 128 only: a layer whose N = 64 block needs it - 256 input channels - is better
-            // off on the persistent kernel's N = 256 tiles; measured 256 -> 256 @80^2: 0.42 ms there, 0.47 ms here)
-            if (hbn == 0 && c_out % cand == 0 && 9ll * c_in * cand * 2 <= (cand == 128 ? w_budget : 147456) &&
-                !(want_stats && cand != kHaloStatBn && !(stats128 && cand == 128))) hbn = cand;
-        // Weights that do not fit at all (256 input channels and more): a pair can still run N = 128 tiles with the weights
-        // STREAMED - each ring stage = halo box + the nine tap slabs of its channel block, 108 KB, two stages.  Per stage
-        // 36 MMAs of 64 cycles: 48 B/cycle of L2->SM traffic per SM, half of what the persistent kernel's 128 x 256 tiles
-        // ask for.  IM2IM_HALO_STREAM_MAX_CIN (default 256, 0 = off) bounds the layers that take this route.
-        int w_stream = 0;
-        if (hbn == 0 && pair && (!want_stats || stats128) && c_out % 128 == 0) {
-            const char* se = getenv("IM2IM_HALO_STREAM_MAX_CIN");
-            const int max_cin = se != nullptr ? atoi(se) : 256;
-            if (c_in <= max_cin) { hbn = 128; w_stream = 1; }
-        }
-        if (hbn != 0) {
-            HaloParams h{};
-            h.c_in1 = c_in1; h.c_in2 = c_in2; h.c_out = c_out; h.B = B; h.H = H; h.W = W;
-            h.tiles_w = W / kHaloTileW; h.tiles_h = H / kHaloTileH; h.bn = hbn; h.relu = relu; h.bias = d_bias;
-            static const bool skip_store = (getenv("IM2IM_HALO_SKIP_STORE") != nullptr);
-            h.debug_skip_store = skip_store ? 1 : 0;
-            h.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16); h.out_f32 = d_out_f32;
-            h.out_planar = nullptr; h.n_real = 0; h.act_kind = 0; h.act_from = 0;
-            if (want_stats) {
-                h.stat_mode = fs.mode; h.stat_sums = fs.sums; h.bn_z = static_cast<const __nv_bfloat16*>(fs.bn_z);
-                h.bn_gamma = fs.gamma; h.bn_beta = fs.beta; h.bn_mean = fs.mean; h.bn_rstd = fs.rstd;
-            }
-            h.w_stream = w_stream;
-            const int w_bytes = w_stream ? 0 : 9 * c_in * hbn * 2 / (pair ? 2 : 1);
-            const int stage_bytes = kHaloBytes + (w_stream ? 9 * (hbn / 2) * kKStep * 2 : 0);
-            const int tail_bytes = 128 + 2 * hbn * 4;      // barriers + scale/shift behind the A ring
-            h.a_stages = (232448 - 1024 - w_bytes - tail_bytes) / stage_bytes;
-            if (h.a_stages > 4) h.a_stages = 4;
-            if (h.a_stages >= 2) {
-                CUtensorMap h1, h2, hw;
-                rc = make_act_map(&h1, d_x1, B, H, W, c_in1, kHaloW, kHaloH, 1);
-                if (rc) return rc;
-                if (c_in2 > 0) { rc = make_act_map(&h2, d_x2, B, H, W, c_in2, kHaloW, kHaloH, 1); if (rc) return rc; }
-                else h2 = h1;
-                rc = make_weight_map(&hw, d_weight, c_out, taps * c_in, pair ? hbn / 2 : hbn);
-                if (rc) return rc;
-                const size_t hsmem = static_cast<size_t>(w_bytes) + static_cast<size_t>(h.a_stages) * stage_bytes + tail_bytes + 1024;
-                IM2IM_CUDA_TRY(cudaFuncSetAttribute(pair ? conv_halo_kernel<true> : conv_halo_kernel<false>,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
-                if (fused) *fused = h.stat_mode != 0 ? 1 : 0;
-                if (d_pool_out != nullptr && h.stat_mode == 0 && d_out_bf16 != nullptr && d_out_f32 == nullptr && H % 2 == 0 && W % 2 == 0) {
-                    h.pool_out = static_cast<__nv_bfloat16*>(d_pool_out);
-                    if (pooled) *pooled = 1;
-                }
-                const int n_blocks_n = c_out / hbn;
-                const long long m_tiles = static_cast<long long>(h.tiles_w) * h.tiles_h * B;
-                long long gx = sm_count() / n_blocks_n;
-                if (gx < 1) gx = 1;
-                if (gx > m_tiles) gx = m_tiles;
-                if (pair) {
-                    // clusters of two CTAs along x; a pair takes two neighbouring tiles per step
-                    const long long pairs = (m_tiles + 1) / 2;
-                    long long gp = sm_count() / 2 / n_blocks_n;
-                    if (gp < 1) gp = 1;
-                    if (gp > pairs) gp = pairs;
-                    cudaLaunchConfig_t cfg{};
-                    cfg.gridDim = dim3(static_cast<unsigned>(2 * gp), static_cast<unsigned>(n_blocks_n));
-                    cfg.blockDim = dim3(kHaloThreads);
-                    cfg.dynamicSmemBytes = hsmem;
-                    cfg.stream = static_cast<cudaStream_t>(stream);
-                    cudaLaunchAttribute attr[1];
-                    attr[0].id = cudaLaunchAttributeClusterDimension;
-                    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-                    cfg.attrs = attr; cfg.numAttrs = 1;
-                    IM2IM_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true>, h1, h2, hw, h));
-                    return check_launch("conv_halo_kernel<pair>");
-                }
-                dim3 hgrid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks_n));
-                conv_halo_kernel<false><<<hgrid, kHaloThreads, hsmem, static_cast<cudaStream_t>(stream)>>>(h1, h2, hw, h);
-                return check_launch("conv_halo_kernel");
-            }
-        }
+    {
+        int launched = 0;
+        rc = halo_dispatch(d_x1, c_in1, d_x2, c_in2, d_weight, d_bias, B, H, W, c_out, taps, relu, d_out_bf16, d_out_f32, fs, fused,
+                           stream, d_pool_out, pooled, false, &launched);
+        if (rc || launched) return rc;
     }
     const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + (2 * p.stages + 4) * sizeof(uint64_t) + 16 + 1024;
     static const bool use_v1 = (getenv("IM2IM_CONV_V1") != nullptr);  // bring-up switch: one tile per CTA
@@ -1831,6 +1877,15 @@ extern "C" int im2im_conv_igemm_tf32(const float* d_x1, int32_t c_in1, const flo
     if (!d_x1 || !d_weight || !d_out || (c_in2 > 0 && !d_x2)) return fail(IM2IM_EINVAL, "null tensor");
     if (reinterpret_cast<uintptr_t>(d_out) & 31u)
         return fail(IM2IM_EINVAL, "conv_igemm_tf32: the output tensor must be 32-byte aligned (the epilogue stores 32 bytes at a time)");
+    {   // the wide layers on the halo kernel (CTA pairs), as in the bf16 path; IM2IM_TF32_HALO=0 keeps them on the persistent kernel
+        const char* e = getenv("IM2IM_TF32_HALO");
+        if (!(e != nullptr && e[0] == '0')) {
+            int launched = 0;
+            const int hrc = halo_dispatch(d_x1, c_in1, d_x2, c_in2, d_weight, d_bias, B, H, W, c_out, taps, relu, nullptr, d_out,
+                                          FusedStats{}, nullptr, stream, nullptr, nullptr, true, &launched);
+            if (hrc || launched) return hrc;
+        }
+    }
     ConvParams p;
     p.taps = taps; p.c_in1 = c_in1; p.c_in2 = c_in2; p.c_out = c_out; p.B = B; p.H = H; p.W = W;
     pick_box(B, H, W, p.bw, p.bh, p.bb);

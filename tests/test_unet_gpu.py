@@ -125,7 +125,11 @@ TF32_L2_TOL, TF32_MAX_TOL = 2e-3, 6e-3   # kind::tf32 (10-bit mantissa operands,
 
 @pytest.mark.parametrize("c1,c2,cout,taps,shape", [(64, 0, 64, 9, (2, 32, 48)), (128, 64, 128, 9, (1, 40, 40)),
                                                    (32, 0, 32, 1, (3, 20, 20)), (512, 512, 256, 9, (2, 16, 16)),
-                                                   (64, 0, 32, 1, (2, 50, 38))])
+                                                   (64, 0, 32, 1, (2, 50, 38)),
+                                                   # halo kernel as CTA pairs (8x16-tile shapes): resident weights with the
+                                                   # doubled budget, N = 128, odd tile count, streamed weights, concatenation
+                                                   (128, 0, 64, 9, (1, 48, 40)), (64, 0, 128, 9, (3, 16, 8)),
+                                                   (128, 0, 128, 9, (2, 32, 32)), (64, 64, 256, 9, (1, 32, 16))])
 def test_conv_igemm_tf32_vs_torch_fp32(c1, c2, cout, taps, shape):
     """The kind::tf32 convolution on TF32-representable inputs is an exact-product / fp32-accumulate GEMM: it must agree
     with torch's fp32 convolution (TF32 off) to accumulation-order rounding."""
