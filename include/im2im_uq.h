@@ -247,6 +247,10 @@ int im2im_fraction_missed_counts(const float* d_lower_edge, const float* d_upper
  *   d_weight    : DEVICE bf16 [c_out, taps, c_in1+c_in2] (taps = 9: ky*3+kx row-major; 1 for 1x1)
  *   d_bias      : DEVICE fp32 [c_out] or NULL;  relu != 0 applies max(x, 0)
  *   outputs     : DEVICE NHWC [B,H,W,c_out] as bf16 and/or fp32 (either may be NULL, not both); c_out % 32 == 0
+ * Which kernel runs is decided per layer shape: 3x3 layers whose map tiles into 8 x 16 pixel tiles
+ * (W % 8 == 0, H % 16 == 0) and whose weights fit (resident, or streamed up to 256 input channels) run on the halo kernel as
+ * clusters of two CTAs (tcgen05 cta_group::2); everything else on the persistent kernel.  The result does not depend on the
+ * CTA pairing (bit-identical, tests/test_conv_gpu.py); INTEGRATION.md lists the IM2IM_* switches that force a route.
  */
 int im2im_conv_igemm_bf16(const void* d_x1, int32_t c_in1, const void* d_x2, int32_t c_in2, const void* d_weight,
                           const float* d_bias, int32_t B, int32_t H, int32_t W, int32_t c_out, int32_t taps,
